@@ -1,0 +1,97 @@
+// Internal helpers shared by every translation unit of libdfb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <atomic>
+
+#include "../../include/dfb200.h"
+
+namespace dfb {
+
+// ---- error reporting ------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+// Lazily creates the context/streams. Returns DFB_OK or an error status (message set).
+dfb_status ensure_init();
+cudaStream_t compute_stream();
+cudaStream_t comm_stream();
+int sm_count();
+
+#define DFB_FAIL(code, ...)         \
+  do {                              \
+    ::dfb::set_error(__VA_ARGS__);  \
+    return (code);                  \
+  } while (0)
+
+#define DFB_REQUIRE(cond, code, ...) \
+  do {                               \
+    if (!(cond)) DFB_FAIL(code, __VA_ARGS__); \
+  } while (0)
+
+#define DFB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      DFB_FAIL(DFB_ERR_RUNTIME, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+               __FILE__, __LINE__);                                                      \
+  } while (0)
+
+#define DFB_INIT()                         \
+  do {                                     \
+    dfb_status _s = ::dfb::ensure_init();  \
+    if (_s != DFB_OK) return _s;           \
+  } while (0)
+
+// Checks the launch like the reference does after every kernel (cudaGetLastError,
+// ndarray_backend_cuda.cu:140) and counts it.
+#define DFB_LAUNCH_CHECK(name)                                                            \
+  do {                                                                                    \
+    ::dfb::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess)                                                                \
+      DFB_FAIL(DFB_ERR_RUNTIME, "%s kernel launch failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Grid size for grid-stride bandwidth kernels: enough CTAs to fill 148 SMs a few times over,
+// never more than the work.
+static inline unsigned bw_grid(size_t work_items, unsigned threads, unsigned ctas_per_sm = 8) {
+  size_t need = (work_items + threads - 1) / threads;
+  size_t cap = (size_t)sm_count() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (unsigned)(need < cap ? need : cap);
+}
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// streaming 128-bit accesses (read-once / write-once data; keeps L1 for the reused operands)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w));
+}
+#endif
+
+}  // namespace dfb

@@ -1,0 +1,101 @@
+// Dispatchers for the dense contractions: matmul / gemm / conv2d fprop, dgrad, wgrad.
+//
+// mode DFB_MODE_FP32 and DFB_MODE_SIMT run the exact-fp32 FFMA kernels (gemm_simt.cu);
+// DFB_MODE_TF32 / DFB_MODE_BF16 run the TMA + tcgen05 kernels (gemm_tc.cu) when the shape
+// qualifies and otherwise the FFMA kernels (which are more accurate, never less).
+#include "kernels.cuh"
+
+using namespace dfb;
+
+static bool want_tc(int mode) { return mode == DFB_MODE_TF32 || mode == DFB_MODE_BF16; }
+
+static dfb_status check_mode(const char* name, int mode) {
+  DFB_REQUIRE(mode >= DFB_MODE_FP32 && mode <= DFB_MODE_SIMT, DFB_ERR_INVALID, "%s: unknown mode %d", name, mode);
+  return DFB_OK;
+}
+
+extern "C" {
+
+dfb_status dfb_gemm(const float* A, const float* B, float* C, int M, int N, int K, int trans_a, int trans_b,
+                    int lda, int ldb, int ldc, int accumulate, const float* bias, int mode) {
+  DFB_INIT();
+  DFB_REQUIRE(A && B && C, DFB_ERR_INVALID, "gemm: null pointer");
+  DFB_REQUIRE(M >= 0 && N >= 0 && K >= 0, DFB_ERR_INVALID, "gemm: negative dimension");
+  dfb_status st = check_mode("gemm", mode);
+  if (st != DFB_OK) return st;
+  DFB_REQUIRE(lda >= (trans_a ? M : K) && ldb >= (trans_b ? K : N) && ldc >= N, DFB_ERR_INVALID,
+              "gemm: leading dimension too small (lda=%d ldb=%d ldc=%d for M=%d N=%d K=%d ta=%d tb=%d)", lda,
+              ldb, ldc, M, N, K, trans_a, trans_b);
+  if (M == 0 || N == 0) return DFB_OK;
+  if (want_tc(mode)) {
+    bool handled = false;
+    st = tc_gemm(A, B, C, M, N, K, trans_a, trans_b, lda, ldb, ldc, accumulate, bias, mode, &handled);
+    if (st != DFB_OK || handled) return st;
+  }
+  return simt_gemm(A, B, C, M, N, K, trans_a, trans_b, lda, ldb, ldc, accumulate, bias);
+}
+
+// matmul: ndarray_backend_cuda.cu:443-466 — out[M,P] = a[M,N] . b[N,P]
+dfb_status dfb_matmul(const float* a, const float* b, float* out, uint32_t M, uint32_t N, uint32_t P, int mode) {
+  DFB_REQUIRE(out != nullptr, DFB_ERR_INVALID, "Matmul: out array cannot be null");
+  DFB_REQUIRE(M < (1u << 31) && N < (1u << 31) && P < (1u << 31), DFB_ERR_INVALID, "Matmul: dimension too large");
+  return dfb_gemm(a, b, out, (int)M, (int)P, (int)N, 0, 0, (int)N, (int)P, (int)P, 0, nullptr, mode);
+}
+
+dfb_status dfb_conv2d_workspace_floats(int N, int C, int H, int W, int K, int R, int pad, int stride,
+                                       size_t* n_floats) {
+  DFB_REQUIRE(n_floats != nullptr, DFB_ERR_INVALID, "conv2d_workspace_floats: null output");
+  *n_floats = tc_conv_workspace_floats(N, C, H, W, K, R, pad, stride);
+  return DFB_OK;
+}
+
+dfb_status dfb_conv2d_fprop(const float* x, int x_layout, const float* w, float* y, int N, int C, int H, int W,
+                            int K, int R, int pad, int stride, int mode, float* workspace,
+                            size_t workspace_floats) {
+  DFB_INIT();
+  DFB_REQUIRE(x && w && y, DFB_ERR_INVALID, "conv2d_fprop: null pointer");
+  DFB_REQUIRE(x_layout == DFB_LAYOUT_NCHW || x_layout == DFB_LAYOUT_NHWC, DFB_ERR_INVALID, "conv2d_fprop: bad layout");
+  dfb_status st = check_mode("conv2d_fprop", mode);
+  if (st != DFB_OK) return st;
+  if (want_tc(mode) && x_layout == DFB_LAYOUT_NHWC) {
+    bool handled = false;
+    st = tc_conv_fprop(x, w, y, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
+    if (st != DFB_OK || handled) return st;
+  }
+  return simt_conv_fprop(x, x_layout, w, y, N, C, H, W, K, R, pad, stride);
+}
+
+dfb_status dfb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int C, int H, int W, int K, int R,
+                            int pad, int stride, int mode, int dgrad_mode, float* workspace,
+                            size_t workspace_floats) {
+  DFB_INIT();
+  DFB_REQUIRE(dy && w && dx, DFB_ERR_INVALID, "conv2d_dgrad: null pointer");
+  DFB_REQUIRE(dgrad_mode == DFB_DGRAD_REFERENCE || dgrad_mode == DFB_DGRAD_EXACT, DFB_ERR_INVALID,
+              "conv2d_dgrad: bad dgrad_mode %d", dgrad_mode);
+  dfb_status st = check_mode("conv2d_dgrad", mode);
+  if (st != DFB_OK) return st;
+  if (want_tc(mode) && dgrad_mode == DFB_DGRAD_EXACT) {
+    bool handled = false;
+    st = tc_conv_dgrad(dy, w, dx, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
+    if (st != DFB_OK || handled) return st;
+  }
+  return simt_conv_dgrad(dy, w, dx, N, C, H, W, K, R, pad, stride, dgrad_mode);
+}
+
+dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float* dw, int N, int C, int H, int W,
+                            int K, int R, int pad, int stride, int mode, float* workspace,
+                            size_t workspace_floats) {
+  DFB_INIT();
+  DFB_REQUIRE(x && dy && dw, DFB_ERR_INVALID, "conv2d_wgrad: null pointer");
+  DFB_REQUIRE(x_layout == DFB_LAYOUT_NCHW || x_layout == DFB_LAYOUT_NHWC, DFB_ERR_INVALID, "conv2d_wgrad: bad layout");
+  dfb_status st = check_mode("conv2d_wgrad", mode);
+  if (st != DFB_OK) return st;
+  if (want_tc(mode) && x_layout == DFB_LAYOUT_NHWC) {
+    bool handled = false;
+    st = tc_conv_wgrad(x, dy, dw, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
+    if (st != DFB_OK || handled) return st;
+  }
+  return simt_conv_wgrad(x, x_layout, dy, dw, N, C, H, W, K, R, pad, stride);
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+// Multi-tensor optimizer steps: one launch updates every parameter tensor.
+//
+// The reference walks the parameter list in Python and issues ~14 (Adam) / ~6 (SGD) out-of-place
+// BackendTensor kernels plus as many allocations per parameter
+// (DeepFlows/optim/adam.py:28-63, DeepFlows/optim/sgd.py:16-24). Here the host packs a table of
+// device pointers, uploads it once per step through a pinned staging buffer, and a single
+// grid-stride kernel walks fixed-size chunks of all tensors. The arithmetic follows the
+// reference's operation order in fp32 (no FMA contraction) so a step is reproducible against it.
+#include "common.cuh"
+
+#include <vector>
+
+namespace dfb {
+
+constexpr int kChunk = 4096;  // elements per work item (16 per thread at 256 threads, as float4)
+
+struct TensorRef {
+  float* p;
+  const float* g;
+  float* m;   // Adam first moment / SGD velocity
+  float* v;   // Adam second moment
+  unsigned long long size;
+  unsigned long long first_chunk;  // prefix sum of chunk counts
+};
+
+struct AdamHyper {
+  float lr, beta1, beta2, one_minus_beta1, one_minus_beta2, bias1, bias2, eps, weight_decay, grad_scale;
+  int use_wd, use_scale;
+};
+struct SgdHyper {
+  float lr, momentum, weight_decay, grad_scale;
+  int use_momentum, nesterov, use_scale;
+};
+
+__device__ __forceinline__ int find_tensor(const TensorRef* __restrict__ t, int count, unsigned long long chunk) {
+  int lo = 0, hi = count - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (t[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, const AdamHyper& h) {
+  if (h.use_scale) g = __fmul_rn(g, h.grad_scale);
+  if (h.use_wd) g = __fadd_rn(g, __fmul_rn(p, h.weight_decay));           // grad + p * wd
+  m = __fadd_rn(__fmul_rn(m, h.beta1), __fmul_rn(g, h.one_minus_beta1));   // v*b1 + g*(1-b1)
+  v = __fadd_rn(__fmul_rn(v, h.beta2), __fmul_rn(__fmul_rn(g, g), h.one_minus_beta2));
+  float mh = __fdiv_rn(m, h.bias1);                                         // v / (1 - b1**t)
+  float vh = __fdiv_rn(v, h.bias2);
+  float upd = __fmul_rn(__fdiv_rn(mh, __fadd_rn(sqrtf(vh), h.eps)), h.lr);  // v_hat/(s_hat**.5+eps)*lr
+  p = __fadd_rn(p, -upd);
+  return p;
+}
+
+__global__ void __launch_bounds__(256)
+multi_adam_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks, AdamHyper h) {
+  for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int ti = find_tensor(tensors, count, chunk);
+    TensorRef t = tensors[ti];
+    unsigned long long begin = (chunk - t.first_chunk) * kChunk;
+    unsigned long long end = begin + kChunk < t.size ? begin + kChunk : t.size;
+    bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
+                 reinterpret_cast<uintptr_t>(t.m) | reinterpret_cast<uintptr_t>(t.v)) & 15) == 0;
+    if (vec) {
+      for (unsigned long long i = begin + threadIdx.x * 4ull; i + 4 <= end; i += blockDim.x * 4ull) {
+        float4 p = *reinterpret_cast<float4*>(t.p + i);
+        float4 g = *reinterpret_cast<const float4*>(t.g + i);
+        float4 m = *reinterpret_cast<float4*>(t.m + i);
+        float4 v = *reinterpret_cast<float4*>(t.v + i);
+        adam_one(p.x, g.x, m.x, v.x, h); adam_one(p.y, g.y, m.y, v.y, h);
+        adam_one(p.z, g.z, m.z, v.z, h); adam_one(p.w, g.w, m.w, v.w, h);
+        *reinterpret_cast<float4*>(t.p + i) = p;
+        *reinterpret_cast<float4*>(t.m + i) = m;
+        *reinterpret_cast<float4*>(t.v + i) = v;
+      }
+    }
+    // scalar part: the <4-element tail of an aligned tensor, or everything when unaligned
+    unsigned long long sbeg = vec ? begin + ((end - begin) & ~3ull) : begin;
+    for (unsigned long long q = sbeg + threadIdx.x; q < end; q += blockDim.x)
+      adam_one(t.p[q], t.g[q], t.m[q], t.v[q], h);
+  }
+}
+
+__device__ __forceinline__ void sgd_one(float& p, float g, float* vel, const SgdHyper& h) {
+  if (h.use_scale) g = __fmul_rn(g, h.grad_scale);
+  g = __fadd_rn(g, __fmul_rn(p, h.weight_decay));  // always, even for wd == 0 (sgd.py:18)
+  float upd = g;
+  if (h.use_momentum) {
+    float v = __fadd_rn(__fmul_rn(*vel, h.momentum), g);
+    *vel = v;
+    upd = h.nesterov ? __fadd_rn(g, __fmul_rn(v, h.momentum)) : v;
+  }
+  p = __fadd_rn(p, -__fmul_rn(upd, h.lr));
+}
+
+__global__ void __launch_bounds__(256)
+multi_sgd_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks, SgdHyper h) {
+  for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int ti = find_tensor(tensors, count, chunk);
+    TensorRef t = tensors[ti];
+    unsigned long long begin = (chunk - t.first_chunk) * kChunk;
+    unsigned long long end = begin + kChunk < t.size ? begin + kChunk : t.size;
+    for (unsigned long long i = begin + threadIdx.x; i < end; i += blockDim.x) {
+      float p = t.p[i];
+      float vel = h.use_momentum ? t.m[i] : 0.f;
+      sgd_one(p, t.g[i], &vel, h);
+      t.p[i] = p;
+      if (h.use_momentum) t.m[i] = vel;
+    }
+  }
+}
+
+// pinned staging for the pointer table: a small ring so consecutive steps do not wait on each other
+struct TableStage {
+  static constexpr int kSlots = 4;
+  void* host[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  void* dev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kSlots] = {0, 0, 0, 0};
+  cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  int next = 0;
+};
+static TableStage g_stage;
+
+static dfb_status upload_table(const std::vector<TensorRef>& tab, const TensorRef** dev_out) {
+  TableStage& st = g_stage;
+  int s = st.next;
+  st.next = (st.next + 1) % TableStage::kSlots;
+  size_t bytes = tab.size() * sizeof(TensorRef);
+  if (st.done[s]) DFB_CUDA(cudaEventSynchronize(st.done[s]));
+  if (st.cap[s] < bytes) {
+    if (st.host[s]) cudaFreeHost(st.host[s]);
+    if (st.dev[s]) cudaFree(st.dev[s]);
+    size_t cap = bytes < 16384 ? 16384 : bytes * 2;
+    DFB_CUDA(cudaHostAlloc(&st.host[s], cap, cudaHostAllocDefault));
+    DFB_CUDA(cudaMalloc(&st.dev[s], cap));
+    st.cap[s] = cap;
+  }
+  if (!st.done[s]) DFB_CUDA(cudaEventCreateWithFlags(&st.done[s], cudaEventDisableTiming));
+  memcpy(st.host[s], tab.data(), bytes);
+  DFB_CUDA(cudaMemcpyAsync(st.dev[s], st.host[s], bytes, cudaMemcpyHostToDevice, compute_stream()));
+  DFB_CUDA(cudaEventRecord(st.done[s], compute_stream()));
+  *dev_out = (const TensorRef*)st.dev[s];
+  return DFB_OK;
+}
+
+static dfb_status build_table(const char* name, float* const* params, const float* const* grads,
+                              float* const* m, float* const* v, const size_t* sizes, int count,
+                              bool need_m, bool need_v, std::vector<TensorRef>* tab,
+                              unsigned long long* total_chunks) {
+  DFB_REQUIRE(count >= 0, DFB_ERR_INVALID, "%s: negative tensor count", name);
+  tab->clear();
+  unsigned long long chunks = 0;
+  for (int i = 0; i < count; ++i) {
+    if (sizes[i] == 0) continue;
+    DFB_REQUIRE(params[i] && grads[i], DFB_ERR_INVALID, "%s: null param/grad pointer for tensor %d", name, i);
+    DFB_REQUIRE(!need_m || (m && m[i]), DFB_ERR_INVALID, "%s: null state pointer for tensor %d", name, i);
+    DFB_REQUIRE(!need_v || (v && v[i]), DFB_ERR_INVALID, "%s: null state pointer for tensor %d", name, i);
+    TensorRef t;
+    t.p = params[i];
+    t.g = grads[i];
+    t.m = m ? m[i] : nullptr;
+    t.v = v ? v[i] : nullptr;
+    t.size = sizes[i];
+    t.first_chunk = chunks;
+    chunks += (sizes[i] + kChunk - 1) / kChunk;
+    tab->push_back(t);
+  }
+  *total_chunks = chunks;
+  return DFB_OK;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+dfb_status dfb_multi_adam_step(float* const* params, const float* const* grads, float* const* exp_avg,
+                               float* const* exp_avg_sq, const size_t* sizes, int count, double lr,
+                               double beta1, double beta2, double eps, double weight_decay, int step_t,
+                               double grad_scale) {
+  DFB_INIT();
+  DFB_REQUIRE(step_t >= 1, DFB_ERR_INVALID, "multi_adam_step: step_t starts at 1 (adam.py:26), got %d", step_t);
+  std::vector<TensorRef> tab;
+  unsigned long long chunks = 0;
+  dfb_status st = build_table("multi_adam_step", params, grads, exp_avg, exp_avg_sq, sizes, count, true, true, &tab, &chunks);
+  if (st != DFB_OK) return st;
+  if (chunks == 0) return DFB_OK;
+  const TensorRef* dev = nullptr;
+  st = upload_table(tab, &dev);
+  if (st != DFB_OK) return st;
+  AdamHyper h;
+  // every scalar is a Python double rounded to float32 when it reaches a scalar_* kernel
+  h.lr = (float)lr;
+  h.beta1 = (float)beta1;
+  h.beta2 = (float)beta2;
+  h.one_minus_beta1 = (float)(1.0 - beta1);
+  h.one_minus_beta2 = (float)(1.0 - beta2);
+  h.bias1 = (float)(1.0 - pow(beta1, (double)step_t));
+  h.bias2 = (float)(1.0 - pow(beta2, (double)step_t));
+  h.eps = (float)eps;
+  h.weight_decay = (float)weight_decay;
+  h.grad_scale = (float)grad_scale;
+  h.use_wd = weight_decay > 0.0;
+  h.use_scale = grad_scale != 1.0;
+  unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
+  multi_adam_kernel<<<grid, 256, 0, compute_stream()>>>(dev, (int)tab.size(), chunks, h);
+  DFB_LAUNCH_CHECK("multi_adam_step");
+  return DFB_OK;
+}
+
+dfb_status dfb_multi_sgd_step(float* const* params, const float* const* grads, float* const* velocity,
+                              const size_t* sizes, int count, double lr, double momentum,
+                              double weight_decay, int nesterov, double grad_scale) {
+  DFB_INIT();
+  std::vector<TensorRef> tab;
+  unsigned long long chunks = 0;
+  bool use_m = momentum > 0.0;
+  dfb_status st = build_table("multi_sgd_step", params, grads, velocity, nullptr, sizes, count, use_m, false, &tab, &chunks);
+  if (st != DFB_OK) return st;
+  if (chunks == 0) return DFB_OK;
+  const TensorRef* dev = nullptr;
+  st = upload_table(tab, &dev);
+  if (st != DFB_OK) return st;
+  SgdHyper h;
+  h.lr = (float)lr;
+  h.momentum = (float)momentum;
+  h.weight_decay = (float)weight_decay;
+  h.grad_scale = (float)grad_scale;
+  h.use_momentum = use_m;
+  h.nesterov = nesterov != 0;
+  h.use_scale = grad_scale != 1.0;
+  unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
+  multi_sgd_kernel<<<grid, 256, 0, compute_stream()>>>(dev, (int)tab.size(), chunks, h);
+  DFB_LAUNCH_CHECK("multi_sgd_step");
+  return DFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+/*
+ * dfb200.h — C ABI of libdfb200.so, the B200 (sm_100a) compute backend for DeepFlows.
+ *
+ * This header is the drop-in boundary. Everything the reference binds through its one
+ * pybind module `CUDA_BACKEND`
+ *   (reference: DeepFlows/backend/backend_src/ndarray_backend_cuda.cu:515-716)
+ * has an `extern "C"` entry point here ("L0", same argument meaning and error behaviour),
+ * plus the fused entry points ("L1") that replace what the reference composes in Python
+ *   (DeepFlows/nn/functional.py, DeepFlows/nn/modules/batchnorm.py, DeepFlows/optim/*.py).
+ *
+ * Conventions
+ *   - every function returns a dfb_status (0 = ok). On error the message is available from
+ *     dfb_last_error() (thread local). The status classes mirror the C++ exception classes the
+ *     reference throws through pybind (std::invalid_argument -> ValueError, ...), see
+ *     ndarray_backend_cuda.cu:113-118,136,167,189,211-212,305.
+ *   - all `float*` / `const float*` arguments are DEVICE pointers unless the name says `host`.
+ *   - sizes are element counts (float32), not bytes.
+ *   - all work is enqueued on the library's compute stream (dfb_stream()); results are visible
+ *     to a subsequent dfb_to_host() without an explicit sync, like the reference's default
+ *     stream + cudaMemcpy (ndarray_backend_cuda.cu:678,708).
+ *   - no function falls back to the CPU. Without a usable CUDA device every call fails with
+ *     DFB_ERR_RUNTIME.
+ */
+#ifndef DFB200_H_
+#define DFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB_API __attribute__((visibility("default")))
+
+typedef int dfb_status;
+enum {
+  DFB_OK = 0,
+  DFB_ERR_INVALID = 1,      /* std::invalid_argument -> ValueError   */
+  DFB_ERR_RUNTIME = 2,      /* std::runtime_error    -> RuntimeError */
+  DFB_ERR_OUT_OF_RANGE = 3, /* std::out_of_range     -> IndexError   */
+  DFB_ERR_NOMEM = 4,        /* std::bad_alloc        -> MemoryError  */
+  DFB_ERR_DOMAIN = 5        /* std::domain_error     -> ValueError   */
+};
+
+#define DFB_MAX_DIMS 8 /* reference: MAX_VEC_SIZE, ndarray_backend_cuda.cu:17 */
+
+/* GEMM / conv operand precision modes (north star: fp32-accurate, TF32, BF16 operand modes;
+ * accumulation is always fp32). */
+enum {
+  DFB_MODE_FP32 = 0,  /* 3xTF32 error-compensated split on tcgen05 (or FFMA for tiny shapes) */
+  DFB_MODE_TF32 = 1,  /* single-pass TF32 operands                                          */
+  DFB_MODE_BF16 = 2,  /* operands rounded to bf16 in shared memory, kind::f16 MMA            */
+  DFB_MODE_SIMT = 3   /* force the FFMA kernel (exact fp32 operands; testing / tiny shapes)  */
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * Runtime: device, streams, events, memory
+ * ------------------------------------------------------------------------------------------- */
+DFB_API const char* dfb_last_error(void);
+DFB_API const char* dfb_version(void);
+/* Select the CUDA device for this process (one process per GPU). Lazy default: device 0,
+ * like the reference (it never calls cudaSetDevice). Must be called before the first
+ * allocation to have an effect. */
+DFB_API dfb_status dfb_set_device(int device);
+DFB_API dfb_status dfb_get_device(int* device);
+DFB_API dfb_status dfb_device_count(int* count);
+DFB_API dfb_status dfb_device_info(char* name, size_t name_cap, int* sm_count, int* cc_major,
+                                   int* cc_minor, size_t* total_mem_bytes);
+DFB_API dfb_status dfb_synchronize(void);
+/* cudaStream_t of the compute stream, as an opaque pointer (for event timing by callers). */
+DFB_API void* dfb_stream(void);
+
+/* CUDA events on the compute stream (bench.py times with these). */
+DFB_API dfb_status dfb_event_create(void** ev);
+DFB_API dfb_status dfb_event_destroy(void* ev);
+DFB_API dfb_status dfb_event_record(void* ev);
+DFB_API dfb_status dfb_event_synchronize(void* ev);
+DFB_API dfb_status dfb_event_elapsed_ms(void* start, void* stop, float* ms);
+
+/* Device buffers. Replaces CudaArray (ndarray_backend_cuda.cu:48-83): an owning 1-D float32
+ * device buffer. Memory comes from a caching pool (no cudaMalloc/cudaFree per temporary). */
+DFB_API dfb_status dfb_malloc(size_t n_floats, float** out_ptr);
+DFB_API dfb_status dfb_free(float* ptr);
+DFB_API dfb_status dfb_empty_cache(void);
+DFB_API dfb_status dfb_mem_stats(size_t* bytes_in_use, size_t* bytes_reserved,
+                                 size_t* n_cuda_malloc);
+/* launches issued by this library since process start (kernels only; bench.py "gpu_launches") */
+DFB_API uint64_t dfb_launch_count(void);
+
+/* Host <-> device. Replaces from_numpy / to_numpy (ndarray_backend_cuda.cu:667-716). The copy
+ * is staged through pinned memory owned by the library and is complete on return. */
+DFB_API dfb_status dfb_from_host(const float* host_src, float* dst, size_t n);
+DFB_API dfb_status dfb_to_host(const float* src, float* host_dst, size_t n);
+/* Async variants on the compute stream for callers that own pinned memory (input pipeline). */
+DFB_API dfb_status dfb_host_alloc_pinned(size_t n_floats, float** host_ptr);
+DFB_API dfb_status dfb_host_free_pinned(float* host_ptr);
+DFB_API dfb_status dfb_from_host_async(const float* pinned_src, float* dst, size_t n);
+DFB_API dfb_status dfb_to_host_async(const float* src, float* pinned_dst, size_t n);
+DFB_API dfb_status dfb_copy(const float* src, float* dst, size_t n); /* device to device */
+
+/* CUDA-graph capture of everything enqueued on the compute stream between begin/end. */
+DFB_API dfb_status dfb_graph_begin_capture(void);
+DFB_API dfb_status dfb_graph_end_capture(void** graph_exec);
+DFB_API dfb_status dfb_graph_launch(void* graph_exec);
+DFB_API dfb_status dfb_graph_destroy(void* graph_exec);
+
+/* ---------------------------------------------------------------------------------------------
+ * L0: the device-module protocol (one entry per binding of the reference module)
+ * ------------------------------------------------------------------------------------------- */
+/* fill: ndarray_backend_cuda.cu:127-144 */
+DFB_API dfb_status dfb_fill(float* out, float value, size_t n);
+/* compact (strided gather): cu:157-176. out[gid] = a[offset + sum_d idx_d*strides[d]] */
+DFB_API dfb_status dfb_compact(const float* a, float* out, size_t out_size, int ndim,
+                               const int32_t* shape, const int32_t* strides, size_t offset);
+/* ewise_setitem (strided scatter): cu:178-198. out[idx(gid)] = a[gid], gid < a_size */
+DFB_API dfb_status dfb_ewise_setitem(const float* a, size_t a_size, float* out, int ndim,
+                                     const int32_t* shape, const int32_t* strides, size_t offset);
+/* scalar_setitem: cu:200-221 */
+DFB_API dfb_status dfb_scalar_setitem(size_t size, float value, float* out, size_t out_size,
+                                      int ndim, const int32_t* shape, const int32_t* strides,
+                                      size_t offset);
+/* binary elementwise: cu:224-243,259-270,285-296,325-336,351-362,377-388 */
+DFB_API dfb_status dfb_ewise_add(const float* a, const float* b, float* out, size_t n);
+DFB_API dfb_status dfb_ewise_mul(const float* a, const float* b, float* out, size_t n);
+DFB_API dfb_status dfb_ewise_div(const float* a, const float* b, float* out, size_t n);
+DFB_API dfb_status dfb_ewise_maximum(const float* a, const float* b, float* out, size_t n);
+DFB_API dfb_status dfb_ewise_eq(const float* a, const float* b, float* out, size_t n);
+DFB_API dfb_status dfb_ewise_ge(const float* a, const float* b, float* out, size_t n);
+/* tensor-scalar: cu:246-257,272-283,298-323,338-349,364-375,390-401.
+ * dfb_scalar_div(value == 0) fails with DFB_ERR_DOMAIN (cu:305). */
+DFB_API dfb_status dfb_scalar_add(const float* a, float value, float* out, size_t n);
+DFB_API dfb_status dfb_scalar_mul(const float* a, float value, float* out, size_t n);
+DFB_API dfb_status dfb_scalar_div(const float* a, float value, float* out, size_t n);
+DFB_API dfb_status dfb_scalar_power(const float* a, float value, float* out, size_t n);
+DFB_API dfb_status dfb_scalar_maximum(const float* a, float value, float* out, size_t n);
+DFB_API dfb_status dfb_scalar_eq(const float* a, float value, float* out, size_t n);
+DFB_API dfb_status dfb_scalar_ge(const float* a, float value, float* out, size_t n);
+/* unary: cu:403-440. log(a <= 0) = -inf (cu:405). */
+DFB_API dfb_status dfb_ewise_log(const float* a, float* out, size_t n);
+DFB_API dfb_status dfb_ewise_exp(const float* a, float* out, size_t n);
+DFB_API dfb_status dfb_ewise_tanh(const float* a, float* out, size_t n);
+/* matmul: cu:443-466. out[M,P] = a[M,N] . b[N,P], row-major (inner dimension is called N). */
+DFB_API dfb_status dfb_matmul(const float* a, const float* b, float* out, uint32_t M, uint32_t N,
+                              uint32_t P, int mode);
+/* reductions over trailing contiguous `reduce_size`: cu:469-509 */
+DFB_API dfb_status dfb_reduce_sum(const float* a, float* out, size_t out_size, size_t reduce_size);
+DFB_API dfb_status dfb_reduce_max(const float* a, float* out, size_t out_size, size_t reduce_size);
+
+/* ---------------------------------------------------------------------------------------------
+ * L1: fused entry points behind nn/ and optim/
+ * ------------------------------------------------------------------------------------------- */
+/* General row-major GEMM on tcgen05:  C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]).
+ *   trans_a = 0: A stored [M,K] (lda >= K);  trans_a = 1: A stored [K,M] (lda >= M)
+ *   trans_b = 0: B stored [K,N] (ldb >= N);  trans_b = 1: B stored [N,K] (ldb >= K)
+ *   accumulate != 0: C += result.  bias may be NULL.
+ * Replaces BackendTensor.__matmul__ + the compact()ed transposes of matmul.grad_fn
+ * (DeepFlows/backend/backend_tensor.py:612-622, DeepFlows/tensor.py:699-716). */
+DFB_API dfb_status dfb_gemm(const float* A, const float* B, float* C, int M, int N, int K,
+                            int trans_a, int trans_b, int lda, int ldb, int ldc, int accumulate,
+                            const float* bias, int mode);
+
+/* Convolution (square kernel R, symmetric zero padding, scalar stride, no dilation/groups),
+ * replacing F.conv2d = __pad2d + __im2col2d + permute/compact + matmul
+ * (DeepFlows/nn/functional.py:249-344).
+ *   x_layout / y layouts: DFB_LAYOUT_NCHW (compact NCHW) or DFB_LAYOUT_NHWC (channels-last).
+ *   w is (K, C, R, R) compact, exactly the reference's Conv2d.weight (nn/modules/conv.py:85-88).
+ *   y, dy, dx are always channels-last (N, OH, OW, K) / (N, H, W, C) physical order — the same
+ *   physical order the reference's conv output has before its transpose(0,3,1,2) view
+ *   (functional.py:343-344).
+ *   workspace: device scratch of at least dfb_conv2d_workspace_floats(...) floats. */
+enum { DFB_LAYOUT_NCHW = 0, DFB_LAYOUT_NHWC = 1 };
+enum {
+  DFB_DGRAD_REFERENCE = 0, /* last-writer-wins scatter of functional.py:285-294 */
+  DFB_DGRAD_EXACT = 1      /* true transposed convolution (sum over taps)                   */
+};
+DFB_API dfb_status dfb_conv2d_workspace_floats(int N, int C, int H, int W, int K, int R, int pad,
+                                               int stride, size_t* n_floats);
+DFB_API dfb_status dfb_conv2d_fprop(const float* x, int x_layout, const float* w, float* y, int N,
+                                    int C, int H, int W, int K, int R, int pad, int stride,
+                                    int mode, float* workspace, size_t workspace_floats);
+DFB_API dfb_status dfb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int C,
+                                    int H, int W, int K, int R, int pad, int stride, int mode,
+                                    int dgrad_mode, float* workspace, size_t workspace_floats);
+DFB_API dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float* dw,
+                                    int N, int C, int H, int W, int K, int R, int pad, int stride,
+                                    int mode, float* workspace, size_t workspace_floats);
+
+/* y[r, c] = x[r, c] + v[c]   (conv bias (1,K,1,1) on channels-last, Linear bias (1,out);
+ * replaces broadcast_to + compact + ewise_add, backend_tensor.py:533-542) */
+DFB_API dfb_status dfb_add_rowvec(const float* x, const float* v, float* y, size_t rows, int cols);
+/* out[c] = sum_r x[r, c]  (broadcast-gradient reduction done on the host by the reference,
+ * DeepFlows/tensor.py:462-483) */
+DFB_API dfb_status dfb_colsum(const float* x, float* out, size_t rows, int cols);
+/* out[r] = sum_c x[r,c] is dfb_reduce_sum. */
+
+/* BatchNorm2d on channels-last data viewed as x[rows = N*H*W, C]
+ * (DeepFlows/nn/modules/batchnorm.py:30-55): batch mean, biased variance,
+ * x_hat = (x-mean)/(var+eps)**0.5, y = x_hat*gamma + beta; running stats updated in place with
+ * the biased variance: run = run*(1-momentum) + batch*momentum (batchnorm.py:44-46).
+ * save_mean / save_invstd (C floats each) are written for the backward pass.
+ * gamma/beta may be NULL (affine=False); running_* may be NULL (track_running_stats=False). */
+DFB_API dfb_status dfb_bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y,
+                                    float* save_mean, float* save_invstd, float* running_mean,
+                                    float* running_var, float momentum, float eps, size_t rows,
+                                    int C);
+DFB_API dfb_status dfb_bn_fwd_eval(const float* x, const float* gamma, const float* beta,
+                                   const float* running_mean, const float* running_var, float* y,
+                                   float eps, size_t rows, int C);
+/* dx, dgamma, dbeta of the composed reference graph (equals the textbook BN backward). dx,
+ * dgamma, dbeta may each be NULL when not needed. */
+DFB_API dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma,
+                              const float* save_mean, const float* save_invstd, float* dx,
+                              float* dgamma, float* dbeta, size_t rows, int C);
+
+/* ReLU (F.relu = maximum(x, 0), functional.py:15-16). Backward follows maximum.grad_fn
+ * (tensor.py:872-877): dx = (y == x) * dy, i.e. the gradient passes where x >= 0. */
+DFB_API dfb_status dfb_relu_fwd(const float* x, float* y, size_t n);
+DFB_API dfb_status dfb_relu_bwd(const float* x, const float* dy, float* dx, size_t n);
+
+/* 2-D max pooling on channels-last data, window k, stride s == k (non-overlapping), no padding
+ * — the only shape the configs use (functional.py:347-374). idx (optional, may be NULL) receives
+ * the first arg-max position inside the window (r*k + s) as int32, bit-exact with numpy argmax.
+ * Backward, reference semantics (tensor.py:779-791): every tied maximum receives the gradient. */
+DFB_API dfb_status dfb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, int N, int H, int W,
+                                     int C, int k);
+DFB_API dfb_status dfb_maxpool2d_bwd(const float* x, const float* y, const float* dy, float* dx,
+                                     int N, int H, int W, int C, int k);
+/* arg-max routed backward (single winner, torch semantics) */
+DFB_API dfb_status dfb_maxpool2d_bwd_idx(const int32_t* idx, const float* dy, float* dx, int N,
+                                         int H, int W, int C, int k);
+/* average pooling, same geometry (the reference's avg_pool2d raises) */
+DFB_API dfb_status dfb_avgpool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int k);
+DFB_API dfb_status dfb_avgpool2d_bwd(const float* dy, float* dx, int N, int H, int W, int C, int k);
+
+/* Fused softmax cross-entropy with dense targets (F.cross_entropy, functional.py:104-115):
+ *   loss = scale * sum_i sum_j -(x_ij - max_i - log sum_j exp(x_ij - max_i)) * t_ij
+ * with scale = 1/rows for reduction='mean', 1 for 'sum'. loss is one float.
+ * dlogits_ij = scale * upstream[0] * (softmax_ij * sum_j t_ij - t_ij). */
+DFB_API dfb_status dfb_softmax_ce_fwd(const float* logits, const float* target, float* loss,
+                                      size_t rows, int cols, float scale);
+DFB_API dfb_status dfb_softmax_ce_bwd(const float* logits, const float* target,
+                                      const float* upstream, float* dlogits, size_t rows, int cols,
+                                      float scale);
+
+/* Multi-tensor optimizer steps: ONE launch updates every parameter.
+ * The pointer tables are HOST arrays of device pointers, `count` entries each.
+ * Adam follows DeepFlows/optim/adam.py:28-63 exactly (L2 decay folded into the gradient,
+ * bias correction with t starting at 1, eps outside the sqrt). grad_scale multiplies every
+ * gradient first (1/world_size for data parallel).
+ * SGD follows DeepFlows/optim/sgd.py:16-24 (velocity v = v*momentum + g, optional nesterov).
+ * Hyper-parameters are doubles because the reference derives its float32 scalars from Python
+ * doubles (e.g. float32(1 - beta1**t)); velocity may be NULL when momentum == 0. */
+DFB_API dfb_status dfb_multi_adam_step(float* const* params, const float* const* grads,
+                                       float* const* exp_avg, float* const* exp_avg_sq,
+                                       const size_t* sizes, int count, double lr, double beta1,
+                                       double beta2, double eps, double weight_decay, int step_t,
+                                       double grad_scale);
+DFB_API dfb_status dfb_multi_sgd_step(float* const* params, const float* const* grads,
+                                      float* const* velocity, const size_t* sizes, int count,
+                                      double lr, double momentum, double weight_decay,
+                                      int nesterov, double grad_scale);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data parallel (new; the reference has no dist/): one process per GPU, NCCL over NVLink
+ * ------------------------------------------------------------------------------------------- */
+/* 128-byte ncclUniqueId created on rank 0 and shipped to the other ranks by the host layer. */
+DFB_API dfb_status dfb_comm_unique_id(unsigned char* id128);
+DFB_API dfb_status dfb_comm_init(const unsigned char* id128, int rank, int world_size);
+DFB_API dfb_status dfb_comm_destroy(void);
+DFB_API dfb_status dfb_comm_rank(int* rank, int* world_size);
+/* In-place sum all-reduce of a gradient bucket on the communication stream. The comm stream
+ * first waits for everything enqueued on the compute stream so far. */
+DFB_API dfb_status dfb_comm_allreduce_async(float* buf, size_t n);
+/* broadcast from rank `root` (initial weights) on the comm stream */
+DFB_API dfb_status dfb_comm_broadcast_async(float* buf, size_t n, int root);
+/* make the compute stream wait for all communication enqueued so far */
+DFB_API dfb_status dfb_comm_wait(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFB200_H_ */
