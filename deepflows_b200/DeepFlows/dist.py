@@ -1,0 +1,191 @@
+"""Data-parallel replicas (new: the reference has no dist/ package).
+
+One process per GPU (the autograd tape and the grad switch are process-global). Rank r trains on
+its shard of the global batch; after `backward()` the gradients of all parameters are packed into
+flat buckets and sum-all-reduced with NCCL on the communication stream while the host goes on;
+`Optimizer.step()` waits for the communication stream and folds the 1/world_size average into the
+fused optimizer kernel's `grad_scale`. Scripts stay unchanged: `init_from_env()` is called by the
+launcher shim (or explicitly), `backward()` and `step()` consult this module's context.
+
+The transport is pluggable so the bucketing logic can be tested on CPU: `NcclTransport` (libdfb200
+dfb_comm_*) for GPUs, `TorchGlooTransport` (torch.distributed, tests only) for the numpy device.
+"""
+import os
+import pickle
+import socket
+import struct
+import time
+
+from .tensor import Tensor, Graph
+from .backend.backend_tensor import BackendTensor
+
+_ctx = None
+
+
+class NcclTransport:
+    """NCCL over NVLink through the C ABI (dfb_comm_*). In-place sum on device buffers."""
+
+    def __init__(self, device, rank, world, master_addr, master_port):
+        self.device, self.rank, self.world = device, rank, world
+        uid = _exchange_unique_id(device, rank, world, master_addr, master_port)
+        device.comm_init(uid, rank, world)
+
+    def allreduce_sum(self, flat: BackendTensor):
+        self.device.comm_allreduce_async((flat._handle, flat._offset), flat.size)
+
+    def broadcast(self, flat: BackendTensor, root=0):
+        self.device.comm_broadcast_async((flat._handle, flat._offset), flat.size, root)
+
+    def wait(self):
+        self.device.comm_wait()
+
+    def close(self):
+        self.device.comm_destroy()
+
+
+def _exchange_unique_id(device, rank, world, addr, port):
+    """Rank 0 creates the NCCL id and serves it over a plain TCP socket on MASTER_PORT + 17."""
+    port = int(port) + 17
+    if rank == 0:
+        uid = device.comm_unique_id()
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((addr, port))
+        srv.listen(world)
+        for _ in range(world - 1):
+            conn, _peer = srv.accept()
+            conn.sendall(struct.pack("!I", len(uid)) + uid)
+            conn.close()
+        srv.close()
+        return uid
+    deadline = time.time() + 120
+    while True:
+        try:
+            conn = socket.create_connection((addr, port), timeout=5)
+            break
+        except OSError:
+            if time.time() > deadline:
+                raise
+            time.sleep(0.1)
+    n = struct.unpack("!I", _recv_exact(conn, 4))[0]
+    uid = _recv_exact(conn, n)
+    conn.close()
+    return uid
+
+
+def _recv_exact(conn, n):
+    buf = b""
+    while len(buf) < n:
+        chunk = conn.recv(n - len(buf))
+        if not chunk:
+            raise ConnectionError("peer closed while receiving the NCCL id")
+        buf += chunk
+    return buf
+
+
+class DataParallel:
+    """Bucketed gradient all-reduce for a fixed parameter list."""
+
+    def __init__(self, params, transport, bucket_mb=25.0):
+        self.params = [p for p in params]
+        self.transport = transport
+        self.world = transport.world
+        self.rank = transport.rank
+        self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
+        self._pending = False
+        self._plan = None  # [(flat BackendTensor, [(param index, offset, size)])]
+
+    # buckets are filled in reverse registration order: the last layers finish backward first
+    def _build_plan(self):
+        dev = self.params[0].device
+        plan, cur, cur_n = [], [], 0
+        for i in reversed(range(len(self.params))):
+            n = self.params[i].data.size
+            if cur and cur_n + n > self.bucket_elems:
+                plan.append((cur, cur_n))
+                cur, cur_n = [], 0
+            cur.append((i, cur_n, n))
+            cur_n += n
+        if cur:
+            plan.append((cur, cur_n))
+        self._plan = [(BackendTensor.make((n,), device=dev), slots) for slots, n in plan]
+
+    def broadcast_parameters(self, root=0):
+        """Make every replica start from rank `root`'s weights."""
+        for p in self.params:
+            if not p.data.is_compact():
+                p.data = p.data.compact()
+            self.transport.broadcast(p.data.reshape((p.data.size,)), root)
+        self.transport.wait()
+
+    def reduce_gradients(self):
+        """Pack gradients into the buckets and launch one all-reduce per bucket (asynchronous)."""
+        if self.world == 1:
+            return
+        if self._plan is None:
+            self._build_plan()
+        for flat, slots in self._plan:
+            for i, off, n in slots:
+                g = self.params[i].grad
+                if g is None:
+                    flat[off:off + n] = 0.0
+                else:
+                    flat[off:off + n] = g.compact().reshape((n,))
+            self.transport.allreduce_sum(flat)
+            # gradients now alias the bucket: the optimizer reads the reduced values in place
+            for i, off, n in slots:
+                p = self.params[i]
+                if p.grad is not None:
+                    p.grad = BackendTensor.make(p.data.shape, None, p.device, flat._handle, off)
+        self._pending = True
+
+    def pre_step(self):
+        """Called by Optimizer.step(): order the compute stream after the reductions and return the
+        gradient scale (1/world) to fold into the fused optimizer kernel."""
+        if self._pending:
+            self.transport.wait()
+            self._pending = False
+        return 1.0 / self.world
+
+
+def init(params, transport=None, bucket_mb=25.0, broadcast=True):
+    """Enable data parallelism for `params` (usually `model.parameters()`)."""
+    global _ctx
+    params = list(params)
+    if transport is None:
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        dev = params[0].device
+        transport = NcclTransport(dev, rank, world, os.environ.get("MASTER_ADDR", "127.0.0.1"),
+                                  os.environ.get("MASTER_PORT", "29500"))
+    _ctx = DataParallel(params, transport, bucket_mb)
+    Tensor._post_backward_hook = _ctx.reduce_gradients
+    if broadcast and _ctx.world > 1:
+        _ctx.broadcast_parameters(0)
+    return _ctx
+
+
+def shutdown():
+    global _ctx
+    if _ctx is not None:
+        Tensor._post_backward_hook = None
+        try:
+            _ctx.transport.close()
+        finally:
+            _ctx = None
+
+
+def context():
+    return _ctx
+
+
+def pre_step():
+    return _ctx.pre_step() if _ctx is not None else 1.0
+
+
+def get_rank():
+    return _ctx.rank if _ctx is not None else int(os.environ.get("RANK", "0"))
+
+
+def get_world_size():
+    return _ctx.world if _ctx is not None else 1

@@ -1,0 +1,2 @@
+from .dataset import Dataset  # noqa: F401
+from .dataloader import DataLoader, data_loader, Sampler, SequentialSampler, RandomSampler, BatchSampler  # noqa: F401
