@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py - the headline benchmark: ResNet-18 (CIFAR-10 shape) training throughput through the unchanged
+DeepFlows API on deepflows_b200's `cuda` device (BASELINE.json: configs[3], batch 256 per GPU, BatchNorm +
+Adam, data-parallel over N GPUs of one node).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision tf32|fp32|bf16] [--impl ours|reference]
+
+One JSON line on stdout (rank 0). A "step" = host batch -> forward -> softmax-CE -> backward ->
+(gradient all-reduce) -> Adam step.
+  value  : images/s with the batch already resident in HBM (device-timed with CUDA events on the compute
+           stream, max over ranks), whole job (all N GPUs).
+  e2e    : the same metric through the public API with HOST inputs: every step copies its batch from pinned
+           host memory and reads the loss back.
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+`--impl reference` times the reference's CPU path for the same workload (the oracle port of the reference
+algorithm: oracle/numpy_device.py under the same host code) on the host cores, on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import deepflows_b200  # noqa: E402,F401
+import workloads  # noqa: E402
+
+F32 = np.float32
+WIDTHS, LAYERS, HW, CLASSES = (32, 64, 128, 256), (2, 2, 2, 2), 32, 10
+
+
+def synthetic_batch(batch, seed):
+    rng = np.random.RandomState(seed)
+    x = np.clip(rng.randn(batch, 3, HW, HW), -1, 1).astype(F32)  # test/ResNet_CIFAR10_cuda.py:147
+    t = (np.eye(CLASSES, dtype=F32)[rng.randint(0, CLASSES, batch)] * (1 - 0.05) + 0.05 / CLASSES).astype(F32)  # :181-183
+    return x, t
+
+
+def conv_layers(batch):
+    """(name, N, C, H, W, K, R, pad, stride, count) of every conv in the model, for FLOP / byte accounting."""
+    out = [("stem", batch, 3, HW, HW, WIDTHS[0], 3, 1, 1, 1)]
+    h, cin = HW // 2, WIDTHS[0]
+    for si, (wd, nb) in enumerate(zip(WIDTHS, LAYERS)):
+        stride = 1 if si == 0 else 2
+        for b in range(nb):
+            s = stride if b == 0 else 1
+            out.append(("l%d.b%d.conv1" % (si + 1, b), batch, cin, h, h, wd, 3, 1, s, 1))
+            h2 = (h + 2 - 3) // s + 1
+            out.append(("l%d.b%d.conv2" % (si + 1, b), batch, wd, h2, h2, wd, 3, 1, 1, 1))
+            if b == 0 and (s != 1 or cin != wd):
+                out.append(("l%d.b%d.down" % (si + 1, b), batch, cin, h, h, wd, 1, 0, s, 1))
+            h, cin = h2, wd
+    return out
+
+
+def gemm_flops_per_step(batch):
+    total = 0
+    for i, (_, n, c, h, w, k, r, p, s, _) in enumerate(conv_layers(batch)):
+        oh = (h + 2 * p - r) // s + 1
+        f = 2.0 * n * oh * oh * k * c * r * r
+        total += f * (2 if i == 0 else 3)  # the stem has no dgrad
+    total += 3 * 2.0 * batch * WIDTHS[-1] * CLASSES
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for nm, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        busy = sorted(v for v in sm if mx is None or v > 0.3 * mx) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_training(device_name, batch, precision, seed=0):
+    import DeepFlows
+    from DeepFlows import backend_api, nn
+    df = workloads.namespace(DeepFlows)
+    if device_name == "cuda":
+        backend_api.set_precision(precision)
+    backend_api.set_dgrad_mode("exact")
+    np.random.seed(seed)
+    model = workloads.resnet_cifar(df, device_name, widths=WIDTHS, layers=LAYERS, num_classes=CLASSES, registered=True)
+    opt = df.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    return df, model, opt, nn.CrossEntropyLoss()
+
+
+def train_step(df, model, opt, crit, x, t):
+    out = model(x)
+    loss = crit(out, t)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cpu(args, batch, steps, warmup):
+    """The reference algorithm on the host cores: same host code on the oracle's numpy device."""
+    from oracle import numpy_device
+    from DeepFlows import backend_api
+    from DeepFlows.tensor import Tensor, Graph
+    backend_api.register_numpy_device(numpy_device)
+    df, model, opt, crit = build_training("cpu", batch, "fp32")
+    dev = backend_api.Device("cpu")
+    x, t = synthetic_batch(batch, 1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = train_step(df, model, opt, crit, Tensor(x, device=dev), Tensor(t, device=dev))
+        float(loss.data.numpy()[0])
+        Graph.free_graph()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    backend_api.register_numpy_device(None)
+    sec = sum(times) / len(times)
+    return {"value": batch / sec, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d steps (+%d warm-up) of ResNet-18/CIFAR at batch %d on the oracle numpy device (reference algorithm: "
+                      "im2col + sgemm, numpy/OpenBLAS threads)" % (steps, warmup, batch), "ms_per_step": sec * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--precision", default=os.environ.get("DEEPFLOWS_PRECISION", "tf32"))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "ResNet-18 CIFAR-10 shape (test/ResNet_CIFAR10_cuda.py, widths 32-64-128-256, all blocks registered), "
+                          "Adam lr 1e-3 wd 5e-4, label-smoothed dense targets, exact dgrad",
+              "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+              "image": "3x32x32", "parallelism": "dp%d" % world,
+              "l2": "per-step activation working set (~1.5 GB at batch 256) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+        base = run_cpu(args, args.cpu_batch, max(1, steps), warmup)
+        line = {"impl": "reference", "metric": "ResNet-18 CIFAR-10 train img/s", "value": base["value"], "unit": "img/s",
+                "n_gpus": args.gpus, "steps": max(1, steps), "warmup": warmup, "ms_per_step": base["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, batch_per_gpu=args.cpu_batch, global_batch=args.cpu_batch),
+                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    from DeepFlows import backend_api, dist
+    from DeepFlows.tensor import Tensor, Graph
+    from DeepFlows.backend.backend_tensor import BackendTensor
+    dev = backend_api.cuda()
+    if not dev.enabled():
+        raise SystemExit("CUDA_BACKEND extension is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+    dev.set_device(local_rank)
+    df, model, opt, crit = build_training("cuda", args.batch, args.precision)
+    if world > 1:
+        dist.init(model.parameters())
+    B = args.batch
+    x_host, t_host = synthetic_batch(B, 100 + rank)
+    px, pt = dev.pinned_empty(x_host.size), dev.pinned_empty(t_host.size)
+    px[:], pt[:] = x_host.reshape(-1), t_host.reshape(-1)
+    x_dev = Tensor(backend_api.Btensor(x_host, device=dev))
+    t_dev = Tensor(backend_api.Btensor(t_host, device=dev))
+
+    def barrier():
+        dev.synchronize()
+        if world > 1:
+            flag = BackendTensor.make((1,), device=dev)
+            flag.fill(1.0)
+            dev.comm_allreduce_async(flag._handle, 1)
+            dev.comm_wait()
+            dev.synchronize()
+
+    def resident_step():
+        train_step(df, model, opt, crit, x_dev, t_dev)
+        Graph.free_graph()
+
+    def e2e_step():
+        xa, ta = dev.Array(x_host.size), dev.Array(t_host.size)
+        dev.from_pinned_async(px, xa, x_host.size)
+        dev.from_pinned_async(pt, ta, t_host.size)
+        xt = Tensor(BackendTensor.make(x_host.shape, device=dev, handle=xa))
+        tt = Tensor(BackendTensor.make(t_host.shape, device=dev, handle=ta))
+        loss = train_step(df, model, opt, crit, xt, tt)
+        val = float(loss.data.numpy()[0])  # device -> host read of the step's result
+        Graph.free_graph()
+        return val
+
+    def timed(fn, steps):
+        ev0, ev1 = dev.event_create(), dev.event_create()
+        barrier()
+        l0 = dev.launch_count()
+        dev.event_record(ev0)
+        for _ in range(steps):
+            fn()
+        dev.event_record(ev1)
+        dev.event_synchronize(ev1)
+        barrier()
+        ms = dev.event_elapsed_ms(ev0, ev1)
+        launches = dev.launch_count() - l0
+        dev.event_destroy(ev0)
+        dev.event_destroy(ev1)
+        return ms, launches
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        v = np.zeros(world, F32)
+        v[rank] = ms
+        buf = backend_api.Btensor(v, device=dev)
+        dev.comm_allreduce_async(buf._handle, world)
+        dev.comm_wait()
+        return float(buf.numpy().max())
+
+    for _ in range(max(3, args.warmup)):
+        resident_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches = timed(resident_step, args.steps)
+    ms_res = max_over_ranks(ms_res)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    ms_e2e = max_over_ranks(ms_e2e)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel profile pass: CUDA events around every fused conv call, same steps ----------------
+    roofline = None
+    if rank == 0:
+        roofline = profile_dominant_kernel(dev, resident_step, args, B)
+
+    if world > 1:
+        barrier()
+        dist.shutdown()
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    total_imgs = B * world * args.steps
+    value = total_imgs / (ms_res / 1e3)
+    flops = gemm_flops_per_step(B)
+    line = {
+        "metric": "ResNet-18 CIFAR-10 train img/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"tf32": "tf32 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate"}.get(args.precision, "f32"),
+        "data": "synthetic", "config": config,
+        "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(4 * (x_host.size + t_host.size)), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
+        "gemm_tflops_per_gpu": flops / (ms_res / args.steps / 1e3) / 1e12,
+        "clocks": clocks, "roofline": roofline,
+    }
+    if roofline is not None:
+        if roofline["bound"] == "hbm":
+            peak, which = peaks.get("hbm_gbs"), "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"
+            if peak is None:
+                peak, which = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        else:
+            peak, which = peaks.get("bf16_tflops_sustained"), "measured sustained bf16 cuBLAS (MEASURED_PEAKS.json)"
+            if peak is None:
+                peak, which = 1400.0, "fallback sustained 1.4 PF (B200_PROFILING.md)"
+        roofline["peak"], roofline["peak_source"] = peak, which
+        roofline["frac"] = roofline["achieved"] / peak
+    if not args.no_cpu_baseline:
+        base = run_cpu(args, args.cpu_batch, 3, 1)
+        line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+
+
+def profile_dominant_kernel(dev, step_fn, args, batch):
+    """Time every conv2d_fprop / dgrad / wgrad and BatchNorm call of `steps` more identical steps with CUDA
+    events on the compute stream, pick the op+geometry with the largest total device time, and report its
+    algorithmic FLOPs (2*M*N*K) and minimum bytes against its duration."""
+    records = {}
+    pending = []
+
+    def wrap(name, geom_of, orig):
+        def fn(*a):
+            e0, e1 = dev.event_create(), dev.event_create()
+            dev.event_record(e0)
+            orig(*a)
+            dev.event_record(e1)
+            pending.append((name, geom_of(a), e0, e1))
+        return fn
+
+    conv_geom = lambda off: (lambda a: tuple(int(v) for v in a[off:off + 8]))  # noqa: E731
+    saved = {}
+    for name, geom in (("conv2d_fprop", conv_geom(4)), ("conv2d_dgrad", conv_geom(3)), ("conv2d_wgrad", conv_geom(4)),
+                       ("bn_fwd_train", lambda a: (int(a[10]), int(a[11]))), ("bn_bwd", lambda a: (int(a[8]), int(a[9])))):
+        orig = getattr(dev, name)
+        saved[name] = orig
+        dev.__dict__[name] = wrap(name, geom, orig)
+    try:
+        steps = max(2, min(args.steps, 5))
+        for _ in range(steps):
+            step_fn()
+        dev.synchronize()
+    finally:
+        for name, orig in saved.items():
+            dev.__dict__[name] = orig
+    for name, geom, e0, e1 in pending:
+        ms = dev.event_elapsed_ms(e0, e1)
+        dev.event_destroy(e0)
+        dev.event_destroy(e1)
+        r = records.setdefault((name, geom), [0.0, 0])
+        r[0] += ms
+        r[1] += 1
+    if not records:
+        return None
+    by_op = {}
+    for (name, geom), (ms, cnt) in records.items():
+        by_op[name] = by_op.get(name, 0.0) + ms / steps
+    (name, geom), (ms, cnt) = max(records.items(), key=lambda kv: kv[1][0])
+    avg_s = ms / cnt / 1e3
+    if name.startswith("conv2d"):
+        n, c, h, w, k, r, p, s = geom
+        oh, ow = (h + 2 * p - r) // s + 1, (w + 2 * p - r) // s + 1
+        flops = 2.0 * n * oh * ow * k * c * r * r
+        bytes_min = 4.0 * (n * c * h * w + k * c * r * r + n * oh * ow * k)
+        t_tc_us = flops / 700e12 * 1e6   # TF32 dense ~ half of sustained bf16
+        t_hbm_us = bytes_min / 6.5456e12 * 1e6
+        bound = "tensor" if t_tc_us > t_hbm_us else "hbm"
+        achieved = flops / avg_s / 1e12 if bound == "tensor" else bytes_min / avg_s / 1e9
+        unit = "TFLOP/s" if bound == "tensor" else "GB/s"
+        desc = "%s N=%d C=%d H=%d W=%d K=%d R=%d pad=%d stride=%d" % ((name,) + geom)
+        extra = {"flops_per_launch": flops, "bytes_per_launch": bytes_min, "tflops": flops / avg_s / 1e12,
+                 "gbs": bytes_min / avg_s / 1e9}
+    else:
+        rows, c = geom
+        per_elem = 12.0 if name == "bn_fwd_train" else 20.0
+        bytes_min = per_elem * rows * c
+        bound, achieved, unit = "hbm", bytes_min / avg_s / 1e9, "GB/s"
+        desc = "%s rows=%d C=%d" % (name, rows, c)
+        extra = {"bytes_per_launch": bytes_min}
+    return dict({"kernel": desc, "bound": bound, "achieved": achieved, "peak": None, "unit": unit, "frac": None,
+                 "traffic": None, "avg_launch_us": avg_s * 1e6, "launches_timed": cnt,
+                 "share_of_step_ms": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])},
+                 "how": "CUDA events on the compute stream around each fused-op call, in a separate pass of identical steps "
+                        "right after the timed region (event pairs would perturb the headline timing)"}, **extra)
+
+
+if __name__ == "__main__":
+    main()
