@@ -15,6 +15,7 @@ namespace dfb {
 // ---- error reporting ------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<uint64_t> g_tc_launches;
 
 // Lazily creates the context/streams. Returns DFB_OK or an error status (message set).
 dfb_status ensure_init();

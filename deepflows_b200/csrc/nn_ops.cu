@@ -118,9 +118,10 @@ col_moments_kernel(const float* __restrict__ x, size_t rows, int C, ColPlan p,
       }
       __syncthreads();
       if (active && lane == 0) {
+        const float n_own = n;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          float na = n, ma = mean[v], qa = m2[v];
+          float na = n_own, ma = mean[v], qa = m2[v];
           for (int l = 1; l < p.lanes; ++l) {
             float nb = sm[(l * 3 + 0) * CV + g * V + v];
             if (nb == 0.f) continue;
@@ -146,27 +147,36 @@ col_moments_kernel(const float* __restrict__ x, size_t rows, int C, ColPlan p,
   }
 }
 
-// Merge the per-CTA partials (fixed order => deterministic), produce mean / invstd, update the
-// running statistics with the *biased* variance like batchnorm.py:44-46.
+// Merge the per-CTA partials (one warp per channel: lanes merge strided subsets with Chan's formula, then a
+// shuffle tree; the order is fixed => deterministic), produce mean / invstd, update the running statistics
+// with the *biased* variance like batchnorm.py:44-46.
+__device__ __forceinline__ void chan_merge(float& na, float& ma, float& qa, float nb, float mb, float qb) {
+  if (nb == 0.f) return;
+  float nt = na + nb, d = mb - ma;
+  ma += d * (nb / nt);
+  qa += qb + d * d * (na * nb / nt);
+  na = nt;
+}
 __global__ void __launch_bounds__(kT)
 bn_finalize_kernel(const float* __restrict__ part_cnt, const float* __restrict__ part_mean,
                    const float* __restrict__ part_m2, int parts, int C, float eps, float momentum,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd,
                    float* __restrict__ running_mean, float* __restrict__ running_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
   if (c >= C) return;
-  double na = 0, ma = 0, qa = 0;
-  for (int i = 0; i < parts; ++i) {
-    double nb = part_cnt[(size_t)i * C + c];
-    if (nb == 0) continue;
-    double mb = part_mean[(size_t)i * C + c], qb = part_m2[(size_t)i * C + c];
-    double nt = na + nb, d = mb - ma;
-    ma += d * (nb / nt);
-    qa += qb + d * d * (na * nb / nt);
-    na = nt;
+  float na = 0.f, ma = 0.f, qa = 0.f;
+  for (int i = lane; i < parts; i += 32)
+    chan_merge(na, ma, qa, part_cnt[(size_t)i * C + c], part_mean[(size_t)i * C + c], part_m2[(size_t)i * C + c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float nb = __shfl_down_sync(0xffffffffu, na, o), mb = __shfl_down_sync(0xffffffffu, ma, o),
+          qb = __shfl_down_sync(0xffffffffu, qa, o);
+    chan_merge(na, ma, qa, nb, mb, qb);
   }
-  float mean = (float)ma;
-  float var = na > 0 ? (float)(qa / na) : 0.f;
+  if (lane != 0) return;
+  float mean = ma;
+  float var = na > 0.f ? qa / na : 0.f;
   save_mean[c] = mean;
   save_invstd[c] = 1.0f / sqrtf(var + eps);
   if (running_mean) running_mean[c] = running_mean[c] * (1.0f - momentum) + mean * momentum;
@@ -272,15 +282,21 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
 __global__ void __launch_bounds__(kT)
 colsum_finalize_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int parts,
                        int C, float* __restrict__ out_a, float* __restrict__ out_b) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel; lanes take strided partials, shuffle tree at the end (fixed order)
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
   if (c >= C) return;
-  double a = 0, b = 0;
-  for (int i = 0; i < parts; ++i) {
+  float a = 0.f, b = 0.f;
+  for (int i = lane; i < parts; i += 32) {
     a += part_a[(size_t)i * C + c];
     if (part_b) b += part_b[(size_t)i * C + c];
   }
-  if (out_a) out_a[c] = (float)a;
-  if (out_b) out_b[c] = (float)b;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    if (out_a) out_a[c] = a;
+    if (out_b) out_b[c] = b;
+  }
 }
 
 // pass 2: dx = gamma * invstd * (dy - dbeta/n - x_hat * dgamma/n)
@@ -626,7 +642,7 @@ dfb_status dfb_colsum(const float* x, float* out, size_t rows, int cols) {
   if (p.V == 4) colsum_partial_kernel<4><<<p.ctas, kT, smem, s>>>(x, rows, cols, p, part);
   else colsum_partial_kernel<1><<<p.ctas, kT, smem, s>>>(x, rows, cols, p, part);
   DFB_LAUNCH_CHECK("colsum");
-  colsum_finalize_kernel<<<cdiv(cols, kT), kT, 0, s>>>(part, nullptr, (int)p.ctas, cols, out, nullptr);
+  colsum_finalize_kernel<<<cdiv((size_t)cols * 32, kT), kT, 0, s>>>(part, nullptr, (int)p.ctas, cols, out, nullptr);
   DFB_LAUNCH_CHECK("colsum");
   dfb_free(part);
   return DFB_OK;
@@ -647,7 +663,7 @@ static dfb_status bn_stats(const float* x, size_t rows, int C, float eps, float 
   if (p.V == 4) col_moments_kernel<4><<<p.ctas, kT, smem, s>>>(x, rows, C, p, pc, pm, pq);
   else col_moments_kernel<1><<<p.ctas, kT, smem, s>>>(x, rows, C, p, pc, pm, pq);
   DFB_LAUNCH_CHECK("bn_stats");
-  bn_finalize_kernel<<<cdiv(C, kT), kT, 0, s>>>(pc, pm, pq, (int)p.ctas, C, eps, momentum, save_mean, save_invstd,
+  bn_finalize_kernel<<<cdiv((size_t)C * 32, kT), kT, 0, s>>>(pc, pm, pq, (int)p.ctas, C, eps, momentum, save_mean, save_invstd,
                                                running_mean, running_var);
   DFB_LAUNCH_CHECK("bn_finalize");
   dfb_free(part);
@@ -722,7 +738,7 @@ dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma, const
   if (p.V == 4) bn_bwd_reduce_kernel<4><<<p.ctas, kT, smem, s>>>(x, dy, rows, C, p, save_mean, save_invstd, pb, pg);
   else bn_bwd_reduce_kernel<1><<<p.ctas, kT, smem, s>>>(x, dy, rows, C, p, save_mean, save_invstd, pb, pg);
   DFB_LAUNCH_CHECK("bn_bwd_reduce");
-  colsum_finalize_kernel<<<cdiv(C, kT), kT, 0, s>>>(pb, pg, (int)p.ctas, C, db, dg);
+  colsum_finalize_kernel<<<cdiv((size_t)C * 32, kT), kT, 0, s>>>(pb, pg, (int)p.ctas, C, db, dg);
   DFB_LAUNCH_CHECK("bn_bwd_finalize");
   if (dx) {
     bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;

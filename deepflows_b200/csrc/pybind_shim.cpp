@@ -162,6 +162,7 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
     return py::make_tuple(a, b, c);
   });
   m.def("launch_count", []() { return (unsigned long long)dfb_launch_count(); });
+  m.def("tc_launch_count", []() { return (unsigned long long)dfb_tc_launch_count(); });
   m.def("set_matmul_mode", [](int mode) { g_matmul_mode = mode; });
   m.def("get_matmul_mode", []() { return g_matmul_mode; });
   m.def("event_create", []() { void* e = nullptr; check(dfb_event_create(&e)); return (size_t)e; });

@@ -14,6 +14,7 @@ namespace dfb {
 
 static thread_local char tl_error[1024] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_tc_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -253,6 +254,7 @@ dfb_status dfb_mem_stats(size_t* bytes_in_use, size_t* bytes_reserved, size_t* n
 }
 
 uint64_t dfb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+uint64_t dfb_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
 
 // ---- host <-> device ------------------------------------------------------------------------
 dfb_status dfb_from_host(const float* host_src, float* dst, size_t n) {

@@ -87,6 +87,9 @@ DFB_API dfb_status dfb_mem_stats(size_t* bytes_in_use, size_t* bytes_reserved,
                                  size_t* n_cuda_malloc);
 /* launches issued by this library since process start (kernels only; bench.py "gpu_launches") */
 DFB_API uint64_t dfb_launch_count(void);
+/* how many of those were tcgen05 (TMA + tensor-core) kernels: lets tests and bench.py prove that a
+ * TF32/BF16-mode call really ran on the tensor pipe and did not fall back to the FFMA kernels */
+DFB_API uint64_t dfb_tc_launch_count(void);
 
 /* Host <-> device. Replaces from_numpy / to_numpy (ndarray_backend_cuda.cu:667-716). The copy
  * is staged through pinned memory owned by the library and is complete on return. */

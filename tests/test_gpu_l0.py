@@ -273,7 +273,9 @@ def test_against_the_reference_cuda_module(cuda_device):
         mod.from_numpy(x, hx)
         mod.compact(hx, ho, shape, strides, 0)
         mod.fill(hz, 0.0)
-        mod.ewise_setitem(ho, hz, (4, 3, 5, 7), (210, 70, 7, 1), 35)
+        hs = mod.Array(420)  # exactly the view's element count, as BackendTensor.__setitem__ guarantees (bt.py:512)
+        mod.from_numpy(x.reshape(-1)[:420].copy(), hs)
+        mod.ewise_setitem(hs, hz, (4, 3, 5, 7), (210, 70, 7, 1), 35)
         mod.scalar_setitem(10, 9.0, hz, (2, 5), (7, 1), 0)
         outs.append((mod.to_numpy(ho, (x.size,), (1,), 0), mod.to_numpy(hz, (x.size,), (1,), 0)))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])

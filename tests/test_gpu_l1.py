@@ -104,12 +104,13 @@ def test_conv_against_oracle(cuda_device, shape, mode):
 @pytest.mark.parametrize("M,N,K,ta,tb", [(64, 10, 3136, 0, 0), (256, 100, 784, 0, 0), (100, 784, 256, 1, 0), (256, 784, 100, 0, 1),
                                          (33, 65, 129, 1, 1), (128, 128, 128, 0, 0), (512, 256, 1024, 0, 1), (4096, 10, 256, 0, 0),
                                          (1000, 36, 77, 1, 0)])
-def test_gemm_variants(cuda_device, M, N, K, ta, tb, mode):
+@pytest.mark.parametrize("pad", [(3, 5, 2), (4, 8, 0)])  # odd leading dimensions (FFMA path) and 16-byte aligned ones (TMA path)
+def test_gemm_variants(cuda_device, M, N, K, ta, tb, mode, pad):
     m = cuda_device.mod
     rng = np.random.RandomState(M + N + K)
-    lda = (M if ta else K) + 3
-    ldb = (K if tb else N) + 5
-    ldc = N + 2
+    lda = (M if ta else K) + pad[0]
+    ldb = (K if tb else N) + pad[1]
+    ldc = N + pad[2]
     A = rng.randn(K if ta else M, lda).astype(F32)
     B = rng.randn(N if tb else K, ldb).astype(F32)
     C0 = rng.randn(M, ldc).astype(F32)
@@ -123,6 +124,29 @@ def test_gemm_variants(cuda_device, M, N, K, ta, tb, mode):
         want = a @ b + (bias if use_bias else 0) + (C0[:, :N] if acc else 0)
         assert rel_err(got[:, :N], want) < TOL[mode]
         assert np.array_equal(got[:, N:], C0[:, N:])  # padding columns untouched
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(256, 128, 512, 0, 0), (256, 128, 512, 0, 1), (256, 128, 512, 1, 0), (256, 128, 512, 1, 1),
+                                         (300, 72, 200, 0, 0), (1000, 260, 36, 1, 0), (8192, 64, 4096, 0, 1), (129, 33, 40, 1, 1)])
+def test_tf32_gemm_runs_on_the_tensor_pipe(cuda_device, M, N, K, ta, tb):
+    """TF32 mode with TMA-compatible operands must launch the tcgen05 kernel (no silent FFMA fallback) and
+    agree with float64 within the TF32 tolerance; the error must also be ABOVE fp32 rounding, i.e. the
+    operands really were consumed as TF32."""
+    m = cuda_device.mod
+    rng = np.random.RandomState(M * 7 + N)
+    ra, ca = (K, M) if ta else (M, K)
+    rb, cb = (N, K) if tb else (K, N)
+    lda, ldb = (ca + 3) // 4 * 4, (cb + 3) // 4 * 4
+    A, B = rng.randn(ra, lda).astype(F32), rng.randn(rb, ldb).astype(F32)
+    a = (A[:, :ca].T if ta else A[:, :ca]).astype(np.float64)
+    b = (B[:, :cb].T if tb else B[:, :cb]).astype(np.float64)
+    hC = m.Array(M * N)
+    before = m.tc_launch_count()
+    m.gemm(up(m, A), up(m, B), hC, M, N, K, ta, tb, lda, ldb, N, 0, None, m.MODE_TF32)
+    assert m.tc_launch_count() == before + 1
+    err = rel_err(down(m, hC, (M, N)), a @ b)
+    assert err < 2e-2
+    assert err > 1e-6
 
 
 def test_batchnorm_against_reference_fixture(cuda_device):
