@@ -404,6 +404,234 @@ static dfb_status run_gemm_bn(const float* A, const float* B, const GemmParams& 
   return run_gemm<A_MAJ, B_MAJ, 128>(A, B, prm, lda, ldb, handled);
 }
 
+
+// =====================================================================================================
+// Implicit-GEMM convolution: fprop, and dgrad for stride 1 (same contraction over dy, taps mirrored)
+// =====================================================================================================
+struct ConvParams {
+  float* out;          // [pixels, n_out] channels-last
+  int n_img, OH, OW;   // output pixel grid
+  int n_out;           // output channels of this contraction (Kout for fprop, C for dgrad)
+  int R, cblks;        // taps per side; 32-channel blocks of the reduction channels (padded count / 32)
+  int dh0, dw0, sgn;   // input row = oh * stride + dh0 + sgn * r   (stride 2: parity view)
+  int stride, c_red;   // 1 or 2; reduction channel count (parity view offset)
+  int ow_t, oh_t, n_t, tiles_w, tiles_h;
+};
+struct ConvTile {
+  int n0, oh0, ow0, col0, kb_begin, kb_end;
+};
+template <int BN_>
+struct ConvProblem {
+  static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = MAJOR_K;
+  using Params = ConvParams;
+  using Tile = ConvTile;
+  __device__ static Tile tile(const Params& p) {
+    int t = blockIdx.x;
+    int tw = t % p.tiles_w;
+    t /= p.tiles_w;
+    int th = t % p.tiles_h;
+    int tn = t / p.tiles_h;
+    return {tn * p.n_t, th * p.oh_t, tw * p.ow_t, (int)blockIdx.y * BN, 0, p.R * p.R * p.cblks};
+  }
+  __device__ static void load_a(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+    const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
+    const int r = tap / p.R, s = tap - r * p.R;
+    const int dh = p.dh0 + p.sgn * r, dw = p.dw0 + p.sgn * s;
+    if (p.stride == 1) {
+      tma_load_4d(dst, m, bar, cb * 32, t.ow0 + dw, t.oh0 + dh, t.n0);
+    } else {
+      // parity view (2C, W/2, 2, H/2, N): input row 2*oh + dh = 2*(oh + (dh >> 1)) + (dh & 1)
+      tma_load_5d(dst, m, bar, (dw & 1) * p.c_red + cb * 32, t.ow0 + (dw >> 1), dh & 1, t.oh0 + (dh >> 1), t.n0);
+    }
+  }
+  __device__ static void load_b(const Params&, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+    tma_load_2d(dst, m, bar, kb * BLOCK_K, t.col0);
+  }
+  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
+    const int owi = row % p.ow_t;
+    const int rest = row / p.ow_t;
+    const int ohi = rest % p.oh_t, ni = rest / p.oh_t;
+    const int n = t.n0 + ni, oh = t.oh0 + ohi, ow = t.ow0 + owi;
+    if (n >= p.n_img || oh >= p.OH || ow >= p.OW) return;
+    const int col = t.col0 + c0;
+    float* dst = p.out + (((size_t)n * p.OH + oh) * p.OW + ow) * p.n_out + col;
+    if ((p.n_out & 3) == 0 && col + 32 <= p.n_out) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col + i < p.n_out) dst[i] = v[i];
+    }
+  }
+};
+
+// =====================================================================================================
+// wgrad: dWt[kout][tap][c] = sum over pixels of dy[pix][kout] * x[pix + tap][c]; both operands MN-major
+// =====================================================================================================
+struct WgradParams {
+  float* partial;      // [splits][Kout][taps][Cp]
+  int Kout, C, Cp, R, pad, stride;
+  int n_img, OH, OW;
+  int ow_t, oh_t, n_t, tiles_w, tiles_h, pix_blocks, blocks_per_split, ctiles;
+};
+struct WgradTile {
+  int m0, tap, c0, kb_begin, kb_end;
+};
+template <int BN_>
+struct WgradProblem {
+  static constexpr int BN = BN_, A_MAJOR = MAJOR_MN, B_MAJOR = MAJOR_MN;
+  using Params = WgradParams;
+  using Tile = WgradTile;
+  __device__ static Tile tile(const Params& p) {
+    const int tap = blockIdx.y / p.ctiles, ct = blockIdx.y - tap * p.ctiles;
+    const int b0 = blockIdx.z * p.blocks_per_split;
+    return {(int)blockIdx.x * BLOCK_M, tap, ct * BN, b0, min(p.pix_blocks, b0 + p.blocks_per_split)};
+  }
+  __device__ static void pix(const Params& p, int kb, int& n0, int& oh0, int& ow0) {
+    int tw = kb % p.tiles_w;
+    kb /= p.tiles_w;
+    int th = kb % p.tiles_h;
+    n0 = (kb / p.tiles_h) * p.n_t;
+    oh0 = th * p.oh_t;
+    ow0 = tw * p.ow_t;
+  }
+  __device__ static void load_a(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+    int n0, oh0, ow0;
+    pix(p, kb, n0, oh0, ow0);
+#pragma unroll
+    for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_4d(dst + j * kChunkBytes, m, bar, t.m0 + j * 32, ow0, oh0, n0);
+  }
+  __device__ static void load_b(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+    int n0, oh0, ow0;
+    pix(p, kb, n0, oh0, ow0);
+    const int r = t.tap / p.R, s = t.tap - r * p.R;
+    const int dh = r - p.pad, dw = s - p.pad;
+#pragma unroll
+    for (int j = 0; j < BN / 32; ++j) {
+      if (p.stride == 1)
+        tma_load_4d(dst + j * kChunkBytes, m, bar, t.c0 + j * 32, ow0 + dw, oh0 + dh, n0);
+      else
+        tma_load_5d(dst + j * kChunkBytes, m, bar, (dw & 1) * p.C + t.c0 + j * 32, ow0 + (dw >> 1), dh & 1, oh0 + (dh >> 1), n0);
+    }
+  }
+  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
+    const int k = t.m0 + row;
+    if (k >= p.Kout) return;
+    const int taps = p.R * p.R;
+    float* dst = p.partial + (((size_t)blockIdx.z * p.Kout + k) * taps + t.tap) * p.Cp + t.c0 + c0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+};
+
+// ---- small helper kernels -----------------------------------------------------------------------------
+// Wt[k][tap][cp] = w[k][c][tap] (DGRAD = false)   or   Wd[c][tap][kp] = w[k][c][tap] (DGRAD = true); zero padding
+template <bool DGRAD>
+__global__ void __launch_bounds__(256) weight_transform_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C,
+                                                              int taps, int inner_pad) {
+  const int rows = DGRAD ? C : K;
+  size_t total = (size_t)rows * taps * inner_pad;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int in = (int)(i % inner_pad);
+    size_t t = i / inner_pad;
+    int tap = (int)(t % taps);
+    int row = (int)(t / taps);
+    int k = DGRAD ? in : row, c = DGRAD ? row : in;
+    out[i] = (k < K && c < C) ? __ldg(w + ((size_t)k * C + c) * taps + tap) : 0.f;
+  }
+}
+// dW[k][c][tap] = sum_z partial[z][k][tap][c]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
+                                                          int K, int C, int Cp, int taps) {
+  size_t total = (size_t)K * C * taps;
+  size_t slab = (size_t)K * taps * Cp;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int tap = (int)(i % taps);
+    size_t t = i / taps;
+    int c = (int)(t % C);
+    int k = (int)(t / C);
+    const float* src = partial + ((size_t)k * taps + tap) * Cp + c;
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += src[(size_t)z * slab];
+    dw[i] = acc;
+  }
+}
+
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+static void pixel_tile(int pixels_per_tile, int OH, int OW, int* ow_t, int* oh_t, int* n_t) {
+  *ow_t = std::min(pixels_per_tile, pow2_ceil(OW));
+  *oh_t = std::min(pixels_per_tile / *ow_t, pow2_ceil(OH));
+  *n_t = pixels_per_tile / (*ow_t * *oh_t);
+}
+
+// activation map for a tile of `pix` pixels: stride 1 -> 4-d (C, W, H, N); stride 2 -> 5-d parity view
+static bool make_act_map(CUtensorMap* map, const float* base, int N, int H, int W, int C, int stride, int ow_t, int oh_t,
+                         int n_t, int major) {
+  if (stride == 1) {
+    uint64_t d[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t s[4] = {1, (uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
+    uint32_t b[4] = {32, (uint32_t)ow_t, (uint32_t)oh_t, (uint32_t)n_t};
+    return make_map(map, base, 4, d, s, b, major);
+  }
+  uint64_t d[5] = {(uint64_t)2 * C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)N};
+  uint64_t s[5] = {1, (uint64_t)2 * C, (uint64_t)W * C, (uint64_t)2 * W * C, (uint64_t)H * W * C};
+  uint32_t b[5] = {32, (uint32_t)ow_t, 1, (uint32_t)oh_t, (uint32_t)n_t};
+  return make_map(map, base, 5, d, s, b, major);
+}
+
+template <int BN>
+static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float* wt, int n_out, int kred_pad, ConvParams prm,
+                           bool* handled) {
+  CUtensorMap mb;
+  uint64_t d[2] = {(uint64_t)kred_pad, (uint64_t)n_out}, s[2] = {1, (uint64_t)kred_pad};
+  uint32_t b[2] = {BLOCK_K, (uint32_t)BN};
+  if (!make_map(&mb, wt, 2, d, s, b, MAJOR_K)) return DFB_OK;
+  *handled = true;
+  int tiles_n = cdiv(prm.n_img, prm.n_t);
+  dim3 grid((unsigned)(prm.tiles_w * prm.tiles_h * tiles_n), cdiv(n_out, BN), 1);
+  return launch<ConvProblem<BN>>(name, ma, mb, prm, grid);
+}
+
+// y[pix, n_out] = sum_{taps, c} act[pix*stride + off(tap), c] * Wt[n_out][tap][c]
+static dfb_status conv_like(const char* name, const float* act, const float* w, float* out, bool dgrad, int N, int actC,
+                            int actH, int actW, int n_out, int R, int OH, int OW, int stride, int dh0, int sgn, int K, int C,
+                            bool* handled) {
+  const int taps = R * R;
+  const int cp = (actC + 31) / 32 * 32;
+  ConvParams prm;
+  prm.out = out; prm.n_img = N; prm.OH = OH; prm.OW = OW; prm.n_out = n_out; prm.R = R; prm.cblks = cp / 32;
+  prm.dh0 = dh0; prm.dw0 = dh0; prm.sgn = sgn; prm.stride = stride; prm.c_red = actC;
+  pixel_tile(BLOCK_M, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
+  prm.tiles_w = cdiv(OW, prm.ow_t);
+  prm.tiles_h = cdiv(OH, prm.oh_t);
+  CUtensorMap ma;
+  if (!make_act_map(&ma, act, N, actH, actW, actC, stride, prm.ow_t, prm.oh_t, prm.n_t, MAJOR_K)) return DFB_OK;
+  float* wt = nullptr;
+  size_t wt_n = (size_t)n_out * taps * cp;
+  dfb_status st = dfb_malloc(wt_n, &wt);
+  if (st != DFB_OK) return st;
+  if (dgrad) weight_transform_kernel<true><<<bw_grid(wt_n, 256), 256, 0, compute_stream()>>>(w, wt, K, C, taps, cp);
+  else weight_transform_kernel<false><<<bw_grid(wt_n, 256), 256, 0, compute_stream()>>>(w, wt, K, C, taps, cp);
+  DFB_LAUNCH_CHECK("weight_transform");
+  if (n_out <= 32) st = run_conv<32>(name, ma, wt, n_out, taps * cp, prm, handled);
+  else if (n_out <= 64) st = run_conv<64>(name, ma, wt, n_out, taps * cp, prm, handled);
+  else st = run_conv<128>(name, ma, wt, n_out, taps * cp, prm, handled);
+  dfb_free(wt);
+  return st;
+}
+
+template <int BN>
+static dfb_status run_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams prm, int splits) {
+  dim3 grid(cdiv(prm.Kout, BLOCK_M), (unsigned)(prm.R * prm.R * prm.ctiles), (unsigned)splits);
+  return launch<WgradProblem<BN>>("tc_conv_wgrad", ma, mb, prm, grid);
+}
 }  // namespace tc
 
 static bool tc_disabled() {
@@ -429,13 +657,82 @@ dfb_status tc_gemm(const float* A, const float* B, float* C, int M, int N, int K
   return run_gemm_bn<MAJOR_MN, MAJOR_K>(A, B, prm, lda, ldb, handled);
 }
 
-// conv entry points: filled in by conv_tc.cu-style code below once the GEMM path is validated on hardware
-dfb_status tc_conv_fprop(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, float*, size_t,
-                         bool* handled) { *handled = false; return DFB_OK; }
-dfb_status tc_conv_dgrad(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, float*, size_t,
-                         bool* handled) { *handled = false; return DFB_OK; }
-dfb_status tc_conv_wgrad(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, float*, size_t,
-                         bool* handled) { *handled = false; return DFB_OK; }
+static bool conv_tc_ok(int N, int C, int H, int W, int K, int R, int pad, int stride, int mode) {
+  if (tc_disabled() || mode != DFB_MODE_TF32) return false;
+  if ((C & 3) || (K & 3) || R > 11 || stride < 1 || stride > 2) return false;
+  if (stride == 2 && ((H & 1) || (W & 1))) return false;
+  if (H + 2 * pad < R || W + 2 * pad < R) return false;
+  return true;
+}
+
+dfb_status tc_conv_fprop(const float* x, const float* w, float* y, int N, int C, int H, int W, int K, int R, int pad,
+                         int stride, int mode, float*, size_t, bool* handled) {
+  *handled = false;
+  if (!conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
+  return tc::conv_like("tc_conv_fprop", x, w, y, false, N, C, H, W, K, R, OH, OW, stride, -pad, +1, K, C, handled);
+}
+
+dfb_status tc_conv_dgrad(const float* dy, const float* w, float* dx, int N, int C, int H, int W, int K, int R, int pad,
+                         int stride, int mode, float*, size_t, bool* handled) {
+  *handled = false;
+  if (stride != 1 || !conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
+  const int OH = H + 2 * pad - R + 1, OW = W + 2 * pad - R + 1;
+  // dx[n,h,w,c] = sum_{r,s,k} dy[n, h + pad - r, w + pad - s, k] * w[k][c][r][s]
+  return tc::conv_like("tc_conv_dgrad", dy, w, dx, true, N, K, OH, OW, C, R, H, W, 1, pad, -1, K, C, handled);
+}
+
+dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int N, int C, int H, int W, int K, int R, int pad,
+                         int stride, int mode, float*, size_t, bool* handled) {
+  using namespace tc;
+  *handled = false;
+  if (!conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
+  WgradParams prm;
+  prm.Kout = K; prm.C = C; prm.Cp = (C + 31) / 32 * 32; prm.R = R; prm.pad = pad; prm.stride = stride;
+  prm.n_img = N; prm.OH = OH; prm.OW = OW;
+  pixel_tile(BLOCK_K, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
+  prm.tiles_w = cdiv(OW, prm.ow_t);
+  prm.tiles_h = cdiv(OH, prm.oh_t);
+  prm.pix_blocks = prm.tiles_w * prm.tiles_h * (int)cdiv(N, prm.n_t);
+  const int bn = prm.Cp % 128 == 0 ? 128 : (prm.Cp % 64 == 0 ? 64 : 32);
+  prm.ctiles = prm.Cp / bn;
+  CUtensorMap ma, mb;
+  {
+    uint64_t d[4] = {(uint64_t)K, (uint64_t)OW, (uint64_t)OH, (uint64_t)N};
+    uint64_t s[4] = {1, (uint64_t)K, (uint64_t)OW * K, (uint64_t)OH * OW * K};
+    uint32_t b[4] = {32, (uint32_t)prm.ow_t, (uint32_t)prm.oh_t, (uint32_t)prm.n_t};
+    if (!make_map(&ma, dy, 4, d, s, b, MAJOR_MN)) return DFB_OK;
+  }
+  if (!make_act_map(&mb, x, N, H, W, C, stride, prm.ow_t, prm.oh_t, prm.n_t, MAJOR_MN)) return DFB_OK;
+  const int taps = R * R;
+  size_t base_ctas = (size_t)cdiv(K, BLOCK_M) * taps * prm.ctiles;
+  int splits = (int)std::max<size_t>(1, ((size_t)sm_count() * 2 + base_ctas - 1) / base_ctas);
+  splits = std::min(splits, std::max(1, prm.pix_blocks / 8));
+  splits = std::min(splits, 128);
+  prm.blocks_per_split = (prm.pix_blocks + splits - 1) / splits;
+  splits = (prm.pix_blocks + prm.blocks_per_split - 1) / prm.blocks_per_split;
+  float* partial = nullptr;
+  dfb_status st = dfb_malloc((size_t)splits * K * taps * prm.Cp, &partial);
+  if (st != DFB_OK) return st;
+  prm.partial = partial;
+  *handled = true;
+  if (bn == 128) st = run_wgrad<128>(ma, mb, prm, splits);
+  else if (bn == 64) st = run_wgrad<64>(ma, mb, prm, splits);
+  else st = run_wgrad<32>(ma, mb, prm, splits);
+  if (st == DFB_OK) {
+    wgrad_reduce_kernel<<<bw_grid((size_t)K * C * taps, 256), 256, 0, compute_stream()>>>(partial, dw, splits, K, C, prm.Cp, taps);
+    cudaError_t e = cudaGetLastError();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) {
+      dfb_free(partial);
+      DFB_FAIL(DFB_ERR_RUNTIME, "wgrad_reduce launch failed: %s", cudaGetErrorString(e));
+    }
+  }
+  dfb_free(partial);
+  return st;
+}
+
 size_t tc_conv_workspace_floats(int, int, int, int, int, int, int, int) { return 0; }
 
 }  // namespace dfb

@@ -100,6 +100,51 @@ def test_conv_against_oracle(cuda_device, shape, mode):
     assert rel_err(dw, ops.conv2d_wgrad(x, gy, wt.shape, p, s)) < tol
 
 
+TC_SHAPES = [  # N, C, H, W, K, R, pad, stride - all TMA-eligible (C, K multiples of 4; stride 2 needs even H, W)
+    (8, 32, 16, 16, 32, 3, 1, 1), (8, 32, 16, 16, 64, 3, 1, 2), (8, 32, 16, 16, 64, 1, 0, 2), (16, 128, 4, 4, 128, 3, 1, 1),
+    (32, 256, 2, 2, 256, 3, 1, 1), (2, 64, 14, 14, 64, 3, 1, 1), (3, 20, 11, 13, 36, 3, 1, 1), (2, 64, 56, 56, 64, 3, 1, 1),
+    (4, 8, 12, 12, 200, 5, 2, 1), (2, 160, 8, 8, 24, 3, 1, 2), (1, 4, 40, 300, 8, 3, 1, 1), (256, 32, 16, 16, 32, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tf32_conv_runs_on_the_tensor_pipe(cuda_device, shape):
+    """TF32 mode: fprop / wgrad (stride 1 and 2) and stride-1 dgrad must launch tcgen05 kernels, and agree with
+    the oracle within the TF32 tolerance (and not better than fp32 rounding: operands really were TF32)."""
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = shape
+    rng = np.random.RandomState(sum(shape))
+    x = rng.randn(n, c, h, w).astype(F32)
+    wt = (rng.randn(k, c, r, r) / np.sqrt(c * r * r)).astype(F32)
+    oh, ow = ops.out_size(h, r, p, s), ops.out_size(w, r, p, s)
+    gy = rng.randn(n, k, oh, ow).astype(F32)
+    hx, hw, hgy = up(m, nhwc(x)), up(m, wt), up(m, nhwc(gy))
+    hy, hdx, hdw = m.Array(n * oh * ow * k), m.Array(x.size), m.Array(wt.size)
+    t0 = m.tc_launch_count()
+    m.conv2d_fprop(hx, m.LAYOUT_NHWC, hw, hy, n, c, h, w, k, r, p, s, m.MODE_TF32, None, 0)
+    t1 = m.tc_launch_count()
+    m.conv2d_dgrad(hgy, hw, hdx, n, c, h, w, k, r, p, s, m.MODE_TF32, m.DGRAD_EXACT, None, 0)
+    t2 = m.tc_launch_count()
+    m.conv2d_wgrad(hx, m.LAYOUT_NHWC, hgy, hdw, n, c, h, w, k, r, p, s, m.MODE_TF32, None, 0)
+    t3 = m.tc_launch_count()
+    assert t1 == t0 + 1 and t3 == t2 + 1 and t2 == t1 + (1 if s == 1 else 0)
+    big = n * oh * ow * k > 50000
+    if big:  # float64 im2col of the largest cases is slow; compare against the exact-fp32 kernels instead
+        ry, rdx, rdw = m.Array(n * oh * ow * k), m.Array(x.size), m.Array(wt.size)
+        m.conv2d_fprop(hx, m.LAYOUT_NHWC, hw, ry, n, c, h, w, k, r, p, s, m.MODE_FP32, None, 0)
+        m.conv2d_dgrad(hgy, hw, rdx, n, c, h, w, k, r, p, s, m.MODE_FP32, m.DGRAD_EXACT, None, 0)
+        m.conv2d_wgrad(hx, m.LAYOUT_NHWC, hgy, rdw, n, c, h, w, k, r, p, s, m.MODE_FP32, None, 0)
+        want = (down(m, ry, (n, oh, ow, k)), down(m, rdx, (n, h, w, c)), down(m, rdw, wt.shape))
+    else:
+        want = (nhwc(ops.conv2d_fprop(x, wt, p, s)), nhwc(ops.conv2d_dgrad_exact(gy, wt, x.shape, p, s)),
+                ops.conv2d_wgrad(x, gy, wt.shape, p, s))
+    got = (down(m, hy, (n, oh, ow, k)), down(m, hdx, (n, h, w, c)), down(m, hdw, wt.shape))
+    for name, a, b in zip(("fprop", "dgrad", "wgrad"), got, want):
+        e = rel_err(a, b)
+        assert e < 2e-2, (name, e)
+    assert rel_err(got[0], want[0]) > 1e-6
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K,ta,tb", [(64, 10, 3136, 0, 0), (256, 100, 784, 0, 0), (100, 784, 256, 1, 0), (256, 784, 100, 0, 1),
                                          (33, 65, 129, 1, 1), (128, 128, 128, 0, 0), (512, 256, 1024, 0, 1), (4096, 10, 256, 0, 0),
