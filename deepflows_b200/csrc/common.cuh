@@ -22,6 +22,10 @@ dfb_status ensure_init();
 cudaStream_t compute_stream();
 cudaStream_t comm_stream();
 int sm_count();
+// CUDA-graph capture support (runtime.cu)
+bool graph_capturing();
+dfb_status graph_staging(size_t bytes, int kind, void** host, void** dev);
+dfb_status graph_hyper_slot(void* graph_exec, int index, int kind, void** host);
 
 #define DFB_FAIL(code, ...)         \
   do {                              \

@@ -410,15 +410,21 @@ static dfb_status run_gemm_bn(const float* A, const float* B, const GemmParams& 
 // =====================================================================================================
 struct ConvParams {
   float* out;          // [pixels, n_out] channels-last
-  int n_img, OH, OW;   // output pixel grid
+  int n_img, OH, OW;   // output pixel grid of one class (the whole output, or one parity class of it)
   int n_out;           // output channels of this contraction (Kout for fprop, C for dgrad)
   int R, cblks;        // taps per side; 32-channel blocks of the reduction channels (padded count / 32)
   int dh0, dw0, sgn;   // input row = oh * stride + dh0 + sgn * r   (stride 2: parity view)
   int stride, c_red;   // 1 or 2; reduction channel count (parity view offset)
   int ow_t, oh_t, n_t, tiles_w, tiles_h;
+  // stride-2 dgrad: blockIdx.z = output parity class (ph, pw) of dx. Class (ph, pw) is a stride-1 contraction
+  // over dy with the taps r = r0 + 2i, r0 = (ph + pad) & 1:  dx[2a+ph] += dy[a + d0 - i] * w[r0 + 2i],
+  // d0 = (ph + pad - r0) / 2. par_pad >= 0 selects this mode; the output is then written at (2a+ph, 2b+pw)
+  // of an image with 2*OH x 2*OW pixels.
+  int par_pad;
 };
 struct ConvTile {
   int n0, oh0, ow0, col0, kb_begin, kb_end;
+  int ns, d0h, d0w, r0h, r0w, ph, pw;  // parity mode only
 };
 template <int BN_>
 struct ConvProblem {
@@ -431,10 +437,27 @@ struct ConvProblem {
     t /= p.tiles_w;
     int th = t % p.tiles_h;
     int tn = t / p.tiles_h;
-    return {tn * p.n_t, th * p.oh_t, tw * p.ow_t, (int)blockIdx.y * BN, 0, p.R * p.R * p.cblks};
+    Tile o{tn * p.n_t, th * p.oh_t, tw * p.ow_t, (int)blockIdx.y * BN, 0, p.R * p.R * p.cblks, 0, 0, 0, 0, 0, 0, 0};
+    if (p.par_pad >= 0) {
+      o.ph = (int)blockIdx.z >> 1;
+      o.pw = (int)blockIdx.z & 1;
+      o.r0h = (o.ph + p.par_pad) & 1;
+      o.r0w = (o.pw + p.par_pad) & 1;
+      const int nr = o.r0h < p.R ? (p.R - o.r0h + 1) / 2 : 0;
+      o.ns = o.r0w < p.R ? (p.R - o.r0w + 1) / 2 : 0;
+      o.d0h = (o.ph + p.par_pad - o.r0h) / 2;
+      o.d0w = (o.pw + p.par_pad - o.r0w) / 2;
+      o.kb_end = nr * o.ns * p.cblks;
+    }
+    return o;
   }
   __device__ static void load_a(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
     const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
+    if (p.par_pad >= 0) {
+      const int i = tap / t.ns, j = tap - i * t.ns;
+      tma_load_4d(dst, m, bar, cb * 32, t.ow0 + t.d0w - j, t.oh0 + t.d0h - i, t.n0);
+      return;
+    }
     const int r = tap / p.R, s = tap - r * p.R;
     const int dh = p.dh0 + p.sgn * r, dw = p.dw0 + p.sgn * s;
     if (p.stride == 1) {
@@ -444,17 +467,30 @@ struct ConvProblem {
       tma_load_5d(dst, m, bar, (dw & 1) * p.c_red + cb * 32, t.ow0 + (dw >> 1), dh & 1, t.oh0 + (dh >> 1), t.n0);
     }
   }
-  __device__ static void load_b(const Params&, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+  __device__ static void load_b(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+    if (p.par_pad >= 0) {
+      const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
+      const int i = tap / t.ns, j = tap - i * t.ns;
+      const int wtap = (t.r0h + 2 * i) * p.R + t.r0w + 2 * j;
+      tma_load_2d(dst, m, bar, (wtap * p.cblks + cb) * BLOCK_K, t.col0);
+      return;
+    }
     tma_load_2d(dst, m, bar, kb * BLOCK_K, t.col0);
   }
   __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
     const int owi = row % p.ow_t;
     const int rest = row / p.ow_t;
     const int ohi = rest % p.oh_t, ni = rest / p.oh_t;
-    const int n = t.n0 + ni, oh = t.oh0 + ohi, ow = t.ow0 + owi;
+    const int n = t.n0 + ni;
+    int oh = t.oh0 + ohi, ow = t.ow0 + owi;
     if (n >= p.n_img || oh >= p.OH || ow >= p.OW) return;
+    int OHf = p.OH, OWf = p.OW;
+    if (p.par_pad >= 0) {
+      oh = 2 * oh + t.ph; ow = 2 * ow + t.pw;
+      OHf *= 2; OWf *= 2;
+    }
     const int col = t.col0 + c0;
-    float* dst = p.out + (((size_t)n * p.OH + oh) * p.OW + ow) * p.n_out + col;
+    float* dst = p.out + (((size_t)n * OHf + oh) * OWf + ow) * p.n_out + col;
     if ((p.n_out & 3) == 0 && col + 32 <= p.n_out) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -595,19 +631,19 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
   if (!make_map(&mb, wt, 2, d, s, b, MAJOR_K)) return DFB_OK;
   *handled = true;
   int tiles_n = cdiv(prm.n_img, prm.n_t);
-  dim3 grid((unsigned)(prm.tiles_w * prm.tiles_h * tiles_n), cdiv(n_out, BN), 1);
+  dim3 grid((unsigned)(prm.tiles_w * prm.tiles_h * tiles_n), cdiv(n_out, BN), prm.par_pad >= 0 ? 4 : 1);
   return launch<ConvProblem<BN>>(name, ma, mb, prm, grid);
 }
 
 // y[pix, n_out] = sum_{taps, c} act[pix*stride + off(tap), c] * Wt[n_out][tap][c]
 static dfb_status conv_like(const char* name, const float* act, const float* w, float* out, bool dgrad, int N, int actC,
                             int actH, int actW, int n_out, int R, int OH, int OW, int stride, int dh0, int sgn, int K, int C,
-                            bool* handled) {
+                            bool* handled, int par_pad = -1) {
   const int taps = R * R;
   const int cp = (actC + 31) / 32 * 32;
   ConvParams prm;
   prm.out = out; prm.n_img = N; prm.OH = OH; prm.OW = OW; prm.n_out = n_out; prm.R = R; prm.cblks = cp / 32;
-  prm.dh0 = dh0; prm.dw0 = dh0; prm.sgn = sgn; prm.stride = stride; prm.c_red = actC;
+  prm.dh0 = dh0; prm.dw0 = dh0; prm.sgn = sgn; prm.stride = stride; prm.c_red = actC; prm.par_pad = par_pad;
   pixel_tile(BLOCK_M, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
   prm.tiles_w = cdiv(OW, prm.ow_t);
   prm.tiles_h = cdiv(OH, prm.oh_t);
@@ -676,10 +712,15 @@ dfb_status tc_conv_fprop(const float* x, const float* w, float* y, int N, int C,
 dfb_status tc_conv_dgrad(const float* dy, const float* w, float* dx, int N, int C, int H, int W, int K, int R, int pad,
                          int stride, int mode, float*, size_t, bool* handled) {
   *handled = false;
-  if (stride != 1 || !conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
-  const int OH = H + 2 * pad - R + 1, OW = W + 2 * pad - R + 1;
-  // dx[n,h,w,c] = sum_{r,s,k} dy[n, h + pad - r, w + pad - s, k] * w[k][c][r][s]
-  return tc::conv_like("tc_conv_dgrad", dy, w, dx, true, N, K, OH, OW, C, R, H, W, 1, pad, -1, K, C, handled);
+  if (!conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
+  if (stride == 1) {
+    // dx[n,h,w,c] = sum_{r,s,k} dy[n, h + pad - r, w + pad - s, k] * w[k][c][r][s]
+    return tc::conv_like("tc_conv_dgrad", dy, w, dx, true, N, K, OH, OW, C, R, H, W, 1, pad, -1, K, C, handled);
+  }
+  // stride 2: four output-parity classes of dx, each a stride-1 contraction over dy with every other tap
+  // (ConvParams::par_pad); one launch, blockIdx.z = class. H and W are even (conv_tc_ok).
+  return tc::conv_like("tc_conv_dgrad_s2", dy, w, dx, true, N, K, OH, OW, C, R, H / 2, W / 2, 1, 0, 0, K, C, handled, pad);
 }
 
 dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int N, int C, int H, int W, int K, int R, int pad,

@@ -38,6 +38,21 @@ struct Runtime {
   std::unordered_map<void*, size_t> live;  // ptr -> rounded bytes
   size_t bytes_in_use = 0, bytes_reserved = 0, n_cuda_malloc = 0;
 
+  // CUDA-graph capture. Every block handed out while a capture is active becomes the property of
+  // that graph: its address is baked into the captured kernel nodes, so when it is freed it goes to
+  // the graph's private free lists (re-usable by later allocations of the same capture, never by
+  // anybody else) until dfb_graph_destroy() returns the pool to the general one.
+  struct GraphPool {
+    std::unordered_map<size_t, std::vector<void*>> free_blocks;
+    std::vector<void*> host_allocs;   // pinned staging owned by the graph (optimizer tables)
+    std::vector<void*> dev_allocs;
+    std::vector<void*> hyper_host;    // one per captured optimizer step, in capture order
+    std::vector<int> hyper_kind;      // 0 = Adam, 1 = SGD
+  };
+  std::unordered_map<void*, GraphPool*> owner;          // block -> pool, for graph-owned blocks
+  std::unordered_map<void*, GraphPool*> pools_by_exec;  // cudaGraphExec_t -> pool
+  GraphPool* active_pool = nullptr;
+
   // pinned staging ring for dfb_from_host (H2D returns without a device sync)
   static constexpr int kSlots = 4;
   struct Slot {
@@ -176,14 +191,20 @@ dfb_status dfb_malloc(size_t n_floats, float** out_ptr) {
   size_t bytes = round_block(n_floats * sizeof(float));
   std::lock_guard<std::mutex> lk(r.mu);
   void* p = nullptr;
+  if (r.active_pool) {
+    auto git = r.active_pool->free_blocks.find(bytes);
+    if (git != r.active_pool->free_blocks.end() && !git->second.empty()) {
+      p = git->second.back();
+      git->second.pop_back();
+    }
+  }
   auto it = r.free_blocks.find(bytes);
-  if (it != r.free_blocks.end() && !it->second.empty()) {
+  if (p) {
+  } else if (it != r.free_blocks.end() && !it->second.empty()) {
     p = it->second.back();
     it->second.pop_back();
   } else {
-    DFB_REQUIRE(!r.capturing, DFB_ERR_RUNTIME,
-                "dfb_malloc: pool miss (%zu bytes) during CUDA-graph capture; run one warm-up "
-                "step before capturing", bytes);
+    // (the capture runs in relaxed mode, so cudaMalloc is legal while capturing)
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {
       // release everything cached and retry once
@@ -209,6 +230,7 @@ dfb_status dfb_malloc(size_t n_floats, float** out_ptr) {
   }
   r.live[p] = bytes;
   r.bytes_in_use += bytes;
+  if (r.active_pool) r.owner[p] = r.active_pool;
   *out_ptr = (float*)p;
   return DFB_OK;
 }
@@ -224,7 +246,9 @@ dfb_status dfb_free(float* ptr) {
   r.bytes_in_use -= bytes;
   // Single compute stream: every consumer of this block was enqueued before any later producer
   // that re-uses it, so the block can be recycled immediately without an event.
-  r.free_blocks[bytes].push_back((void*)ptr);
+  auto ow = r.owner.find((void*)ptr);
+  if (ow != r.owner.end()) ow->second->free_blocks[bytes].push_back((void*)ptr);
+  else r.free_blocks[bytes].push_back((void*)ptr);
   return DFB_OK;
 }
 
@@ -261,9 +285,12 @@ dfb_status dfb_from_host(const float* host_src, float* dst, size_t n) {
   DFB_INIT();
   if (n == 0) return DFB_OK;
   Runtime& r = rt();
+  DFB_REQUIRE(!r.capturing, DFB_ERR_RUNTIME,
+              "from_numpy during CUDA-graph capture: a captured step must not copy host data (keep inputs in "
+              "device buffers that are refreshed before each replay)");
   size_t bytes = n * sizeof(float);
   const size_t kMaxStage = size_t(64) << 20;
-  if (bytes > kMaxStage || r.capturing) {
+  if (bytes > kMaxStage) {
     DFB_CUDA(cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, r.compute));
     DFB_CUDA(cudaStreamSynchronize(r.compute));
     return DFB_OK;
@@ -294,6 +321,9 @@ dfb_status dfb_to_host(const float* src, float* host_dst, size_t n) {
   DFB_INIT();
   if (n == 0) return DFB_OK;
   Runtime& r = rt();
+  DFB_REQUIRE(!r.capturing, DFB_ERR_RUNTIME,
+              "to_numpy during CUDA-graph capture: a captured step must not read results back (read them after "
+              "the replay)");
   DFB_CUDA(cudaMemcpyAsync(host_dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, r.compute));
   DFB_CUDA(cudaStreamSynchronize(r.compute));
   return DFB_OK;
@@ -328,12 +358,49 @@ dfb_status dfb_copy(const float* src, float* dst, size_t n) {
 }
 
 // ---- CUDA graph capture ---------------------------------------------------------------------
+}  // extern "C"
+
+namespace dfb {
+bool graph_capturing() { return rt().capturing; }
+// Persistent pinned + device staging owned by the graph being captured (optimizer pointer table and
+// hyper-parameters: the captured memcpy node re-reads the pinned copy at every replay, which is how
+// lr / bias corrections change between replays without re-capturing).
+dfb_status graph_staging(size_t bytes, int kind, void** host, void** dev) {
+  Runtime& r = rt();
+  DFB_REQUIRE(r.active_pool != nullptr, DFB_ERR_RUNTIME, "graph_staging outside a capture");
+  DFB_CUDA(cudaHostAlloc(host, bytes, cudaHostAllocDefault));
+  DFB_CUDA(cudaMalloc(dev, bytes));
+  std::lock_guard<std::mutex> lk(r.mu);
+  r.active_pool->host_allocs.push_back(*host);
+  r.active_pool->dev_allocs.push_back(*dev);
+  r.active_pool->hyper_host.push_back(*host);
+  r.active_pool->hyper_kind.push_back(kind);
+  return DFB_OK;
+}
+dfb_status graph_hyper_slot(void* graph_exec, int index, int kind, void** host) {
+  Runtime& r = rt();
+  std::lock_guard<std::mutex> lk(r.mu);
+  auto it = r.pools_by_exec.find(graph_exec);
+  DFB_REQUIRE(it != r.pools_by_exec.end(), DFB_ERR_INVALID, "unknown graph handle");
+  DFB_REQUIRE(index >= 0 && index < (int)it->second->hyper_host.size(), DFB_ERR_OUT_OF_RANGE,
+              "graph has %zu captured optimizer steps, index %d requested", it->second->hyper_host.size(), index);
+  DFB_REQUIRE(it->second->hyper_kind[index] == kind, DFB_ERR_INVALID, "captured optimizer step %d is of another kind", index);
+  *host = it->second->hyper_host[index];
+  return DFB_OK;
+}
+}  // namespace dfb
+
+extern "C" {
+
 dfb_status dfb_graph_begin_capture(void) {
   DFB_INIT();
   Runtime& r = rt();
   DFB_REQUIRE(!r.capturing, DFB_ERR_RUNTIME, "graph capture already active");
   DFB_CUDA(cudaStreamSynchronize(r.compute));
-  DFB_CUDA(cudaStreamBeginCapture(r.compute, cudaStreamCaptureModeThreadLocal));
+  DFB_CUDA(cudaStreamSynchronize(r.comm));
+  DFB_CUDA(cudaStreamBeginCapture(r.compute, cudaStreamCaptureModeRelaxed));
+  std::lock_guard<std::mutex> lk(r.mu);
+  r.active_pool = new Runtime::GraphPool();
   r.capturing = true;
   return DFB_OK;
 }
@@ -341,12 +408,33 @@ dfb_status dfb_graph_end_capture(void** graph_exec) {
   Runtime& r = rt();
   DFB_REQUIRE(r.capturing, DFB_ERR_RUNTIME, "no graph capture active");
   cudaGraph_t g = nullptr;
-  r.capturing = false;
-  DFB_CUDA(cudaStreamEndCapture(r.compute, &g));
+  Runtime::GraphPool* pool;
+  {
+    std::lock_guard<std::mutex> lk(r.mu);
+    r.capturing = false;
+    pool = r.active_pool;
+    r.active_pool = nullptr;
+  }
+  cudaError_t e = cudaStreamEndCapture(r.compute, &g);
   cudaGraphExec_t ge = nullptr;
-  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
-  cudaGraphDestroy(g);
-  if (e != cudaSuccess) DFB_FAIL(DFB_ERR_RUNTIME, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  if (e == cudaSuccess) {
+    e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    // the pool's blocks stay owned by a graph that does not exist: hand them back
+    std::lock_guard<std::mutex> lk(r.mu);
+    for (auto it = r.owner.begin(); it != r.owner.end();) it = it->second == pool ? r.owner.erase(it) : std::next(it);
+    for (auto& kv : pool->free_blocks)
+      for (void* q : kv.second) r.free_blocks[kv.first].push_back(q);
+    for (void* h : pool->host_allocs) cudaFreeHost(h);
+    for (void* d : pool->dev_allocs) cudaFree(d);
+    delete pool;
+    DFB_FAIL(DFB_ERR_RUNTIME, "CUDA-graph capture failed: %s", cudaGetErrorString(e));
+  }
+  std::lock_guard<std::mutex> lk(r.mu);
+  r.pools_by_exec[(void*)ge] = pool;
   *graph_exec = (void*)ge;
   return DFB_OK;
 }
@@ -356,7 +444,24 @@ dfb_status dfb_graph_launch(void* graph_exec) {
   return DFB_OK;
 }
 dfb_status dfb_graph_destroy(void* graph_exec) {
+  Runtime& r = rt();
+  DFB_CUDA(cudaStreamSynchronize(r.compute));
   DFB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  std::lock_guard<std::mutex> lk(r.mu);
+  auto it = r.pools_by_exec.find(graph_exec);
+  if (it == r.pools_by_exec.end()) return DFB_OK;
+  Runtime::GraphPool* pool = it->second;
+  r.pools_by_exec.erase(it);
+  for (auto ow = r.owner.begin(); ow != r.owner.end();) ow = ow->second == pool ? r.owner.erase(ow) : std::next(ow);
+  for (auto& kv : pool->free_blocks)
+    for (void* q : kv.second) r.free_blocks[kv.first].push_back(q);
+  for (void* h : pool->host_allocs) cudaFreeHost(h);
+  for (void* d : pool->dev_allocs) cudaFree(d);
+  delete pool;
+  return DFB_OK;
+}
+dfb_status dfb_graph_capturing(int* capturing) {
+  *capturing = rt().capturing ? 1 : 0;
   return DFB_OK;
 }
 
