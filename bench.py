@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
     ap.add_argument("--precision", default=os.environ.get("DEEPFLOWS_PRECISION", "tf32"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph: the step is captured once and replayed as one CUDA graph; eager: every kernel launched from Python")
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -175,6 +177,8 @@ def main():
                           "Adam lr 1e-3 wd 5e-4, label-smoothed dense targets, exact dgrad",
               "batch_per_gpu": args.batch, "global_batch": args.batch * world,
               "image": "3x32x32", "parallelism": "dp%d" % world,
+              "launch": "one CUDA graph per step (captured from the unchanged DeepFlows step)" if args.mode == "graph"
+                        else "eager (every kernel launched from Python)",
               "l2": "per-step activation working set (~1.5 GB at batch 256) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
@@ -217,20 +221,23 @@ def main():
             dev.comm_wait()
             dev.synchronize()
 
-    def resident_step():
-        train_step(df, model, opt, crit, x_dev, t_dev)
+    def eager_step():
+        loss = train_step(df, model, opt, crit, x_dev, t_dev)
         Graph.free_graph()
+        return loss
+
+    captured = None
+    if args.mode == "graph":
+        from DeepFlows.cuda_graph import CapturedStep
+        captured = CapturedStep(eager_step, device=dev, warmup=1)  # call 1 eager, call 2 captures, then replays
+    resident_step = captured if captured is not None else eager_step
 
     def e2e_step():
-        xa, ta = dev.Array(x_host.size), dev.Array(t_host.size)
-        dev.from_pinned_async(px, xa, x_host.size)
-        dev.from_pinned_async(pt, ta, t_host.size)
-        xt = Tensor(BackendTensor.make(x_host.shape, device=dev, handle=xa))
-        tt = Tensor(BackendTensor.make(t_host.shape, device=dev, handle=ta))
-        loss = train_step(df, model, opt, crit, xt, tt)
-        val = float(loss.data.numpy()[0])  # device -> host read of the step's result
-        Graph.free_graph()
-        return val
+        # the batch comes from pinned host memory into the step's input buffers, the loss goes back to the host
+        dev.from_pinned_async(px, x_dev.data._handle, x_host.size)
+        dev.from_pinned_async(pt, t_dev.data._handle, t_host.size)
+        loss = resident_step()
+        return float(loss.data.numpy()[0])
 
     def timed(fn, steps):
         ev0, ev1 = dev.event_create(), dev.event_create()
@@ -244,6 +251,8 @@ def main():
         barrier()
         ms = dev.event_elapsed_ms(ev0, ev1)
         launches = dev.launch_count() - l0
+        if captured is not None and captured.captured:
+            launches += captured.node_counts()[0] * steps  # kernel nodes replayed by the graph launches
         dev.event_destroy(ev0)
         dev.event_destroy(ev1)
         return ms, launches
@@ -274,7 +283,7 @@ def main():
     # ---- per-kernel profile pass: CUDA events around every fused conv call, same steps ----------------
     roofline = None
     if rank == 0:
-        roofline = profile_dominant_kernel(dev, resident_step, args, B)
+        roofline = profile_dominant_kernel(dev, eager_step, args, B)
 
     if world > 1:
         barrier()

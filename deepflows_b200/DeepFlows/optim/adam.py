@@ -3,7 +3,7 @@ second moments `v` / `s`, bias correction with the step counter `t` starting at 
 the square root. The reference issues ~14 out-of-place BackendTensor kernels per parameter; here all
 parameters are updated in place by one `multi_adam_step` launch."""
 from .optimier import Optimizer
-from .. import backend_api
+from .. import backend_api, cuda_graph
 
 
 class Adam(Optimizer):
@@ -35,4 +35,11 @@ class Adam(Optimizer):
             for _, p, _ in active:
                 p.children.clear()
                 p.parents.clear()
+            cuda_graph.note_optimizer_step(self)
+        self.t += 1
+
+    def _graph_refresh(self, dev, graph_exec, index):
+        """Hyper-parameters for the next replay of a captured step (cuda_graph.CapturedStep)."""
+        dev.graph_set_adam(graph_exec, index, float(self.lr), float(self.beta1), float(self.beta2), float(self.eps),
+                           float(self.weight_decay), int(self.t), float(self._grad_scale_value()))
         self.t += 1

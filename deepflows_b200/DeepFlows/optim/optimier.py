@@ -36,3 +36,9 @@ class Optimizer:
     def _grad_scale():
         from .. import dist
         return dist.pre_step()
+
+    @staticmethod
+    def _grad_scale_value():
+        """1/world_size without touching the streams (graph replays already contain the wait)."""
+        from .. import dist
+        return 1.0 / dist.get_world_size()

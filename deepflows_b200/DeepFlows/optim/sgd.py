@@ -5,7 +5,7 @@ from typing import List
 
 from .optimier import Optimizer
 from ..tensor import Tensor
-from .. import backend_api
+from .. import backend_api, cuda_graph
 
 
 class SGD(Optimizer):
@@ -25,3 +25,8 @@ class SGD(Optimizer):
             [p.data._handle for _, p, _ in active], [(g._handle, g._offset) for _, _, g in active],
             [self.v[i]._handle for i, _, _ in active], [p.data.size for _, p, _ in active], float(self.lr),
             float(self.momentum), float(self.weight_decay), bool(self.nesterov), float(grad_scale))
+        cuda_graph.note_optimizer_step(self)
+
+    def _graph_refresh(self, dev, graph_exec, index):
+        dev.graph_set_sgd(graph_exec, index, float(self.lr), float(self.momentum), float(self.weight_decay),
+                          bool(self.nesterov), float(self._grad_scale_value()))

@@ -54,7 +54,9 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 }
 
 __global__ void __launch_bounds__(256)
-multi_adam_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks, AdamHyper h) {
+multi_adam_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks,
+                  const AdamHyper* __restrict__ hp) {
+  const AdamHyper h = *hp;
   for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int ti = find_tensor(tensors, count, chunk);
     TensorRef t = tensors[ti];
@@ -95,7 +97,9 @@ __device__ __forceinline__ void sgd_one(float& p, float g, float* vel, const Sgd
 }
 
 __global__ void __launch_bounds__(256)
-multi_sgd_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks, SgdHyper h) {
+multi_sgd_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks,
+                 const SgdHyper* __restrict__ hp) {
+  const SgdHyper h = *hp;
   for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int ti = find_tensor(tensors, count, chunk);
     TensorRef t = tensors[ti];
@@ -111,7 +115,12 @@ multi_sgd_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long
   }
 }
 
-// pinned staging for the pointer table: a small ring so consecutive steps do not wait on each other
+// Staging of one optimizer step: [hyper-parameters, 256 bytes][pointer table]. The kernel reads both from
+// device memory. Eager steps go through a small pinned ring so consecutive steps do not wait on each other;
+// a step issued during CUDA-graph capture gets staging that the graph owns, and the captured memcpy node
+// re-reads the pinned copy at every replay - dfb_graph_set_adam / dfb_graph_set_sgd rewrite the hyper-
+// parameters there between replays (learning-rate schedules, Adam's bias corrections).
+constexpr size_t kHyperBytes = 256;
 struct TableStage {
   static constexpr int kSlots = 4;
   void* host[kSlots] = {nullptr, nullptr, nullptr, nullptr};
@@ -122,26 +131,71 @@ struct TableStage {
 };
 static TableStage g_stage;
 
-static dfb_status upload_table(const std::vector<TensorRef>& tab, const TensorRef** dev_out) {
-  TableStage& st = g_stage;
-  int s = st.next;
-  st.next = (st.next + 1) % TableStage::kSlots;
-  size_t bytes = tab.size() * sizeof(TensorRef);
-  if (st.done[s]) DFB_CUDA(cudaEventSynchronize(st.done[s]));
-  if (st.cap[s] < bytes) {
-    if (st.host[s]) cudaFreeHost(st.host[s]);
-    if (st.dev[s]) cudaFree(st.dev[s]);
-    size_t cap = bytes < 16384 ? 16384 : bytes * 2;
-    DFB_CUDA(cudaHostAlloc(&st.host[s], cap, cudaHostAllocDefault));
-    DFB_CUDA(cudaMalloc(&st.dev[s], cap));
-    st.cap[s] = cap;
+static dfb_status upload_table(const std::vector<TensorRef>& tab, const void* hyper, size_t hyper_bytes, int kind,
+                               const TensorRef** dev_table, const void** dev_hyper) {
+  size_t bytes = kHyperBytes + tab.size() * sizeof(TensorRef);
+  void *host = nullptr, *dev = nullptr;
+  if (graph_capturing()) {
+    dfb_status st = graph_staging(bytes, kind, &host, &dev);
+    if (st != DFB_OK) return st;
+  } else {
+    TableStage& st = g_stage;
+    int s = st.next;
+    st.next = (st.next + 1) % TableStage::kSlots;
+    if (st.done[s]) DFB_CUDA(cudaEventSynchronize(st.done[s]));
+    if (st.cap[s] < bytes) {
+      if (st.host[s]) cudaFreeHost(st.host[s]);
+      if (st.dev[s]) cudaFree(st.dev[s]);
+      size_t cap = bytes < 16384 ? 16384 : bytes * 2;
+      DFB_CUDA(cudaHostAlloc(&st.host[s], cap, cudaHostAllocDefault));
+      DFB_CUDA(cudaMalloc(&st.dev[s], cap));
+      st.cap[s] = cap;
+    }
+    if (!st.done[s]) DFB_CUDA(cudaEventCreateWithFlags(&st.done[s], cudaEventDisableTiming));
+    host = st.host[s];
+    dev = st.dev[s];
   }
-  if (!st.done[s]) DFB_CUDA(cudaEventCreateWithFlags(&st.done[s], cudaEventDisableTiming));
-  memcpy(st.host[s], tab.data(), bytes);
-  DFB_CUDA(cudaMemcpyAsync(st.dev[s], st.host[s], bytes, cudaMemcpyHostToDevice, compute_stream()));
-  DFB_CUDA(cudaEventRecord(st.done[s], compute_stream()));
-  *dev_out = (const TensorRef*)st.dev[s];
+  memcpy(host, hyper, hyper_bytes);
+  memcpy((char*)host + kHyperBytes, tab.data(), tab.size() * sizeof(TensorRef));
+  DFB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, compute_stream()));
+  if (!graph_capturing()) {
+    TableStage& st = g_stage;
+    int s = (st.next + TableStage::kSlots - 1) % TableStage::kSlots;
+    DFB_CUDA(cudaEventRecord(st.done[s], compute_stream()));
+  }
+  *dev_hyper = dev;
+  *dev_table = (const TensorRef*)((char*)dev + kHyperBytes);
   return DFB_OK;
+}
+
+static AdamHyper make_adam_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, int step_t,
+                                 double grad_scale) {
+  AdamHyper h;
+  // every scalar is a Python double rounded to float32 when it reaches a scalar_* kernel
+  h.lr = (float)lr;
+  h.beta1 = (float)beta1;
+  h.beta2 = (float)beta2;
+  h.one_minus_beta1 = (float)(1.0 - beta1);
+  h.one_minus_beta2 = (float)(1.0 - beta2);
+  h.bias1 = (float)(1.0 - pow(beta1, (double)step_t));
+  h.bias2 = (float)(1.0 - pow(beta2, (double)step_t));
+  h.eps = (float)eps;
+  h.weight_decay = (float)weight_decay;
+  h.grad_scale = (float)grad_scale;
+  h.use_wd = weight_decay > 0.0;
+  h.use_scale = grad_scale != 1.0;
+  return h;
+}
+static SgdHyper make_sgd_hyper(double lr, double momentum, double weight_decay, int nesterov, double grad_scale) {
+  SgdHyper h;
+  h.lr = (float)lr;
+  h.momentum = (float)momentum;
+  h.weight_decay = (float)weight_decay;
+  h.grad_scale = (float)grad_scale;
+  h.use_momentum = momentum > 0.0;
+  h.nesterov = nesterov != 0;
+  h.use_scale = grad_scale != 1.0;
+  return h;
 }
 
 static dfb_status build_table(const char* name, float* const* params, const float* const* grads,
@@ -187,25 +241,14 @@ dfb_status dfb_multi_adam_step(float* const* params, const float* const* grads, 
   dfb_status st = build_table("multi_adam_step", params, grads, exp_avg, exp_avg_sq, sizes, count, true, true, &tab, &chunks);
   if (st != DFB_OK) return st;
   if (chunks == 0) return DFB_OK;
+  static_assert(sizeof(AdamHyper) <= kHyperBytes && sizeof(SgdHyper) <= kHyperBytes, "hyper block too small");
+  AdamHyper h = make_adam_hyper(lr, beta1, beta2, eps, weight_decay, step_t, grad_scale);
   const TensorRef* dev = nullptr;
-  st = upload_table(tab, &dev);
+  const void* dev_h = nullptr;
+  st = upload_table(tab, &h, sizeof(h), 0, &dev, &dev_h);
   if (st != DFB_OK) return st;
-  AdamHyper h;
-  // every scalar is a Python double rounded to float32 when it reaches a scalar_* kernel
-  h.lr = (float)lr;
-  h.beta1 = (float)beta1;
-  h.beta2 = (float)beta2;
-  h.one_minus_beta1 = (float)(1.0 - beta1);
-  h.one_minus_beta2 = (float)(1.0 - beta2);
-  h.bias1 = (float)(1.0 - pow(beta1, (double)step_t));
-  h.bias2 = (float)(1.0 - pow(beta2, (double)step_t));
-  h.eps = (float)eps;
-  h.weight_decay = (float)weight_decay;
-  h.grad_scale = (float)grad_scale;
-  h.use_wd = weight_decay > 0.0;
-  h.use_scale = grad_scale != 1.0;
   unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
-  multi_adam_kernel<<<grid, 256, 0, compute_stream()>>>(dev, (int)tab.size(), chunks, h);
+  multi_adam_kernel<<<grid, 256, 0, compute_stream()>>>(dev, (int)tab.size(), chunks, (const AdamHyper*)dev_h);
   DFB_LAUNCH_CHECK("multi_adam_step");
   return DFB_OK;
 }
@@ -220,20 +263,35 @@ dfb_status dfb_multi_sgd_step(float* const* params, const float* const* grads, f
   dfb_status st = build_table("multi_sgd_step", params, grads, velocity, nullptr, sizes, count, use_m, false, &tab, &chunks);
   if (st != DFB_OK) return st;
   if (chunks == 0) return DFB_OK;
+  SgdHyper h = make_sgd_hyper(lr, momentum, weight_decay, nesterov, grad_scale);
   const TensorRef* dev = nullptr;
-  st = upload_table(tab, &dev);
+  const void* dev_h = nullptr;
+  st = upload_table(tab, &h, sizeof(h), 1, &dev, &dev_h);
   if (st != DFB_OK) return st;
-  SgdHyper h;
-  h.lr = (float)lr;
-  h.momentum = (float)momentum;
-  h.weight_decay = (float)weight_decay;
-  h.grad_scale = (float)grad_scale;
-  h.use_momentum = use_m;
-  h.nesterov = nesterov != 0;
-  h.use_scale = grad_scale != 1.0;
   unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
-  multi_sgd_kernel<<<grid, 256, 0, compute_stream()>>>(dev, (int)tab.size(), chunks, h);
+  multi_sgd_kernel<<<grid, 256, 0, compute_stream()>>>(dev, (int)tab.size(), chunks, (const SgdHyper*)dev_h);
   DFB_LAUNCH_CHECK("multi_sgd_step");
+  return DFB_OK;
+}
+
+// Hyper-parameters of the index-th optimizer step captured in `graph_exec`, for its next replay.
+dfb_status dfb_graph_set_adam(void* graph_exec, int index, double lr, double beta1, double beta2, double eps,
+                              double weight_decay, int step_t, double grad_scale) {
+  DFB_REQUIRE(step_t >= 1, DFB_ERR_INVALID, "graph_set_adam: step_t starts at 1, got %d", step_t);
+  void* host = nullptr;
+  dfb_status st = graph_hyper_slot(graph_exec, index, 0, &host);
+  if (st != DFB_OK) return st;
+  AdamHyper h = make_adam_hyper(lr, beta1, beta2, eps, weight_decay, step_t, grad_scale);
+  memcpy(host, &h, sizeof(h));
+  return DFB_OK;
+}
+dfb_status dfb_graph_set_sgd(void* graph_exec, int index, double lr, double momentum, double weight_decay,
+                             int nesterov, double grad_scale) {
+  void* host = nullptr;
+  dfb_status st = graph_hyper_slot(graph_exec, index, 1, &host);
+  if (st != DFB_OK) return st;
+  SgdHyper h = make_sgd_hyper(lr, momentum, weight_decay, nesterov, grad_scale);
+  memcpy(host, &h, sizeof(h));
   return DFB_OK;
 }
 

@@ -174,6 +174,18 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
   m.def("graph_end_capture", []() { void* g = nullptr; check(dfb_graph_end_capture(&g)); return (size_t)g; });
   m.def("graph_launch", [](size_t g) { check(dfb_graph_launch((void*)g)); });
   m.def("graph_destroy", [](size_t g) { check(dfb_graph_destroy((void*)g)); });
+  m.def("graph_node_counts", [](size_t g) {
+    int k = 0, n = 0;
+    check(dfb_graph_node_counts((void*)g, &k, &n));
+    return py::make_tuple(k, n);
+  });
+  m.def("graph_capturing", []() { int c = 0; check(dfb_graph_capturing(&c)); return c != 0; });
+  m.def("graph_set_adam", [](size_t g, int index, double lr, double b1, double b2, double eps, double wd, int t, double gs) {
+    check(dfb_graph_set_adam((void*)g, index, lr, b1, b2, eps, wd, t, gs));
+  });
+  m.def("graph_set_sgd", [](size_t g, int index, double lr, double mom, double wd, bool nesterov, double gs) {
+    check(dfb_graph_set_sgd((void*)g, index, lr, mom, wd, nesterov ? 1 : 0, gs));
+  });
 
   // ---- L0: the reference protocol -------------------------------------------------------------
   m.def("fill", [](const py::object& out, float v) {

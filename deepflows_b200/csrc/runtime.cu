@@ -48,6 +48,7 @@ struct Runtime {
     std::vector<void*> dev_allocs;
     std::vector<void*> hyper_host;    // one per captured optimizer step, in capture order
     std::vector<int> hyper_kind;      // 0 = Adam, 1 = SGD
+    int n_nodes = 0, n_kernel_nodes = 0;
   };
   std::unordered_map<void*, GraphPool*> owner;          // block -> pool, for graph-owned blocks
   std::unordered_map<void*, GraphPool*> pools_by_exec;  // cudaGraphExec_t -> pool
@@ -418,6 +419,16 @@ dfb_status dfb_graph_end_capture(void** graph_exec) {
   cudaError_t e = cudaStreamEndCapture(r.compute, &g);
   cudaGraphExec_t ge = nullptr;
   if (e == cudaSuccess) {
+    size_t n = 0;
+    if (cudaGraphGetNodes(g, nullptr, &n) == cudaSuccess && n > 0) {
+      std::vector<cudaGraphNode_t> nodes(n);
+      cudaGraphGetNodes(g, nodes.data(), &n);
+      pool->n_nodes = (int)n;
+      for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) pool->n_kernel_nodes++;
+      }
+    }
     e = cudaGraphInstantiate(&ge, g, 0);
     cudaGraphDestroy(g);
   }
@@ -458,6 +469,15 @@ dfb_status dfb_graph_destroy(void* graph_exec) {
   for (void* h : pool->host_allocs) cudaFreeHost(h);
   for (void* d : pool->dev_allocs) cudaFree(d);
   delete pool;
+  return DFB_OK;
+}
+dfb_status dfb_graph_node_counts(void* graph_exec, int* kernel_nodes, int* all_nodes) {
+  Runtime& r = rt();
+  std::lock_guard<std::mutex> lk(r.mu);
+  auto it = r.pools_by_exec.find(graph_exec);
+  DFB_REQUIRE(it != r.pools_by_exec.end(), DFB_ERR_INVALID, "unknown graph handle");
+  if (kernel_nodes) *kernel_nodes = it->second->n_kernel_nodes;
+  if (all_nodes) *all_nodes = it->second->n_nodes;
   return DFB_OK;
 }
 dfb_status dfb_graph_capturing(int* capturing) {

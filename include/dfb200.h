@@ -102,11 +102,27 @@ DFB_API dfb_status dfb_from_host_async(const float* pinned_src, float* dst, size
 DFB_API dfb_status dfb_to_host_async(const float* src, float* pinned_dst, size_t n);
 DFB_API dfb_status dfb_copy(const float* src, float* dst, size_t n); /* device to device */
 
-/* CUDA-graph capture of everything enqueued on the compute stream between begin/end. */
+/* CUDA-graph capture of everything enqueued on the compute stream (and, through the comm events, on the
+ * communication stream) between begin/end: a whole training step - forward, loss, backward, gradient
+ * all-reduce, optimizer - replays as ONE graph launch, with no per-kernel host cost. The reference has
+ * nothing comparable (one blocking launch per op, ndarray_backend_cuda.cu passim).
+ *   - every block dfb_malloc hands out during the capture belongs to the graph until dfb_graph_destroy:
+ *     freed blocks return to the graph's private pool, so replays never alias memory somebody else got.
+ *   - host copies (dfb_from_host / dfb_to_host) fail with DFB_ERR_RUNTIME during a capture.
+ *   - optimizer steps captured in the graph read their hyper-parameters from pinned host memory at each
+ *     replay; dfb_graph_set_adam / dfb_graph_set_sgd set them for the next replay (index = order of the
+ *     optimizer steps inside the capture). */
 DFB_API dfb_status dfb_graph_begin_capture(void);
 DFB_API dfb_status dfb_graph_end_capture(void** graph_exec);
 DFB_API dfb_status dfb_graph_launch(void* graph_exec);
 DFB_API dfb_status dfb_graph_destroy(void* graph_exec);
+DFB_API dfb_status dfb_graph_capturing(int* capturing);
+/* kernel nodes / all nodes (kernels, memcpys, NCCL, event waits) that one launch of the graph replays */
+DFB_API dfb_status dfb_graph_node_counts(void* graph_exec, int* kernel_nodes, int* all_nodes);
+DFB_API dfb_status dfb_graph_set_adam(void* graph_exec, int index, double lr, double beta1, double beta2,
+                                      double eps, double weight_decay, int step_t, double grad_scale);
+DFB_API dfb_status dfb_graph_set_sgd(void* graph_exec, int index, double lr, double momentum,
+                                     double weight_decay, int nesterov, double grad_scale);
 
 /* ---------------------------------------------------------------------------------------------
  * L0: the device-module protocol (one entry per binding of the reference module)
