@@ -332,6 +332,9 @@ def profile_dominant_kernel(dev, step_fn, args, batch):
     algorithmic FLOPs (2*M*N*K) and minimum bytes against its duration."""
     records = {}
     pending = []
+    for _ in range(2):  # un-instrumented eager steps: refill the allocator pool after the graph capture
+        step_fn()
+    dev.synchronize()
 
     def wrap(name, geom_of, orig):
         def fn(*a):

@@ -22,6 +22,8 @@ dfb_status ensure_init();
 cudaStream_t compute_stream();
 cudaStream_t comm_stream();
 int sm_count();
+// persistent zero-initialised device words for last-CTA-arrives reductions, one per kernel family (runtime.cu)
+unsigned* ticket_counter(int slot);
 // CUDA-graph capture support (runtime.cu)
 bool graph_capturing();
 dfb_status graph_staging(size_t bytes, int kind, void** host, void** dev);

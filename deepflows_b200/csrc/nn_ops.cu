@@ -45,9 +45,12 @@ struct ColPlan {
   int G;            // column groups = C / V
   int lanes;        // row lanes per CTA = max(1, kT / G)
   int gpass;        // column-group passes per CTA = ceil(G / kT)
-  unsigned ctas;    // CTAs (row chunks)
+  unsigned ctas;    // CTAs (row chunks) = partial results per channel
   size_t rows_per_cta;
 };
+// Row chunking for the column reductions. Every thread should see only a handful of rows (the loop is a
+// chain of dependent-latency loads otherwise), but the number of CTAs is also the number of partials the last
+// CTA has to merge, so it is capped at two CTAs per SM.
 static ColPlan plan_cols(size_t rows, int C, const void* p0, const void* p1 = nullptr) {
   ColPlan p;
   bool al = ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
@@ -55,132 +58,221 @@ static ColPlan plan_cols(size_t rows, int C, const void* p0, const void* p1 = nu
   p.G = C / p.V;
   p.lanes = std::max(1, kT / p.G);
   p.gpass = (p.G + kT - 1) / kT;
-  size_t want = (rows + (size_t)p.lanes * 8 - 1) / ((size_t)p.lanes * 8);  // >= 8 rows per lane
-  size_t cap = (size_t)sm_count() * 4;
+  size_t want = (rows + (size_t)p.lanes * 4 - 1) / ((size_t)p.lanes * 4);  // ~4 rows per thread
+  size_t cap = (size_t)sm_count() * 2;
   p.ctas = (unsigned)std::max<size_t>(1, std::min(want, cap));
   p.rows_per_cta = (rows + p.ctas - 1) / p.ctas;
+  p.ctas = (unsigned)((rows + p.rows_per_cta - 1) / p.rows_per_cta);
   return p;
 }
 
-// Partial moments of one CTA's row chunk, per channel: count, mean, M2 (sum of squared
-// deviations). Threads accumulate shifted sums (shift = first sample seen, which keeps
-// sum(d^2) - sum(d)^2/n well conditioned), lanes are merged with Chan's formula.
-template <int V>
+// Ticket counters for "the last CTA to finish merges the partials" (threadfence-reduction pattern): one
+// persistent zero-initialised word per kernel family, reset by the last CTA. All users run on the single
+// compute stream, so two kernels never share a counter concurrently.
+// returns true in every thread of the last CTA to arrive; all global writes made by the CTA's threads before
+// the call are visible to the last CTA afterwards (read them with __ldcg).
+__device__ __forceinline__ bool last_cta_arrives(unsigned* ticket) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *ticket = 0;  // ready for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+// Two sums per channel over all rows, in one launch: sum f0(row), sum f1(row), where (f0, f1) is
+//   STATS : (x - shift, (x - shift)^2)  with shift = x[row 0] (keeps the variance well conditioned when
+//           |mean| >> std without Welford's divisions; partials merge by plain addition in a fixed order)
+//   BNBWD : (dy, dy * x_hat)
+//   COLSUM: (x, -)
+// Thread t owns column group (t % G) on row lane (t / G); a warp reads whole 128-byte lines. Each CTA writes
+// its partial sums, the last CTA to finish adds the partials (fixed order => deterministic) and hands the
+// totals to `Fin`.
+enum { SUMS_STATS = 0, SUMS_BNBWD = 1, SUMS_COLSUM = 2 };
+struct SumsArgs {
+  const float* x;
+  const float* dy;       // BNBWD
+  const float* mean;     // BNBWD
+  const float* invstd;   // BNBWD
+  float* part;           // [ctas][2][C]
+  unsigned* ticket;
+  // finalisation
+  float* out0;           // STATS: save_mean   BNBWD: dbeta   COLSUM: out
+  float* out1;           // STATS: save_invstd BNBWD: dgamma
+  float* running_mean;   // STATS
+  float* running_var;    // STATS
+  float eps, momentum;
+};
+
+// Pairwise (tree) sum over the row lanes of a CTA through shared memory; the result lands in lane 0. A tree
+// keeps the rounding error at O(log lanes) like numpy's pairwise summation (the oracle), and the order is
+// fixed, so results are reproducible. Must be called by all threads of the CTA.
+template <int V, bool TWO>
+__device__ __forceinline__ void lane_tree_sum(float* sm, float (&s0)[V], float (&s1)[V], int lane, int lanes, int g, int C,
+                                              bool active) {
+  int top = 1;
+  while (top < lanes) top <<= 1;
+  __syncthreads();  // shared memory may still be read by a previous user
+  if (active) {
+    Vec<V>::put(sm + (size_t)(lane * 2 + 0) * C + g * V, s0);
+    if (TWO) Vec<V>::put(sm + (size_t)(lane * 2 + 1) * C + g * V, s1);
+  }
+  for (int off = top >> 1; off > 0; off >>= 1) {
+    __syncthreads();
+    const bool take = active && lane < off && lane + off < lanes;
+    if (take) {
+      float t0[V], t1[V];
+      Vec<V>::get(sm + (size_t)((lane + off) * 2 + 0) * C + g * V, t0);
+      if (TWO) Vec<V>::get(sm + (size_t)((lane + off) * 2 + 1) * C + g * V, t1);
+#pragma unroll
+      for (int v = 0; v < V; ++v) { s0[v] += t0[v]; if (TWO) s1[v] += t1[v]; }
+    }
+    __syncthreads();
+    if (take && off > 1) {
+      Vec<V>::put(sm + (size_t)(lane * 2 + 0) * C + g * V, s0);
+      if (TWO) Vec<V>::put(sm + (size_t)(lane * 2 + 1) * C + g * V, s1);
+    }
+  }
+}
+
+template <int V, int KIND>
 __global__ void __launch_bounds__(kT)
-col_moments_kernel(const float* __restrict__ x, size_t rows, int C, ColPlan p,
-                   float* __restrict__ part_cnt, float* __restrict__ part_mean, float* __restrict__ part_m2) {
-  extern __shared__ float sm[];  // [lanes][3][G*V] when lanes > 1
+col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
+  extern __shared__ float sm[];  // [lanes][2][C] when lanes > 1
   const int G = p.G;
-  size_t r0 = (size_t)blockIdx.x * p.rows_per_cta;
-  size_t r1 = r0 + p.rows_per_cta < rows ? r0 + p.rows_per_cta : rows;
+  const size_t r0 = (size_t)blockIdx.x * p.rows_per_cta;
+  const size_t r1 = r0 + p.rows_per_cta < rows ? r0 + p.rows_per_cta : rows;
+  const int gsel = threadIdx.x % (G < kT ? G : kT);
+  const int lane = G < kT ? threadIdx.x / G : 0;
   for (int gp = 0; gp < p.gpass; ++gp) {
-    int g = gp * kT + (threadIdx.x % (G < kT ? G : kT));
-    int lane = G < kT ? threadIdx.x / G : 0;
-    bool active = g < G && lane < p.lanes;
-    float n = 0.f, shift[V], s1[V], s2[V];
+    const int g = gp * kT + gsel;
+    const bool active = g < G && lane < p.lanes;
+    float s0[V], s1[V], c0[V], c1[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) { shift[v] = 0.f; s1[v] = 0.f; s2[v] = 0.f; }
+    for (int v = 0; v < V; ++v) { s0[v] = 0.f; s1[v] = 0.f; c0[v] = 0.f; c1[v] = 0.f; }
     if (active) {
-      for (size_t r = r0 + lane; r < r1; r += p.lanes) {
-        float xv[V];
-        Vec<V>::get(x + r * C + (size_t)g * V, xv);
-        if (n == 0.f) {
+      if (KIND == SUMS_STATS) Vec<V>::get(a.x + (size_t)g * V, c0);  // shift = row 0
+      if (KIND == SUMS_BNBWD) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) shift[v] = xv[v];
-        }
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          float d = xv[v] - shift[v];
-          s1[v] += d;
-          s2[v] = fmaf(d, d, s2[v]);
-        }
-        n += 1.f;
+        for (int v = 0; v < V; ++v) { c0[v] = a.mean[g * V + v]; c1[v] = a.invstd[g * V + v]; }
       }
-    }
-    float mean[V], m2[V];
+      const size_t step = p.lanes;
+      size_t r = r0 + lane;
+      // four independent rows in flight per thread
+      for (; r + 3 * step < r1; r += 4 * step) {
+        float xv[4][V], dv[4][V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      float dm = n > 0.f ? s1[v] / n : 0.f;
-      mean[v] = shift[v] + dm;
-      m2[v] = n > 0.f ? fmaxf(s2[v] - s1[v] * dm, 0.f) : 0.f;
-    }
-    if (p.lanes > 1) {
-      // merge lanes through shared memory (lane 0 of each column group does the merge)
-      int CV = G * V;
-      __syncthreads();
-      if (active) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          sm[(lane * 3 + 0) * CV + g * V + v] = n;
-          sm[(lane * 3 + 1) * CV + g * V + v] = mean[v];
-          sm[(lane * 3 + 2) * CV + g * V + v] = m2[v];
+        for (int u = 0; u < 4; ++u) {
+          Vec<V>::get(a.x + (r + u * step) * C + (size_t)g * V, xv[u]);
+          if (KIND == SUMS_BNBWD) Vec<V>::get(a.dy + (r + u * step) * C + (size_t)g * V, dv[u]);
         }
-      }
-      __syncthreads();
-      if (active && lane == 0) {
-        const float n_own = n;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          float na = n_own, ma = mean[v], qa = m2[v];
-          for (int l = 1; l < p.lanes; ++l) {
-            float nb = sm[(l * 3 + 0) * CV + g * V + v];
-            if (nb == 0.f) continue;
-            float mb = sm[(l * 3 + 1) * CV + g * V + v], qb = sm[(l * 3 + 2) * CV + g * V + v];
-            float nt = na + nb, d = mb - ma;
-            ma += d * (nb / nt);
-            qa += qb + d * d * (na * nb / nt);
-            na = nt;
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            if (KIND == SUMS_STATS) { float d = xv[u][v] - c0[v]; s0[v] += d; s1[v] = fmaf(d, d, s1[v]); }
+            if (KIND == SUMS_BNBWD) { s0[v] += dv[u][v]; s1[v] = fmaf(dv[u][v], (xv[u][v] - c0[v]) * c1[v], s1[v]); }
+            if (KIND == SUMS_COLSUM) s0[v] += xv[u][v];
           }
-          n = na; mean[v] = ma; m2[v] = qa;
+      }
+      for (; r < r1; r += step) {
+        float xv[V], dv[V];
+        Vec<V>::get(a.x + r * C + (size_t)g * V, xv);
+        if (KIND == SUMS_BNBWD) Vec<V>::get(a.dy + r * C + (size_t)g * V, dv);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (KIND == SUMS_STATS) { float d = xv[v] - c0[v]; s0[v] += d; s1[v] = fmaf(d, d, s1[v]); }
+          if (KIND == SUMS_BNBWD) { s0[v] += dv[v]; s1[v] = fmaf(dv[v], (xv[v] - c0[v]) * c1[v], s1[v]); }
+          if (KIND == SUMS_COLSUM) s0[v] += xv[v];
         }
       }
     }
+    if (p.lanes > 1) lane_tree_sum<V, KIND != SUMS_COLSUM>(sm, s0, s1, lane, p.lanes, g, C, active);
+    if (active && lane == 0) {
+      Vec<V>::put(a.part + ((size_t)blockIdx.x * 2 + 0) * C + g * V, s0);
+      if (KIND != SUMS_COLSUM) Vec<V>::put(a.part + ((size_t)blockIdx.x * 2 + 1) * C + g * V, s1);
+    }
+  }
+  if (!last_cta_arrives(a.ticket)) return;
+
+  // ---- last CTA: totals over the partials. Same thread mapping: lane l adds partials l, l+lanes, ... -----
+  const int parts = gridDim.x;
+  for (int gp = 0; gp < p.gpass; ++gp) {
+    const int g = gp * kT + gsel;
+    const bool active = g < G && lane < p.lanes;
+    float s0[V], s1[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { s0[v] = 0.f; s1[v] = 0.f; }
+    if (active) {
+      int q = lane;
+      for (; q + 3 * p.lanes < parts; q += 4 * p.lanes) {
+        float t0[4][V], t1[4][V];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            t0[u][v] = __ldcg(a.part + ((size_t)(q + u * p.lanes) * 2 + 0) * C + g * V + v);
+            t1[u][v] = KIND != SUMS_COLSUM ? __ldcg(a.part + ((size_t)(q + u * p.lanes) * 2 + 1) * C + g * V + v) : 0.f;
+          }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) { s0[v] += t0[u][v]; s1[v] += t1[u][v]; }
+      }
+      for (; q < parts; q += p.lanes)
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          s0[v] += __ldcg(a.part + ((size_t)q * 2 + 0) * C + g * V + v);
+          if (KIND != SUMS_COLSUM) s1[v] += __ldcg(a.part + ((size_t)q * 2 + 1) * C + g * V + v);
+        }
+    }
+    if (p.lanes > 1) lane_tree_sum<V, true>(sm, s0, s1, lane, p.lanes, g, C, active);
     if (active && lane == 0) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        size_t o = (size_t)blockIdx.x * C + (size_t)g * V + v;
-        part_cnt[o] = n;
-        part_mean[o] = mean[v];
-        part_m2[o] = m2[v];
+        const int c = g * V + v;
+        if (KIND == SUMS_STATS) {
+          // mean = shift + s0/n ; biased var = s1/n - (s0/n)^2 ; running stats use the biased variance
+          // like batchnorm.py:44-46
+          const float n = (float)rows;
+          const float dm = s0[v] / n;
+          const float mean = a.x[c] + dm;
+          const float var = fmaxf(s1[v] / n - dm * dm, 0.f);
+          a.out0[c] = mean;
+          a.out1[c] = 1.0f / sqrtf(var + a.eps);
+          if (a.running_mean) a.running_mean[c] = a.running_mean[c] * (1.0f - a.momentum) + mean * a.momentum;
+          if (a.running_var) a.running_var[c] = a.running_var[c] * (1.0f - a.momentum) + var * a.momentum;
+        } else {
+          if (a.out0) a.out0[c] = s0[v];
+          if (KIND == SUMS_BNBWD && a.out1) a.out1[c] = s1[v];
+        }
       }
     }
   }
 }
 
-// Merge the per-CTA partials (one warp per channel: lanes merge strided subsets with Chan's formula, then a
-// shuffle tree; the order is fixed => deterministic), produce mean / invstd, update the running statistics
-// with the *biased* variance like batchnorm.py:44-46.
-__device__ __forceinline__ void chan_merge(float& na, float& ma, float& qa, float nb, float mb, float qb) {
-  if (nb == 0.f) return;
-  float nt = na + nb, d = mb - ma;
-  ma += d * (nb / nt);
-  qa += qb + d * d * (na * nb / nt);
-  na = nt;
-}
-__global__ void __launch_bounds__(kT)
-bn_finalize_kernel(const float* __restrict__ part_cnt, const float* __restrict__ part_mean,
-                   const float* __restrict__ part_m2, int parts, int C, float eps, float momentum,
-                   float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                   float* __restrict__ running_mean, float* __restrict__ running_var) {
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (c >= C) return;
-  float na = 0.f, ma = 0.f, qa = 0.f;
-  for (int i = lane; i < parts; i += 32)
-    chan_merge(na, ma, qa, part_cnt[(size_t)i * C + c], part_mean[(size_t)i * C + c], part_m2[(size_t)i * C + c]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float nb = __shfl_down_sync(0xffffffffu, na, o), mb = __shfl_down_sync(0xffffffffu, ma, o),
-          qb = __shfl_down_sync(0xffffffffu, qa, o);
-    chan_merge(na, ma, qa, nb, mb, qb);
-  }
-  if (lane != 0) return;
-  float mean = ma;
-  float var = na > 0.f ? qa / na : 0.f;
-  save_mean[c] = mean;
-  save_invstd[c] = 1.0f / sqrtf(var + eps);
-  if (running_mean) running_mean[c] = running_mean[c] * (1.0f - momentum) + mean * momentum;
-  if (running_var) running_var[c] = running_var[c] * (1.0f - momentum) + var * momentum;
+template <int KIND>
+static dfb_status launch_col_sums(const char* name, SumsArgs a, size_t rows, int C, const void* p0, const void* p1 = nullptr) {
+  ColPlan p = plan_cols(rows, C, p0, p1);
+  size_t smem = p.lanes > 1 ? (size_t)p.lanes * 2 * C * sizeof(float) : 0;
+  DFB_REQUIRE(smem <= 48 * 1024, DFB_ERR_INVALID, "%s: %d channels need %zu B of shared memory", name, C, smem);
+  a.ticket = ticket_counter(KIND);
+  DFB_REQUIRE(a.ticket != nullptr, DFB_ERR_NOMEM, "%s: cannot allocate the ticket counters", name);
+  float* part = nullptr;
+  dfb_status st = dfb_malloc((size_t)p.ctas * 2 * C, &part);
+  if (st != DFB_OK) return st;
+  a.part = part;
+  cudaStream_t s = compute_stream();
+  if (p.V == 4) col_sums_kernel<4, KIND><<<p.ctas, kT, smem, s>>>(a, rows, C, p);
+  else col_sums_kernel<1, KIND><<<p.ctas, kT, smem, s>>>(a, rows, C, p);
+  dfb_free(part);  // stream-ordered: the next user of the block runs after this kernel
+  DFB_LAUNCH_CHECK(name);
+  return DFB_OK;
 }
 
 // y = (x - mean) * (invstd * gamma) + beta, optionally followed by max(.,0)
@@ -213,89 +305,6 @@ bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows,
       yv[v] = RELU ? fmaxf(t, 0.f) : t;
     }
     Vec<V>::put(y + i * V, yv);
-  }
-}
-
-// BatchNorm backward, pass 1: per-CTA partial sums of dy and dy * x_hat per channel.
-template <int V>
-__global__ void __launch_bounds__(kT)
-bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, size_t rows, int C,
-                     ColPlan p, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     float* __restrict__ part_dbeta, float* __restrict__ part_dgamma) {
-  extern __shared__ float sm[];  // [lanes][2][C]
-  const int G = p.G;
-  size_t r0 = (size_t)blockIdx.x * p.rows_per_cta;
-  size_t r1 = r0 + p.rows_per_cta < rows ? r0 + p.rows_per_cta : rows;
-  for (int gp = 0; gp < p.gpass; ++gp) {
-    int g = gp * kT + (threadIdx.x % (G < kT ? G : kT));
-    int lane = G < kT ? threadIdx.x / G : 0;
-    bool active = g < G && lane < p.lanes;
-    float sb[V], sg[V], mu[V], is[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      sb[v] = 0.f; sg[v] = 0.f;
-      mu[v] = active ? mean[g * V + v] : 0.f;
-      is[v] = active ? invstd[g * V + v] : 0.f;
-    }
-    if (active) {
-      for (size_t r = r0 + lane; r < r1; r += p.lanes) {
-        float xv[V], dv[V];
-        Vec<V>::get(x + r * C + (size_t)g * V, xv);
-        Vec<V>::get(dy + r * C + (size_t)g * V, dv);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          sb[v] += dv[v];
-          sg[v] = fmaf(dv[v], (xv[v] - mu[v]) * is[v], sg[v]);
-        }
-      }
-    }
-    if (p.lanes > 1) {
-      __syncthreads();
-      if (active) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          sm[(lane * 2 + 0) * C + g * V + v] = sb[v];
-          sm[(lane * 2 + 1) * C + g * V + v] = sg[v];
-        }
-      }
-      __syncthreads();
-      if (active && lane == 0) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          for (int l = 1; l < p.lanes; ++l) {
-            sb[v] += sm[(l * 2 + 0) * C + g * V + v];
-            sg[v] += sm[(l * 2 + 1) * C + g * V + v];
-          }
-        }
-      }
-    }
-    if (active && lane == 0) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        part_dbeta[(size_t)blockIdx.x * C + g * V + v] = sb[v];
-        part_dgamma[(size_t)blockIdx.x * C + g * V + v] = sg[v];
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kT)
-colsum_finalize_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int parts,
-                       int C, float* __restrict__ out_a, float* __restrict__ out_b) {
-  // one warp per channel; lanes take strided partials, shuffle tree at the end (fixed order)
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (c >= C) return;
-  float a = 0.f, b = 0.f;
-  for (int i = lane; i < parts; i += 32) {
-    a += part_a[(size_t)i * C + c];
-    if (part_b) b += part_b[(size_t)i * C + c];
-  }
-  a = warp_sum(a);
-  b = warp_sum(b);
-  if (lane == 0) {
-    if (out_a) out_a[c] = a;
-    if (out_b) out_b[c] = b;
   }
 }
 
@@ -336,49 +345,6 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
       ov[v] = s_k1[c] * (dv[v] - s_mb[c] - xh * s_mg[c]);
     }
     Vec<V>::put(dx + i * V, ov);
-  }
-}
-
-// plain column sum partials (bias gradients)
-template <int V>
-__global__ void __launch_bounds__(kT)
-colsum_partial_kernel(const float* __restrict__ x, size_t rows, int C, ColPlan p, float* __restrict__ part) {
-  extern __shared__ float sm[];  // [lanes][C]
-  const int G = p.G;
-  size_t r0 = (size_t)blockIdx.x * p.rows_per_cta;
-  size_t r1 = r0 + p.rows_per_cta < rows ? r0 + p.rows_per_cta : rows;
-  for (int gp = 0; gp < p.gpass; ++gp) {
-    int g = gp * kT + (threadIdx.x % (G < kT ? G : kT));
-    int lane = G < kT ? threadIdx.x / G : 0;
-    bool active = g < G && lane < p.lanes;
-    float s[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) s[v] = 0.f;
-    if (active) {
-      for (size_t r = r0 + lane; r < r1; r += p.lanes) {
-        float xv[V];
-        Vec<V>::get(x + r * C + (size_t)g * V, xv);
-#pragma unroll
-        for (int v = 0; v < V; ++v) s[v] += xv[v];
-      }
-    }
-    if (p.lanes > 1) {
-      __syncthreads();
-      if (active) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) sm[lane * C + g * V + v] = s[v];
-      }
-      __syncthreads();
-      if (active && lane == 0) {
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          for (int l = 1; l < p.lanes; ++l) s[v] += sm[l * C + g * V + v];
-      }
-    }
-    if (active && lane == 0) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) part[(size_t)blockIdx.x * C + g * V + v] = s[v];
-    }
   }
 }
 
@@ -633,41 +599,23 @@ dfb_status dfb_colsum(const float* x, float* out, size_t rows, int cols) {
   DFB_REQUIRE(x && out, DFB_ERR_INVALID, "colsum: null pointer");
   DFB_REQUIRE(cols > 0, DFB_ERR_INVALID, "colsum: cols must be positive");
   if (rows == 0) return dfb_fill(out, 0.f, cols);
-  ColPlan p = plan_cols(rows, cols, x);
-  float* part = nullptr;
-  dfb_status st = dfb_malloc((size_t)p.ctas * cols, &part);
-  if (st != DFB_OK) return st;
-  size_t smem = p.lanes > 1 ? (size_t)p.lanes * cols * sizeof(float) : 0;
-  cudaStream_t s = compute_stream();
-  if (p.V == 4) colsum_partial_kernel<4><<<p.ctas, kT, smem, s>>>(x, rows, cols, p, part);
-  else colsum_partial_kernel<1><<<p.ctas, kT, smem, s>>>(x, rows, cols, p, part);
-  DFB_LAUNCH_CHECK("colsum");
-  colsum_finalize_kernel<<<cdiv((size_t)cols * 32, kT), kT, 0, s>>>(part, nullptr, (int)p.ctas, cols, out, nullptr);
-  DFB_LAUNCH_CHECK("colsum");
-  dfb_free(part);
-  return DFB_OK;
+  SumsArgs a{};
+  a.x = x;
+  a.out0 = out;
+  return launch_col_sums<SUMS_COLSUM>("colsum", a, rows, cols, x);
 }
 
 static dfb_status bn_stats(const float* x, size_t rows, int C, float eps, float momentum, float* save_mean,
                            float* save_invstd, float* running_mean, float* running_var) {
-  ColPlan p = plan_cols(rows, C, x);
-  float* part = nullptr;
-  dfb_status st = dfb_malloc((size_t)p.ctas * C * 3, &part);
-  if (st != DFB_OK) return st;
-  float* pc = part;
-  float* pm = part + (size_t)p.ctas * C;
-  float* pq = part + (size_t)p.ctas * C * 2;
-  size_t smem = p.lanes > 1 ? (size_t)p.lanes * 3 * C * sizeof(float) : 0;
-  cudaStream_t s = compute_stream();
-  DFB_REQUIRE(smem <= 48 * 1024, DFB_ERR_INVALID, "batchnorm: %d channels need %zu B of shared memory", C, smem);
-  if (p.V == 4) col_moments_kernel<4><<<p.ctas, kT, smem, s>>>(x, rows, C, p, pc, pm, pq);
-  else col_moments_kernel<1><<<p.ctas, kT, smem, s>>>(x, rows, C, p, pc, pm, pq);
-  DFB_LAUNCH_CHECK("bn_stats");
-  bn_finalize_kernel<<<cdiv((size_t)C * 32, kT), kT, 0, s>>>(pc, pm, pq, (int)p.ctas, C, eps, momentum, save_mean, save_invstd,
-                                               running_mean, running_var);
-  DFB_LAUNCH_CHECK("bn_finalize");
-  dfb_free(part);
-  return DFB_OK;
+  SumsArgs a{};
+  a.x = x;
+  a.out0 = save_mean;
+  a.out1 = save_invstd;
+  a.running_mean = running_mean;
+  a.running_var = running_var;
+  a.eps = eps;
+  a.momentum = momentum;
+  return launch_col_sums<SUMS_STATS>("bn_stats", a, rows, C, x);
 }
 
 static dfb_status bn_apply(const float* x, float* y, size_t rows, int C, const float* mean, const float* invstd,
@@ -725,21 +673,24 @@ dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma, const
   DFB_INIT();
   DFB_REQUIRE(x && dy && save_mean && save_invstd, DFB_ERR_INVALID, "bn_bwd: null pointer");
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_bwd: empty input");
-  ColPlan p = plan_cols(rows, C, x, dy);
   float* scratch = nullptr;
-  dfb_status st = dfb_malloc((size_t)p.ctas * C * 2 + 2 * (size_t)C, &scratch);
+  dfb_status st = dfb_malloc(2 * (size_t)C, &scratch);
   if (st != DFB_OK) return st;
-  float* pb = scratch;
-  float* pg = scratch + (size_t)p.ctas * C;
-  float* db = dbeta ? dbeta : scratch + (size_t)p.ctas * C * 2;
-  float* dg = dgamma ? dgamma : scratch + (size_t)p.ctas * C * 2 + C;
-  size_t smem = p.lanes > 1 ? (size_t)p.lanes * 2 * C * sizeof(float) : 0;
+  float* db = dbeta ? dbeta : scratch;
+  float* dg = dgamma ? dgamma : scratch + C;
+  SumsArgs a{};
+  a.x = x;
+  a.dy = dy;
+  a.mean = save_mean;
+  a.invstd = save_invstd;
+  a.out0 = db;
+  a.out1 = dg;
+  st = launch_col_sums<SUMS_BNBWD>("bn_bwd_reduce", a, rows, C, x, dy);
+  if (st != DFB_OK) {
+    dfb_free(scratch);
+    return st;
+  }
   cudaStream_t s = compute_stream();
-  if (p.V == 4) bn_bwd_reduce_kernel<4><<<p.ctas, kT, smem, s>>>(x, dy, rows, C, p, save_mean, save_invstd, pb, pg);
-  else bn_bwd_reduce_kernel<1><<<p.ctas, kT, smem, s>>>(x, dy, rows, C, p, save_mean, save_invstd, pb, pg);
-  DFB_LAUNCH_CHECK("bn_bwd_reduce");
-  colsum_finalize_kernel<<<cdiv((size_t)C * 32, kT), kT, 0, s>>>(pb, pg, (int)p.ctas, C, db, dg);
-  DFB_LAUNCH_CHECK("bn_bwd_finalize");
   if (dx) {
     bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
     size_t sm2 = (size_t)5 * C * sizeof(float);

@@ -31,6 +31,7 @@ struct Runtime {
   int sms = 148;
   cudaStream_t compute = nullptr;
   cudaStream_t comm = nullptr;
+  unsigned* tickets = nullptr;
 
   // caching allocator: exact (rounded) size classes; blocks are never returned to the driver
   // unless dfb_empty_cache() is called or cudaMalloc fails.
@@ -98,6 +99,9 @@ dfb_status ensure_init() {
   r.sms = prop.multiProcessorCount;
   DFB_CUDA(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking));
   DFB_CUDA(cudaStreamCreateWithFlags(&r.comm, cudaStreamNonBlocking));
+  DFB_CUDA(cudaMalloc(&r.tickets, 64 * sizeof(unsigned)));
+  DFB_CUDA(cudaMemset(r.tickets, 0, 64 * sizeof(unsigned)));
+  DFB_CUDA(cudaDeviceSynchronize());
   r.ready = true;
   return DFB_OK;
 }
@@ -105,6 +109,7 @@ dfb_status ensure_init() {
 cudaStream_t compute_stream() { return rt().compute; }
 cudaStream_t comm_stream() { return rt().comm; }
 int sm_count() { return rt().sms; }
+unsigned* ticket_counter(int slot) { return rt().tickets + slot; }
 
 }  // namespace dfb
 
