@@ -214,15 +214,26 @@ class _conv2d(FusedOperator):
         gy = grad.channels_last()
         ws, ws_n = self._workspace(dev)
         dx = dw = None
+        # dgrad and wgrad only share their inputs: when both are needed the wgrad goes to the side stream
+        # and the two kernels (neither fills 148 SMs on the small layers) run concurrently
+        both = needs[0] and needs[1] and dev.has("side_begin")
+        if needs[1]:
+            dw = BackendTensor.make((k, c, r, r), device=dev)
+            if both:
+                dev.side_begin()
+            try:
+                dev.conv2d_wgrad(self._x._handle, self._layout, gy._handle, dw._handle, n, c, h, w, k, r, p, s,
+                                 self._mode, ws, ws_n)
+            finally:
+                if both:
+                    dev.side_end()
         if needs[0]:
             buf = dev.Array(n * h * w * c)
             dmode = 0 if get_dgrad_mode() == "reference" else 1
             dev.conv2d_dgrad(gy._handle, self._w._handle, buf, n, c, h, w, k, r, p, s, self._mode, dmode, ws, ws_n)
             dx = _nhwc_view(buf, n, c, h, w, dev)
-        if needs[1]:
-            dw = BackendTensor.make((k, c, r, r), device=dev)
-            dev.conv2d_wgrad(self._x._handle, self._layout, gy._handle, dw._handle, n, c, h, w, k, r, p, s,
-                             self._mode, ws, ws_n)
+        if both:
+            dev.side_join()
         return dx, dw
 
     def release(self):

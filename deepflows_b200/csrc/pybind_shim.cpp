@@ -170,6 +170,9 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
   m.def("event_record", [](size_t e) { check(dfb_event_record((void*)e)); });
   m.def("event_synchronize", [](size_t e) { py::gil_scoped_release nogil; check(dfb_event_synchronize((void*)e)); });
   m.def("event_elapsed_ms", [](size_t a, size_t b) { float ms = 0; check(dfb_event_elapsed_ms((void*)a, (void*)b, &ms)); return ms; });
+  m.def("side_begin", []() { check(dfb_side_begin()); });
+  m.def("side_end", []() { check(dfb_side_end()); });
+  m.def("side_join", []() { check(dfb_side_join()); });
   m.def("graph_begin_capture", []() { check(dfb_graph_begin_capture()); });
   m.def("graph_end_capture", []() { void* g = nullptr; check(dfb_graph_end_capture(&g)); return (size_t)g; });
   m.def("graph_launch", [](size_t g) { check(dfb_graph_launch((void*)g)); });

@@ -32,6 +32,12 @@ struct Runtime {
   cudaStream_t compute = nullptr;
   cudaStream_t comm = nullptr;
   unsigned* tickets = nullptr;
+  // side stream: independent work of one op (the wgrad of a conv backward) runs beside the main stream
+  // between dfb_side_begin() and dfb_side_end(); dfb_side_join() orders the main stream after it.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool on_side = false;
+  std::vector<void*> side_frees;  // blocks freed while on the side stream: recycled at the join
 
   // caching allocator: exact (rounded) size classes; blocks are never returned to the driver
   // unless dfb_empty_cache() is called or cudaMalloc fails.
@@ -99,6 +105,9 @@ dfb_status ensure_init() {
   r.sms = prop.multiProcessorCount;
   DFB_CUDA(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking));
   DFB_CUDA(cudaStreamCreateWithFlags(&r.comm, cudaStreamNonBlocking));
+  DFB_CUDA(cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking));
+  DFB_CUDA(cudaEventCreateWithFlags(&r.ev_fork, cudaEventDisableTiming));
+  DFB_CUDA(cudaEventCreateWithFlags(&r.ev_join, cudaEventDisableTiming));
   DFB_CUDA(cudaMalloc(&r.tickets, 64 * sizeof(unsigned)));
   DFB_CUDA(cudaMemset(r.tickets, 0, 64 * sizeof(unsigned)));
   DFB_CUDA(cudaDeviceSynchronize());
@@ -106,7 +115,7 @@ dfb_status ensure_init() {
   return DFB_OK;
 }
 
-cudaStream_t compute_stream() { return rt().compute; }
+cudaStream_t compute_stream() { return rt().on_side ? rt().side : rt().compute; }
 cudaStream_t comm_stream() { return rt().comm; }
 int sm_count() { return rt().sms; }
 unsigned* ticket_counter(int slot) { return rt().tickets + slot; }
@@ -155,6 +164,7 @@ dfb_status dfb_device_info(char* name, size_t name_cap, int* sm_count_out, int* 
 dfb_status dfb_synchronize(void) {
   DFB_INIT();
   DFB_CUDA(cudaStreamSynchronize(rt().compute));
+  DFB_CUDA(cudaStreamSynchronize(rt().side));
   DFB_CUDA(cudaStreamSynchronize(rt().comm));
   return DFB_OK;
 }
@@ -248,6 +258,10 @@ dfb_status dfb_free(float* ptr) {
   auto it = r.live.find((void*)ptr);
   DFB_REQUIRE(it != r.live.end(), DFB_ERR_INVALID, "dfb_free: pointer %p not owned by the pool", (void*)ptr);
   size_t bytes = it->second;
+  if (r.on_side) {  // still in use by side-stream work the main stream is not ordered after yet
+    r.side_frees.push_back((void*)ptr);
+    return DFB_OK;
+  }
   r.live.erase(it);
   r.bytes_in_use -= bytes;
   // Single compute stream: every consumer of this block was enqueued before any later producer
@@ -360,6 +374,37 @@ dfb_status dfb_copy(const float* src, float* dst, size_t n) {
   DFB_INIT();
   if (n == 0) return DFB_OK;
   DFB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, rt().compute));
+  return DFB_OK;
+}
+
+// ---- side stream ------------------------------------------------------------------------------
+dfb_status dfb_side_begin(void) {
+  DFB_INIT();
+  Runtime& r = rt();
+  DFB_REQUIRE(!r.on_side, DFB_ERR_RUNTIME, "side_begin: already on the side stream");
+  DFB_CUDA(cudaEventRecord(r.ev_fork, r.compute));
+  DFB_CUDA(cudaStreamWaitEvent(r.side, r.ev_fork, 0));
+  r.on_side = true;
+  return DFB_OK;
+}
+dfb_status dfb_side_end(void) {
+  Runtime& r = rt();
+  DFB_REQUIRE(r.on_side, DFB_ERR_RUNTIME, "side_end: not on the side stream");
+  r.on_side = false;
+  DFB_CUDA(cudaEventRecord(r.ev_join, r.side));
+  return DFB_OK;
+}
+dfb_status dfb_side_join(void) {
+  DFB_INIT();
+  Runtime& r = rt();
+  DFB_REQUIRE(!r.on_side, DFB_ERR_RUNTIME, "side_join: still on the side stream");
+  DFB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_join, 0));
+  std::vector<void*> frees;
+  {
+    std::lock_guard<std::mutex> lk(r.mu);
+    frees.swap(r.side_frees);
+  }
+  for (void* p : frees) dfb_free((float*)p);
   return DFB_OK;
 }
 

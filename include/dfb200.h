@@ -102,6 +102,15 @@ DFB_API dfb_status dfb_from_host_async(const float* pinned_src, float* dst, size
 DFB_API dfb_status dfb_to_host_async(const float* src, float* pinned_dst, size_t n);
 DFB_API dfb_status dfb_copy(const float* src, float* dst, size_t n); /* device to device */
 
+/* Side stream: work enqueued between dfb_side_begin() and dfb_side_end() runs on a second stream that is
+ * ordered after everything enqueued on the compute stream so far, concurrently with what the compute
+ * stream gets next (used for the wgrad of a convolution's backward, which nothing on the dgrad chain
+ * depends on). dfb_side_join() makes the compute stream wait for it; buffers freed while on the side
+ * stream are recycled only then. Call the three from one thread, in this order. */
+DFB_API dfb_status dfb_side_begin(void);
+DFB_API dfb_status dfb_side_end(void);
+DFB_API dfb_status dfb_side_join(void);
+
 /* CUDA-graph capture of everything enqueued on the compute stream (and, through the comm events, on the
  * communication stream) between begin/end: a whole training step - forward, loss, backward, gradient
  * all-reduce, optimizer - replays as ONE graph launch, with no per-kernel host cost. The reference has

@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--mode", default="tf32")
     ap.add_argument("--json", default=None)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="time each op as 20 back-to-back calls replayed from one CUDA graph (no host launch cost, "
+                         "warm L2): what the op costs inside the captured training step")
     args = ap.parse_args()
     from DeepFlows import backend_api
     dev = backend_api.cuda()
@@ -40,6 +43,25 @@ def main():
     def time_it(fn):
         for _ in range(3):
             fn()
+        if args.graph:
+            reps = 20
+            m.graph_begin_capture()
+            for _ in range(reps):
+                fn()
+            g = m.graph_end_capture()
+            for _ in range(2):
+                m.graph_launch(g)
+            e0, e1 = m.event_create(), m.event_create()
+            m.event_record(e0)
+            for _ in range(5):
+                m.graph_launch(g)
+            m.event_record(e1)
+            m.event_synchronize(e1)
+            us = m.event_elapsed_ms(e0, e1) / (5 * reps) * 1e3
+            m.event_destroy(e0)
+            m.event_destroy(e1)
+            m.graph_destroy(g)
+            return us
         tot = 0.0
         e0, e1 = m.event_create(), m.event_create()
         for _ in range(args.iters):
