@@ -325,6 +325,26 @@ class BackendTensor:
         nhwc = self.permute((0, 2, 3, 1)).compact()
         return BackendTensor.make((n, c, h, w), (h * w * c, 1, w * c, c), self._device, nhwc._handle)
 
+    def with_layout_of(self, ref):
+        """This tensor's values in `ref`'s memory layout (same shape): returned as is when the strides already
+        agree, otherwise copied into a new buffer with ref's strides. `ref` must be dense. Used wherever two
+        tensors are walked as flat buffers side by side (fused optimizer steps, gradient buckets)."""
+        assert self._shape == ref._shape, (self._shape, ref._shape)
+        if self._strides == ref._strides and self._offset == 0 and self.is_dense():
+            return self
+        if ref.is_compact():
+            return self.compact()
+        if ref.is_channels_last():
+            return self.channels_last()
+        out = ref._like()
+        out[tuple(slice(None) for _ in self._shape)] = self
+        return out
+
+    def flat_storage(self):
+        """1-d view of the whole underlying buffer in memory order (the tensor must be dense)."""
+        assert self.is_dense(), "flat_storage needs a dense tensor"
+        return BackendTensor.make((self._handle.size,), None, self._device, self._handle, 0)
+
     # ---- basic manipulation ---------------------------------------------------------------------------
     def fill(self, value):
         self._device.fill(self._handle, value)

@@ -113,9 +113,9 @@ class DataParallel:
     def broadcast_parameters(self, root=0):
         """Make every replica start from rank `root`'s weights."""
         for p in self.params:
-            if not p.data.is_compact():
+            if not p.data.is_dense():
                 p.data = p.data.compact()
-            self.transport.broadcast(p.data.reshape((p.data.size,)), root)
+            self.transport.broadcast(p.data.flat_storage(), root)  # memory order; every rank has the same layout
         self.transport.wait()
 
     def reduce_gradients(self):
@@ -126,17 +126,20 @@ class DataParallel:
             self._build_plan()
         for flat, slots in self._plan:
             for i, off, n in slots:
-                g = self.params[i].grad
+                p = self.params[i]
+                g = p.grad
+                if not p.data.is_dense():
+                    p.data = p.data.compact()
                 if g is None:
                     flat[off:off + n] = 0.0
-                else:
-                    flat[off:off + n] = g.compact().reshape((n,))
+                else:  # packed in the parameter's memory order (channels-last conv weights stay as they are)
+                    flat[off:off + n] = g.with_layout_of(p.data).flat_storage()
             self.transport.allreduce_sum(flat)
             # gradients now alias the bucket: the optimizer reads the reduced values in place
             for i, off, n in slots:
                 p = self.params[i]
                 if p.grad is not None:
-                    p.grad = BackendTensor.make(p.data.shape, None, p.device, flat._handle, off)
+                    p.grad = BackendTensor.make(p.data.shape, p.data.strides, p.device, flat._handle, off)
         self._pending = True
 
     def pre_step(self):

@@ -19,11 +19,12 @@ from typing import Optional
 import numpy as np
 
 from .. import tensor
-from ..tensor import Tensor, FusedOperator, UnaryOperator
+from ..tensor import Tensor, FusedOperator, UnaryOperator, BinaryOperator
 from .. import backend_api
 from ..backend.backend_tensor import BackendTensor, precision_mode, get_dgrad_mode
 
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+WLAYOUT_KCRS, WLAYOUT_KRSC = 0, 1
 
 
 def _nhwc_view(handle, n, c, h, w, device):
@@ -183,11 +184,23 @@ class _conv2d(FusedOperator):
         super().__init__(x, kernel)
 
     def forward(self, x, kernel):
-        xd, wd = x.data, kernel.data.compact()
+        xd, wd = x.data, kernel.data
+        dev = xd.device
+        # Weights live channels-last (K,R,R,C) on the B200 device - the layout the tensor-core kernels read
+        # in place, for fprop and (as the transposed operand) for dgrad. A Parameter that arrives compact
+        # (fresh from init / load_state_dict / a checkpoint) is re-laid out once, here; its logical shape,
+        # `.numpy()` and every other consumer are unaffected (strides carry the layout).
+        if wd.ndim == 4 and wd.is_channels_last():
+            w_layout = WLAYOUT_KRSC
+        elif (wd.ndim == 4 and dev.name == "cuda" and dev.has("WLAYOUT_KRSC")
+              and not isinstance(kernel, (UnaryOperator, BinaryOperator, FusedOperator))):  # a stored tensor, not an op result
+            kernel.data = wd = wd.channels_last()
+            w_layout = WLAYOUT_KRSC
+        else:
+            wd, w_layout = wd.compact(), WLAYOUT_KCRS
         n, c, h, w = xd.shape
         k, c2, r, r2 = wd.shape
         assert c == c2 and r == r2, "conv2d: kernel %s does not match input %s" % (wd.shape, xd.shape)
-        dev = xd.device
         mode = precision_mode()
         if xd.is_channels_last():
             layout = LAYOUT_NHWC
@@ -199,9 +212,10 @@ class _conv2d(FusedOperator):
         oh, ow = (h + 2 * p - r) // s + 1, (w + 2 * p - r) // s + 1
         self._geom = (n, c, h, w, k, r, p, s)
         self._x, self._layout, self._w, self._mode = xd, layout, wd, mode
+        self._wl = (w_layout,) if w_layout else ()  # trailing argument only when it is not the default
         y = dev.Array(n * oh * ow * k)
         ws, ws_n = self._workspace(dev)
-        dev.conv2d_fprop(xd._handle, layout, wd._handle, y, n, c, h, w, k, r, p, s, mode, ws, ws_n)
+        dev.conv2d_fprop(xd._handle, layout, wd._handle, y, n, c, h, w, k, r, p, s, mode, ws, ws_n, *self._wl)
         return _nhwc_view(y, n, k, oh, ow, dev)
 
     def _workspace(self, dev):
@@ -218,19 +232,22 @@ class _conv2d(FusedOperator):
         # and the two kernels (neither fills 148 SMs on the small layers) run concurrently
         both = needs[0] and needs[1] and dev.has("side_begin")
         if needs[1]:
-            dw = BackendTensor.make((k, c, r, r), device=dev)
+            # the weight gradient is produced in the weight's own layout, so optimizer and all-reduce walk
+            # the two buffers side by side
+            dw = _nhwc_view(dev.Array(k * c * r * r), k, c, r, r, dev) if self._wl else BackendTensor.make((k, c, r, r), device=dev)
             if both:
                 dev.side_begin()
             try:
                 dev.conv2d_wgrad(self._x._handle, self._layout, gy._handle, dw._handle, n, c, h, w, k, r, p, s,
-                                 self._mode, ws, ws_n)
+                                 self._mode, ws, ws_n, *self._wl)
             finally:
                 if both:
                     dev.side_end()
         if needs[0]:
             buf = dev.Array(n * h * w * c)
             dmode = 0 if get_dgrad_mode() == "reference" else 1
-            dev.conv2d_dgrad(gy._handle, self._w._handle, buf, n, c, h, w, k, r, p, s, self._mode, dmode, ws, ws_n)
+            dev.conv2d_dgrad(gy._handle, self._w._handle, buf, n, c, h, w, k, r, p, s, self._mode, dmode, ws, ws_n,
+                             *self._wl)
             dx = _nhwc_view(buf, n, c, h, w, dev)
         if both:
             dev.side_join()

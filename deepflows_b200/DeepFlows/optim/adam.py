@@ -23,10 +23,8 @@ class Adam(Optimizer):
         if active:
             dev = active[0][1].device
             for i, p, _ in active:
-                if not self.v[i].is_compact():
-                    self.v[i] = self.v[i].compact()
-                if not self.s[i].is_compact():
-                    self.s[i] = self.s[i].compact()
+                self.v[i] = self._state_like(self.v[i], p)
+                self.s[i] = self._state_like(self.s[i], p)
             dev.multi_adam_step(
                 [p.data._handle for _, p, _ in active], [(g._handle, g._offset) for _, _, g in active],
                 [self.v[i]._handle for i, _, _ in active], [self.s[i]._handle for i, _, _ in active],

@@ -18,8 +18,10 @@ class Optimizer:
 
     # ---- shared by the fused steps ----------------------------------------------------------------------
     def _active(self):
-        """(index, param, compact grad) for every parameter that has a gradient. Parameter storage is
-        made compact (once) so the fused kernel can update it in place."""
+        """(index, param, grad) for every parameter that has a gradient. The fused kernels walk parameter,
+        gradient and optimizer state as flat buffers side by side, so the parameter storage is made dense
+        (once; any permutation of a compact array, e.g. channels-last conv weights, qualifies) and the
+        gradient is brought to the parameter's memory layout."""
         out = []
         for i, p in enumerate(self.params):
             g = p.grad
@@ -27,10 +29,16 @@ class Optimizer:
                 continue
             if hasattr(g, "data") and not hasattr(g, "_handle"):
                 g = g.data
-            if not p.data.is_compact():
+            if not p.data.is_dense():
                 p.data = p.data.compact()
-            out.append((i, p, g.compact()))
+            out.append((i, p, g.with_layout_of(p.data)))
         return out
+
+    @staticmethod
+    def _state_like(state, p):
+        """Optimizer state in the parameter's current memory layout (it changes when a conv weight is re-laid
+        out channels-last at its first use, or when a checkpoint is loaded)."""
+        return state if state.strides == p.data.strides and state.is_dense() else state.with_layout_of(p.data)
 
     @staticmethod
     def _grad_scale():

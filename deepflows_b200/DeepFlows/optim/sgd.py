@@ -21,6 +21,8 @@ class SGD(Optimizer):
         if not active:
             return
         dev = active[0][1].device
+        for i, p, _ in active:
+            self.v[i] = self._state_like(self.v[i], p)
         dev.multi_sgd_step(
             [p.data._handle for _, p, _ in active], [(g._handle, g._offset) for _, _, g in active],
             [self.v[i]._handle for i, _, _ in active], [p.data.size for _, p, _ in active], float(self.lr),

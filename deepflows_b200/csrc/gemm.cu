@@ -49,8 +49,8 @@ dfb_status dfb_conv2d_workspace_floats(int N, int C, int H, int W, int K, int R,
   return DFB_OK;
 }
 
-dfb_status dfb_conv2d_fprop(const float* x, int x_layout, const float* w, float* y, int N, int C, int H, int W,
-                            int K, int R, int pad, int stride, int mode, float* workspace,
+dfb_status dfb_conv2d_fprop(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H,
+                            int W, int K, int R, int pad, int stride, int mode, float* workspace,
                             size_t workspace_floats) {
   DFB_INIT();
   DFB_REQUIRE(x && w && y, DFB_ERR_INVALID, "conv2d_fprop: null pointer");
@@ -59,14 +59,14 @@ dfb_status dfb_conv2d_fprop(const float* x, int x_layout, const float* w, float*
   if (st != DFB_OK) return st;
   if (want_tc(mode) && x_layout == DFB_LAYOUT_NHWC) {
     bool handled = false;
-    st = tc_conv_fprop(x, w, y, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
+    st = tc_conv_fprop(x, w, w_layout, y, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
     if (st != DFB_OK || handled) return st;
   }
-  return simt_conv_fprop(x, x_layout, w, y, N, C, H, W, K, R, pad, stride);
+  return simt_conv_fprop(x, x_layout, w, w_layout, y, N, C, H, W, K, R, pad, stride);
 }
 
-dfb_status dfb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int C, int H, int W, int K, int R,
-                            int pad, int stride, int mode, int dgrad_mode, float* workspace,
+dfb_status dfb_conv2d_dgrad(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
+                            int R, int pad, int stride, int mode, int dgrad_mode, float* workspace,
                             size_t workspace_floats) {
   DFB_INIT();
   DFB_REQUIRE(dy && w && dx, DFB_ERR_INVALID, "conv2d_dgrad: null pointer");
@@ -76,14 +76,14 @@ dfb_status dfb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, i
   if (st != DFB_OK) return st;
   if (want_tc(mode) && dgrad_mode == DFB_DGRAD_EXACT) {
     bool handled = false;
-    st = tc_conv_dgrad(dy, w, dx, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
+    st = tc_conv_dgrad(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
     if (st != DFB_OK || handled) return st;
   }
-  return simt_conv_dgrad(dy, w, dx, N, C, H, W, K, R, pad, stride, dgrad_mode);
+  return simt_conv_dgrad(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, dgrad_mode);
 }
 
-dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float* dw, int N, int C, int H, int W,
-                            int K, int R, int pad, int stride, int mode, float* workspace,
+dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H,
+                            int W, int K, int R, int pad, int stride, int mode, float* workspace,
                             size_t workspace_floats) {
   DFB_INIT();
   DFB_REQUIRE(x && dy && dw, DFB_ERR_INVALID, "conv2d_wgrad: null pointer");
@@ -92,10 +92,10 @@ dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float
   if (st != DFB_OK) return st;
   if (want_tc(mode) && x_layout == DFB_LAYOUT_NHWC) {
     bool handled = false;
-    st = tc_conv_wgrad(x, dy, dw, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
+    st = tc_conv_wgrad(x, dy, dw, w_layout, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
     if (st != DFB_OK || handled) return st;
   }
-  return simt_conv_wgrad(x, x_layout, dy, dw, N, C, H, W, K, R, pad, stride);
+  return simt_conv_wgrad(x, x_layout, dy, dw, w_layout, N, C, H, W, K, R, pad, stride);
 }
 
 }  // extern "C"

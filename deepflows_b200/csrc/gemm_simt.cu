@@ -41,7 +41,12 @@ struct PlainLoader {
 
 struct ConvGeom {
   int N, C, H, W, K, R, pad, stride, OH, OW;
+  int krsc;  // weights (and dW) stored channels-last (K,R,R,C) instead of (K,C,R,R)
 };
+__device__ __forceinline__ size_t weight_index(const ConvGeom& g, int kout, int c, int tap) {
+  const int RR = g.R * g.R;
+  return g.krsc ? ((size_t)kout * RR + tap) * g.C + c : ((size_t)kout * g.C + c) * RR + tap;
+}
 
 // A operand of fprop: rows = output pixels (n, oh, ow), k = (r, s, c) with c fastest.
 template <bool NCHW>
@@ -105,7 +110,7 @@ struct WeightLoader {
   __device__ float load(const MN& a, const KK& b) const {
     if (!(a.ok && b.ok)) return 0.f;
     int kout = DGRAD ? b.j : a.i, c = DGRAD ? a.i : b.j;
-    return __ldg(w + ((size_t)kout * g.C + c) * g.R * g.R + b.tap);
+    return __ldg(w + weight_index(g, kout, c, b.tap));
   }
 };
 
@@ -170,12 +175,18 @@ struct WgradBLoader {  // B(k=p, n=(c,r,s))
   int Ncols, P;
   struct MN { int c, r, s; bool ok; };
   struct KK { int n, ih0, iw0; bool ok; };
-  __device__ MN mn(int j) const {
+  __device__ MN mn(int j) const {  // column j of dW's row: (c, tap) for KCRS, (tap, c) for KRSC
     MN o;
     o.ok = j < Ncols;
     int rr = g.R * g.R;
-    o.c = j / rr;
-    int tap = j - o.c * rr;
+    int tap;
+    if (g.krsc) {
+      tap = j / g.C;
+      o.c = j - tap * g.C;
+    } else {
+      o.c = j / rr;
+      tap = j - o.c * rr;
+    }
     o.r = tap / g.R;
     o.s = tap - o.r * g.R;
     return o;
@@ -414,8 +425,8 @@ dgrad_lastwriter_kernel(const float* __restrict__ dy, const float* __restrict__ 
       int oh = (ph - r) / g.stride, ow = (pw - sidx) / g.stride;
       if (oh < g.OH && ow < g.OW) {
         const float* dyp = dy + (((size_t)n * g.OH + oh) * g.OW + ow) * g.K;
-        const float* wp = w + (size_t)c * RR + r * g.R + sidx;
-        for (int k = 0; k < g.K; ++k) acc = fmaf(__ldg(dyp + k), __ldg(wp + (size_t)k * g.C * RR), acc);
+        const int tap = r * g.R + sidx;
+        for (int k = 0; k < g.K; ++k) acc = fmaf(__ldg(dyp + k), __ldg(w + weight_index(g, k, c, tap)), acc);
       }
     }
     dx[i] = acc;
@@ -423,7 +434,10 @@ dgrad_lastwriter_kernel(const float* __restrict__ dy, const float* __restrict__ 
 }
 
 static dfb_status make_geom(const char* name, int N, int C, int H, int W, int K, int R, int pad,
-                            int stride, ConvGeom* g) {
+                            int stride, int w_layout, ConvGeom* g) {
+  DFB_REQUIRE(w_layout == DFB_WLAYOUT_KCRS || w_layout == DFB_WLAYOUT_KRSC, DFB_ERR_INVALID, "%s: bad weight layout %d", name,
+              w_layout);
+  g->krsc = w_layout == DFB_WLAYOUT_KRSC;
   DFB_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && K > 0 && R > 0 && pad >= 0 && stride > 0,
               DFB_ERR_INVALID, "%s: bad geometry N=%d C=%d H=%d W=%d K=%d R=%d pad=%d stride=%d", name, N,
               C, H, W, K, R, pad, stride);
@@ -451,10 +465,10 @@ dfb_status simt_gemm(const float* A, const float* B, float* C, int M, int N, int
   return launch_simt("Matmul", PlainLoader<true>{A, lda, M, K}, PlainLoader<false>{B, ldb, N, K}, C, ldc, accumulate, bias, M, N, K);
 }
 
-dfb_status simt_conv_fprop(const float* x, int x_layout, const float* w, float* y, int N, int C, int H,
+dfb_status simt_conv_fprop(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H,
                            int W, int K, int R, int pad, int stride) {
   ConvGeom g;
-  dfb_status st = make_geom("conv2d_fprop", N, C, H, W, K, R, pad, stride, &g);
+  dfb_status st = make_geom("conv2d_fprop", N, C, H, W, K, R, pad, stride, w_layout, &g);
   if (st != DFB_OK) return st;
   int M = N * g.OH * g.OW, Kred = C * R * R;
   WeightLoader<false> B{w, g, K, Kred};
@@ -463,10 +477,10 @@ dfb_status simt_conv_fprop(const float* x, int x_layout, const float* w, float* 
   return launch_simt("conv2d_fprop", FpropALoader<false>{x, g, M, Kred}, B, y, K, 0, nullptr, M, K, Kred);
 }
 
-dfb_status simt_conv_dgrad(const float* dy, const float* w, float* dx, int N, int C, int H, int W, int K,
+dfb_status simt_conv_dgrad(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
                            int R, int pad, int stride, int dgrad_mode) {
   ConvGeom g;
-  dfb_status st = make_geom("conv2d_dgrad", N, C, H, W, K, R, pad, stride, &g);
+  dfb_status st = make_geom("conv2d_dgrad", N, C, H, W, K, R, pad, stride, w_layout, &g);
   if (st != DFB_OK) return st;
   if (dgrad_mode == DFB_DGRAD_REFERENCE) {
     size_t total = (size_t)N * H * W * C;
@@ -479,10 +493,10 @@ dfb_status simt_conv_dgrad(const float* dy, const float* w, float* dx, int N, in
                      nullptr, M, C, Kred);
 }
 
-dfb_status simt_conv_wgrad(const float* x, int x_layout, const float* dy, float* dw, int N, int C, int H,
+dfb_status simt_conv_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H,
                            int W, int K, int R, int pad, int stride) {
   ConvGeom g;
-  dfb_status st = make_geom("conv2d_wgrad", N, C, H, W, K, R, pad, stride, &g);
+  dfb_status st = make_geom("conv2d_wgrad", N, C, H, W, K, R, pad, stride, w_layout, &g);
   if (st != DFB_OK) return st;
   int P = N * g.OH * g.OW, Ncols = C * R * R;
   WgradALoader A{dy, K, P};

@@ -79,6 +79,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -131,6 +137,33 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- thread-block cluster helpers (split-K reduction through distributed shared memory) ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  // volatile: stays behind the preceding cluster barrier, and the dependent loads with it
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  return remote;
+}
+// not volatile / no memory clobber: the loads of one reduction step are independent and must pipeline
+// (ordering against the cluster barriers comes from the barriers' own memory clobbers)
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t remote) {
+  float4 v;
+  asm("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
+  return v;
+}
+
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64): SWIZZLE_128B = 2, SWIZZLE_128B_BASE32B = 1
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -163,6 +196,9 @@ struct SmemLayout {
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kTotal = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
+  // split-K partial tile staged in the (idle) pipeline stages: 128 rows, padded pitch against bank conflicts
+  static constexpr uint32_t kRedPitch = BN + 4;
+  static_assert(BLOCK_M * kRedPitch * 4 <= kBarOffset, "partial tile does not fit the pipeline stages");
 };
 
 template <class P>
@@ -180,7 +216,17 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   typename P::Tile tile = P::tile(prm);
-  const int kb_begin = tile.kb_begin, kb_end = tile.kb_end;
+  // Split-K: the CTAs of a cluster (cluster dims (1,1,S), P::kClusterSplit) share one output tile; CTA `rank`
+  // takes the rank-th slice of the k-blocks, accumulates it in its own TMEM, and the S partial tiles are
+  // summed through distributed shared memory, each CTA finishing 128/S rows of the tile.
+  const int nsplit = P::kClusterSplit ? (int)cluster_nctarank() : 1;
+  const int rank = P::kClusterSplit ? (int)cluster_ctarank() : 0;
+  int kb_begin = tile.kb_begin, kb_end = tile.kb_end;
+  if (nsplit > 1) {
+    const int per = (kb_end - kb_begin + nsplit - 1) / nsplit;
+    kb_begin = min(kb_end, kb_begin + rank * per);
+    kb_end = min(kb_end, kb_begin + per);
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -241,6 +287,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
+    float* red = reinterpret_cast<float*>(smem);  // the pipeline stages are idle once the accumulator is complete
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
@@ -250,11 +297,46 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      P::store(prm, tile, row, c0, v);
+      if (nsplit == 1) {
+        P::store(prm, tile, row, c0, v);
+      } else {
+        float* dst = red + (size_t)row * L::kRedPitch + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
     }
     tc_fence_before();
   }
-  __syncthreads();
+  if (P::kClusterSplit && nsplit > 1) {
+    cluster_arrive();
+    cluster_wait();  // every partial tile is in its CTA's shared memory
+    if (warp >= 2) {
+      const int rows_per = BLOCK_M / nsplit;
+      const int t = (warp - 2) * 32 + lane;   // 0..127
+      constexpr int kVecPerRow = BN / 4;
+      const uint32_t red_base = smem_u32(smem);
+      for (int idx = t; idx < rows_per * kVecPerRow; idx += 128) {
+        const int r = rank * rows_per + idx / kVecPerRow;
+        const int c = (idx % kVecPerRow) * 4;
+        const uint32_t addr = red_base + (uint32_t)(r * L::kRedPitch + c) * 4u;
+        float4 pv[8];
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2)
+          if (s2 < nsplit) pv[s2] = ld_dsmem_f4(dsmem_addr(addr, (uint32_t)s2));
+        float4 acc = pv[0];
+#pragma unroll
+        for (int s2 = 1; s2 < 8; ++s2)  // fixed order: deterministic
+          if (s2 < nsplit) { acc.x += pv[s2].x; acc.y += pv[s2].y; acc.z += pv[s2].z; acc.w += pv[s2].w; }
+        P::store4(prm, tile, r, c, acc);
+      }
+    }
+    // nobody leaves while its shared memory may still be read: arrive once this CTA's remote reads have
+    // landed in registers (the global stores above only consume registers), wait just before the exit
+    cluster_arrive();
+    cluster_wait();
+  } else {
+    __syncthreads();
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<BN>(tmem_base);
@@ -305,17 +387,46 @@ static bool make_map(CUtensorMap* map, const float* base, int rank, const uint64
 
 template <class P>
 static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
-                         dim3 grid) {
+                         dim3 grid, int splits = 1) {
   using L = SmemLayout<P::BN>;
   static bool configured = false;
   if (!configured) {
     DFB_CUDA(cudaFuncSetAttribute(tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
     configured = true;
   }
-  tc_kernel<P><<<grid, kThreads, L::kTotal, compute_stream()>>>(ma, mb, prm);
+  if (P::kClusterSplit) {
+    // grid.z already counts the splits; the S CTAs that share a tile form one cluster along z
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = compute_stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)splits;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel<P>, ma, mb, prm);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      DFB_FAIL(DFB_ERR_RUNTIME, "%s cluster launch (splits %d) failed: %s", name, splits, cudaGetErrorString(e));
+    }
+  } else {
+    tc_kernel<P><<<grid, kThreads, L::kTotal, compute_stream()>>>(ma, mb, prm);
+  }
   DFB_LAUNCH_CHECK(name);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return DFB_OK;
+}
+
+// Split-K factor (cluster size along z, a power of two <= 8): enough CTAs to occupy the machine, at least
+// four k-blocks per CTA.
+static int pick_splits(size_t base_ctas, int k_blocks) {
+  int s = 1;
+  while (s < 8 && base_ctas * (size_t)(s * 2) <= (size_t)sm_count() * 3 / 2 && k_blocks / (s * 2) >= 4) s *= 2;
+  return s;
 }
 
 // =====================================================================================================
@@ -332,6 +443,7 @@ struct GemmTile {
 template <int A_MAJ, int B_MAJ, int BN_>
 struct GemmProblem {
   static constexpr int BN = BN_, A_MAJOR = A_MAJ, B_MAJOR = B_MAJ;
+  static constexpr bool kClusterSplit = true;
   using Params = GemmParams;
   using Tile = GemmTile;
   __device__ static Tile tile(const Params& p) {
@@ -351,6 +463,20 @@ struct GemmProblem {
     } else {
 #pragma unroll
       for (int j = 0; j < BN / 32; ++j) tma_load_2d(dst + j * kChunkBytes, m, bar, t.n0 + j * 32, kb * BLOCK_K);
+    }
+  }
+  __device__ static void store4(const Params& p, const Tile& t, int row, int c, const float4& q) {
+    const int m = t.m0 + row;
+    if (m >= p.M) return;
+    const float v[4] = {q.x, q.y, q.z, q.w};
+    float* dst = p.C + (size_t)m * p.ldc + t.n0 + c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (t.n0 + c + i < p.N) {
+        float x = v[i];
+        if (p.bias) x += __ldg(p.bias + t.n0 + c + i);
+        dst[i] = p.accumulate ? dst[i] + x : x;
+      }
     }
   }
   __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
@@ -394,7 +520,9 @@ static dfb_status run_gemm(const float* A, const float* B, const GemmParams& prm
   if (!ok) return DFB_OK;  // not representable as a tensor map -> FFMA path
   *handled = true;
   dim3 grid(cdiv(prm.M, BLOCK_M), cdiv(prm.N, BN), 1);
-  return launch<GemmProblem<A_MAJ, B_MAJ, BN>>("tc_gemm", ma, mb, prm, grid);
+  const int splits = pick_splits((size_t)grid.x * grid.y, (prm.K + BLOCK_K - 1) / BLOCK_K);
+  grid.z = (unsigned)splits;
+  return launch<GemmProblem<A_MAJ, B_MAJ, BN>>("tc_gemm", ma, mb, prm, grid, splits);
 }
 
 template <int A_MAJ, int B_MAJ>
@@ -421,14 +549,21 @@ struct ConvParams {
   // d0 = (ph + pad - r0) / 2. par_pad >= 0 selects this mode; the output is then written at (2a+ph, 2b+pw)
   // of an image with 2*OH x 2*OW pixels.
   int par_pad;
+  int splits;          // split-K cluster size along z
 };
 struct ConvTile {
   int n0, oh0, ow0, col0, kb_begin, kb_end;
   int ns, d0h, d0w, r0h, r0w, ph, pw;  // parity mode only
 };
-template <int BN_>
+// WMODE selects where the weight operand comes from:
+//   W_PACKED    : a packed copy Wt[n_out][tap][cp] made by weight_transform_kernel (weights stored (K,C,R,R))
+//   W_KRSC_FPROP: the weights themselves, stored channels-last (K,R,R,C): K-major rows Wt[k][tap][c]
+//   W_KRSC_DGRAD: the same buffer read as the MN-major operand Wd[(tap,k)][c] - no copy in either direction
+enum { W_PACKED = 0, W_KRSC_FPROP = 1, W_KRSC_DGRAD = 2 };
+template <int BN_, int WMODE>
 struct ConvProblem {
-  static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = MAJOR_K;
+  static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = (WMODE == W_KRSC_DGRAD ? MAJOR_MN : MAJOR_K);
+  static constexpr bool kClusterSplit = true;
   using Params = ConvParams;
   using Tile = ConvTile;
   __device__ static Tile tile(const Params& p) {
@@ -439,8 +574,9 @@ struct ConvProblem {
     int tn = t / p.tiles_h;
     Tile o{tn * p.n_t, th * p.oh_t, tw * p.ow_t, (int)blockIdx.y * BN, 0, p.R * p.R * p.cblks, 0, 0, 0, 0, 0, 0, 0};
     if (p.par_pad >= 0) {
-      o.ph = (int)blockIdx.z >> 1;
-      o.pw = (int)blockIdx.z & 1;
+      const int cls = (int)blockIdx.z / p.splits;  // blockIdx.z = class * splits + split
+      o.ph = cls >> 1;
+      o.pw = cls & 1;
       o.r0h = (o.ph + p.par_pad) & 1;
       o.r0w = (o.pw + p.par_pad) & 1;
       const int nr = o.r0h < p.R ? (p.R - o.r0h + 1) / 2 : 0;
@@ -468,29 +604,54 @@ struct ConvProblem {
     }
   }
   __device__ static void load_b(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+    int tap = kb / p.cblks;
+    const int cb = kb - tap * p.cblks;
     if (p.par_pad >= 0) {
-      const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
       const int i = tap / t.ns, j = tap - i * t.ns;
-      const int wtap = (t.r0h + 2 * i) * p.R + t.r0w + 2 * j;
-      tma_load_2d(dst, m, bar, (wtap * p.cblks + cb) * BLOCK_K, t.col0);
-      return;
+      tap = (t.r0h + 2 * i) * p.R + t.r0w + 2 * j;
     }
-    tma_load_2d(dst, m, bar, kb * BLOCK_K, t.col0);
+    if (WMODE == W_PACKED) {
+      tma_load_2d(dst, m, bar, (tap * p.cblks + cb) * BLOCK_K, t.col0);
+    } else if (WMODE == W_KRSC_FPROP) {
+      tma_load_3d(dst, m, bar, cb * 32, tap, t.col0);           // rows = output channels, 32 input channels each
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j)                          // rows = 32 k (output channels of the conv), 32 c each
+        tma_load_3d(dst + j * kChunkBytes, m, bar, t.col0 + j * 32, tap, cb * 32);
+    }
   }
-  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
+  __device__ static float* row_ptr(const Params& p, const Tile& t, int row) {
     const int owi = row % p.ow_t;
     const int rest = row / p.ow_t;
     const int ohi = rest % p.oh_t, ni = rest / p.oh_t;
     const int n = t.n0 + ni;
     int oh = t.oh0 + ohi, ow = t.ow0 + owi;
-    if (n >= p.n_img || oh >= p.OH || ow >= p.OW) return;
+    if (n >= p.n_img || oh >= p.OH || ow >= p.OW) return nullptr;
     int OHf = p.OH, OWf = p.OW;
     if (p.par_pad >= 0) {
       oh = 2 * oh + t.ph; ow = 2 * ow + t.pw;
       OHf *= 2; OWf *= 2;
     }
+    return p.out + (((size_t)n * OHf + oh) * OWf + ow) * p.n_out;
+  }
+  __device__ static void store4(const Params& p, const Tile& t, int row, int c, const float4& q) {
+    float* base = row_ptr(p, t, row);
+    if (!base) return;
+    const int col = t.col0 + c;
+    if ((p.n_out & 3) == 0 && col + 4 <= p.n_out) {
+      *reinterpret_cast<float4*>(base + col) = q;
+    } else {
+      const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (col + i < p.n_out) base[col + i] = v[i];
+    }
+  }
+  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
+    float* base = row_ptr(p, t, row);
+    if (!base) return;
     const int col = t.col0 + c0;
-    float* dst = p.out + (((size_t)n * OHf + oh) * OWf + ow) * p.n_out + col;
+    float* dst = base + col;
     if ((p.n_out & 3) == 0 && col + 32 <= p.n_out) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -517,6 +678,8 @@ struct WgradTile {
 template <int BN_>
 struct WgradProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_MN, B_MAJOR = MAJOR_MN;
+  static constexpr bool kClusterSplit = false;
+  __device__ static void store4(const WgradParams&, const WgradTile&, int, int, const float4&) {}
   using Params = WgradParams;
   using Tile = WgradTile;
   __device__ static Tile tile(const Params& p) {
@@ -578,17 +741,25 @@ __global__ void __launch_bounds__(256) weight_transform_kernel(const float* __re
     out[i] = (k < K && c < C) ? __ldg(w + ((size_t)k * C + c) * taps + tap) : 0.f;
   }
 }
-// dW[k][c][tap] = sum_z partial[z][k][tap][c]
+// dW[k][c][tap] (KCRS) or dW[k][tap][c] (KRSC) = sum_z partial[z][k][tap][c]
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
-                                                          int K, int C, int Cp, int taps) {
+                                                          int K, int C, int Cp, int taps, int krsc) {
   size_t total = (size_t)K * C * taps;
   size_t slab = (size_t)K * taps * Cp;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int tap = (int)(i % taps);
-    size_t t = i / taps;
-    int c = (int)(t % C);
-    int k = (int)(t / C);
+    int tap, c, k;
+    if (krsc) {
+      c = (int)(i % C);
+      size_t t = i / C;
+      tap = (int)(t % taps);
+      k = (int)(t / taps);
+    } else {
+      tap = (int)(i % taps);
+      size_t t = i / taps;
+      c = (int)(t % C);
+      k = (int)(t / C);
+    }
     const float* src = partial + ((size_t)k * taps + tap) * Cp + c;
     float acc = 0.f;
     for (int z = 0; z < splits; ++z) acc += src[(size_t)z * slab];
@@ -622,23 +793,43 @@ static bool make_act_map(CUtensorMap* map, const float* base, int N, int H, int 
   return make_map(map, base, 5, d, s, b, major);
 }
 
-template <int BN>
-static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float* wt, int n_out, int kred_pad, ConvParams prm,
-                           bool* handled) {
+template <int BN, int WMODE>
+static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float* wt, int n_out, int taps, int cp, int K, int C,
+                           ConvParams prm, bool* handled) {
   CUtensorMap mb;
-  uint64_t d[2] = {(uint64_t)kred_pad, (uint64_t)n_out}, s[2] = {1, (uint64_t)kred_pad};
-  uint32_t b[2] = {BLOCK_K, (uint32_t)BN};
-  if (!make_map(&mb, wt, 2, d, s, b, MAJOR_K)) return DFB_OK;
+  bool ok;
+  if (WMODE == W_PACKED) {
+    uint64_t d[2] = {(uint64_t)taps * cp, (uint64_t)n_out}, s[2] = {1, (uint64_t)taps * cp};
+    uint32_t b[2] = {BLOCK_K, (uint32_t)BN};
+    ok = make_map(&mb, wt, 2, d, s, b, MAJOR_K);
+  } else {
+    uint64_t d[3] = {(uint64_t)C, (uint64_t)taps, (uint64_t)K}, s[3] = {1, (uint64_t)C, (uint64_t)taps * C};
+    uint32_t b[3] = {32, 1, (uint32_t)(WMODE == W_KRSC_FPROP ? BN : 32)};
+    ok = make_map(&mb, wt, 3, d, s, b, WMODE == W_KRSC_FPROP ? MAJOR_K : MAJOR_MN);
+  }
+  if (!ok) return DFB_OK;
   *handled = true;
   int tiles_n = cdiv(prm.n_img, prm.n_t);
-  dim3 grid((unsigned)(prm.tiles_w * prm.tiles_h * tiles_n), cdiv(n_out, BN), prm.par_pad >= 0 ? 4 : 1);
-  return launch<ConvProblem<BN>>(name, ma, mb, prm, grid);
+  const int classes = prm.par_pad >= 0 ? 4 : 1;
+  dim3 grid((unsigned)(prm.tiles_w * prm.tiles_h * tiles_n), cdiv(n_out, BN), 1);
+  // stride-2 dgrad classes hold about a quarter of the taps each
+  const int kblocks = prm.R * prm.R * prm.cblks / (classes == 4 ? 4 : 1);
+  prm.splits = pick_splits((size_t)grid.x * grid.y * classes, kblocks > 0 ? kblocks : 1);
+  grid.z = (unsigned)(classes * prm.splits);
+  return launch<ConvProblem<BN, WMODE>>(name, ma, mb, prm, grid, prm.splits);
+}
+template <int WMODE>
+static dfb_status run_conv_bn(const char* name, const CUtensorMap& ma, const float* wt, int n_out, int taps, int cp, int K, int C,
+                              const ConvParams& prm, bool* handled) {
+  if (n_out <= 32) return run_conv<32, WMODE>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
+  if (n_out <= 64) return run_conv<64, WMODE>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
+  return run_conv<128, WMODE>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
 }
 
 // y[pix, n_out] = sum_{taps, c} act[pix*stride + off(tap), c] * Wt[n_out][tap][c]
-static dfb_status conv_like(const char* name, const float* act, const float* w, float* out, bool dgrad, int N, int actC,
-                            int actH, int actW, int n_out, int R, int OH, int OW, int stride, int dh0, int sgn, int K, int C,
-                            bool* handled, int par_pad = -1) {
+static dfb_status conv_like(const char* name, const float* act, const float* w, int w_layout, float* out, bool dgrad, int N,
+                            int actC, int actH, int actW, int n_out, int R, int OH, int OW, int stride, int dh0, int sgn, int K,
+                            int C, bool* handled, int par_pad = -1) {
   const int taps = R * R;
   const int cp = (actC + 31) / 32 * 32;
   ConvParams prm;
@@ -649,6 +840,10 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
   prm.tiles_h = cdiv(OH, prm.oh_t);
   CUtensorMap ma;
   if (!make_act_map(&ma, act, N, actH, actW, actC, stride, prm.ow_t, prm.oh_t, prm.n_t, MAJOR_K)) return DFB_OK;
+  if (w_layout == DFB_WLAYOUT_KRSC) {  // channels-last weights are consumed in place
+    if (dgrad) return run_conv_bn<W_KRSC_DGRAD>(name, ma, w, n_out, taps, cp, K, C, prm, handled);
+    return run_conv_bn<W_KRSC_FPROP>(name, ma, w, n_out, taps, cp, K, C, prm, handled);
+  }
   float* wt = nullptr;
   size_t wt_n = (size_t)n_out * taps * cp;
   dfb_status st = dfb_malloc(wt_n, &wt);
@@ -656,9 +851,7 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
   if (dgrad) weight_transform_kernel<true><<<bw_grid(wt_n, 256), 256, 0, compute_stream()>>>(w, wt, K, C, taps, cp);
   else weight_transform_kernel<false><<<bw_grid(wt_n, 256), 256, 0, compute_stream()>>>(w, wt, K, C, taps, cp);
   DFB_LAUNCH_CHECK("weight_transform");
-  if (n_out <= 32) st = run_conv<32>(name, ma, wt, n_out, taps * cp, prm, handled);
-  else if (n_out <= 64) st = run_conv<64>(name, ma, wt, n_out, taps * cp, prm, handled);
-  else st = run_conv<128>(name, ma, wt, n_out, taps * cp, prm, handled);
+  st = run_conv_bn<W_PACKED>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
   dfb_free(wt);
   return st;
 }
@@ -701,29 +894,29 @@ static bool conv_tc_ok(int N, int C, int H, int W, int K, int R, int pad, int st
   return true;
 }
 
-dfb_status tc_conv_fprop(const float* x, const float* w, float* y, int N, int C, int H, int W, int K, int R, int pad,
+dfb_status tc_conv_fprop(const float* x, const float* w, int w_layout, float* y, int N, int C, int H, int W, int K, int R, int pad,
                          int stride, int mode, float*, size_t, bool* handled) {
   *handled = false;
   if (!conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
-  return tc::conv_like("tc_conv_fprop", x, w, y, false, N, C, H, W, K, R, OH, OW, stride, -pad, +1, K, C, handled);
+  return tc::conv_like("tc_conv_fprop", x, w, w_layout, y, false, N, C, H, W, K, R, OH, OW, stride, -pad, +1, K, C, handled);
 }
 
-dfb_status tc_conv_dgrad(const float* dy, const float* w, float* dx, int N, int C, int H, int W, int K, int R, int pad,
+dfb_status tc_conv_dgrad(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K, int R, int pad,
                          int stride, int mode, float*, size_t, bool* handled) {
   *handled = false;
   if (!conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
   if (stride == 1) {
     // dx[n,h,w,c] = sum_{r,s,k} dy[n, h + pad - r, w + pad - s, k] * w[k][c][r][s]
-    return tc::conv_like("tc_conv_dgrad", dy, w, dx, true, N, K, OH, OW, C, R, H, W, 1, pad, -1, K, C, handled);
+    return tc::conv_like("tc_conv_dgrad", dy, w, w_layout, dx, true, N, K, OH, OW, C, R, H, W, 1, pad, -1, K, C, handled);
   }
   // stride 2: four output-parity classes of dx, each a stride-1 contraction over dy with every other tap
   // (ConvParams::par_pad); one launch, blockIdx.z = class. H and W are even (conv_tc_ok).
-  return tc::conv_like("tc_conv_dgrad_s2", dy, w, dx, true, N, K, OH, OW, C, R, H / 2, W / 2, 1, 0, 0, K, C, handled, pad);
+  return tc::conv_like("tc_conv_dgrad_s2", dy, w, w_layout, dx, true, N, K, OH, OW, C, R, H / 2, W / 2, 1, 0, 0, K, C, handled, pad);
 }
 
-dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int N, int C, int H, int W, int K, int R, int pad,
+dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K, int R, int pad,
                          int stride, int mode, float*, size_t, bool* handled) {
   using namespace tc;
   *handled = false;
@@ -762,7 +955,8 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int N, int 
   else if (bn == 64) st = run_wgrad<64>(ma, mb, prm, splits);
   else st = run_wgrad<32>(ma, mb, prm, splits);
   if (st == DFB_OK) {
-    wgrad_reduce_kernel<<<bw_grid((size_t)K * C * taps, 256), 256, 0, compute_stream()>>>(partial, dw, splits, K, C, prm.Cp, taps);
+    wgrad_reduce_kernel<<<bw_grid((size_t)K * C * taps, 256), 256, 0, compute_stream()>>>(partial, dw, splits, K, C, prm.Cp, taps,
+                                                                                          w_layout == DFB_WLAYOUT_KRSC ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) {

@@ -7,11 +7,11 @@ namespace dfb {
 // gemm_simt.cu — exact fp32 FFMA path
 dfb_status simt_gemm(const float* A, const float* B, float* C, int M, int N, int K, int trans_a,
                      int trans_b, int lda, int ldb, int ldc, int accumulate, const float* bias);
-dfb_status simt_conv_fprop(const float* x, int x_layout, const float* w, float* y, int N, int C, int H,
+dfb_status simt_conv_fprop(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H,
                            int W, int K, int R, int pad, int stride);
-dfb_status simt_conv_dgrad(const float* dy, const float* w, float* dx, int N, int C, int H, int W, int K,
+dfb_status simt_conv_dgrad(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
                            int R, int pad, int stride, int dgrad_mode);
-dfb_status simt_conv_wgrad(const float* x, int x_layout, const float* dy, float* dw, int N, int C, int H,
+dfb_status simt_conv_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H,
                            int W, int K, int R, int pad, int stride);
 
 // gemm_tc.cu — TMA + tcgen05/TMEM path. Each returns DFB_OK and sets *handled = true when it ran
@@ -19,13 +19,13 @@ dfb_status simt_conv_wgrad(const float* x, int x_layout, const float* dy, float*
 // take (the dispatcher then uses the SIMT path), or returns an error status.
 dfb_status tc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int trans_a, int trans_b,
                    int lda, int ldb, int ldc, int accumulate, const float* bias, int mode, bool* handled);
-dfb_status tc_conv_fprop(const float* x, const float* w, float* y, int N, int C, int H, int W, int K, int R,
+dfb_status tc_conv_fprop(const float* x, const float* w, int w_layout, float* y, int N, int C, int H, int W, int K, int R,
                          int pad, int stride, int mode, float* workspace, size_t workspace_floats,
                          bool* handled);
-dfb_status tc_conv_dgrad(const float* dy, const float* w, float* dx, int N, int C, int H, int W, int K,
+dfb_status tc_conv_dgrad(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
                          int R, int pad, int stride, int mode, float* workspace, size_t workspace_floats,
                          bool* handled);
-dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int N, int C, int H, int W, int K,
+dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K,
                          int R, int pad, int stride, int mode, float* workspace, size_t workspace_floats,
                          bool* handled);
 size_t tc_conv_workspace_floats(int N, int C, int H, int W, int K, int R, int pad, int stride);

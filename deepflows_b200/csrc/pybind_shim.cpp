@@ -127,6 +127,8 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
   m.attr("MODE_SIMT") = (int)DFB_MODE_SIMT;
   m.attr("LAYOUT_NCHW") = (int)DFB_LAYOUT_NCHW;
   m.attr("LAYOUT_NHWC") = (int)DFB_LAYOUT_NHWC;
+  m.attr("WLAYOUT_KCRS") = (int)DFB_WLAYOUT_KCRS;
+  m.attr("WLAYOUT_KRSC") = (int)DFB_WLAYOUT_KRSC;
   m.attr("DGRAD_REFERENCE") = (int)DFB_DGRAD_REFERENCE;
   m.attr("DGRAD_EXACT") = (int)DFB_DGRAD_EXACT;
 
@@ -297,17 +299,30 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
     check(dfb_conv2d_workspace_floats(N, C, H, W, K, R, pad, stride, &n));
     return n;
   });
+  // the trailing w_layout (WLAYOUT_KCRS = 0 default, WLAYOUT_KRSC = 1) is optional: two overloads per op
   m.def("conv2d_fprop", [](const py::object& x, int x_layout, const py::object& w, const py::object& y, int N, int C, int H,
                            int W, int K, int R, int pad, int stride, int mode, const py::object& ws, size_t ws_floats) {
-    check(dfb_conv2d_fprop(dptr(x), x_layout, dptr(w), dptr(y), N, C, H, W, K, R, pad, stride, mode, dptr(ws), ws_floats));
+    check(dfb_conv2d_fprop(dptr(x), x_layout, dptr(w), DFB_WLAYOUT_KCRS, dptr(y), N, C, H, W, K, R, pad, stride, mode, dptr(ws), ws_floats));
+  });
+  m.def("conv2d_fprop", [](const py::object& x, int x_layout, const py::object& w, const py::object& y, int N, int C, int H,
+                           int W, int K, int R, int pad, int stride, int mode, const py::object& ws, size_t ws_floats, int w_layout) {
+    check(dfb_conv2d_fprop(dptr(x), x_layout, dptr(w), w_layout, dptr(y), N, C, H, W, K, R, pad, stride, mode, dptr(ws), ws_floats));
   });
   m.def("conv2d_dgrad", [](const py::object& dy, const py::object& w, const py::object& dx, int N, int C, int H, int W, int K,
                            int R, int pad, int stride, int mode, int dgrad_mode, const py::object& ws, size_t ws_floats) {
-    check(dfb_conv2d_dgrad(dptr(dy), dptr(w), dptr(dx), N, C, H, W, K, R, pad, stride, mode, dgrad_mode, dptr(ws), ws_floats));
+    check(dfb_conv2d_dgrad(dptr(dy), dptr(w), DFB_WLAYOUT_KCRS, dptr(dx), N, C, H, W, K, R, pad, stride, mode, dgrad_mode, dptr(ws), ws_floats));
+  });
+  m.def("conv2d_dgrad", [](const py::object& dy, const py::object& w, const py::object& dx, int N, int C, int H, int W, int K,
+                           int R, int pad, int stride, int mode, int dgrad_mode, const py::object& ws, size_t ws_floats, int w_layout) {
+    check(dfb_conv2d_dgrad(dptr(dy), dptr(w), w_layout, dptr(dx), N, C, H, W, K, R, pad, stride, mode, dgrad_mode, dptr(ws), ws_floats));
   });
   m.def("conv2d_wgrad", [](const py::object& x, int x_layout, const py::object& dy, const py::object& dw, int N, int C, int H,
                            int W, int K, int R, int pad, int stride, int mode, const py::object& ws, size_t ws_floats) {
-    check(dfb_conv2d_wgrad(dptr(x), x_layout, dptr(dy), dptr(dw), N, C, H, W, K, R, pad, stride, mode, dptr(ws), ws_floats));
+    check(dfb_conv2d_wgrad(dptr(x), x_layout, dptr(dy), dptr(dw), DFB_WLAYOUT_KCRS, N, C, H, W, K, R, pad, stride, mode, dptr(ws), ws_floats));
+  });
+  m.def("conv2d_wgrad", [](const py::object& x, int x_layout, const py::object& dy, const py::object& dw, int N, int C, int H,
+                           int W, int K, int R, int pad, int stride, int mode, const py::object& ws, size_t ws_floats, int w_layout) {
+    check(dfb_conv2d_wgrad(dptr(x), x_layout, dptr(dy), dptr(dw), w_layout, N, C, H, W, K, R, pad, stride, mode, dptr(ws), ws_floats));
   });
   m.def("add_rowvec", [](const py::object& x, const py::object& v, const py::object& y, size_t rows, int cols) {
     check(dfb_add_rowvec(dptr(x), dptr(v), dptr(y), rows, cols));

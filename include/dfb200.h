@@ -198,21 +198,25 @@ DFB_API dfb_status dfb_gemm(const float* A, const float* B, float* C, int M, int
  *   (functional.py:343-344).
  *   workspace: device scratch of at least dfb_conv2d_workspace_floats(...) floats. */
 enum { DFB_LAYOUT_NCHW = 0, DFB_LAYOUT_NHWC = 1 };
+/* weight (and weight-gradient) storage: (K,C,R,R) compact like the reference's Conv2d.weight, or
+ * channels-last (K,R,R,C) - the same logical tensor viewed through strides, which the tensor-core kernels
+ * consume in place (no per-step repacking) */
+enum { DFB_WLAYOUT_KCRS = 0, DFB_WLAYOUT_KRSC = 1 };
 enum {
   DFB_DGRAD_REFERENCE = 0, /* last-writer-wins scatter of functional.py:285-294 */
   DFB_DGRAD_EXACT = 1      /* true transposed convolution (sum over taps)                   */
 };
 DFB_API dfb_status dfb_conv2d_workspace_floats(int N, int C, int H, int W, int K, int R, int pad,
                                                int stride, size_t* n_floats);
-DFB_API dfb_status dfb_conv2d_fprop(const float* x, int x_layout, const float* w, float* y, int N,
-                                    int C, int H, int W, int K, int R, int pad, int stride,
-                                    int mode, float* workspace, size_t workspace_floats);
-DFB_API dfb_status dfb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int C,
-                                    int H, int W, int K, int R, int pad, int stride, int mode,
+DFB_API dfb_status dfb_conv2d_fprop(const float* x, int x_layout, const float* w, int w_layout,
+                                    float* y, int N, int C, int H, int W, int K, int R, int pad,
+                                    int stride, int mode, float* workspace, size_t workspace_floats);
+DFB_API dfb_status dfb_conv2d_dgrad(const float* dy, const float* w, int w_layout, float* dx, int N,
+                                    int C, int H, int W, int K, int R, int pad, int stride, int mode,
                                     int dgrad_mode, float* workspace, size_t workspace_floats);
 DFB_API dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float* dw,
-                                    int N, int C, int H, int W, int K, int R, int pad, int stride,
-                                    int mode, float* workspace, size_t workspace_floats);
+                                    int w_layout, int N, int C, int H, int W, int K, int R, int pad,
+                                    int stride, int mode, float* workspace, size_t workspace_floats);
 
 /* y[r, c] = x[r, c] + v[c]   (conv bias (1,K,1,1) on channels-last, Linear bias (1,out);
  * replaces broadcast_to + compact + ewise_add, backend_tensor.py:533-542) */

@@ -250,25 +250,36 @@ def conv2d_workspace_floats(N, C, H, W, K, R, pad, stride):
     return 0
 
 
-def conv2d_fprop(x, x_layout, w, y, N, C, H, W, K, R, pad, stride, mode, ws, ws_floats):
+WLAYOUT_KCRS, WLAYOUT_KRSC = 0, 1
+
+
+def _kcrs(w, K, C, R, w_layout):
+    """Logical (K,C,R,R) weights from a flat buffer stored (K,C,R,R) or channels-last (K,R,R,C)."""
+    flat = _flat(w)[: K * C * R * R]
+    return flat.reshape(K, R, R, C).transpose(0, 3, 1, 2) if w_layout == WLAYOUT_KRSC else flat.reshape(K, C, R, R)
+
+
+def conv2d_fprop(x, x_layout, w, y, N, C, H, W, K, R, pad, stride, mode, ws, ws_floats, w_layout=WLAYOUT_KCRS):
     _count("conv2d_fprop")
-    out = ops.conv2d_fprop(_nchw(_flat(x), N, C, H, W, x_layout), _flat(w)[: K * C * R * R].reshape(K, C, R, R), pad, stride)
+    out = ops.conv2d_fprop(_nchw(_flat(x), N, C, H, W, x_layout), _kcrs(w, K, C, R, w_layout), pad, stride)
     _store_nhwc(_flat(y), out)
 
 
-def conv2d_dgrad(dy, w, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, ws, ws_floats):
+def conv2d_dgrad(dy, w, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, ws, ws_floats, w_layout=WLAYOUT_KCRS):
     _count("conv2d_dgrad")
     oh, ow = ops.out_size(H, R, pad, stride), ops.out_size(W, R, pad, stride)
     fn = ops.conv2d_dgrad_reference if dgrad_mode == DGRAD_REFERENCE else ops.conv2d_dgrad_exact
-    out = fn(_nchw(_flat(dy), N, K, oh, ow), _flat(w)[: K * C * R * R].reshape(K, C, R, R), (N, C, H, W), pad, stride)
+    out = fn(_nchw(_flat(dy), N, K, oh, ow), _kcrs(w, K, C, R, w_layout), (N, C, H, W), pad, stride)
     _store_nhwc(_flat(dx), out)
 
 
-def conv2d_wgrad(x, x_layout, dy, dw, N, C, H, W, K, R, pad, stride, mode, ws, ws_floats):
+def conv2d_wgrad(x, x_layout, dy, dw, N, C, H, W, K, R, pad, stride, mode, ws, ws_floats, w_layout=WLAYOUT_KCRS):
     _count("conv2d_wgrad")
     oh, ow = ops.out_size(H, R, pad, stride), ops.out_size(W, R, pad, stride)
     out = ops.conv2d_wgrad(_nchw(_flat(x), N, C, H, W, x_layout), _nchw(_flat(dy), N, K, oh, ow), (K, C, R, R), pad, stride)
-    _flat(dw)[: out.size] = out.reshape(-1)
+    if w_layout == WLAYOUT_KRSC:
+        out = out.transpose(0, 2, 3, 1)
+    _flat(dw)[: out.size] = np.ascontiguousarray(out).reshape(-1)
 
 
 def add_rowvec(x, v, y, rows, cols):

@@ -87,7 +87,7 @@ def main():
         b = 32
         layers += [("vgg.c1_2", b, 64, 224, 224, 64, 3, 1, 1, 1), ("vgg.c2_2", b, 128, 112, 112, 128, 3, 1, 1, 1),
                    ("vgg.c3_2", b, 256, 56, 56, 256, 3, 1, 1, 1), ("vgg.c4_2", b, 512, 28, 28, 512, 3, 1, 1, 1)]
-    seen = set()
+    seen = {}
     print("%-14s %-28s %9s %9s %7s  %9s %7s  %9s %7s" % ("layer", "N,C,H,W,K,R,p,s", "roof us", "fprop us", "frac", "dgrad us", "frac", "wgrad us", "frac"))
     tot = {"roof": 0.0, "fprop": 0.0, "dgrad": 0.0, "wgrad": 0.0}
     for (name, n, c, h, w, k, r, p, s, _cnt) in layers:
@@ -102,11 +102,10 @@ def main():
             tf = time_it(lambda: m.conv2d_fprop(x, m.LAYOUT_NHWC, wt, y, n, c, h, w, k, r, p, s, mode, None, 0))
             td = time_it(lambda: m.conv2d_dgrad(gy, wt, dx, n, c, h, w, k, r, p, s, mode, m.DGRAD_EXACT, None, 0))
             tw = time_it(lambda: m.conv2d_wgrad(x, m.LAYOUT_NHWC, gy, dw, n, c, h, w, k, r, p, s, mode, None, 0))
-            seen.add(geom)
-            last = (tf, td, tw)
+            seen[geom] = (tf, td, tw)
             del x, wt, y, gy, dx, dw
         else:
-            tf, td, tw = last
+            tf, td, tw = seen[geom]
         print("%-14s %-28s %9.1f %9.1f %7.3f  %9.1f %7.3f  %9.1f %7.3f" % (name, ",".join(map(str, geom)), roof, tf, roof / tf, td, roof / td, tw, roof / tw))
         rows.append({"layer": name, "geom": geom, "roof_us": roof, "fprop_us": tf, "dgrad_us": td, "wgrad_us": tw, "gflop": flops / 1e9,
                      "min_mb": bytes_min / 1e6})

@@ -32,7 +32,9 @@ def from_nhwc(a):
     return a.transpose(0, 3, 1, 2)
 
 
-def run_conv(m, x, w, gy, p, s, mode, x_layout_nchw=False):
+def run_conv(m, x, w, gy, p, s, mode, x_layout_nchw=False, krsc=False):
+    """krsc: weights and weight gradient stored channels-last (K,R,R,C), the layout the host layer keeps conv
+    parameters in; the results are returned in logical (K,C,R,R) order either way."""
     n, c, h, wd = x.shape
     k, _, r, _ = w.shape
     oh, ow = ops.out_size(h, r, p, s), ops.out_size(wd, r, p, s)
@@ -40,14 +42,16 @@ def run_conv(m, x, w, gy, p, s, mode, x_layout_nchw=False):
     ws = m.Array(ws_n) if ws_n else None
     hx = up(m, x if x_layout_nchw else nhwc(x))
     layout = m.LAYOUT_NCHW if x_layout_nchw else m.LAYOUT_NHWC
-    hw, hgy = up(m, w), up(m, nhwc(gy))
+    hw, hgy = up(m, nhwc(w) if krsc else w), up(m, nhwc(gy))
+    wl = (m.WLAYOUT_KRSC,) if krsc else ()
     hy, hdx_r, hdx_e, hdw = m.Array(n * oh * ow * k), m.Array(x.size), m.Array(x.size), m.Array(w.size)
-    m.conv2d_fprop(hx, layout, hw, hy, n, c, h, wd, k, r, p, s, mode, ws, ws_n)
-    m.conv2d_dgrad(hgy, hw, hdx_r, n, c, h, wd, k, r, p, s, mode, m.DGRAD_REFERENCE, ws, ws_n)
-    m.conv2d_dgrad(hgy, hw, hdx_e, n, c, h, wd, k, r, p, s, mode, m.DGRAD_EXACT, ws, ws_n)
-    m.conv2d_wgrad(hx, layout, hgy, hdw, n, c, h, wd, k, r, p, s, mode, ws, ws_n)
+    m.conv2d_fprop(hx, layout, hw, hy, n, c, h, wd, k, r, p, s, mode, ws, ws_n, *wl)
+    m.conv2d_dgrad(hgy, hw, hdx_r, n, c, h, wd, k, r, p, s, mode, m.DGRAD_REFERENCE, ws, ws_n, *wl)
+    m.conv2d_dgrad(hgy, hw, hdx_e, n, c, h, wd, k, r, p, s, mode, m.DGRAD_EXACT, ws, ws_n, *wl)
+    m.conv2d_wgrad(hx, layout, hgy, hdw, n, c, h, wd, k, r, p, s, mode, ws, ws_n, *wl)
+    dw = from_nhwc(down(m, hdw, (k, r, r, c))) if krsc else down(m, hdw, w.shape)
     return (from_nhwc(down(m, hy, (n, oh, ow, k))), from_nhwc(down(m, hdx_r, (n, h, wd, c))),
-            from_nhwc(down(m, hdx_e, (n, h, wd, c))), down(m, hdw, w.shape))
+            from_nhwc(down(m, hdx_e, (n, h, wd, c))), dw)
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
@@ -98,6 +102,33 @@ def test_conv_against_oracle(cuda_device, shape, mode):
     assert rel_err(dx_ref, ops.conv2d_dgrad_reference(gy, wt, x.shape, p, s)) < tol
     assert rel_err(dx_exact, ops.conv2d_dgrad_exact(gy, wt, x.shape, p, s)) < tol
     assert rel_err(dw, ops.conv2d_wgrad(x, gy, wt.shape, p, s)) < tol
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", SHAPES + [(3, 16, 10, 14, 40, 5, 2, 2), (2, 8, 12, 12, 16, 2, 0, 2), (4, 64, 8, 8, 128, 3, 1, 2),
+                                            (2, 160, 8, 8, 24, 3, 1, 2), (64, 256, 2, 2, 256, 3, 1, 1)])
+def test_conv_channels_last_weights(cuda_device, shape, mode):
+    """Weights / weight gradients stored (K,R,R,C): consumed in place by the tensor-core kernels (fprop as the
+    K-major, dgrad as the MN-major operand) and by the FFMA kernels; same results as the (K,C,R,R) layout."""
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = shape
+    rng = np.random.RandomState(sum(shape) + 1)
+    x = rng.randn(n, c, h, w).astype(F32)
+    wt = (rng.randn(k, c, r, r) / np.sqrt(c * r * r)).astype(F32)
+    oh, ow = ops.out_size(h, r, p, s), ops.out_size(w, r, p, s)
+    gy = rng.randn(n, k, oh, ow).astype(F32)
+    t0 = m.tc_launch_count()
+    got = run_conv(m, x, wt, gy, p, s, mode, krsc=True)
+    tc_launches = m.tc_launch_count() - t0
+    want = run_conv(m, x, wt, gy, p, s, mode, krsc=False)
+    tol = TOL[mode]
+    for name, a, b in zip(("fprop", "dgrad_ref", "dgrad_exact", "wgrad"), got, want):
+        assert rel_err(a, b) < (1e-6 if mode == 0 else 1e-3), name  # same arithmetic, possibly another summation order
+    assert rel_err(got[0], ops.conv2d_fprop(x, wt, p, s)) < tol
+    assert rel_err(got[2], ops.conv2d_dgrad_exact(gy, wt, x.shape, p, s)) < tol
+    assert rel_err(got[3], ops.conv2d_wgrad(x, gy, wt.shape, p, s)) < tol
+    if mode == 1 and c % 4 == 0 and k % 4 == 0 and (s == 1 or (h % 2 == 0 and w % 2 == 0)):
+        assert tc_launches == 3  # fprop, exact dgrad, wgrad all on tcgen05 (the reference-mode dgrad is a gather kernel)
 
 
 TC_SHAPES = [  # N, C, H, W, K, R, pad, stride - all TMA-eligible (C, K multiples of 4; stride 2 needs even H, W)
