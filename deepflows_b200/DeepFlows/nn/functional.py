@@ -204,8 +204,8 @@ class _conv2d(FusedOperator):
         mode = precision_mode()
         if xd.is_channels_last():
             layout = LAYOUT_NHWC
-        elif xd.is_compact() and mode in (0, 3):
-            layout = LAYOUT_NCHW  # the FFMA kernels gather straight from NCHW (network input)
+        elif xd.is_compact() and (mode in (0, 3) or c <= 4):
+            layout = LAYOUT_NCHW  # the FFMA / first-layer kernels gather straight from NCHW (network input)
         else:
             xd, layout = xd.channels_last(), LAYOUT_NHWC
         p, s = self.padding, self.stride

@@ -23,6 +23,7 @@ cudaStream_t compute_stream();
 cudaStream_t comm_stream();
 int sm_count();
 // persistent zero-initialised device words for last-CTA-arrives reductions, one per kernel family (runtime.cu)
+constexpr int kTicketWords = 8192;  // slots 0..63: one per kernel family; 64..: per-tile counters of the wgrad kernel
 unsigned* ticket_counter(int slot);
 // CUDA-graph capture support (runtime.cu)
 bool graph_capturing();

@@ -57,6 +57,11 @@ dfb_status dfb_conv2d_fprop(const float* x, int x_layout, const float* w, int w_
   DFB_REQUIRE(x_layout == DFB_LAYOUT_NCHW || x_layout == DFB_LAYOUT_NHWC, DFB_ERR_INVALID, "conv2d_fprop: bad layout");
   dfb_status st = check_mode("conv2d_fprop", mode);
   if (st != DFB_OK) return st;
+  if (mode != DFB_MODE_SIMT) {  // image-like inputs (C <= 4): exact-fp32 direct kernel in every precision mode
+    bool handled = false;
+    st = direct_conv_fprop(x, x_layout, w, w_layout, y, N, C, H, W, K, R, pad, stride, &handled);
+    if (st != DFB_OK || handled) return st;
+  }
   if (want_tc(mode) && x_layout == DFB_LAYOUT_NHWC) {
     bool handled = false;
     st = tc_conv_fprop(x, w, w_layout, y, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);
@@ -90,6 +95,11 @@ dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float
   DFB_REQUIRE(x_layout == DFB_LAYOUT_NCHW || x_layout == DFB_LAYOUT_NHWC, DFB_ERR_INVALID, "conv2d_wgrad: bad layout");
   dfb_status st = check_mode("conv2d_wgrad", mode);
   if (st != DFB_OK) return st;
+  if (mode != DFB_MODE_SIMT) {
+    bool handled = false;
+    st = direct_conv_wgrad(x, x_layout, dy, dw, w_layout, N, C, H, W, K, R, pad, stride, &handled);
+    if (st != DFB_OK || handled) return st;
+  }
   if (want_tc(mode) && x_layout == DFB_LAYOUT_NHWC) {
     bool handled = false;
     st = tc_conv_wgrad(x, dy, dw, w_layout, N, C, H, W, K, R, pad, stride, mode, workspace, workspace_floats, &handled);

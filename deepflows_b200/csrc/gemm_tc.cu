@@ -32,7 +32,6 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;               // fp32/tf32 elements per stage = one 128-byte swizzle row
 constexpr int UMMA_K = 8;                 // tf32
-constexpr int kStages = 4;
 constexpr int kThreads = 192;
 constexpr int MAJOR_K = 0, MAJOR_MN = 1;
 constexpr uint32_t kChunkBytes = BLOCK_K * 128;  // one [32 k-rows x 128 B] MN-major chunk
@@ -191,6 +190,9 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32() {
 // ---- kernel skeleton ----------------------------------------------------------------------------------
 template <int BN>
 struct SmemLayout {
+  // Bytes in flight per SM bound what one SM can pull through TMA (latency x bandwidth): the BN = 128 kernels
+  // (one CTA per SM) get six 32 KB stages, the narrower ones stay at two CTAs per SM.
+  static constexpr int kStages = BN >= 128 ? 6 : (BN >= 64 ? 4 : 5);
   static constexpr uint32_t kABytes = BLOCK_M * 128;   // 16 KB
   static constexpr uint32_t kBBytes = BN * 128;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  constexpr int kStages = L::kStages;
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
         mbar_wait(empty_bar + stage, phase ^ 1);
         const uint32_t a_dst = smem_u32(smem + stage * L::kStageBytes);
         const uint32_t b_dst = a_dst + L::kABytes;
-        mbar_expect_tx(full_bar + stage, L::kStageBytes);
+        mbar_expect_tx(full_bar + stage, P::tx_bytes(prm, tile));
         P::load_a(prm, tile, &map_a, full_bar + stage, a_dst, kb);
         P::load_b(prm, tile, &map_b, full_bar + stage, b_dst, kb);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -306,6 +309,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       }
     }
     tc_fence_before();
+    P::finish(prm, tile, (warp - 2) * 32 + lane);  // the 128 epilogue threads (wgrad: last CTA of a tile sums the splits)
   }
   if (P::kClusterSplit && nsplit > 1) {
     cluster_arrive();
@@ -444,6 +448,8 @@ template <int A_MAJ, int B_MAJ, int BN_>
 struct GemmProblem {
   static constexpr int BN = BN_, A_MAJOR = A_MAJ, B_MAJOR = B_MAJ;
   static constexpr bool kClusterSplit = true;
+  __device__ static uint32_t tx_bytes(const GemmParams&, const GemmTile&) { return SmemLayout<BN_>::kStageBytes; }
+  __device__ static void finish(const GemmParams&, const GemmTile&, int) {}
   using Params = GemmParams;
   using Tile = GemmTile;
   __device__ static Tile tile(const Params& p) {
@@ -564,6 +570,8 @@ template <int BN_, int WMODE>
 struct ConvProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = (WMODE == W_KRSC_DGRAD ? MAJOR_MN : MAJOR_K);
   static constexpr bool kClusterSplit = true;
+  __device__ static uint32_t tx_bytes(const ConvParams&, const ConvTile&) { return SmemLayout<BN_>::kStageBytes; }
+  __device__ static void finish(const ConvParams&, const ConvTile&, int) {}
   using Params = ConvParams;
   using Tile = ConvTile;
   __device__ static Tile tile(const Params& p) {
@@ -668,12 +676,16 @@ struct ConvProblem {
 // =====================================================================================================
 struct WgradParams {
   float* partial;      // [splits][Kout][taps][Cp]
+  float* dw;           // final gradient, (K,C,R,R) or (K,R,R,C); written by the last CTA of each tile when tickets != 0
+  unsigned* tickets;   // one self-resetting arrival counter per output tile (null: separate reduction kernel)
+  int krsc;
   int Kout, C, Cp, R, pad, stride;
   int n_img, OH, OW;
   int ow_t, oh_t, n_t, tiles_w, tiles_h, pix_blocks, blocks_per_split, ctiles;
 };
 struct WgradTile {
   int m0, tap, c0, kb_begin, kb_end;
+  int a_chunks;  // 32-row chunks of the dy tile that hold real output channels (the rest is never loaded)
 };
 template <int BN_>
 struct WgradProblem {
@@ -685,8 +697,11 @@ struct WgradProblem {
   __device__ static Tile tile(const Params& p) {
     const int tap = blockIdx.y / p.ctiles, ct = blockIdx.y - tap * p.ctiles;
     const int b0 = blockIdx.z * p.blocks_per_split;
-    return {(int)blockIdx.x * BLOCK_M, tap, ct * BN, b0, min(p.pix_blocks, b0 + p.blocks_per_split)};
+    const int m0 = (int)blockIdx.x * BLOCK_M;
+    return {m0, tap, ct * BN, b0, min(p.pix_blocks, b0 + p.blocks_per_split), min(BLOCK_M / 32, (p.Kout - m0 + 31) / 32)};
   }
+  // rows of the accumulator beyond Kout multiply whatever the idle part of the stage holds; they are never stored
+  __device__ static uint32_t tx_bytes(const Params&, const Tile& t) { return t.a_chunks * kChunkBytes + SmemLayout<BN_>::kBBytes; }
   __device__ static void pix(const Params& p, int kb, int& n0, int& oh0, int& ow0) {
     int tw = kb % p.tiles_w;
     kb /= p.tiles_w;
@@ -699,7 +714,8 @@ struct WgradProblem {
     int n0, oh0, ow0;
     pix(p, kb, n0, oh0, ow0);
 #pragma unroll
-    for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_4d(dst + j * kChunkBytes, m, bar, t.m0 + j * 32, ow0, oh0, n0);
+    for (int j = 0; j < BLOCK_M / 32; ++j)
+      if (j < t.a_chunks) tma_load_4d(dst + j * kChunkBytes, m, bar, t.m0 + j * 32, ow0, oh0, n0);
   }
   __device__ static void load_b(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
     int n0, oh0, ow0;
@@ -721,6 +737,53 @@ struct WgradProblem {
     float* dst = p.partial + (((size_t)blockIdx.z * p.Kout + k) * taps + t.tap) * p.Cp + t.c0 + c0;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+  // The last of the gridDim.z CTAs that share this output tile adds their partial tiles in split order
+  // (deterministic) and writes the gradient in the weight's layout. Called by the 128 epilogue threads.
+  __device__ static void finish(const Params& p, const Tile& t, int tid) {
+    if (!p.tickets) return;
+    __shared__ int s_last;
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) {
+      unsigned* ticket = p.tickets + blockIdx.x + gridDim.x * blockIdx.y;
+      const unsigned arrived = atomicAdd(ticket, 1u);
+      s_last = arrived == gridDim.z - 1;
+      if (s_last) *ticket = 0;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (!s_last) return;
+    __threadfence();
+    const int taps = p.R * p.R;
+    const int rows = min(BLOCK_M, p.Kout - t.m0);
+    constexpr int kVec = BN / 4;
+    const size_t slab = (size_t)p.Kout * taps * p.Cp;
+    const int splits = gridDim.z;
+    for (int idx = tid; idx < rows * kVec; idx += 128) {
+      const int k = t.m0 + idx / kVec;
+      const int c = t.c0 + (idx % kVec) * 4;
+      if (c >= p.C) continue;  // channel padding
+      const float4* src = reinterpret_cast<const float4*>(p.partial + ((size_t)k * taps + t.tap) * p.Cp + c);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int z = 0;
+      for (; z + 4 <= splits; z += 4) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = __ldcg(src + (size_t)(z + u) * (slab / 4));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc.x += q[u].x; acc.y += q[u].y; acc.z += q[u].z; acc.w += q[u].w; }
+      }
+      for (; z < splits; ++z) {
+        const float4 q = __ldcg(src + (size_t)z * (slab / 4));
+        acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+      }
+      if (p.krsc) {
+        *reinterpret_cast<float4*>(p.dw + ((size_t)k * taps + t.tap) * p.C + c) = acc;
+      } else {
+        float* o = p.dw + ((size_t)k * p.C + c) * taps + t.tap;
+        o[0] = acc.x; o[taps] = acc.y; o[2 * taps] = acc.z; o[3 * taps] = acc.w;
+      }
+    }
   }
 };
 
@@ -950,11 +1013,18 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   dfb_status st = dfb_malloc((size_t)splits * K * taps * prm.Cp, &partial);
   if (st != DFB_OK) return st;
   prm.partial = partial;
+  prm.dw = dw;
+  prm.krsc = w_layout == DFB_WLAYOUT_KRSC ? 1 : 0;
+  // one arrival counter per output tile; (K * taps * Cp) % 4 == 0 keeps the float4 walk of the slabs aligned
+  // The in-kernel reduction is done by ONE CTA per tile: worth it (one launch less) while a tile's partials are
+  // small; beyond that the separate reduction kernel, which spreads over the machine, is faster.
+  const size_t tile_partial_bytes = (size_t)splits * std::min(K, BLOCK_M) * bn * sizeof(float);
+  prm.tickets = (base_ctas <= (size_t)kTicketWords - 64 && tile_partial_bytes <= (192u << 10)) ? ticket_counter(64) : nullptr;
   *handled = true;
   if (bn == 128) st = run_wgrad<128>(ma, mb, prm, splits);
   else if (bn == 64) st = run_wgrad<64>(ma, mb, prm, splits);
   else st = run_wgrad<32>(ma, mb, prm, splits);
-  if (st == DFB_OK) {
+  if (st == DFB_OK && !prm.tickets) {
     wgrad_reduce_kernel<<<bw_grid((size_t)K * C * taps, 256), 256, 0, compute_stream()>>>(partial, dw, splits, K, C, prm.Cp, taps,
                                                                                           w_layout == DFB_WLAYOUT_KRSC ? 1 : 0);
     cudaError_t e = cudaGetLastError();

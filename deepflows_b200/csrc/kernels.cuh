@@ -14,6 +14,12 @@ dfb_status simt_conv_dgrad(const float* dy, const float* w, int w_layout, float*
 dfb_status simt_conv_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H,
                            int W, int K, int R, int pad, int stride);
 
+// conv_direct.cu — first-layer convolutions (C <= 4 input channels): bandwidth-bound FFMA kernels. *handled as below.
+dfb_status direct_conv_fprop(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H, int W,
+                             int K, int R, int pad, int stride, bool* handled);
+dfb_status direct_conv_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H, int W,
+                             int K, int R, int pad, int stride, bool* handled);
+
 // gemm_tc.cu — TMA + tcgen05/TMEM path. Each returns DFB_OK and sets *handled = true when it ran
 // the problem, leaves *handled = false when the shape is outside what the tensor-core kernels
 // take (the dispatcher then uses the SIMT path), or returns an error status.

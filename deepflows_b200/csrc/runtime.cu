@@ -108,8 +108,8 @@ dfb_status ensure_init() {
   DFB_CUDA(cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking));
   DFB_CUDA(cudaEventCreateWithFlags(&r.ev_fork, cudaEventDisableTiming));
   DFB_CUDA(cudaEventCreateWithFlags(&r.ev_join, cudaEventDisableTiming));
-  DFB_CUDA(cudaMalloc(&r.tickets, 64 * sizeof(unsigned)));
-  DFB_CUDA(cudaMemset(r.tickets, 0, 64 * sizeof(unsigned)));
+  DFB_CUDA(cudaMalloc(&r.tickets, kTicketWords * sizeof(unsigned)));
+  DFB_CUDA(cudaMemset(r.tickets, 0, kTicketWords * sizeof(unsigned)));
   DFB_CUDA(cudaDeviceSynchronize());
   r.ready = true;
   return DFB_OK;
@@ -118,7 +118,8 @@ dfb_status ensure_init() {
 cudaStream_t compute_stream() { return rt().on_side ? rt().side : rt().compute; }
 cudaStream_t comm_stream() { return rt().comm; }
 int sm_count() { return rt().sms; }
-unsigned* ticket_counter(int slot) { return rt().tickets + slot; }
+// work on the side stream may overlap main-stream kernels of the same family: it gets its own counters (32..63)
+unsigned* ticket_counter(int slot) { return rt().tickets + slot + ((rt().on_side && slot < 32) ? 32 : 0); }
 
 }  // namespace dfb
 

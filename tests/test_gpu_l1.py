@@ -73,6 +73,10 @@ def test_conv_against_reference_fixture(cuda_device, case, mode):
 
 
 SHAPES = [  # N, C, H, W, K, R, pad, stride   (scaled-down versions of the C2-C5 layers + ragged edges)
+    (5, 3, 32, 32, 64, 3, 1, 1),     # VGG first layer (direct first-layer kernels, K = 64)
+    (3, 3, 17, 19, 32, 5, 2, 1),     # CNN-CIFAR10 conv1 (C = 3, 5x5: 75 taps), ragged image
+    (2, 2, 9, 9, 8, 3, 0, 2),        # direct kernels: stride 2, no padding
+    (2, 4, 8, 8, 12, 3, 1, 1),       # C = 4 but K % 8 != 0: not eligible for the direct kernels
     (8, 32, 16, 16, 32, 3, 1, 1),    # ResNet layer1
     (8, 32, 16, 16, 64, 3, 1, 2),    # layer2 b0.conv1
     (8, 32, 16, 16, 64, 1, 0, 2),    # layer2 shortcut
@@ -127,14 +131,14 @@ def test_conv_channels_last_weights(cuda_device, shape, mode):
     assert rel_err(got[0], ops.conv2d_fprop(x, wt, p, s)) < tol
     assert rel_err(got[2], ops.conv2d_dgrad_exact(gy, wt, x.shape, p, s)) < tol
     assert rel_err(got[3], ops.conv2d_wgrad(x, gy, wt.shape, p, s)) < tol
-    if mode == 1 and c % 4 == 0 and k % 4 == 0 and (s == 1 or (h % 2 == 0 and w % 2 == 0)):
+    if mode == 1 and c > 4 and c % 4 == 0 and k % 4 == 0 and (s == 1 or (h % 2 == 0 and w % 2 == 0)):
         assert tc_launches == 3  # fprop, exact dgrad, wgrad all on tcgen05 (the reference-mode dgrad is a gather kernel)
 
 
 TC_SHAPES = [  # N, C, H, W, K, R, pad, stride - all TMA-eligible (C, K multiples of 4; stride 2 needs even H, W)
     (8, 32, 16, 16, 32, 3, 1, 1), (8, 32, 16, 16, 64, 3, 1, 2), (8, 32, 16, 16, 64, 1, 0, 2), (16, 128, 4, 4, 128, 3, 1, 1),
     (32, 256, 2, 2, 256, 3, 1, 1), (2, 64, 14, 14, 64, 3, 1, 1), (3, 20, 11, 13, 36, 3, 1, 1), (2, 64, 56, 56, 64, 3, 1, 1),
-    (4, 8, 12, 12, 200, 5, 2, 1), (2, 160, 8, 8, 24, 3, 1, 2), (1, 4, 40, 300, 8, 3, 1, 1), (256, 32, 16, 16, 32, 3, 1, 1),
+    (4, 8, 12, 12, 200, 5, 2, 1), (2, 160, 8, 8, 24, 3, 1, 2), (1, 8, 40, 300, 8, 3, 1, 1), (256, 32, 16, 16, 32, 3, 1, 1),
     (3, 16, 10, 14, 40, 5, 2, 2), (2, 8, 12, 12, 16, 2, 0, 2), (4, 64, 8, 8, 128, 3, 1, 2), (2, 12, 6, 6, 8, 4, 1, 2),
 ]
 
