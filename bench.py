@@ -281,14 +281,15 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel profile pass: CUDA events around every fused conv call, same steps ----------------
-    roofline = None
-    if rank == 0:
-        roofline = profile_dominant_kernel(dev, eager_step, args, B)
+    # every rank runs it: the steps contain the data-parallel all-reduces, so the ranks must stay in lockstep
+    roofline = profile_dominant_kernel(dev, eager_step, args, B)
 
     if world > 1:
         barrier()
         dist.shutdown()
     if rank != 0:
+        if world > 1:
+            os._exit(0)
         return
     peaks = {}
     try:
@@ -324,6 +325,10 @@ def main():
         base = run_cpu(args, args.cpu_batch, 3, 1)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        # leave without running destructors that could wait on the other ranks (NCCL, captured graphs)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def profile_dominant_kernel(dev, step_fn, args, batch):

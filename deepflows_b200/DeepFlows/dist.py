@@ -27,6 +27,7 @@ class NcclTransport:
 
     def __init__(self, device, rank, world, master_addr, master_port):
         self.device, self.rank, self.world = device, rank, world
+        _prefer_bundled_nccl()
         uid = _exchange_unique_id(device, rank, world, master_addr, master_port)
         device.comm_init(uid, rank, world)
 
@@ -41,6 +42,25 @@ class NcclTransport:
 
     def close(self):
         self.device.comm_destroy()
+
+
+def _prefer_bundled_nccl():
+    """libdfb200 dlopens NCCL (DFB_NCCL_LIB, else libnccl.so.2 from the loader path). When the Python
+    environment ships its own NCCL wheel (nvidia-nccl-cu12, the build PyTorch is tested against on this
+    machine) that one is preferred: on the B200 pool the system's libnccl 2.27.3 hung inside
+    ncclCommInitRank in more than half of the two-rank launches, the bundled 2.28.9 never did."""
+    if os.environ.get("DFB_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["DFB_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
 
 
 def _exchange_unique_id(device, rank, world, addr, port):

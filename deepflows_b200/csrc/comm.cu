@@ -25,6 +25,7 @@ struct Nccl {
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*CommAbort)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -48,6 +49,7 @@ dfb_status load_nccl() {
   SYM(GetUniqueId, "ncclGetUniqueId");
   SYM(CommInitRank, "ncclCommInitRank");
   SYM(CommDestroy, "ncclCommDestroy");
+  SYM(CommAbort, "ncclCommAbort");
   SYM(AllReduce, "ncclAllReduce");
   SYM(Broadcast, "ncclBroadcast");
   SYM(GetErrorString, "ncclGetErrorString");
@@ -99,8 +101,15 @@ dfb_status dfb_comm_init(const unsigned char* id128, int rank, int world_size) {
 
 dfb_status dfb_comm_destroy(void) {
   if (!g_comm) return DFB_OK;
+  // All collectives this rank enqueued have completed once the streams are idle. The communicator object
+  // itself is then dropped, not destroyed: ncclCommDestroy / ncclCommAbort block for as long as a captured
+  // CUDA graph still references the communicator (NCCL 2.27.3: both were observed to hang here with the
+  // training-step graph alive), and a process that is about to exit must not wait on that. The driver
+  // reclaims NCCL's resources with the process (set DFB_NCCL_DESTROY=1 to call ncclCommDestroy anyway).
+  cudaStreamSynchronize(compute_stream());
   cudaStreamSynchronize(comm_stream());
-  DFB_NCCL(g_nccl.CommDestroy(g_comm));
+  const char* env = getenv("DFB_NCCL_DESTROY");
+  if (env && env[0] == '1') DFB_NCCL(g_nccl.CommDestroy(g_comm));
   g_comm = nullptr;
   g_rank = 0;
   g_world = 1;
