@@ -275,6 +275,186 @@ static dfb_status launch_col_sums(const char* name, SumsArgs a, size_t rows, int
   return DFB_OK;
 }
 
+// -------------------------------------------------------------------------------------------------
+// BatchNorm for small activations (a few MB: the deep layers of a CIFAR-size net): ONE kernel per
+// direction. A CTA of 1024 threads owns a block of CB channels for ALL rows, so the statistics need no
+// cross-CTA step: pass 1 accumulates the two sums per channel (thread = (float4 channel group, row lane),
+// four rows in flight), a fixed-order shuffle + shared-memory tree adds the lanes, pass 2 re-reads the rows
+// (L2 hits) and writes the result. Versus the two-kernel path this saves a launch and a dependent
+// global-memory round trip per BatchNorm, which is what these launch-latency-bound layers cost.
+// -------------------------------------------------------------------------------------------------
+constexpr int kSmallT = 1024;
+// sums s0, s1 (float4 each) over all row lanes of the CTA; result valid in lane 0 of each group (tid < GPB)
+template <int GPB>
+__device__ __forceinline__ void block_lane_sum(float (&s0)[4], float (&s1)[4], float* sm /* [32 warps][GPB][8] */) {
+  // threads are (lane * GPB + g): xor offsets >= GPB stay inside a channel group
+#pragma unroll
+  for (int off = 16; off >= GPB; off >>= 1)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      s0[v] += __shfl_xor_sync(0xffffffffu, s0[v], off);
+      s1[v] += __shfl_xor_sync(0xffffffffu, s1[v], off);
+    }
+  const int warp = threadIdx.x >> 5, lane_in_warp = threadIdx.x & 31;
+  __syncthreads();
+  if (lane_in_warp < GPB) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      sm[(warp * GPB + lane_in_warp) * 8 + v] = s0[v];
+      sm[(warp * GPB + lane_in_warp) * 8 + 4 + v] = s1[v];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < GPB) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { s0[v] = 0.f; s1[v] = 0.f; }
+    for (int w = 0; w < kSmallT / 32; ++w)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        s0[v] += sm[(w * GPB + threadIdx.x) * 8 + v];
+        s1[v] += sm[(w * GPB + threadIdx.x) * 8 + 4 + v];
+      }
+  }
+}
+
+template <int GPB>  // float4 channel groups per CTA (CB = 4 * GPB channels)
+__global__ void __launch_bounds__(kSmallT)
+bn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps, int rows,
+                    int C) {
+  __shared__ float sm[(kSmallT / 32) * GPB * 8];
+  __shared__ float s_scale[GPB * 4], s_shift[GPB * 4];
+  const int g = threadIdx.x % GPB, lane = threadIdx.x / GPB;
+  constexpr int kLanes = kSmallT / GPB;
+  const int c0 = (blockIdx.x * GPB + g) * 4;
+  const float* xc = x + c0;
+  float shift[4], s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  Vec<4>::get(xc, shift);  // row 0
+  int r = lane;
+  for (; r + 3 * kLanes < rows; r += 4 * kLanes) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Vec<4>::get(xc + (size_t)(r + u * kLanes) * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { float d = v[u][q] - shift[q]; s0[q] += d; s1[q] = fmaf(d, d, s1[q]); }
+  }
+  for (; r < rows; r += kLanes) {
+    float v[4];
+    Vec<4>::get(xc + (size_t)r * C, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { float d = v[q] - shift[q]; s0[q] += d; s1[q] = fmaf(d, d, s1[q]); }
+  }
+  block_lane_sum<GPB>(s0, s1, sm);
+  if (threadIdx.x < GPB) {
+    const float n = (float)rows;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + q;
+      const float dm = s0[q] / n;
+      const float mean = shift[q] + dm;
+      const float var = fmaxf(s1[q] / n - dm * dm, 0.f);   // biased, like batchnorm.py:38-42
+      const float invstd = 1.0f / sqrtf(var + eps);
+      save_mean[c] = mean;
+      save_invstd[c] = invstd;
+      if (running_mean) running_mean[c] = running_mean[c] * (1.0f - momentum) + mean * momentum;
+      if (running_var) running_var[c] = running_var[c] * (1.0f - momentum) + var * momentum;
+      const float sc = invstd * (gamma ? gamma[c] : 1.0f);
+      s_scale[g * 4 + q] = sc;
+      s_shift[g * 4 + q] = (beta ? beta[c] : 0.0f) - mean * sc;
+    }
+  }
+  __syncthreads();
+  float sc[4], sh[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { sc[q] = s_scale[g * 4 + q]; sh[q] = s_shift[g * 4 + q]; }
+  // y = (x - mean) * invstd * gamma + beta, evaluated as x * sc + (beta - mean * sc)
+  for (r = lane; r < rows; r += kLanes) {
+    float v[4], o[4];
+    Vec<4>::get(xc + (size_t)r * C, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = fmaf(v[q], sc[q], sh[q]);
+    Vec<4>::put(y + c0 + (size_t)r * C, o);
+  }
+}
+
+template <int GPB>
+__global__ void __launch_bounds__(kSmallT)
+bn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dx,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
+  __shared__ float sm[(kSmallT / 32) * GPB * 8];
+  __shared__ float s_mb[GPB * 4], s_mg[GPB * 4];
+  const int g = threadIdx.x % GPB, lane = threadIdx.x / GPB;
+  constexpr int kLanes = kSmallT / GPB;
+  const int c0 = (blockIdx.x * GPB + g) * 4;
+  const float* xc = x + c0;
+  const float* dc = dy + c0;
+  float mu[4], is[4], s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  Vec<4>::get(mean + c0, mu);
+  Vec<4>::get(invstd + c0, is);
+  int r = lane;
+  for (; r + 1 * kLanes < rows; r += 2 * kLanes) {
+    float xv[2][4], dv[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      Vec<4>::get(xc + (size_t)(r + u * kLanes) * C, xv[u]);
+      Vec<4>::get(dc + (size_t)(r + u * kLanes) * C, dv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { s0[q] += dv[u][q]; s1[q] = fmaf(dv[u][q], (xv[u][q] - mu[q]) * is[q], s1[q]); }
+  }
+  for (; r < rows; r += kLanes) {
+    float xv[4], dv[4];
+    Vec<4>::get(xc + (size_t)r * C, xv);
+    Vec<4>::get(dc + (size_t)r * C, dv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { s0[q] += dv[q]; s1[q] = fmaf(dv[q], (xv[q] - mu[q]) * is[q], s1[q]); }
+  }
+  block_lane_sum<GPB>(s0, s1, sm);
+  if (threadIdx.x < GPB) {
+    const float inv_n = 1.0f / (float)rows;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (dbeta) dbeta[c0 + q] = s0[q];
+      if (dgamma) dgamma[c0 + q] = s1[q];
+      s_mb[g * 4 + q] = s0[q] * inv_n;
+      s_mg[g * 4 + q] = s1[q] * inv_n;
+    }
+  }
+  __syncthreads();
+  if (!dx) return;
+  float k1[4], mb[4], mg[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    k1[q] = is[q] * (gamma ? gamma[c0 + q] : 1.0f);
+    mb[q] = s_mb[g * 4 + q];
+    mg[q] = s_mg[g * 4 + q];
+  }
+  for (r = lane; r < rows; r += kLanes) {
+    float xv[4], dv[4], o[4];
+    Vec<4>::get(xc + (size_t)r * C, xv);
+    Vec<4>::get(dc + (size_t)r * C, dv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = k1[q] * (dv[q] - mb[q] - (xv[q] - mu[q]) * is[q] * mg[q]);
+    Vec<4>::put(dx + c0 + (size_t)r * C, o);
+  }
+}
+
+// channel groups per CTA for the single-kernel path, 0 = use the two-kernel path
+static int bn_small_gpb(size_t rows, int C, const void* a, const void* b = nullptr, const void* c = nullptr) {
+  // Only while a thread sees at most four rows per pass (one batch of loads in flight): with more, the few
+  // CTAs of this path become a chain of dependent-latency loads and the two-kernel path (hundreds of CTAs) wins.
+  if (C % 16 != 0 || rows < 64 || rows > 1024) return 0;
+  if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) != 0) return 0;
+  const int gpb = rows > 512 ? 4 : (rows > 256 ? 2 : 1);   // 256 / 512 / 1024 row lanes per CTA
+  return (C / 4) % gpb == 0 ? gpb : 0;
+}
+
 // y = (x - mean) * (invstd * gamma) + beta, optionally followed by max(.,0)
 template <int V, bool RELU>
 __global__ void __launch_bounds__(kT)
@@ -643,6 +823,18 @@ dfb_status dfb_bn_fwd_train(const float* x, const float* gamma, const float* bet
   DFB_INIT();
   DFB_REQUIRE(x && y && save_mean && save_invstd, DFB_ERR_INVALID, "bn_fwd_train: null pointer");
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_fwd_train: empty input");
+  if (const int gpb = bn_small_gpb(rows, C, x, y)) {
+    const unsigned grid = (unsigned)(C / 4 / gpb);
+    cudaStream_t s = compute_stream();
+#define DFB_BN_SMALL_FWD(G) bn_small_fwd_kernel<G><<<grid, kSmallT, 0, s>>>(x, gamma, beta, y, save_mean, save_invstd, running_mean, \
+                                                                          running_var, momentum, eps, (int)rows, C)
+    if (gpb == 1) DFB_BN_SMALL_FWD(1);
+    else if (gpb == 2) DFB_BN_SMALL_FWD(2);
+    else DFB_BN_SMALL_FWD(4);
+#undef DFB_BN_SMALL_FWD
+    DFB_LAUNCH_CHECK("bn_fwd_train(small)");
+    return DFB_OK;
+  }
   dfb_status st = bn_stats(x, rows, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
   if (st != DFB_OK) return st;
   return bn_apply(x, y, rows, C, save_mean, save_invstd, gamma, beta, false);
@@ -673,6 +865,18 @@ dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma, const
   DFB_INIT();
   DFB_REQUIRE(x && dy && save_mean && save_invstd, DFB_ERR_INVALID, "bn_bwd: null pointer");
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_bwd: empty input");
+  if (const int gpb = bn_small_gpb(rows, C, x, dy, dx)) {
+    const unsigned grid = (unsigned)(C / 4 / gpb);
+    cudaStream_t s = compute_stream();
+#define DFB_BN_SMALL_BWD(G) bn_small_bwd_kernel<G><<<grid, kSmallT, 0, s>>>(x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, \
+                                                                          (int)rows, C)
+    if (gpb == 1) DFB_BN_SMALL_BWD(1);
+    else if (gpb == 2) DFB_BN_SMALL_BWD(2);
+    else DFB_BN_SMALL_BWD(4);
+#undef DFB_BN_SMALL_BWD
+    DFB_LAUNCH_CHECK("bn_bwd(small)");
+    return DFB_OK;
+  }
   float* scratch = nullptr;
   dfb_status st = dfb_malloc(2 * (size_t)C, &scratch);
   if (st != DFB_OK) return st;
