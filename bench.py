@@ -332,10 +332,14 @@ def main():
 
 
 def profile_dominant_kernel(dev, step_fn, args, batch):
-    """Time every conv2d_fprop / dgrad / wgrad and BatchNorm call of `steps` more identical steps with CUDA
-    events on the compute stream, pick the op+geometry with the largest total device time, and report its
-    algorithmic FLOPs (2*M*N*K) and minimum bytes against its duration."""
-    records = {}
+    """Find the fused op + geometry that costs the step most device time and report it against its roofline.
+
+    Pass 1 (eager, CUDA events around every conv2d_fprop / dgrad / wgrad / BatchNorm call of a few identical
+    steps) finds the distinct (op, geometry) pairs, how often each runs per step, and keeps one set of live
+    arguments for each. Pass 2 times each pair the way it runs inside the captured step: 16 back-to-back calls
+    replayed from a CUDA graph (no host launch cost), CUDA events around three replays. The pair with the
+    largest per-step total is the dominant kernel; `achieved` = its algorithmic bytes or FLOPs
+    over that duration."""
     pending = []
     for _ in range(2):  # un-instrumented eager steps: refill the allocator pool after the graph capture
         step_fn()
@@ -347,7 +351,7 @@ def profile_dominant_kernel(dev, step_fn, args, batch):
             dev.event_record(e0)
             orig(*a)
             dev.event_record(e1)
-            pending.append((name, geom_of(a), e0, e1))
+            pending.append((name, geom_of(a), e0, e1, a))
         return fn
 
     conv_geom = lambda off: (lambda a: tuple(int(v) for v in a[off:off + 8]))  # noqa: E731
@@ -357,33 +361,59 @@ def profile_dominant_kernel(dev, step_fn, args, batch):
         orig = getattr(dev, name)
         saved[name] = orig
         dev.__dict__[name] = wrap(name, geom, orig)
+    steps = 2
     try:
-        steps = max(2, min(args.steps, 5))
         for _ in range(steps):
             step_fn()
         dev.synchronize()
     finally:
         for name, orig in saved.items():
             dev.__dict__[name] = orig
-    for name, geom, e0, e1 in pending:
-        ms = dev.event_elapsed_ms(e0, e1)
+    pairs = {}
+    for name, geom, e0, e1, a in pending:
+        eager_ms = dev.event_elapsed_ms(e0, e1)
         dev.event_destroy(e0)
         dev.event_destroy(e1)
-        r = records.setdefault((name, geom), [0.0, 0])
-        r[0] += ms
-        r[1] += 1
-    if not records:
+        r = pairs.setdefault((name, geom), {"count": 0, "eager_ms": 0.0, "args": a})
+        r["count"] += 1
+        r["eager_ms"] += eager_ms
+    if not pairs:
         return None
+    # pass 2: graph-replayed timing of every distinct pair
+    reps = 16
+    for (name, geom), r in pairs.items():
+        fn, a = saved[name], r["args"]
+        if dev.has("side_begin") and name == "conv2d_wgrad":
+            pass  # timed on the compute stream here; inside the step it overlaps dgrad on the side stream
+        for _ in range(2):
+            fn(*a)
+        dev.graph_begin_capture()
+        for _ in range(reps):
+            fn(*a)
+        g = dev.graph_end_capture()
+        dev.graph_launch(g)
+        e0, e1 = dev.event_create(), dev.event_create()
+        dev.event_record(e0)
+        for _ in range(3):
+            dev.graph_launch(g)
+        dev.event_record(e1)
+        dev.event_synchronize(e1)
+        r["us"] = dev.event_elapsed_ms(e0, e1) / (3 * reps) * 1e3
+        r["per_step"] = r["count"] / steps
+        dev.event_destroy(e0)
+        dev.event_destroy(e1)
+        dev.graph_destroy(g)
+        r["args"] = None
     by_op = {}
-    for (name, geom), (ms, cnt) in records.items():
-        by_op[name] = by_op.get(name, 0.0) + ms / steps
-    (name, geom), (ms, cnt) = max(records.items(), key=lambda kv: kv[1][0])
-    avg_s = ms / cnt / 1e3
+    for (name, geom), r in pairs.items():
+        by_op[name] = by_op.get(name, 0.0) + r["us"] * r["per_step"] / 1e3
+    (name, geom), r = max(pairs.items(), key=lambda kv: kv[1]["us"] * kv[1]["per_step"])
+    avg_s = r["us"] * 1e-6
     if name.startswith("conv2d"):
-        n, c, h, w, k, r, p, s = geom
-        oh, ow = (h + 2 * p - r) // s + 1, (w + 2 * p - r) // s + 1
-        flops = 2.0 * n * oh * ow * k * c * r * r
-        bytes_min = 4.0 * (n * c * h * w + k * c * r * r + n * oh * ow * k)
+        n, c, h, w, k, rr, p, s = geom
+        oh, ow = (h + 2 * p - rr) // s + 1, (w + 2 * p - rr) // s + 1
+        flops = 2.0 * n * oh * ow * k * c * rr * rr
+        bytes_min = 4.0 * (n * c * h * w + k * c * rr * rr + n * oh * ow * k)
         t_tc_us = flops / 700e12 * 1e6   # TF32 dense ~ half of sustained bf16
         t_hbm_us = bytes_min / 6.5456e12 * 1e6
         bound = "tensor" if t_tc_us > t_hbm_us else "hbm"
@@ -399,11 +429,19 @@ def profile_dominant_kernel(dev, step_fn, args, batch):
         bound, achieved, unit = "hbm", bytes_min / avg_s / 1e9, "GB/s"
         desc = "%s rows=%d C=%d" % (name, rows, c)
         extra = {"bytes_per_launch": bytes_min}
+    traffic = None
+    try:  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture, when there is one
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = table.get(desc, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     return dict({"kernel": desc, "bound": bound, "achieved": achieved, "peak": None, "unit": unit, "frac": None,
-                 "traffic": None, "avg_launch_us": avg_s * 1e6, "launches_timed": cnt,
+                 "traffic": traffic, "avg_launch_us": r["us"], "launches_per_step": r["per_step"],
                  "share_of_step_ms": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])},
-                 "how": "CUDA events on the compute stream around each fused-op call, in a separate pass of identical steps "
-                        "right after the timed region (event pairs would perturb the headline timing)"}, **extra)
+                 "how": "each distinct fused call of the step (found with CUDA events around the calls of eager steps) is "
+                        "re-timed as 16 back-to-back calls replayed from a CUDA graph, CUDA events on the compute stream "
+                        "around 3 replays - the cost it has inside the captured step, free of host launch latency"},
+                **extra)
 
 
 if __name__ == "__main__":

@@ -30,6 +30,12 @@ struct Vec<4> {
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  // streaming load as volatile asm: a run of these is issued back to back (the compiler otherwise pairs each
+  // load with its consumer and keeps only two in flight), which is what a bandwidth-bound loop needs
+  static __device__ __forceinline__ void get_stream(const float* p, float (&v)[4]) {
+    float4 t = ld_stream(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
   static __device__ __forceinline__ void put(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -37,6 +43,7 @@ struct Vec<4> {
 template <>
 struct Vec<1> {
   static __device__ __forceinline__ void get(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void get_stream(const float* p, float (&v)[1]) { v[0] = *p; }
   static __device__ __forceinline__ void put(float* p, const float (&v)[1]) { *p = v[0]; }
 };
 
@@ -59,7 +66,9 @@ static ColPlan plan_cols(size_t rows, int C, const void* p0, const void* p1 = nu
   p.lanes = std::max(1, kT / p.G);
   p.gpass = (p.G + kT - 1) / kT;
   size_t want = (rows + (size_t)p.lanes * 4 - 1) / ((size_t)p.lanes * 4);  // ~4 rows per thread
-  size_t cap = (size_t)sm_count() * 2;
+  // big inputs are bandwidth problems (more CTAs = more loads in flight), small ones latency problems (fewer
+  // partials for the last CTA to merge)
+  size_t cap = (size_t)sm_count() * (rows * (size_t)C >= ((size_t)4 << 20) ? 4 : 2);
   p.ctas = (unsigned)std::max<size_t>(1, std::min(want, cap));
   p.rows_per_cta = (rows + p.ctas - 1) / p.ctas;
   p.ctas = (unsigned)((rows + p.rows_per_cta - 1) / p.rows_per_cta);
@@ -141,7 +150,7 @@ __device__ __forceinline__ void lane_tree_sum(float* sm, float (&s0)[V], float (
 }
 
 template <int V, int KIND>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 2)
 col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
   extern __shared__ float sm[];  // [lanes][2][C] when lanes > 1
   const int G = p.G;
@@ -163,16 +172,27 @@ col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
       }
       const size_t step = p.lanes;
       size_t r = r0 + lane;
-      // four independent rows in flight per thread
-      for (; r + 3 * step < r1; r += 4 * step) {
-        float xv[4][V], dv[4][V];
+      // kU independent rows in flight per thread: ~64-128 bytes per thread, enough outstanding loads across the
+      // grid to cover HBM latency at full bandwidth
+      constexpr int kU = KIND == SUMS_BNBWD ? 4 : 8;
+      for (; r + (kU - 1) * step < r1; r += kU * step) {
+        float xv[kU][V], dv[KIND == SUMS_BNBWD ? kU : 1][V];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          Vec<V>::get(a.x + (r + u * step) * C + (size_t)g * V, xv[u]);
-          if (KIND == SUMS_BNBWD) Vec<V>::get(a.dy + (r + u * step) * C + (size_t)g * V, dv[u]);
+        for (int u = 0; u < kU; ++u) {
+          Vec<V>::get_stream(a.x + (r + u * step) * C + (size_t)g * V, xv[u]);
+          if (KIND == SUMS_BNBWD) Vec<V>::get_stream(a.dy + (r + u * step) * C + (size_t)g * V, dv[u]);
         }
+        // compiler fence on the loaded values: keeps the arithmetic below behind ALL the loads above, so the
+        // loads are issued back to back instead of being paired with their consumers
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < kU; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            asm volatile("" : "+f"(xv[u][v]));
+            if (KIND == SUMS_BNBWD) asm volatile("" : "+f"(dv[u][v]));
+          }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
 #pragma unroll
           for (int v = 0; v < V; ++v) {
             if (KIND == SUMS_STATS) { float d = xv[u][v] - c0[v]; s0[v] += d; s1[v] = fmaf(d, d, s1[v]); }
