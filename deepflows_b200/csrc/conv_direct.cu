@@ -48,6 +48,7 @@ __device__ __forceinline__ size_t w_index(const Geom& g, int k, int t) {
 template <int RT>
 __global__ void __launch_bounds__(kThreads)
 direct_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, Geom g) {
+  pdl_sync();
   extern __shared__ float w_s[];
   const int R = RT ? RT : g.R;
   const int T = g.C * R * R, K = g.K;
@@ -108,6 +109,7 @@ constexpr int kMaxBlocksPerThread = 4;   // (K/4) * ceil(T/2) <= 16 * 40 = 640 r
 __global__ void __launch_bounds__(kThreads)
 direct_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial, Geom g,
                     size_t pix_per_cta) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int T = g.C * g.R * g.R, K = g.K;
   const int Tp = (T + 1) & ~1;                    // taps padded to an even count
@@ -228,9 +230,9 @@ dfb_status direct_conv_fprop(const float* x, int x_layout, const float* w, int w
   const size_t smem = (size_t)C * R * R * K * sizeof(float);
   *handled = true;
   const unsigned grid = bw_grid(items, kThreads, 8);
-  if (R == 3) direct_fprop_kernel<3><<<grid, kThreads, smem, compute_stream()>>>(x, w, y, g);
-  else if (R == 5) direct_fprop_kernel<5><<<grid, kThreads, smem, compute_stream()>>>(x, w, y, g);
-  else direct_fprop_kernel<0><<<grid, kThreads, smem, compute_stream()>>>(x, w, y, g);
+  if (R == 3) launch_k(direct_fprop_kernel<3>, grid, kThreads, smem, compute_stream(), x, w, y, g);
+  else if (R == 5) launch_k(direct_fprop_kernel<5>, grid, kThreads, smem, compute_stream(), x, w, y, g);
+  else launch_k(direct_fprop_kernel<0>, grid, kThreads, smem, compute_stream(), x, w, y, g);
   DFB_LAUNCH_CHECK("conv2d_fprop(direct)");
   return DFB_OK;
 }
@@ -254,7 +256,7 @@ dfb_status direct_conv_wgrad(const float* x, int x_layout, const float* dy, floa
   if (st != DFB_OK) return st;
   *handled = true;
   const size_t smem = (size_t)kPixTile * (K + Tp) * sizeof(float);
-  direct_wgrad_kernel<<<(unsigned)ctas, kThreads, smem, compute_stream()>>>(x, dy, partial, g, pix_per_cta);
+  launch_k(direct_wgrad_kernel, (unsigned)ctas, kThreads, smem, compute_stream(), x, dy, partial, g, pix_per_cta);
   DFB_LAUNCH_CHECK("conv2d_wgrad(direct)");
   st = dfb_colsum(partial, dw, ctas, K * T);  // fixed-order sum of the CTA partials
   dfb_free(partial);  // stream-ordered

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kThreads) binary_vec_kernel(const float4* __re
                                                               const float4* __restrict__ b,
                                                               float4* __restrict__ out, size_t n4,
                                                               Op op) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 x = ld_stream(a + i), y = ld_stream(b + i), r;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(kThreads) binary_tail_kernel(const float* __re
                                                                const float* __restrict__ b,
                                                                float* __restrict__ out, size_t begin,
                                                                size_t n, Op op) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = op(a[i], b[i]);
@@ -54,6 +56,7 @@ template <class Op>
 __global__ void __launch_bounds__(kThreads) scalar_vec_kernel(const float4* __restrict__ a, float v,
                                                               float4* __restrict__ out, size_t n4,
                                                               Op op) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 x = ld_stream(a + i), r;
@@ -65,6 +68,7 @@ template <class Op>
 __global__ void __launch_bounds__(kThreads) scalar_tail_kernel(const float* __restrict__ a, float v,
                                                                float* __restrict__ out, size_t begin,
                                                                size_t n, Op op) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = op(a[i], v);
@@ -73,6 +77,7 @@ template <class Op>
 __global__ void __launch_bounds__(kThreads) unary_vec_kernel(const float4* __restrict__ a,
                                                              float4* __restrict__ out, size_t n4,
                                                              Op op) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 x = ld_stream(a + i), r;
@@ -84,6 +89,7 @@ template <class Op>
 __global__ void __launch_bounds__(kThreads) unary_tail_kernel(const float* __restrict__ a,
                                                               float* __restrict__ out, size_t begin,
                                                               size_t n, Op op) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = op(a[i]);
@@ -99,12 +105,12 @@ dfb_status run_binary(const char* name, const float* a, const float* b, float* o
   cudaStream_t s = compute_stream();
   size_t n4 = (aligned16(a) && aligned16(b) && aligned16(out)) ? n / 4 : 0;
   if (n4) {
-    binary_vec_kernel<<<bw_grid(n4, kThreads), kThreads, 0, s>>>((const float4*)a, (const float4*)b,
+    launch_k(binary_vec_kernel<Op>, bw_grid(n4, kThreads), kThreads, 0, s, (const float4*)a, (const float4*)b,
                                                                  (float4*)out, n4, op);
     DFB_LAUNCH_CHECK(name);
   }
   if (n4 * 4 < n) {
-    binary_tail_kernel<<<bw_grid(n - n4 * 4, kThreads), kThreads, 0, s>>>(a, b, out, n4 * 4, n, op);
+    launch_k(binary_tail_kernel<Op>, bw_grid(n - n4 * 4, kThreads), kThreads, 0, s, a, b, out, n4 * 4, n, op);
     DFB_LAUNCH_CHECK(name);
   }
   return DFB_OK;
@@ -117,11 +123,11 @@ dfb_status run_scalar(const char* name, const float* a, float v, float* out, siz
   cudaStream_t s = compute_stream();
   size_t n4 = (aligned16(a) && aligned16(out)) ? n / 4 : 0;
   if (n4) {
-    scalar_vec_kernel<<<bw_grid(n4, kThreads), kThreads, 0, s>>>((const float4*)a, v, (float4*)out, n4, op);
+    launch_k(scalar_vec_kernel<Op>, bw_grid(n4, kThreads), kThreads, 0, s, (const float4*)a, v, (float4*)out, n4, op);
     DFB_LAUNCH_CHECK(name);
   }
   if (n4 * 4 < n) {
-    scalar_tail_kernel<<<bw_grid(n - n4 * 4, kThreads), kThreads, 0, s>>>(a, v, out, n4 * 4, n, op);
+    launch_k(scalar_tail_kernel<Op>, bw_grid(n - n4 * 4, kThreads), kThreads, 0, s, a, v, out, n4 * 4, n, op);
     DFB_LAUNCH_CHECK(name);
   }
   return DFB_OK;
@@ -134,11 +140,11 @@ dfb_status run_unary(const char* name, const float* a, float* out, size_t n, Op 
   cudaStream_t s = compute_stream();
   size_t n4 = (aligned16(a) && aligned16(out)) ? n / 4 : 0;
   if (n4) {
-    unary_vec_kernel<<<bw_grid(n4, kThreads), kThreads, 0, s>>>((const float4*)a, (float4*)out, n4, op);
+    launch_k(unary_vec_kernel<Op>, bw_grid(n4, kThreads), kThreads, 0, s, (const float4*)a, (float4*)out, n4, op);
     DFB_LAUNCH_CHECK(name);
   }
   if (n4 * 4 < n) {
-    unary_tail_kernel<<<bw_grid(n - n4 * 4, kThreads), kThreads, 0, s>>>(a, out, n4 * 4, n, op);
+    launch_k(unary_tail_kernel<Op>, bw_grid(n - n4 * 4, kThreads), kThreads, 0, s, a, out, n4 * 4, n, op);
     DFB_LAUNCH_CHECK(name);
   }
   return DFB_OK;
@@ -148,6 +154,7 @@ dfb_status run_unary(const char* name, const float* a, float* out, size_t n, Op 
 // fill
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) fill_kernel(float* __restrict__ out, float v, size_t n) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   // head (to 16-byte alignment) and tail scalars are handled by the first threads
@@ -218,6 +225,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads) strided_kernel(const float* __restrict__ a,
                                                            float* __restrict__ out, float value,
                                                            size_t n, StridedView v, int64_t offset) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < n; gid += stride) {
     int64_t idx = offset + view_index(gid, v);
@@ -244,6 +252,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
                                                         float* __restrict__ out, TransposeView v,
                                                         int64_t offset, uint32_t tiles_r,
                                                         uint32_t tiles_c) {
+  pdl_sync();
   __shared__ float tile[32][33];
   size_t n_tiles = (size_t)tiles_r * tiles_c;
   size_t n_outer = 1;
@@ -334,7 +343,7 @@ static bool try_transpose(const float* a, float* out, const StridedView& v, int6
   size_t total = (size_t)tiles_r * tiles_c;
   for (int d = 0; d < t.n_outer; ++d) total *= t.outer_shape[d];
   unsigned grid = (unsigned)std::min<size_t>(total, (size_t)sm_count() * 16);
-  transpose_kernel<MODE><<<grid, 256, 0, s>>>(a, out, t, offset, tiles_r, tiles_c);
+  launch_k(transpose_kernel<MODE>, grid, 256, 0, s, a, out, t, offset, tiles_r, tiles_c);
   return true;
 }
 
@@ -348,7 +357,7 @@ dfb_status dfb_fill(float* out, float value, size_t n) {
   DFB_INIT();
   DFB_REQUIRE(out != nullptr, DFB_ERR_INVALID, "Fill: out array cannot be null");
   if (n == 0) return DFB_OK;
-  fill_kernel<<<bw_grid(n / 4 + 1, kThreads), kThreads, 0, compute_stream()>>>(out, value, n);
+  launch_k(fill_kernel, bw_grid(n / 4 + 1, kThreads), kThreads, 0, compute_stream(), out, value, n);
   DFB_LAUNCH_CHECK("Fill");
   return DFB_OK;
 }
@@ -371,7 +380,7 @@ dfb_status dfb_compact(const float* a, float* out, size_t out_size, int ndim, co
     DFB_LAUNCH_CHECK("Compact(transpose)");
     return DFB_OK;
   }
-  strided_kernel<0><<<bw_grid(out_size, kThreads), kThreads, 0, s>>>(a, out, 0.f, out_size, v, (int64_t)offset);
+  launch_k(strided_kernel<0>, bw_grid(out_size, kThreads), kThreads, 0, s, a, out, 0.f, out_size, v, (int64_t)offset);
   DFB_LAUNCH_CHECK("Compact");
   return DFB_OK;
 }
@@ -396,7 +405,7 @@ dfb_status dfb_ewise_setitem(const float* a, size_t a_size, float* out, int ndim
     DFB_LAUNCH_CHECK("EwiseSetitem(transpose)");
     return DFB_OK;
   }
-  strided_kernel<1><<<bw_grid(a_size, kThreads), kThreads, 0, s>>>(a, out, 0.f, a_size, v, (int64_t)offset);
+  launch_k(strided_kernel<1>, bw_grid(a_size, kThreads), kThreads, 0, s, a, out, 0.f, a_size, v, (int64_t)offset);
   DFB_LAUNCH_CHECK("EwiseSetitem");
   return DFB_OK;
 }
@@ -410,7 +419,7 @@ dfb_status dfb_scalar_setitem(size_t size, float value, float* out, size_t out_s
   dfb_status st = check_view("ScalarSetitem", ndim, shape);
   if (st != DFB_OK) return st;
   StridedView v = collapse(ndim, shape, strides);
-  strided_kernel<2><<<bw_grid(size, kThreads), kThreads, 0, compute_stream()>>>(nullptr, out, value, size, v,
+  launch_k(strided_kernel<2>, bw_grid(size, kThreads), kThreads, 0, compute_stream(), nullptr, out, value, size, v,
                                                                                (int64_t)offset);
   DFB_LAUNCH_CHECK("ScalarSetitem");
   return DFB_OK;
@@ -461,6 +470,7 @@ template <class R>
 __global__ void __launch_bounds__(kThreads) reduce_thread_kernel(const float* __restrict__ a,
                                                                  float* __restrict__ out, size_t rows,
                                                                  uint32_t len) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
     const float* p = a + r * len;
@@ -474,6 +484,7 @@ template <class R>
 __global__ void __launch_bounds__(kThreads) reduce_warp_kernel(const float* __restrict__ a,
                                                                float* __restrict__ out, size_t rows,
                                                                size_t len) {
+  pdl_sync();
   int lane = threadIdx.x & 31;
   size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -490,6 +501,7 @@ template <class R>
 __global__ void __launch_bounds__(kThreads) reduce_block_kernel(const float* __restrict__ a,
                                                                 float* __restrict__ out, size_t rows,
                                                                 size_t len) {
+  pdl_sync();
   __shared__ float partial[kThreads / 32];
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (size_t r = blockIdx.x; r < rows; r += gridDim.x) {
@@ -518,6 +530,7 @@ __global__ void __launch_bounds__(kThreads) reduce_block_kernel(const float* __r
 template <class R>
 __global__ void __launch_bounds__(kThreads) reduce_split_kernel(const float* __restrict__ a,
                                                                 float* __restrict__ partials, size_t len) {
+  pdl_sync();
   __shared__ float partial[kThreads / 32];
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float acc = R::init();
@@ -541,21 +554,21 @@ dfb_status run_reduce(const char* name, const float* a, float* out, size_t out_s
   if (out_size == 0) return DFB_OK;
   cudaStream_t s = compute_stream();
   if (reduce_size <= 32) {
-    reduce_thread_kernel<R><<<bw_grid(out_size, kThreads), kThreads, 0, s>>>(a, out, out_size, (uint32_t)reduce_size);
+    launch_k(reduce_thread_kernel<R>, bw_grid(out_size, kThreads), kThreads, 0, s, a, out, out_size, (uint32_t)reduce_size);
   } else if (out_size == 1 && reduce_size >= (size_t)1 << 16) {
     unsigned blocks = bw_grid(reduce_size, kThreads, 4);
     float* partials = nullptr;
     dfb_status st = dfb_malloc(blocks, &partials);
     if (st != DFB_OK) return st;
-    reduce_split_kernel<R><<<blocks, kThreads, 0, s>>>(a, partials, reduce_size);
+    launch_k(reduce_split_kernel<R>, blocks, kThreads, 0, s, a, partials, reduce_size);
     DFB_LAUNCH_CHECK(name);
-    reduce_block_kernel<R><<<1, kThreads, 0, s>>>(partials, out, 1, blocks);
+    launch_k(reduce_block_kernel<R>, 1, kThreads, 0, s, partials, out, 1, blocks);
     dfb_free(partials);
   } else if (reduce_size < 1024) {
-    reduce_warp_kernel<R><<<bw_grid(out_size * 32, kThreads), kThreads, 0, s>>>(a, out, out_size, reduce_size);
+    launch_k(reduce_warp_kernel<R>, bw_grid(out_size * 32, kThreads), kThreads, 0, s, a, out, out_size, reduce_size);
   } else {
     unsigned grid = (unsigned)std::min<size_t>(out_size, (size_t)sm_count() * 8);
-    reduce_block_kernel<R><<<grid, kThreads, 0, s>>>(a, out, out_size, reduce_size);
+    launch_k(reduce_block_kernel<R>, grid, kThreads, 0, s, a, out, out_size, reduce_size);
   }
   DFB_LAUNCH_CHECK(name);
   return DFB_OK;

@@ -224,6 +224,7 @@ struct Epilogue {
 template <class AL, class BL>
 __global__ void __launch_bounds__(kGemmThreads)
 simt_gemm_kernel(AL A, BL B, Epilogue ep, int M, int N, int K, int k_per_split) {
+  pdl_sync();
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -344,6 +345,7 @@ simt_gemm_kernel(AL A, BL B, Epilogue ep, int M, int N, int K, int k_per_split) 
 // deterministic split-K reduction (fixed summation order over the slabs)
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, Epilogue ep) {
+  pdl_sync();
   size_t total = (size_t)M * N;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -387,11 +389,11 @@ dfb_status launch_simt(const char* name, AL A, BL B, float* C, int ldc, int accu
     if (st != DFB_OK) return st;
     ep.partial = partial;
   }
-  simt_gemm_kernel<AL, BL><<<dim3(gx, gy, splits), kGemmThreads, 0, s>>>(A, B, ep, M, N, K, k_per_split);
+  launch_k(simt_gemm_kernel<AL, BL>, dim3(gx, gy, splits), kGemmThreads, 0, s, A, B, ep, M, N, K, k_per_split);
   DFB_LAUNCH_CHECK(name);
   if (splits > 1) {
     ep.partial = nullptr;
-    splitk_reduce_kernel<<<bw_grid((size_t)M * N, 256), 256, 0, s>>>(partial, splits, M, N, ep);
+    launch_k(splitk_reduce_kernel, bw_grid((size_t)M * N, 256), 256, 0, s, partial, splits, M, N, ep);
     DFB_LAUNCH_CHECK(name);
     dfb_free(partial);
   }
@@ -405,6 +407,7 @@ dfb_status launch_simt(const char* name, AL A, BL B, float* C, int ldc, int accu
 __global__ void __launch_bounds__(256)
 dgrad_lastwriter_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                         float* __restrict__ dx, ConvGeom g) {
+  pdl_sync();
   size_t total = (size_t)g.N * g.H * g.W * g.C;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   const int RR = g.R * g.R;
@@ -484,7 +487,7 @@ dfb_status simt_conv_dgrad(const float* dy, const float* w, int w_layout, float*
   if (st != DFB_OK) return st;
   if (dgrad_mode == DFB_DGRAD_REFERENCE) {
     size_t total = (size_t)N * H * W * C;
-    dgrad_lastwriter_kernel<<<bw_grid(total, 256), 256, 0, compute_stream()>>>(dy, w, dx, g);
+    launch_k(dgrad_lastwriter_kernel, bw_grid(total, 256), 256, 0, compute_stream(), dy, w, dx, g);
     DFB_LAUNCH_CHECK("conv2d_dgrad(reference)");
     return DFB_OK;
   }

@@ -246,6 +246,9 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, descriptor prefetch, TMEM allocation) overlapped the previous kernel's tail;
+  // global memory is touched only from here on
+  pdl_sync();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -405,20 +408,22 @@ static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensor
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = L::kTotal;
     cfg.stream = compute_stream();
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = (unsigned)splits;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel<P>, ma, mb, prm);
     if (e != cudaSuccess) {
       cudaGetLastError();
       DFB_FAIL(DFB_ERR_RUNTIME, "%s cluster launch (splits %d) failed: %s", name, splits, cudaGetErrorString(e));
     }
   } else {
-    tc_kernel<P><<<grid, kThreads, L::kTotal, compute_stream()>>>(ma, mb, prm);
+    launch_k(tc_kernel<P>, grid, kThreads, L::kTotal, compute_stream(), ma, mb, prm);
   }
   DFB_LAUNCH_CHECK(name);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
@@ -792,6 +797,7 @@ struct WgradProblem {
 template <bool DGRAD>
 __global__ void __launch_bounds__(256) weight_transform_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C,
                                                               int taps, int inner_pad) {
+  pdl_sync();
   const int rows = DGRAD ? C : K;
   size_t total = (size_t)rows * taps * inner_pad;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -807,6 +813,7 @@ __global__ void __launch_bounds__(256) weight_transform_kernel(const float* __re
 // dW[k][c][tap] (KCRS) or dW[k][tap][c] (KRSC) = sum_z partial[z][k][tap][c]
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
                                                           int K, int C, int Cp, int taps, int krsc) {
+  pdl_sync();
   size_t total = (size_t)K * C * taps;
   size_t slab = (size_t)K * taps * Cp;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -911,8 +918,8 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
   size_t wt_n = (size_t)n_out * taps * cp;
   dfb_status st = dfb_malloc(wt_n, &wt);
   if (st != DFB_OK) return st;
-  if (dgrad) weight_transform_kernel<true><<<bw_grid(wt_n, 256), 256, 0, compute_stream()>>>(w, wt, K, C, taps, cp);
-  else weight_transform_kernel<false><<<bw_grid(wt_n, 256), 256, 0, compute_stream()>>>(w, wt, K, C, taps, cp);
+  if (dgrad) launch_k(weight_transform_kernel<true>, bw_grid(wt_n, 256), 256, 0, compute_stream(), w, wt, K, C, taps, cp);
+  else launch_k(weight_transform_kernel<false>, bw_grid(wt_n, 256), 256, 0, compute_stream(), w, wt, K, C, taps, cp);
   DFB_LAUNCH_CHECK("weight_transform");
   st = run_conv_bn<W_PACKED>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
   dfb_free(wt);
@@ -1025,7 +1032,7 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   else if (bn == 64) st = run_wgrad<64>(ma, mb, prm, splits);
   else st = run_wgrad<32>(ma, mb, prm, splits);
   if (st == DFB_OK && !prm.tickets) {
-    wgrad_reduce_kernel<<<bw_grid((size_t)K * C * taps, 256), 256, 0, compute_stream()>>>(partial, dw, splits, K, C, prm.Cp, taps,
+    launch_k(wgrad_reduce_kernel, bw_grid((size_t)K * C * taps, 256), 256, 0, compute_stream(), partial, dw, splits, K, C, prm.Cp, taps,
                                                                                           w_layout == DFB_WLAYOUT_KRSC ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     g_launches.fetch_add(1, std::memory_order_relaxed);

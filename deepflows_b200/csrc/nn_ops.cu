@@ -152,6 +152,7 @@ __device__ __forceinline__ void lane_tree_sum(float* sm, float (&s0)[V], float (
 template <int V, int KIND>
 __global__ void __launch_bounds__(kT, 2)
 col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
+  pdl_sync();
   extern __shared__ float sm[];  // [lanes][2][C] when lanes > 1
   const int G = p.G;
   const size_t r0 = (size_t)blockIdx.x * p.rows_per_cta;
@@ -288,8 +289,8 @@ static dfb_status launch_col_sums(const char* name, SumsArgs a, size_t rows, int
   if (st != DFB_OK) return st;
   a.part = part;
   cudaStream_t s = compute_stream();
-  if (p.V == 4) col_sums_kernel<4, KIND><<<p.ctas, kT, smem, s>>>(a, rows, C, p);
-  else col_sums_kernel<1, KIND><<<p.ctas, kT, smem, s>>>(a, rows, C, p);
+  if (p.V == 4) launch_k(col_sums_kernel<4, KIND>, p.ctas, kT, smem, s, a, rows, C, p);
+  else launch_k(col_sums_kernel<1, KIND>, p.ctas, kT, smem, s, a, rows, C, p);
   dfb_free(part);  // stream-ordered: the next user of the block runs after this kernel
   DFB_LAUNCH_CHECK(name);
   return DFB_OK;
@@ -343,6 +344,7 @@ bn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
                     float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_invstd,
                     float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps, int rows,
                     int C) {
+  pdl_sync();
   __shared__ float sm[(kSmallT / 32) * GPB * 8];
   __shared__ float s_scale[GPB * 4], s_shift[GPB * 4];
   const int g = threadIdx.x % GPB, lane = threadIdx.x / GPB;
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(kSmallT)
 bn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dx,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
+  pdl_sync();
   __shared__ float sm[(kSmallT / 32) * GPB * 8];
   __shared__ float s_mb[GPB * 4], s_mg[GPB * 4];
   const int g = threadIdx.x % GPB, lane = threadIdx.x / GPB;
@@ -481,6 +484,7 @@ __global__ void __launch_bounds__(kT)
 bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows, int C,
                 const float* __restrict__ mean, const float* __restrict__ invstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta) {
+  pdl_sync();
   extern __shared__ float sm[];  // mean[C], scale[C], shift[C]
   float* s_mean = sm;
   float* s_scale = sm + C;
@@ -515,6 +519,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
                     size_t rows, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const float* __restrict__ dbeta,
                     const float* __restrict__ dgamma) {
+  pdl_sync();
   extern __shared__ float sm[];  // mean, invstd, k1 = gamma*invstd, mb = dbeta/n, mg = dgamma/n
   float* s_mean = sm;
   float* s_is = sm + C;
@@ -555,6 +560,7 @@ template <int V>
 __global__ void __launch_bounds__(kT)
 add_rowvec_kernel(const float* __restrict__ x, const float* __restrict__ vec, float* __restrict__ y,
                   size_t rows, int C) {
+  pdl_sync();
   const int G = C / V;
   size_t total = rows * G;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -571,6 +577,7 @@ add_rowvec_kernel(const float* __restrict__ x, const float* __restrict__ vec, fl
 
 __global__ void __launch_bounds__(kT)
 relu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, size_t n) {
+  pdl_sync();
   size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t n4 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
                 reinterpret_cast<uintptr_t>(dx)) & 15) == 0 ? n / 4 : 0;
@@ -594,6 +601,7 @@ template <int V>
 __global__ void __launch_bounds__(kT)
 maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int32_t* __restrict__ idx, int N,
                    int H, int W, int C, int k, int OH, int OW) {
+  pdl_sync();
   const int G = C / V;
   size_t total = (size_t)N * OH * OW * G;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -630,6 +638,7 @@ __global__ void __launch_bounds__(kT)
 maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const int32_t* __restrict__ idx,
                    const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int k,
                    int OH, int OW) {
+  pdl_sync();
   const int G = C / V;
   size_t total = (size_t)N * H * W * G;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -668,6 +677,7 @@ template <int V>
 __global__ void __launch_bounds__(kT)
 avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int k,
                    int OH, int OW) {
+  pdl_sync();
   const int G = C / V;
   size_t total = (size_t)N * OH * OW * G;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -698,6 +708,7 @@ template <int V>
 __global__ void __launch_bounds__(kT)
 avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int k,
                    int OH, int OW) {
+  pdl_sync();
   const int G = C / V;
   size_t total = (size_t)N * H * W * G;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -730,6 +741,7 @@ constexpr int kCeThreads = 1024;
 __global__ void __launch_bounds__(kCeThreads)
 softmax_ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                       float* __restrict__ loss, size_t rows, int cols, float scale) {
+  pdl_sync();
   __shared__ float warp_part[kCeThreads / 32];
   float acc = 0.f;
   for (size_t r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -757,6 +769,7 @@ __global__ void __launch_bounds__(kT)
 softmax_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                       const float* __restrict__ upstream, float* __restrict__ dlogits, size_t rows,
                       int cols, float scale) {
+  pdl_sync();
   float k = scale * (upstream ? upstream[0] : 1.0f);
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
@@ -787,9 +800,9 @@ dfb_status dfb_add_rowvec(const float* x, const float* v, float* y, size_t rows,
   if (rows == 0) return DFB_OK;
   bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   if (cols % 4 == 0 && al)
-    add_rowvec_kernel<4><<<ew_grid(rows * (cols / 4)), kT, 0, compute_stream()>>>(x, v, y, rows, cols);
+    launch_k(add_rowvec_kernel<4>, ew_grid(rows * (cols / 4)), kT, 0, compute_stream(), x, v, y, rows, cols);
   else
-    add_rowvec_kernel<1><<<ew_grid(rows * cols), kT, 0, compute_stream()>>>(x, v, y, rows, cols);
+    launch_k(add_rowvec_kernel<1>, ew_grid(rows * cols), kT, 0, compute_stream(), x, v, y, rows, cols);
   DFB_LAUNCH_CHECK("add_rowvec");
   return DFB_OK;
 }
@@ -826,12 +839,12 @@ static dfb_status bn_apply(const float* x, float* y, size_t rows, int C, const f
   cudaStream_t s = compute_stream();
   if (C % 4 == 0 && al) {
     unsigned grid = ew_grid(rows * (C / 4));
-    if (relu) bn_apply_kernel<4, true><<<grid, kT, smem, s>>>(x, y, rows, C, mean, invstd, gamma, beta);
-    else bn_apply_kernel<4, false><<<grid, kT, smem, s>>>(x, y, rows, C, mean, invstd, gamma, beta);
+    if (relu) launch_k(bn_apply_kernel<4, true>, grid, kT, smem, s, x, y, rows, C, mean, invstd, gamma, beta);
+    else launch_k(bn_apply_kernel<4, false>, grid, kT, smem, s, x, y, rows, C, mean, invstd, gamma, beta);
   } else {
     unsigned grid = ew_grid(rows * C);
-    if (relu) bn_apply_kernel<1, true><<<grid, kT, smem, s>>>(x, y, rows, C, mean, invstd, gamma, beta);
-    else bn_apply_kernel<1, false><<<grid, kT, smem, s>>>(x, y, rows, C, mean, invstd, gamma, beta);
+    if (relu) launch_k(bn_apply_kernel<1, true>, grid, kT, smem, s, x, y, rows, C, mean, invstd, gamma, beta);
+    else launch_k(bn_apply_kernel<1, false>, grid, kT, smem, s, x, y, rows, C, mean, invstd, gamma, beta);
   }
   DFB_LAUNCH_CHECK("bn_apply");
   return DFB_OK;
@@ -846,7 +859,7 @@ dfb_status dfb_bn_fwd_train(const float* x, const float* gamma, const float* bet
   if (const int gpb = bn_small_gpb(rows, C, x, y)) {
     const unsigned grid = (unsigned)(C / 4 / gpb);
     cudaStream_t s = compute_stream();
-#define DFB_BN_SMALL_FWD(G) bn_small_fwd_kernel<G><<<grid, kSmallT, 0, s>>>(x, gamma, beta, y, save_mean, save_invstd, running_mean, \
+#define DFB_BN_SMALL_FWD(G) launch_k(bn_small_fwd_kernel<G>, grid, kSmallT, 0, s, x, gamma, beta, y, save_mean, save_invstd, running_mean, \
                                                                           running_var, momentum, eps, (int)rows, C)
     if (gpb == 1) DFB_BN_SMALL_FWD(1);
     else if (gpb == 2) DFB_BN_SMALL_FWD(2);
@@ -862,6 +875,7 @@ dfb_status dfb_bn_fwd_train(const float* x, const float* gamma, const float* bet
 
 // eval: x_hat = (x - running_mean) / (running_var + eps)**0.5 (batchnorm.py:49-50)
 __global__ void bn_eval_prep_kernel(const float* __restrict__ rv, float eps, int C, float* __restrict__ invstd) {
+  pdl_sync();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) invstd[c] = 1.0f / sqrtf(rv[c] + eps);
 }
@@ -873,7 +887,7 @@ dfb_status dfb_bn_fwd_eval(const float* x, const float* gamma, const float* beta
   float* invstd = nullptr;
   dfb_status st = dfb_malloc(C, &invstd);
   if (st != DFB_OK) return st;
-  bn_eval_prep_kernel<<<cdiv(C, kT), kT, 0, compute_stream()>>>(running_var, eps, C, invstd);
+  launch_k(bn_eval_prep_kernel, cdiv(C, kT), kT, 0, compute_stream(), running_var, eps, C, invstd);
   DFB_LAUNCH_CHECK("bn_eval_prep");
   st = bn_apply(x, y, rows, C, running_mean, invstd, gamma, beta, false);
   dfb_free(invstd);
@@ -888,7 +902,7 @@ dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma, const
   if (const int gpb = bn_small_gpb(rows, C, x, dy, dx)) {
     const unsigned grid = (unsigned)(C / 4 / gpb);
     cudaStream_t s = compute_stream();
-#define DFB_BN_SMALL_BWD(G) bn_small_bwd_kernel<G><<<grid, kSmallT, 0, s>>>(x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, \
+#define DFB_BN_SMALL_BWD(G) launch_k(bn_small_bwd_kernel<G>, grid, kSmallT, 0, s, x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, \
                                                                           (int)rows, C)
     if (gpb == 1) DFB_BN_SMALL_BWD(1);
     else if (gpb == 2) DFB_BN_SMALL_BWD(2);
@@ -919,9 +933,9 @@ dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma, const
     bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
     size_t sm2 = (size_t)5 * C * sizeof(float);
     if (C % 4 == 0 && al)
-      bn_bwd_apply_kernel<4><<<ew_grid(rows * (C / 4)), kT, sm2, s>>>(x, dy, dx, rows, C, save_mean, save_invstd, gamma, db, dg);
+      launch_k(bn_bwd_apply_kernel<4>, ew_grid(rows * (C / 4)), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, db, dg);
     else
-      bn_bwd_apply_kernel<1><<<ew_grid(rows * C), kT, sm2, s>>>(x, dy, dx, rows, C, save_mean, save_invstd, gamma, db, dg);
+      launch_k(bn_bwd_apply_kernel<1>, ew_grid(rows * C), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, db, dg);
     DFB_LAUNCH_CHECK("bn_bwd_apply");
   }
   dfb_free(scratch);
@@ -934,7 +948,7 @@ dfb_status dfb_relu_bwd(const float* x, const float* dy, float* dx, size_t n) {
   DFB_INIT();
   DFB_REQUIRE(x && dy && dx, DFB_ERR_INVALID, "relu_bwd: null pointer");
   if (n == 0) return DFB_OK;
-  relu_bwd_kernel<<<ew_grid(n / 4 + 1), kT, 0, compute_stream()>>>(x, dy, dx, n);
+  launch_k(relu_bwd_kernel, ew_grid(n / 4 + 1), kT, 0, compute_stream(), x, dy, dx, n);
   DFB_LAUNCH_CHECK("relu_bwd");
   return DFB_OK;
 }
@@ -948,8 +962,8 @@ static dfb_status pool_geom(const char* name, int N, int H, int W, int C, int k,
 }
 #define POOL_DISPATCH(KERNEL, items_scalar, ...)                                               \
   do {                                                                                         \
-    if (vec) KERNEL<4><<<ew_grid((items_scalar) / 4), kT, 0, compute_stream()>>>(__VA_ARGS__); \
-    else KERNEL<1><<<ew_grid(items_scalar), kT, 0, compute_stream()>>>(__VA_ARGS__);           \
+    if (vec) launch_k(KERNEL<4>, ew_grid((items_scalar) / 4), kT, 0, compute_stream(), __VA_ARGS__); \
+    else launch_k(KERNEL<1>, ew_grid(items_scalar), kT, 0, compute_stream(), __VA_ARGS__);           \
   } while (0)
 
 static bool all_aligned(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr) {
@@ -977,8 +991,8 @@ dfb_status dfb_maxpool2d_bwd(const float* x, const float* y, const float* dy, fl
   if (st != DFB_OK) return st;
   bool vec = C % 4 == 0 && all_aligned(x, y, dy, dx);
   size_t items = (size_t)N * H * W * C;
-  if (vec) maxpool_bwd_kernel<4, 0><<<ew_grid(items / 4), kT, 0, compute_stream()>>>(x, y, nullptr, dy, dx, N, H, W, C, k, OH, OW);
-  else maxpool_bwd_kernel<1, 0><<<ew_grid(items), kT, 0, compute_stream()>>>(x, y, nullptr, dy, dx, N, H, W, C, k, OH, OW);
+  if (vec) launch_k(maxpool_bwd_kernel<4, 0>, ew_grid(items / 4), kT, 0, compute_stream(), x, y, nullptr, dy, dx, N, H, W, C, k, OH, OW);
+  else launch_k(maxpool_bwd_kernel<1, 0>, ew_grid(items), kT, 0, compute_stream(), x, y, nullptr, dy, dx, N, H, W, C, k, OH, OW);
   DFB_LAUNCH_CHECK("maxpool2d_bwd");
   return DFB_OK;
 }
@@ -990,8 +1004,8 @@ dfb_status dfb_maxpool2d_bwd_idx(const int32_t* idx, const float* dy, float* dx,
   if (st != DFB_OK) return st;
   bool vec = C % 4 == 0 && all_aligned(idx, dy, dx);
   size_t items = (size_t)N * H * W * C;
-  if (vec) maxpool_bwd_kernel<4, 1><<<ew_grid(items / 4), kT, 0, compute_stream()>>>(nullptr, nullptr, idx, dy, dx, N, H, W, C, k, OH, OW);
-  else maxpool_bwd_kernel<1, 1><<<ew_grid(items), kT, 0, compute_stream()>>>(nullptr, nullptr, idx, dy, dx, N, H, W, C, k, OH, OW);
+  if (vec) launch_k(maxpool_bwd_kernel<4, 1>, ew_grid(items / 4), kT, 0, compute_stream(), nullptr, nullptr, idx, dy, dx, N, H, W, C, k, OH, OW);
+  else launch_k(maxpool_bwd_kernel<1, 1>, ew_grid(items), kT, 0, compute_stream(), nullptr, nullptr, idx, dy, dx, N, H, W, C, k, OH, OW);
   DFB_LAUNCH_CHECK("maxpool2d_bwd_idx");
   return DFB_OK;
 }
@@ -1023,7 +1037,7 @@ dfb_status dfb_softmax_ce_fwd(const float* logits, const float* target, float* l
   DFB_INIT();
   DFB_REQUIRE(logits && target && loss, DFB_ERR_INVALID, "softmax_ce_fwd: null pointer");
   DFB_REQUIRE(cols > 0, DFB_ERR_INVALID, "softmax_ce_fwd: cols must be positive");
-  softmax_ce_fwd_kernel<<<1, kCeThreads, 0, compute_stream()>>>(logits, target, loss, rows, cols, scale);
+  launch_k(softmax_ce_fwd_kernel, 1, kCeThreads, 0, compute_stream(), logits, target, loss, rows, cols, scale);
   DFB_LAUNCH_CHECK("softmax_ce_fwd");
   return DFB_OK;
 }
@@ -1032,7 +1046,7 @@ dfb_status dfb_softmax_ce_bwd(const float* logits, const float* target, const fl
   DFB_INIT();
   DFB_REQUIRE(logits && target && dlogits, DFB_ERR_INVALID, "softmax_ce_bwd: null pointer");
   if (rows == 0) return DFB_OK;
-  softmax_ce_bwd_kernel<<<bw_grid(rows, kT), kT, 0, compute_stream()>>>(logits, target, upstream, dlogits, rows, cols, scale);
+  launch_k(softmax_ce_bwd_kernel, bw_grid(rows, kT), kT, 0, compute_stream(), logits, target, upstream, dlogits, rows, cols, scale);
   DFB_LAUNCH_CHECK("softmax_ce_bwd");
   return DFB_OK;
 }

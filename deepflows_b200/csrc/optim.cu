@@ -56,6 +56,7 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 multi_adam_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks,
                   const AdamHyper* __restrict__ hp) {
+  pdl_sync();
   const AdamHyper h = *hp;
   for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int ti = find_tensor(tensors, count, chunk);
@@ -99,6 +100,7 @@ __device__ __forceinline__ void sgd_one(float& p, float g, float* vel, const Sgd
 __global__ void __launch_bounds__(256)
 multi_sgd_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks,
                  const SgdHyper* __restrict__ hp) {
+  pdl_sync();
   const SgdHyper h = *hp;
   for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int ti = find_tensor(tensors, count, chunk);
@@ -248,7 +250,7 @@ dfb_status dfb_multi_adam_step(float* const* params, const float* const* grads, 
   st = upload_table(tab, &h, sizeof(h), 0, &dev, &dev_h);
   if (st != DFB_OK) return st;
   unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
-  multi_adam_kernel<<<grid, 256, 0, compute_stream()>>>(dev, (int)tab.size(), chunks, (const AdamHyper*)dev_h);
+  launch_k(multi_adam_kernel, grid, 256, 0, compute_stream(), dev, (int)tab.size(), chunks, (const AdamHyper*)dev_h);
   DFB_LAUNCH_CHECK("multi_adam_step");
   return DFB_OK;
 }
@@ -269,7 +271,7 @@ dfb_status dfb_multi_sgd_step(float* const* params, const float* const* grads, f
   st = upload_table(tab, &h, sizeof(h), 1, &dev, &dev_h);
   if (st != DFB_OK) return st;
   unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
-  multi_sgd_kernel<<<grid, 256, 0, compute_stream()>>>(dev, (int)tab.size(), chunks, (const SgdHyper*)dev_h);
+  launch_k(multi_sgd_kernel, grid, 256, 0, compute_stream(), dev, (int)tab.size(), chunks, (const SgdHyper*)dev_h);
   DFB_LAUNCH_CHECK("multi_sgd_step");
   return DFB_OK;
 }

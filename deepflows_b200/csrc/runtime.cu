@@ -118,6 +118,14 @@ dfb_status ensure_init() {
 cudaStream_t compute_stream() { return rt().on_side ? rt().side : rt().compute; }
 cudaStream_t comm_stream() { return rt().comm; }
 int sm_count() { return rt().sms; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 // work on the side stream may overlap main-stream kernels of the same family: it gets its own counters (32..63)
 unsigned* ticket_counter(int slot) { return rt().tickets + slot + ((rt().on_side && slot < 32) ? 32 : 0); }
 
