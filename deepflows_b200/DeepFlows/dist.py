@@ -104,16 +104,32 @@ def _recv_exact(conn, n):
 
 
 class DataParallel:
-    """Bucketed gradient all-reduce for a fixed parameter list."""
+    """Bucketed gradient all-reduce for a fixed parameter list, overlapped with backward.
 
-    def __init__(self, params, transport, bucket_mb=25.0):
+    Parameters are assigned to flat buckets in reverse registration order (the last layers finish backward
+    first). During `backward()` every gradient contribution to a leaf is counted; when all parameters of a
+    bucket have received all their contributions (one per use in the forward pass), the bucket is packed - one
+    multi-tensor copy launch - and its all-reduce is enqueued on the communication stream, while backward goes
+    on producing the gradients of earlier layers on the compute stream. Whatever is still open when backward
+    ends (parameters without gradient) is flushed then. Inside a captured CUDA graph the same calls become
+    parallel branches of the step graph."""
+
+    def __init__(self, params, transport, bucket_mb=4.0):
         self.params = [p for p in params]
         self.transport = transport
         self.world = transport.world
         self.rank = transport.rank
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
         self._pending = False
-        self._plan = None  # [(flat BackendTensor, [(param index, offset, size)])]
+        self._plan = None       # [(flat BackendTensor, [(param index, offset, size)])]
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._bucket_of = None  # param index -> bucket index
+        self._reset_step()
+
+    def _reset_step(self):
+        self._arrived = {}      # param index -> contributions seen in this backward
+        self._open = None       # bucket index -> parameters still missing
+        self._launched = set()
 
     # buckets are filled in reverse registration order: the last layers finish backward first
     def _build_plan(self):
@@ -129,6 +145,10 @@ class DataParallel:
         if cur:
             plan.append((cur, cur_n))
         self._plan = [(BackendTensor.make((n,), device=dev), slots) for slots, n in plan]
+        self._bucket_of = {}
+        for b, (_, slots) in enumerate(self._plan):
+            for i, _, _ in slots:
+                self._bucket_of[i] = b
 
     def broadcast_parameters(self, root=0):
         """Make every replica start from rank `root`'s weights."""
@@ -138,29 +158,72 @@ class DataParallel:
             self.transport.broadcast(p.data.flat_storage(), root)  # memory order; every rank has the same layout
         self.transport.wait()
 
+    # ---- during backward ----------------------------------------------------------------------------------
+    def grad_arrived(self, param):
+        """Tensor._grad_ready_hook: one more gradient contribution reached leaf `param`."""
+        if self.world == 1:
+            return
+        i = self._index.get(id(param))
+        if i is None:
+            return
+        if self._plan is None:
+            self._build_plan()
+        if self._open is None:
+            self._open = {b: len(slots) for b, (_, slots) in enumerate(self._plan)}
+        seen = self._arrived.get(i, 0) + 1
+        self._arrived[i] = seen
+        if seen == max(1, len(param.children)):  # one contribution per use in the forward pass
+            b = self._bucket_of[i]
+            self._open[b] -= 1
+            if self._open[b] == 0:
+                self._launch_bucket(b)
+
+    def _launch_bucket(self, b):
+        flat, slots = self._plan[b]
+        dev = flat.device
+        srcs, dsts, sizes = [], [], []
+        for i, off, n in slots:
+            p = self.params[i]
+            g = p.grad
+            if not p.data.is_dense():
+                p.data = p.data.compact()
+            if g is None:
+                flat[off:off + n] = 0.0
+                continue
+            g = g.with_layout_of(p.data)  # packed in the parameter's memory order (channels-last conv weights stay so)
+            if dev.has("multi_copy"):
+                srcs.append((g._handle, g._offset))
+                dsts.append((flat._handle, flat._offset + off))
+                sizes.append(n)
+            else:
+                flat[off:off + n] = g.flat_storage()
+        if sizes:
+            dev.multi_copy(srcs, dsts, sizes)
+        self.transport.allreduce_sum(flat)
+        # gradients now alias the bucket: the optimizer reads the reduced values in place
+        for i, off, n in slots:
+            p = self.params[i]
+            if p.grad is not None:
+                p.grad = BackendTensor.make(p.data.shape, p.data.strides, p.device, flat._handle, off)
+        self._launched.add(b)
+        self._pending = True
+
+    # ---- after backward -----------------------------------------------------------------------------------
     def reduce_gradients(self):
-        """Pack gradients into the buckets and launch one all-reduce per bucket (asynchronous)."""
+        """Tensor._post_backward_hook: flush the buckets that did not complete during backward."""
         if self.world == 1:
             return
         if self._plan is None:
             self._build_plan()
-        for flat, slots in self._plan:
-            for i, off, n in slots:
-                p = self.params[i]
-                g = p.grad
-                if not p.data.is_dense():
-                    p.data = p.data.compact()
-                if g is None:
-                    flat[off:off + n] = 0.0
-                else:  # packed in the parameter's memory order (channels-last conv weights stay as they are)
-                    flat[off:off + n] = g.with_layout_of(p.data).flat_storage()
-            self.transport.allreduce_sum(flat)
-            # gradients now alias the bucket: the optimizer reads the reduced values in place
-            for i, off, n in slots:
-                p = self.params[i]
-                if p.grad is not None:
-                    p.grad = BackendTensor.make(p.data.shape, p.data.strides, p.device, flat._handle, off)
-        self._pending = True
+        for b, (flat, slots) in enumerate(self._plan):
+            if b in self._launched:
+                for i, off, n in slots:  # a late contribution would have replaced the bucket view
+                    g = self.params[i].grad
+                    if g is not None and (g._handle is not flat._handle or g._offset != off):
+                        raise RuntimeError("data parallel: parameter %d received a gradient after its bucket was reduced" % i)
+            else:
+                self._launch_bucket(b)
+        self._reset_step()
 
     def pre_step(self):
         """Called by Optimizer.step(): order the compute stream after the reductions and return the
@@ -171,7 +234,7 @@ class DataParallel:
         return 1.0 / self.world
 
 
-def init(params, transport=None, bucket_mb=25.0, broadcast=True):
+def init(params, transport=None, bucket_mb=4.0, broadcast=True):
     """Enable data parallelism for `params` (usually `model.parameters()`)."""
     global _ctx
     params = list(params)
@@ -183,6 +246,7 @@ def init(params, transport=None, bucket_mb=25.0, broadcast=True):
                                   os.environ.get("MASTER_PORT", "29500"))
     _ctx = DataParallel(params, transport, bucket_mb)
     Tensor._post_backward_hook = _ctx.reduce_gradients
+    Tensor._grad_ready_hook = _ctx.grad_arrived
     if broadcast and _ctx.world > 1:
         _ctx.broadcast_parameters(0)
     return _ctx
@@ -192,6 +256,7 @@ def shutdown():
     global _ctx
     if _ctx is not None:
         Tensor._post_backward_hook = None
+        Tensor._grad_ready_hook = None
         try:
             _ctx.transport.close()
         finally:

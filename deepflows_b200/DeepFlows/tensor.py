@@ -295,6 +295,9 @@ class Tensor:
         if g.shape != self.data.shape:
             g = _reduce_broadcast_grad(g, self.data.shape)
         self.grad = g if self.grad is None else self.grad + g
+        hook = Tensor._grad_ready_hook
+        if hook is not None and not self.parents:
+            hook(self)
 
     def backward(self, retain_graph: bool = False):
         nodes = Graph.node_list
@@ -336,6 +339,7 @@ class Tensor:
             Graph.free_graph()
 
     _post_backward_hook = None  # set by DeepFlows.dist to launch bucketed all-reduces
+    _grad_ready_hook = None     # set by DeepFlows.dist: called for a leaf every time a gradient contribution arrives
 
     def zero_grad(self):
         self.grad = None

@@ -117,6 +117,26 @@ multi_sgd_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long
   }
 }
 
+// Many flat device-to-device copies in one launch (gradient buckets of the data-parallel layer: one launch per
+// bucket instead of one strided-copy kernel per parameter). TensorRef::p = destination, ::g = source.
+__global__ void __launch_bounds__(256)
+multi_copy_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks) {
+  pdl_sync();
+  for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int ti = find_tensor(tensors, count, chunk);
+    TensorRef t = tensors[ti];
+    unsigned long long begin = (chunk - t.first_chunk) * kChunk;
+    unsigned long long end = begin + kChunk < t.size ? begin + kChunk : t.size;
+    bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g)) & 15) == 0;
+    if (vec) {
+      for (unsigned long long i = begin + threadIdx.x * 4ull; i + 4 <= end; i += blockDim.x * 4ull)
+        *reinterpret_cast<float4*>(t.p + i) = *reinterpret_cast<const float4*>(t.g + i);
+    }
+    unsigned long long sbeg = vec ? begin + ((end - begin) & ~3ull) : begin;
+    for (unsigned long long q = sbeg + threadIdx.x; q < end; q += blockDim.x) t.p[q] = t.g[q];
+  }
+}
+
 // Staging of one optimizer step: [hyper-parameters, 256 bytes][pointer table]. The kernel reads both from
 // device memory. Eager steps go through a small pinned ring so consecutive steps do not wait on each other;
 // a step issued during CUDA-graph capture gets staging that the graph owns, and the captured memcpy node
@@ -273,6 +293,24 @@ dfb_status dfb_multi_sgd_step(float* const* params, const float* const* grads, f
   unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
   launch_k(multi_sgd_kernel, grid, 256, 0, compute_stream(), dev, (int)tab.size(), chunks, (const SgdHyper*)dev_h);
   DFB_LAUNCH_CHECK("multi_sgd_step");
+  return DFB_OK;
+}
+
+dfb_status dfb_multi_copy(const float* const* srcs, float* const* dsts, const size_t* sizes, int count) {
+  DFB_INIT();
+  std::vector<TensorRef> tab;
+  unsigned long long chunks = 0;
+  dfb_status st = build_table("multi_copy", dsts, srcs, nullptr, nullptr, sizes, count, false, false, &tab, &chunks);
+  if (st != DFB_OK) return st;
+  if (chunks == 0) return DFB_OK;
+  const TensorRef* dev = nullptr;
+  const void* dev_h = nullptr;
+  char none[16] = {0};
+  st = upload_table(tab, none, sizeof(none), 2, &dev, &dev_h);
+  if (st != DFB_OK) return st;
+  unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
+  launch_k(multi_copy_kernel, grid, 256, 0, compute_stream(), dev, (int)tab.size(), chunks);
+  DFB_LAUNCH_CHECK("multi_copy");
   return DFB_OK;
 }
 

@@ -415,6 +415,14 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
                              weight_decay, nesterov ? 1 : 0, grad_scale));
   });
 
+  m.def("multi_copy", [ptr_table](const py::sequence& srcs, const py::sequence& dsts, const std::vector<size_t>& sizes) {
+    std::vector<float*> s, d;
+    ptr_table(srcs, &s, false);
+    ptr_table(dsts, &d, false);
+    if (s.size() != sizes.size() || d.size() != sizes.size()) throw py::value_error("multi_copy: table lengths differ");
+    check(dfb_multi_copy((const float* const*)s.data(), d.data(), sizes.data(), (int)sizes.size()));
+  });
+
   // ---- pinned host buffers + async copies (input pipeline / bench e2e) ------------------------------
   m.def("pinned_empty", [](size_t n) {
     float* p = nullptr;

@@ -433,8 +433,10 @@ dfb_status graph_staging(size_t bytes, int kind, void** host, void** dev) {
   std::lock_guard<std::mutex> lk(r.mu);
   r.active_pool->host_allocs.push_back(*host);
   r.active_pool->dev_allocs.push_back(*dev);
-  r.active_pool->hyper_host.push_back(*host);
-  r.active_pool->hyper_kind.push_back(kind);
+  if (kind == 0 || kind == 1) {  // optimizer steps are addressable afterwards (dfb_graph_set_adam / _sgd)
+    r.active_pool->hyper_host.push_back(*host);
+    r.active_pool->hyper_kind.push_back(kind);
+  }
   return DFB_OK;
 }
 dfb_status graph_hyper_slot(void* graph_exec, int index, int kind, void** host) {

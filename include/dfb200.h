@@ -293,6 +293,10 @@ DFB_API dfb_status dfb_multi_sgd_step(float* const* params, const float* const* 
                                       double lr, double momentum, double weight_decay,
                                       int nesterov, double grad_scale);
 
+/* `count` flat device-to-device copies dsts[i][0:sizes[i]] = srcs[i][0:sizes[i]] in ONE launch (packing the
+ * gradients of a bucket before its all-reduce). The pointer tables are HOST arrays of device pointers. */
+DFB_API dfb_status dfb_multi_copy(const float* const* srcs, float* const* dsts, const size_t* sizes, int count);
+
 /* ---------------------------------------------------------------------------------------------
  * Data parallel (new; the reference has no dist/): one process per GPU, NCCL over NVLink
  * ------------------------------------------------------------------------------------------- */
