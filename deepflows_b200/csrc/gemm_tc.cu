@@ -188,19 +188,26 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32() {
 }
 
 // ---- kernel skeleton ----------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int AROWS = BLOCK_M>
 struct SmemLayout {
-  // Bytes in flight per SM bound what one SM can pull through TMA (latency x bandwidth): the BN = 128 kernels
-  // (one CTA per SM) get six 32 KB stages, the narrower ones stay at two CTAs per SM.
-  static constexpr int kStages = BN >= 128 ? 6 : (BN >= 64 ? 4 : 5);
-  static constexpr uint32_t kABytes = BLOCK_M * 128;   // 16 KB
+  // What one SM can pull through TMA is bounded by the bytes it keeps in flight (loads take microseconds to
+  // return under load), so the ring is as deep as the shared-memory budget allows: ~192 KB for the BN = 128
+  // kernels (one CTA per SM), ~96 KB for the narrower ones (two CTAs per SM). AROWS < 128 (wgrad with few
+  // output channels) shrinks the A tile to the rows that are really loaded, which buys more stages.
+  static constexpr uint32_t kABytes = AROWS * 128;
   static constexpr uint32_t kBBytes = BN * 128;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kBudget = BN >= 128 ? (192u << 10) : (100u << 10);
+  static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
+  static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < 3 ? 3 : kStagesFit);
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
-  static constexpr uint32_t kTotal = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
+  // the M = 128 MMA always addresses four 32-row chunks of A: with AROWS < 128 it reads past the A tile (into the
+  // B tile / the next stage: rows that are never stored), so the last stage needs that much slack behind it
+  static constexpr uint32_t kOverRead = (BLOCK_M - AROWS) * 128;
+  static constexpr uint32_t kTotal = kBarOffset + kOverRead + (2 * kStages + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
   // split-K partial tile staged in the (idle) pipeline stages: 128 rows, padded pitch against bank conflicts
   static constexpr uint32_t kRedPitch = BN + 4;
-  static_assert(BLOCK_M * kRedPitch * 4 <= kBarOffset, "partial tile does not fit the pipeline stages");
+  static_assert(AROWS < BLOCK_M || BLOCK_M * kRedPitch * 4 <= kBarOffset, "partial tile does not fit the pipeline stages");
 };
 
 template <class P>
@@ -208,10 +215,10 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap map_b,
                                                       const typename P::Params prm) {
   constexpr int BN = P::BN;
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, P::AROWS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset + L::kOverRead);
   constexpr int kStages = L::kStages;
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
@@ -253,15 +260,21 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      // One thread issues every load of the CTA, so its per-k-block instruction count bounds the whole
+      // pipeline: the k-block -> (tap, channel block / pixel block) decomposition is an iterator advanced with
+      // adds and compares (the integer divisions happen once, in iter_init).
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t tx = P::tx_bytes(prm, tile);
+      typename P::Iter it = P::iter_init(prm, tile, kb_begin);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
         const uint32_t a_dst = smem_u32(smem + stage * L::kStageBytes);
         const uint32_t b_dst = a_dst + L::kABytes;
-        mbar_expect_tx(full_bar + stage, P::tx_bytes(prm, tile));
-        P::load_a(prm, tile, &map_a, full_bar + stage, a_dst, kb);
-        P::load_b(prm, tile, &map_b, full_bar + stage, b_dst, kb);
+        mbar_expect_tx(full_bar + stage, tx);
+        P::load_a(prm, tile, it, &map_a, full_bar + stage, a_dst);
+        P::load_b(prm, tile, it, &map_b, full_bar + stage, b_dst);
+        P::iter_next(prm, tile, it);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -395,7 +408,7 @@ static bool make_map(CUtensorMap* map, const float* base, int rank, const uint64
 template <class P>
 static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
                          dim3 grid, int splits = 1) {
-  using L = SmemLayout<P::BN>;
+  using L = SmemLayout<P::BN, P::AROWS>;
   static bool configured = false;
   if (!configured) {
     DFB_CUDA(cudaFuncSetAttribute(tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
@@ -453,6 +466,7 @@ template <int A_MAJ, int B_MAJ, int BN_>
 struct GemmProblem {
   static constexpr int BN = BN_, A_MAJOR = A_MAJ, B_MAJOR = B_MAJ;
   static constexpr bool kClusterSplit = true;
+  static constexpr int AROWS = BLOCK_M;
   __device__ static uint32_t tx_bytes(const GemmParams&, const GemmTile&) { return SmemLayout<BN_>::kStageBytes; }
   __device__ static void finish(const GemmParams&, const GemmTile&, int) {}
   using Params = GemmParams;
@@ -460,7 +474,11 @@ struct GemmProblem {
   __device__ static Tile tile(const Params& p) {
     return {(int)blockIdx.x * BLOCK_M, (int)blockIdx.y * BN, 0, (p.K + BLOCK_K - 1) / BLOCK_K};
   }
-  __device__ static void load_a(const Params&, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+  struct Iter { int kb; };
+  __device__ static Iter iter_init(const Params&, const Tile&, int kb) { return {kb}; }
+  __device__ static void iter_next(const Params&, const Tile&, Iter& it) { ++it.kb; }
+  __device__ static void load_a(const Params&, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
+    const int kb = it.kb;
     if (A_MAJ == MAJOR_K) {
       tma_load_2d(dst, m, bar, kb * BLOCK_K, t.m0);
     } else {
@@ -468,7 +486,8 @@ struct GemmProblem {
       for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(dst + j * kChunkBytes, m, bar, t.m0 + j * 32, kb * BLOCK_K);
     }
   }
-  __device__ static void load_b(const Params&, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
+  __device__ static void load_b(const Params&, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
+    const int kb = it.kb;
     if (B_MAJ == MAJOR_K) {
       tma_load_2d(dst, m, bar, kb * BLOCK_K, t.n0);
     } else {
@@ -575,6 +594,7 @@ template <int BN_, int WMODE>
 struct ConvProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = (WMODE == W_KRSC_DGRAD ? MAJOR_MN : MAJOR_K);
   static constexpr bool kClusterSplit = true;
+  static constexpr int AROWS = BLOCK_M;
   __device__ static uint32_t tx_bytes(const ConvParams&, const ConvTile&) { return SmemLayout<BN_>::kStageBytes; }
   __device__ static void finish(const ConvParams&, const ConvTile&, int) {}
   using Params = ConvParams;
@@ -600,29 +620,35 @@ struct ConvProblem {
     }
     return o;
   }
-  __device__ static void load_a(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
-    const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
-    if (p.par_pad >= 0) {
-      const int i = tap / t.ns, j = tap - i * t.ns;
-      tma_load_4d(dst, m, bar, cb * 32, t.ow0 + t.d0w - j, t.oh0 + t.d0h - i, t.n0);
-      return;
-    }
-    const int r = tap / p.R, s = tap - r * p.R;
-    const int dh = p.dh0 + p.sgn * r, dw = p.dw0 + p.sgn * s;
-    if (p.stride == 1) {
-      tma_load_4d(dst, m, bar, cb * 32, t.ow0 + dw, t.oh0 + dh, t.n0);
-    } else {
-      // parity view (2C, W/2, 2, H/2, N): input row 2*oh + dh = 2*(oh + (dh >> 1)) + (dh & 1)
-      tma_load_5d(dst, m, bar, (dw & 1) * p.c_red + cb * 32, t.ow0 + (dw >> 1), dh & 1, t.oh0 + (dh >> 1), t.n0);
+  // k-block = (tap, 32-channel block); tap = (i, j): (r, s) of the filter, or the (i, j)-th tap of a parity class
+  struct Iter { int i, j, cb, nj; };
+  __device__ static Iter iter_init(const Params& p, const Tile& t, int kb) {
+    const int tap = kb / p.cblks;
+    const int nj = p.par_pad >= 0 ? max(t.ns, 1) : p.R;
+    return {tap / nj, tap % nj, kb - tap * p.cblks, nj};
+  }
+  __device__ static void iter_next(const Params& p, const Tile&, Iter& it) {
+    if (++it.cb == p.cblks) {
+      it.cb = 0;
+      if (++it.j == it.nj) { it.j = 0; ++it.i; }
     }
   }
-  __device__ static void load_b(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
-    int tap = kb / p.cblks;
-    const int cb = kb - tap * p.cblks;
+  __device__ static void load_a(const Params& p, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
     if (p.par_pad >= 0) {
-      const int i = tap / t.ns, j = tap - i * t.ns;
-      tap = (t.r0h + 2 * i) * p.R + t.r0w + 2 * j;
+      tma_load_4d(dst, m, bar, it.cb * 32, t.ow0 + t.d0w - it.j, t.oh0 + t.d0h - it.i, t.n0);
+      return;
     }
+    const int dh = p.dh0 + p.sgn * it.i, dw = p.dw0 + p.sgn * it.j;
+    if (p.stride == 1) {
+      tma_load_4d(dst, m, bar, it.cb * 32, t.ow0 + dw, t.oh0 + dh, t.n0);
+    } else {
+      // parity view (2C, W/2, 2, H/2, N): input row 2*oh + dh = 2*(oh + (dh >> 1)) + (dh & 1)
+      tma_load_5d(dst, m, bar, (dw & 1) * p.c_red + it.cb * 32, t.ow0 + (dw >> 1), dh & 1, t.oh0 + (dh >> 1), t.n0);
+    }
+  }
+  __device__ static void load_b(const Params& p, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
+    const int tap = p.par_pad >= 0 ? (t.r0h + 2 * it.i) * p.R + t.r0w + 2 * it.j : it.i * p.R + it.j;
+    const int cb = it.cb;
     if (WMODE == W_PACKED) {
       tma_load_2d(dst, m, bar, (tap * p.cblks + cb) * BLOCK_K, t.col0);
     } else if (WMODE == W_KRSC_FPROP) {
@@ -692,9 +718,9 @@ struct WgradTile {
   int m0, tap, c0, kb_begin, kb_end;
   int a_chunks;  // 32-row chunks of the dy tile that hold real output channels (the rest is never loaded)
 };
-template <int BN_>
+template <int BN_, int AROWS_>   // AROWS_: rows of the dy tile that are loaded (32 / 64 / 128 >= output channels of the tile)
 struct WgradProblem {
-  static constexpr int BN = BN_, A_MAJOR = MAJOR_MN, B_MAJOR = MAJOR_MN;
+  static constexpr int BN = BN_, A_MAJOR = MAJOR_MN, B_MAJOR = MAJOR_MN, AROWS = AROWS_;
   static constexpr bool kClusterSplit = false;
   __device__ static void store4(const WgradParams&, const WgradTile&, int, int, const float4&) {}
   using Params = WgradParams;
@@ -703,30 +729,33 @@ struct WgradProblem {
     const int tap = blockIdx.y / p.ctiles, ct = blockIdx.y - tap * p.ctiles;
     const int b0 = blockIdx.z * p.blocks_per_split;
     const int m0 = (int)blockIdx.x * BLOCK_M;
-    return {m0, tap, ct * BN, b0, min(p.pix_blocks, b0 + p.blocks_per_split), min(BLOCK_M / 32, (p.Kout - m0 + 31) / 32)};
+    return {m0, tap, ct * BN, b0, min(p.pix_blocks, b0 + p.blocks_per_split), min(AROWS / 32, (p.Kout - m0 + 31) / 32)};
   }
   // rows of the accumulator beyond Kout multiply whatever the idle part of the stage holds; they are never stored
-  __device__ static uint32_t tx_bytes(const Params&, const Tile& t) { return t.a_chunks * kChunkBytes + SmemLayout<BN_>::kBBytes; }
-  __device__ static void pix(const Params& p, int kb, int& n0, int& oh0, int& ow0) {
-    int tw = kb % p.tiles_w;
+  __device__ static uint32_t tx_bytes(const Params&, const Tile& t) { return t.a_chunks * kChunkBytes + SmemLayout<BN_, AROWS_>::kBBytes; }
+  // k-block = a block of 32 output pixels (tw, th, tn); the tap offset is fixed per CTA
+  struct Iter { int tw, th, tn, dh, dw; };
+  __device__ static Iter iter_init(const Params& p, const Tile& t, int kb) {
+    const int tw = kb % p.tiles_w;
     kb /= p.tiles_w;
-    int th = kb % p.tiles_h;
-    n0 = (kb / p.tiles_h) * p.n_t;
-    oh0 = th * p.oh_t;
-    ow0 = tw * p.ow_t;
+    const int r = t.tap / p.R, s = t.tap - r * p.R;
+    return {tw, kb % p.tiles_h, kb / p.tiles_h, r - p.pad, s - p.pad};
   }
-  __device__ static void load_a(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
-    int n0, oh0, ow0;
-    pix(p, kb, n0, oh0, ow0);
+  __device__ static void iter_next(const Params& p, const Tile&, Iter& it) {
+    if (++it.tw == p.tiles_w) {
+      it.tw = 0;
+      if (++it.th == p.tiles_h) { it.th = 0; ++it.tn; }
+    }
+  }
+  __device__ static void load_a(const Params& p, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
+    const int n0 = it.tn * p.n_t, oh0 = it.th * p.oh_t, ow0 = it.tw * p.ow_t;
 #pragma unroll
-    for (int j = 0; j < BLOCK_M / 32; ++j)
+    for (int j = 0; j < AROWS / 32; ++j)
       if (j < t.a_chunks) tma_load_4d(dst + j * kChunkBytes, m, bar, t.m0 + j * 32, ow0, oh0, n0);
   }
-  __device__ static void load_b(const Params& p, const Tile& t, const CUtensorMap* m, uint64_t* bar, uint32_t dst, int kb) {
-    int n0, oh0, ow0;
-    pix(p, kb, n0, oh0, ow0);
-    const int r = t.tap / p.R, s = t.tap - r * p.R;
-    const int dh = r - p.pad, dw = s - p.pad;
+  __device__ static void load_b(const Params& p, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
+    const int n0 = it.tn * p.n_t, oh0 = it.th * p.oh_t, ow0 = it.tw * p.ow_t;
+    const int dh = it.dh, dw = it.dw;
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) {
       if (p.stride == 1)
@@ -929,7 +958,9 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
 template <int BN>
 static dfb_status run_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams prm, int splits) {
   dim3 grid(cdiv(prm.Kout, BLOCK_M), (unsigned)(prm.R * prm.R * prm.ctiles), (unsigned)splits);
-  return launch<WgradProblem<BN>>("tc_conv_wgrad", ma, mb, prm, grid);
+  if (prm.Kout <= 32) return launch<WgradProblem<BN, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
+  if (prm.Kout <= 64) return launch<WgradProblem<BN, 64>>("tc_conv_wgrad", ma, mb, prm, grid);
+  return launch<WgradProblem<BN, 128>>("tc_conv_wgrad", ma, mb, prm, grid);
 }
 }  // namespace tc
 
