@@ -65,6 +65,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// one lane of a converged warp (the same one every time while all 32 lanes are active)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -258,46 +268,53 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   pdl_sync();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      // One thread issues every load of the CTA, so its per-k-block instruction count bounds the whole
-      // pipeline: the k-block -> (tap, channel block / pixel block) decomposition is an iterator advanced with
-      // adds and compares (the integer divisions happen once, in iter_init).
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = P::tx_bytes(prm, tile);
-      typename P::Iter it = P::iter_init(prm, tile, kb_begin);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(empty_bar + stage, phase ^ 1);
-        const uint32_t a_dst = smem_u32(smem + stage * L::kStageBytes);
-        const uint32_t b_dst = a_dst + L::kABytes;
+    // ===== TMA producer =====
+    // The whole warp runs the loop convergently (waits, address arithmetic and the k-block iterator then live
+    // on the uniform datapath) and one elected lane issues the copies. Issuing from inside `if (lane == 0)`
+    // instead makes the compiler wrap every UTMALDG in a uniformisation loop, and the single producer
+    // thread's instruction stream is what bounds the pipeline of these short k-blocks. The k-block ->
+    // (tap, channel block / pixel block) decomposition is an iterator advanced with adds and compares (the
+    // integer divisions happen once, in iter_init).
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx = P::tx_bytes(prm, tile);
+    typename P::Iter it = P::iter_init(prm, tile, kb_begin);
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(empty_bar + stage, phase ^ 1);
+      const uint32_t a_dst = smem_u32(smem + stage * L::kStageBytes);
+      const uint32_t b_dst = a_dst + L::kABytes;
+      if (elect_one()) {
         mbar_expect_tx(full_bar + stage, tx);
         P::load_a(prm, tile, it, &map_a, full_bar + stage, a_dst);
         P::load_b(prm, tile, it, &map_b, full_bar + stage, b_dst);
-        P::iter_next(prm, tile, it);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      P::iter_next(prm, tile, it);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (one thread) =====
-      constexpr uint32_t idesc = instr_desc_tf32<P::A_MAJOR, P::B_MAJOR, BN>();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(full_bar + stage, phase);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
-        const uint32_t b_base = a_base + L::kABytes;
+    // ===== MMA issuer: the warp waits convergently, one elected lane (always the same one: tcgen05.commit tracks
+    // the MMAs of the thread that executes it) issues =====
+    constexpr uint32_t idesc = instr_desc_tf32<P::A_MAJOR, P::B_MAJOR, BN>();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(full_bar + stage, phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
+      const uint32_t b_base = a_base + L::kABytes;
+      if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
           umma_tf32(tmem_base, operand_desc<P::A_MAJOR>(a_base, j), operand_desc<P::B_MAJOR>(b_base, j), idesc,
                     (kb > kb_begin || j > 0) ? 1u : 0u);
         umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs have read it
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
+    __syncwarp();
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int quarter = warp & 3;
