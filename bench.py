@@ -81,22 +81,30 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:  # nvidia-smi takes a moment to start reporting
+                time.sleep(0.01)
         except OSError:
             self.proc = None
+
+    def mark(self):
+        """Index of the next sample: samples from here on were taken after this call."""
+        return len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[first:last] or self.rows[max(0, first - 1):]  # at least the sample that straddles the region
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
@@ -271,14 +279,18 @@ def main():
         resident_step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()      # 10 ms samples; returns once nvidia-smi reports
+    for _ in range(3):
+        resident_step()      # every rank (the step holds collectives): the GPU is under load when timing starts
+    s0 = sampler.mark()
     ms_res, launches = timed(resident_step, args.steps)
     ms_res = max_over_ranks(ms_res)
     for _ in range(2):
         e2e_step()
     ms_e2e, _ = timed(e2e_step, args.steps)
     ms_e2e = max_over_ranks(ms_e2e)
-    clocks = sampler.stop() if rank == 0 else None
+    s1 = sampler.mark()
+    clocks = sampler.stop(s0, s1) if rank == 0 else None
 
     # ---- per-kernel profile pass: CUDA events around every fused conv call, same steps ----------------
     # every rank runs it: the steps contain the data-parallel all-reduces, so the ranks must stay in lockstep
