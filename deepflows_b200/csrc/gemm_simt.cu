@@ -369,7 +369,7 @@ dfb_status launch_simt(const char* name, AL A, BL B, float* C, int ldc, int accu
   int splits = 1;
   size_t tiles = (size_t)gx * gy;
   size_t target = (size_t)sm_count() * 2;
-  if (tiles < target && K >= 4 * BK * 8) {
+  if (tiles < target && K >= 4 * BK * 2) {
     splits = (int)std::min<size_t>((target + tiles - 1) / tiles, (size_t)K / (4 * BK));
     if (splits > 256) splits = 256;
     if (splits < 1) splits = 1;

@@ -185,10 +185,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 //             transpose need the 128B swizzle with 32-BYTE atoms (cute: SWIZZLE_128B_BASE32B,
 //             TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), whose pattern repeats every 4 k-rows:
 //             SBO = 512 B between 4-row groups, LBO = bytes between 32-wide m/n chunks.
-template <int MAJOR>
+template <int MAJOR, uint32_t CHUNK_BYTES = kChunkBytes>
 __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int j) {
   if (MAJOR == MAJOR_K) return smem_desc(base + j * (UMMA_K * 4), 0, 1024, 2);
-  return smem_desc(base + j * (UMMA_K * 128), kChunkBytes, 512, 1);
+  return smem_desc(base + j * (UMMA_K * 128), CHUNK_BYTES, 512, 1);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
 template <int A_MAJOR, int B_MAJOR, int N>
@@ -198,14 +198,15 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32() {
 }
 
 // ---- kernel skeleton ----------------------------------------------------------------------------------
-template <int BN, int AROWS = BLOCK_M>
+template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K>   // KR: reduction rows per stage (MN-major operands only: 32 or 128)
 struct SmemLayout {
   // What one SM can pull through TMA is bounded by the bytes it keeps in flight (loads take microseconds to
   // return under load), so the ring is as deep as the shared-memory budget allows: ~192 KB for the BN = 128
   // kernels (one CTA per SM), ~96 KB for the narrower ones (two CTAs per SM). AROWS < 128 (wgrad with few
   // output channels) shrinks the A tile to the rows that are really loaded, which buys more stages.
-  static constexpr uint32_t kABytes = AROWS * 128;
-  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kChunk = KR * 128;                 // one [KR k-rows x 128 B] chunk (32 m/n wide)
+  static constexpr uint32_t kABytes = (AROWS / 32) * kChunk;
+  static constexpr uint32_t kBBytes = (BN / 32) * kChunk;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kBudget = BN >= 128 ? (192u << 10) : (100u << 10);
   static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
@@ -213,7 +214,8 @@ struct SmemLayout {
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   // the M = 128 MMA always addresses four 32-row chunks of A: with AROWS < 128 it reads past the A tile (into the
   // B tile / the next stage: rows that are never stored), so the last stage needs that much slack behind it
-  static constexpr uint32_t kOverRead = (BLOCK_M - AROWS) * 128;
+  // (AROWS == 32: the A descriptor's chunk stride is 0, all four chunks alias the one that is loaded - no over-read)
+  static constexpr uint32_t kOverRead = AROWS == 32 ? 0 : ((BLOCK_M - AROWS) / 32) * kChunk;
   static constexpr uint32_t kTotal = kBarOffset + kOverRead + (2 * kStages + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
   // split-K partial tile staged in the (idle) pipeline stages: 128 rows, padded pitch against bank conflicts
   static constexpr uint32_t kRedPitch = BN + 4;
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap map_b,
                                                       const typename P::Params prm) {
   constexpr int BN = P::BN;
-  using L = SmemLayout<BN, P::AROWS>;
+  using L = SmemLayout<BN, P::AROWS, P::KR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset + L::kOverRead);
@@ -305,8 +307,9 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       const uint32_t b_base = a_base + L::kABytes;
       if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < BLOCK_K / UMMA_K; ++j)
-          umma_tf32(tmem_base, operand_desc<P::A_MAJOR>(a_base, j), operand_desc<P::B_MAJOR>(b_base, j), idesc,
+        for (int j = 0; j < P::KR / UMMA_K; ++j)
+          umma_tf32(tmem_base, operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_base, j),
+                    operand_desc<P::B_MAJOR, L::kChunk>(b_base, j), idesc,
                     (kb > kb_begin || j > 0) ? 1u : 0u);
         umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs have read it
       }
@@ -425,7 +428,7 @@ static bool make_map(CUtensorMap* map, const float* base, int rank, const uint64
 template <class P>
 static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
                          dim3 grid, int splits = 1) {
-  using L = SmemLayout<P::BN, P::AROWS>;
+  using L = SmemLayout<P::BN, P::AROWS, P::KR>;
   static bool configured = false;
   if (!configured) {
     DFB_CUDA(cudaFuncSetAttribute(tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
@@ -483,7 +486,7 @@ template <int A_MAJ, int B_MAJ, int BN_>
 struct GemmProblem {
   static constexpr int BN = BN_, A_MAJOR = A_MAJ, B_MAJOR = B_MAJ;
   static constexpr bool kClusterSplit = true;
-  static constexpr int AROWS = BLOCK_M;
+  static constexpr int AROWS = BLOCK_M, KR = BLOCK_K;
   __device__ static uint32_t tx_bytes(const GemmParams&, const GemmTile&) { return SmemLayout<BN_>::kStageBytes; }
   __device__ static void finish(const GemmParams&, const GemmTile&, int) {}
   using Params = GemmParams;
@@ -611,7 +614,7 @@ template <int BN_, int WMODE>
 struct ConvProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = (WMODE == W_KRSC_DGRAD ? MAJOR_MN : MAJOR_K);
   static constexpr bool kClusterSplit = true;
-  static constexpr int AROWS = BLOCK_M;
+  static constexpr int AROWS = BLOCK_M, KR = BLOCK_K;
   __device__ static uint32_t tx_bytes(const ConvParams&, const ConvTile&) { return SmemLayout<BN_>::kStageBytes; }
   __device__ static void finish(const ConvParams&, const ConvTile&, int) {}
   using Params = ConvParams;
@@ -727,6 +730,7 @@ struct WgradParams {
   float* dw;           // final gradient, (K,C,R,R) or (K,R,R,C); written by the last CTA of each tile when tickets != 0
   unsigned* tickets;   // one self-resetting arrival counter per output tile (null: separate reduction kernel)
   int krsc;
+  int kr;              // output pixels per pipeline stage (32 or 128)
   int Kout, C, Cp, R, pad, stride;
   int n_img, OH, OW;
   int ow_t, oh_t, n_t, tiles_w, tiles_h, pix_blocks, blocks_per_split, ctiles;
@@ -735,9 +739,12 @@ struct WgradTile {
   int m0, tap, c0, kb_begin, kb_end;
   int a_chunks;  // 32-row chunks of the dy tile that hold real output channels (the rest is never loaded)
 };
-template <int BN_, int AROWS_>   // AROWS_: rows of the dy tile that are loaded (32 / 64 / 128 >= output channels of the tile)
+// AROWS_: rows of the dy tile that are loaded (32 / 64 / 128 >= output channels of the tile). KR_: output pixels per
+// pipeline stage: 32, or 128 for the small-channel layers, whose 8 KB stages are otherwise all barrier hand-offs
+template <int BN_, int AROWS_, int KR_>
 struct WgradProblem {
-  static constexpr int BN = BN_, A_MAJOR = MAJOR_MN, B_MAJOR = MAJOR_MN, AROWS = AROWS_;
+  static constexpr int BN = BN_, A_MAJOR = MAJOR_MN, B_MAJOR = MAJOR_MN, AROWS = AROWS_, KR = KR_;
+  static constexpr uint32_t kChunkW = KR_ * 128;
   static constexpr bool kClusterSplit = false;
   __device__ static void store4(const WgradParams&, const WgradTile&, int, int, const float4&) {}
   using Params = WgradParams;
@@ -749,7 +756,7 @@ struct WgradProblem {
     return {m0, tap, ct * BN, b0, min(p.pix_blocks, b0 + p.blocks_per_split), min(AROWS / 32, (p.Kout - m0 + 31) / 32)};
   }
   // rows of the accumulator beyond Kout multiply whatever the idle part of the stage holds; they are never stored
-  __device__ static uint32_t tx_bytes(const Params&, const Tile& t) { return t.a_chunks * kChunkBytes + SmemLayout<BN_, AROWS_>::kBBytes; }
+  __device__ static uint32_t tx_bytes(const Params&, const Tile& t) { return t.a_chunks * kChunkW + SmemLayout<BN_, AROWS_, KR_>::kBBytes; }
   // k-block = a block of 32 output pixels (tw, th, tn); the tap offset is fixed per CTA
   struct Iter { int tw, th, tn, dh, dw; };
   __device__ static Iter iter_init(const Params& p, const Tile& t, int kb) {
@@ -768,7 +775,7 @@ struct WgradProblem {
     const int n0 = it.tn * p.n_t, oh0 = it.th * p.oh_t, ow0 = it.tw * p.ow_t;
 #pragma unroll
     for (int j = 0; j < AROWS / 32; ++j)
-      if (j < t.a_chunks) tma_load_4d(dst + j * kChunkBytes, m, bar, t.m0 + j * 32, ow0, oh0, n0);
+      if (j < t.a_chunks) tma_load_4d(dst + j * kChunkW, m, bar, t.m0 + j * 32, ow0, oh0, n0);
   }
   __device__ static void load_b(const Params& p, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
     const int n0 = it.tn * p.n_t, oh0 = it.th * p.oh_t, ow0 = it.tw * p.ow_t;
@@ -776,9 +783,9 @@ struct WgradProblem {
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) {
       if (p.stride == 1)
-        tma_load_4d(dst + j * kChunkBytes, m, bar, t.c0 + j * 32, ow0 + dw, oh0 + dh, n0);
+        tma_load_4d(dst + j * kChunkW, m, bar, t.c0 + j * 32, ow0 + dw, oh0 + dh, n0);
       else
-        tma_load_5d(dst + j * kChunkBytes, m, bar, (dw & 1) * p.C + t.c0 + j * 32, ow0 + (dw >> 1), dh & 1, oh0 + (dh >> 1), n0);
+        tma_load_5d(dst + j * kChunkW, m, bar, (dw & 1) * p.C + t.c0 + j * 32, ow0 + (dw >> 1), dh & 1, oh0 + (dh >> 1), n0);
     }
   }
   __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
@@ -975,9 +982,10 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
 template <int BN>
 static dfb_status run_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams prm, int splits) {
   dim3 grid(cdiv(prm.Kout, BLOCK_M), (unsigned)(prm.R * prm.R * prm.ctiles), (unsigned)splits);
-  if (prm.Kout <= 32) return launch<WgradProblem<BN, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
-  if (prm.Kout <= 64) return launch<WgradProblem<BN, 64>>("tc_conv_wgrad", ma, mb, prm, grid);
-  return launch<WgradProblem<BN, 128>>("tc_conv_wgrad", ma, mb, prm, grid);
+  if (prm.kr == 128) return launch<WgradProblem<32, 32, 128>>("tc_conv_wgrad", ma, mb, prm, grid);  // BN == 32 (host)
+  if (prm.Kout <= 32) return launch<WgradProblem<BN, 32, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
+  if (prm.Kout <= 64) return launch<WgradProblem<BN, 64, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
+  return launch<WgradProblem<BN, 128, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
 }
 }  // namespace tc
 
@@ -1043,11 +1051,13 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   WgradParams prm;
   prm.Kout = K; prm.C = C; prm.Cp = (C + 31) / 32 * 32; prm.R = R; prm.pad = pad; prm.stride = stride;
   prm.n_img = N; prm.OH = OH; prm.OW = OW;
-  pixel_tile(BLOCK_K, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
+  const int bn = prm.Cp % 128 == 0 ? 128 : (prm.Cp % 64 == 0 ? 64 : 32);
+  // few channels on both sides and many pixels: 128-pixel stages (32 KB) instead of 32-pixel ones (8 KB)
+  prm.kr = (K <= 32 && bn == 32 && (size_t)N * OH * OW >= 16384) ? 128 : BLOCK_K;
+  pixel_tile(prm.kr, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
   prm.tiles_w = cdiv(OW, prm.ow_t);
   prm.tiles_h = cdiv(OH, prm.oh_t);
   prm.pix_blocks = prm.tiles_w * prm.tiles_h * (int)cdiv(N, prm.n_t);
-  const int bn = prm.Cp % 128 == 0 ? 128 : (prm.Cp % 64 == 0 ? 64 : 32);
   prm.ctiles = prm.Cp / bn;
   CUtensorMap ma, mb;
   {
