@@ -208,7 +208,7 @@ struct SmemLayout {
   static constexpr uint32_t kABytes = (AROWS / 32) * kChunk;
   static constexpr uint32_t kBBytes = (BN / 32) * kChunk;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kBudget = BN >= 128 ? (192u << 10) : (100u << 10);
+  static constexpr uint32_t kBudget = BN >= 128 ? (BN >= 256 ? (208u << 10) : (192u << 10)) : (100u << 10);
   static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
   static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < 3 ? 3 : kStagesFit);
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
@@ -579,6 +579,10 @@ template <int A_MAJ, int B_MAJ>
 static dfb_status run_gemm_bn(const float* A, const float* B, const GemmParams& prm, int lda, int ldb, bool* handled) {
   if (prm.N <= 32) return run_gemm<A_MAJ, B_MAJ, 32>(A, B, prm, lda, ldb, handled);
   if (prm.N <= 64) return run_gemm<A_MAJ, B_MAJ, 64>(A, B, prm, lda, ldb, handled);
+  // 128 x 256 tiles move a third fewer operand bytes per FLOP through L2 -> SM, which is what bounds the big
+  // problems; only when they still fill the machine twice over
+  if (prm.N > 128 && (size_t)cdiv(prm.M, BLOCK_M) * cdiv(prm.N, 256) >= (size_t)sm_count() * 2)
+    return run_gemm<A_MAJ, B_MAJ, 256>(A, B, prm, lda, ldb, handled);
   return run_gemm<A_MAJ, B_MAJ, 128>(A, B, prm, lda, ldb, handled);
 }
 
@@ -946,6 +950,9 @@ static dfb_status run_conv_bn(const char* name, const CUtensorMap& ma, const flo
                               const ConvParams& prm, bool* handled) {
   if (n_out <= 32) return run_conv<32, WMODE>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
   if (n_out <= 64) return run_conv<64, WMODE>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
+  const size_t m_tiles = (size_t)prm.tiles_w * prm.tiles_h * cdiv(prm.n_img, prm.n_t) * (prm.par_pad >= 0 ? 4 : 1);
+  if (n_out > 128 && m_tiles * cdiv(n_out, 256) >= (size_t)sm_count() * 2)  // big layers: 128 x 256 tiles (see run_gemm_bn)
+    return run_conv<256, WMODE>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
   return run_conv<128, WMODE>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
 }
 

@@ -140,6 +140,7 @@ TC_SHAPES = [  # N, C, H, W, K, R, pad, stride - all TMA-eligible (C, K multiple
     (32, 256, 2, 2, 256, 3, 1, 1), (2, 64, 14, 14, 64, 3, 1, 1), (3, 20, 11, 13, 36, 3, 1, 1), (2, 64, 56, 56, 64, 3, 1, 1),
     (4, 8, 12, 12, 200, 5, 2, 1), (2, 160, 8, 8, 24, 3, 1, 2), (1, 8, 40, 300, 8, 3, 1, 1), (256, 32, 16, 16, 32, 3, 1, 1),
     (3, 16, 10, 14, 40, 5, 2, 2), (2, 8, 12, 12, 16, 2, 0, 2), (4, 64, 8, 8, 128, 3, 1, 2), (2, 12, 6, 6, 8, 4, 1, 2),
+    (10, 16, 64, 64, 256, 3, 1, 1), (10, 256, 64, 64, 16, 3, 1, 1),   # enough tiles for the 128 x 256 kernels (fprop / dgrad)
 ]
 
 
@@ -208,7 +209,8 @@ def test_gemm_variants(cuda_device, M, N, K, ta, tb, mode, pad):
 
 
 @pytest.mark.parametrize("M,N,K,ta,tb", [(256, 128, 512, 0, 0), (256, 128, 512, 0, 1), (256, 128, 512, 1, 0), (256, 128, 512, 1, 1),
-                                         (300, 72, 200, 0, 0), (1000, 260, 36, 1, 0), (8192, 64, 4096, 0, 1), (129, 33, 40, 1, 1)])
+                                         (300, 72, 200, 0, 0), (1000, 260, 36, 1, 0), (8192, 64, 4096, 0, 1), (129, 33, 40, 1, 1),
+                                         (19000, 512, 64, 0, 0), (19000, 512, 64, 0, 1), (19000, 300, 40, 1, 0), (19000, 512, 64, 1, 1)])
 def test_tf32_gemm_runs_on_the_tensor_pipe(cuda_device, M, N, K, ta, tb):
     """TF32 mode with TMA-compatible operands must launch the tcgen05 kernel (no silent FFMA fallback) and
     agree with float64 within the TF32 tolerance; the error must also be ABOVE fp32 rounding, i.e. the
