@@ -1058,7 +1058,8 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   WgradParams prm;
   prm.Kout = K; prm.C = C; prm.Cp = (C + 31) / 32 * 32; prm.R = R; prm.pad = pad; prm.stride = stride;
   prm.n_img = N; prm.OH = OH; prm.OW = OW;
-  const int bn = prm.Cp % 128 == 0 ? 128 : (prm.Cp % 64 == 0 ? 64 : 32);
+  int bn = prm.Cp % 128 == 0 ? 128 : (prm.Cp % 64 == 0 ? 64 : 32);
+  if (prm.Cp % 256 == 0 && (size_t)N * OH * OW >= 16384) bn = 256;  // big layers: 128 x 256 tiles (see run_gemm_bn)
   // few channels on both sides and many pixels: 128-pixel stages (32 KB) instead of 32-pixel ones (8 KB)
   prm.kr = (K <= 32 && bn == 32 && (size_t)N * OH * OW >= 16384) ? 128 : BLOCK_K;
   pixel_tile(prm.kr, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
@@ -1093,7 +1094,8 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   const size_t tile_partial_bytes = (size_t)splits * std::min(K, BLOCK_M) * bn * sizeof(float);
   prm.tickets = (base_ctas <= (size_t)kTicketWords - 64 && tile_partial_bytes <= (192u << 10)) ? ticket_counter(64) : nullptr;
   *handled = true;
-  if (bn == 128) st = run_wgrad<128>(ma, mb, prm, splits);
+  if (bn == 256) st = run_wgrad<256>(ma, mb, prm, splits);
+  else if (bn == 128) st = run_wgrad<128>(ma, mb, prm, splits);
   else if (bn == 64) st = run_wgrad<64>(ma, mb, prm, splits);
   else st = run_wgrad<32>(ma, mb, prm, splits);
   if (st == DFB_OK && !prm.tickets) {
