@@ -9,8 +9,10 @@ One JSON line on stdout (rank 0). A "step" = host batch -> forward -> softmax-CE
 (gradient all-reduce) -> Adam step.
   value  : images/s with the batch already resident in HBM (device-timed with CUDA events on the compute
            stream, max over ranks), whole job (all N GPUs).
-  e2e    : the same metric through the public API with HOST inputs: every step copies its batch from pinned
-           host memory and reads the loss back.
+  e2e    : the same metric through the public API with HOST inputs: every step's batch is copied from pinned
+           host memory (prefetched on a copy stream while the previous step computes, then moved into the
+           step's input buffers) and every step's loss is read back to the host (async copy into pinned
+           memory, picked up one step later); all inside the timed region.
   roofline / cpu_baseline : see DESIGN.md "Measurement".
 `--impl reference` times the reference's CPU path for the same workload (the oracle port of the reference
 algorithm: oracle/numpy_device.py under the same host code) on the host cores, on a bounded sample.
@@ -240,12 +242,38 @@ def main():
         captured = CapturedStep(eager_step, device=dev, warmup=1)  # call 1 eager, call 2 captures, then replays
     resident_step = captured if captured is not None else eager_step
 
+    # End-to-end step: every step's batch travels from pinned host memory to the device and the loss travels
+    # back. The copy of batch i+1 goes to a staging buffer on the copy stream while step i computes (double
+    # buffering, the input pipeline of SURVEY 8f rank 2); at the start of step i+1 it is moved into the step's
+    # input buffers device-to-device. All of it happens inside the timed region, once per step.
+    stage_x, stage_t = dev.Array(x_host.size), dev.Array(t_host.size)
+
+    def prefetch_batch():
+        dev.prefetch_from_pinned(px, stage_x, x_host.size)
+        dev.prefetch_from_pinned(pt, stage_t, t_host.size)
+
+    loss_host = dev.pinned_empty(2)                           # the loss of step i lands in loss_host[i % 2]
+    loss_ev = [dev.event_create(), dev.event_create()]
+    e2e = {"i": 0, "pending": None, "last": None}
+
     def e2e_step():
-        # the batch comes from pinned host memory into the step's input buffers, the loss goes back to the host
-        dev.from_pinned_async(px, x_dev.data._handle, x_host.size)
-        dev.from_pinned_async(pt, t_dev.data._handle, t_host.size)
-        loss = resident_step()
-        return float(loss.data.numpy()[0])
+        i = e2e["i"]
+        dev.prefetch_wait()                                   # this step's batch has landed in the staging buffers
+        dev.copy(stage_x, x_dev.data._handle, x_host.size)
+        dev.copy(stage_t, t_dev.data._handle, t_host.size)
+        prefetch_batch()                                      # next step's batch: waits for the two copies above only,
+        loss = resident_step()                                # then runs beside this step's kernels
+        # device -> host read of this step's result: an async copy into pinned memory behind the step; the host
+        # picks it up one step later, so the read does not stall the launch of the next step
+        dev.to_pinned_async(loss.data._handle, loss_host[i % 2:i % 2 + 1], 1)
+        dev.event_record(loss_ev[i % 2])
+        if e2e["pending"] is not None:
+            j = e2e["pending"]
+            dev.event_synchronize(loss_ev[j])
+            e2e["last"] = float(loss_host[j])
+        e2e["pending"] = i % 2
+        e2e["i"] = i + 1
+        return e2e["last"]
 
     def timed(fn, steps):
         ev0, ev1 = dev.event_create(), dev.event_create()
@@ -285,6 +313,7 @@ def main():
     s0 = sampler.mark()
     ms_res, launches = timed(resident_step, args.steps)
     ms_res = max_over_ranks(ms_res)
+    prefetch_batch()
     for _ in range(2):
         e2e_step()
     ms_e2e, _ = timed(e2e_step, args.steps)
@@ -333,7 +362,7 @@ def main():
                 peak, which = 1400.0, "fallback sustained 1.4 PF (B200_PROFILING.md)"
         roofline["peak"], roofline["peak_source"] = peak, which
         roofline["frac"] = roofline["achieved"] / peak
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
         base = run_cpu(args, args.cpu_batch, 3, 1)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)

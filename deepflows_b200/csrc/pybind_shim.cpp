@@ -434,6 +434,11 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
     if ((size_t)a.size() < n) throw py::value_error("from_pinned_async: source too small");
     check(dfb_from_host_async(a.data(), dptr(out), n));
   });
+  m.def("prefetch_from_pinned", [](py::array_t<float, py::array::c_style> a, const py::object& out, size_t n) {
+    if ((size_t)a.size() < n) throw py::value_error("prefetch_from_pinned: source too small");
+    check(dfb_prefetch_from_host(a.data(), dptr(out), n));
+  });
+  m.def("prefetch_wait", []() { check(dfb_prefetch_wait()); });
   m.def("to_pinned_async", [](const py::object& src, py::array_t<float, py::array::c_style> a, size_t n) {
     if ((size_t)a.size() < n) throw py::value_error("to_pinned_async: destination too small");
     check(dfb_to_host_async(dptr(src), a.mutable_data(), n));

@@ -36,6 +36,10 @@ struct Runtime {
   // between dfb_side_begin() and dfb_side_end(); dfb_side_join() orders the main stream after it.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // copy stream of the input pipeline: host -> device prefetch of the next batch beside the running step
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_copy_ready = nullptr, ev_copy_done = nullptr;
+  bool prefetch_pending = false;
   bool on_side = false;
   std::vector<void*> side_frees;  // blocks freed while on the side stream: recycled at the join
 
@@ -108,6 +112,9 @@ dfb_status ensure_init() {
   DFB_CUDA(cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking));
   DFB_CUDA(cudaEventCreateWithFlags(&r.ev_fork, cudaEventDisableTiming));
   DFB_CUDA(cudaEventCreateWithFlags(&r.ev_join, cudaEventDisableTiming));
+  DFB_CUDA(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
+  DFB_CUDA(cudaEventCreateWithFlags(&r.ev_copy_ready, cudaEventDisableTiming));
+  DFB_CUDA(cudaEventCreateWithFlags(&r.ev_copy_done, cudaEventDisableTiming));
   DFB_CUDA(cudaMalloc(&r.tickets, kTicketWords * sizeof(unsigned)));
   DFB_CUDA(cudaMemset(r.tickets, 0, kTicketWords * sizeof(unsigned)));
   DFB_CUDA(cudaDeviceSynchronize());
@@ -174,6 +181,7 @@ dfb_status dfb_synchronize(void) {
   DFB_INIT();
   DFB_CUDA(cudaStreamSynchronize(rt().compute));
   DFB_CUDA(cudaStreamSynchronize(rt().side));
+  DFB_CUDA(cudaStreamSynchronize(rt().copy));
   DFB_CUDA(cudaStreamSynchronize(rt().comm));
   return DFB_OK;
 }
@@ -383,6 +391,31 @@ dfb_status dfb_copy(const float* src, float* dst, size_t n) {
   DFB_INIT();
   if (n == 0) return DFB_OK;
   DFB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, rt().compute));
+  return DFB_OK;
+}
+
+// ---- input prefetch ---------------------------------------------------------------------------
+// dfb_prefetch_from_host: the copy stream first waits for everything enqueued on the compute stream so far
+// (the consumers of the destination's previous contents), then copies; dfb_prefetch_wait orders the compute
+// stream after all prefetches enqueued so far. Between the two calls the copy runs beside the compute stream.
+dfb_status dfb_prefetch_from_host(const float* pinned_src, float* dst, size_t n) {
+  DFB_INIT();
+  Runtime& r = rt();
+  DFB_REQUIRE(!r.capturing, DFB_ERR_RUNTIME, "prefetch_from_host during CUDA-graph capture");
+  if (n == 0) return DFB_OK;
+  DFB_CUDA(cudaEventRecord(r.ev_copy_ready, r.compute));
+  DFB_CUDA(cudaStreamWaitEvent(r.copy, r.ev_copy_ready, 0));
+  DFB_CUDA(cudaMemcpyAsync(dst, pinned_src, n * sizeof(float), cudaMemcpyHostToDevice, r.copy));
+  r.prefetch_pending = true;
+  return DFB_OK;
+}
+dfb_status dfb_prefetch_wait(void) {
+  DFB_INIT();
+  Runtime& r = rt();
+  if (!r.prefetch_pending) return DFB_OK;
+  DFB_CUDA(cudaEventRecord(r.ev_copy_done, r.copy));
+  DFB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_copy_done, 0));
+  r.prefetch_pending = false;
   return DFB_OK;
 }
 

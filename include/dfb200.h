@@ -101,6 +101,13 @@ DFB_API dfb_status dfb_host_free_pinned(float* host_ptr);
 DFB_API dfb_status dfb_from_host_async(const float* pinned_src, float* dst, size_t n);
 DFB_API dfb_status dfb_to_host_async(const float* src, float* pinned_dst, size_t n);
 DFB_API dfb_status dfb_copy(const float* src, float* dst, size_t n); /* device to device */
+/* Input pipeline (the reference's DataLoader only hands numpy batches to a blocking
+ * cudaMemcpy, utils/data/dataloader.py:60-139 + cu:700-716): the next batch is copied from pinned host memory
+ * into a staging buffer on a copy stream WHILE the current step runs. dfb_prefetch_from_host orders the copy
+ * after everything enqueued on the compute stream so far (the readers of the staging buffer's old contents);
+ * dfb_prefetch_wait makes the compute stream wait for the prefetches issued so far. */
+DFB_API dfb_status dfb_prefetch_from_host(const float* pinned_src, float* dst, size_t n);
+DFB_API dfb_status dfb_prefetch_wait(void);
 
 /* Side stream: work enqueued between dfb_side_begin() and dfb_side_end() runs on a second stream that is
  * ordered after everything enqueued on the compute stream so far, concurrently with what the compute
