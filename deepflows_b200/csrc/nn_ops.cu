@@ -336,6 +336,45 @@ __device__ __forceinline__ void block_lane_sum(float (&s0)[4], float (&s1)[4], f
         s1[v] += sm[(w * GPB + threadIdx.x) * 8 + 4 + v];
       }
   }
+  // The CTAs of a cluster own the same channels and different rows: publish this CTA's totals, then add all
+  // ranks' totals in rank order (every CTA gets the same bits) through distributed shared memory.
+  const int nrank = (int)cluster_nctarank();
+  if (nrank > 1) {
+    float* pub = sm + (kSmallT / 32) * GPB * 8;  // [GPB][8]
+    if (threadIdx.x < GPB) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        pub[threadIdx.x * 8 + v] = s0[v];
+        pub[threadIdx.x * 8 + 4 + v] = s1[v];
+      }
+    }
+    cluster_arrive();
+    cluster_wait();
+    if (threadIdx.x < GPB) {
+      const uint32_t mine = smem_addr_u32(pub + threadIdx.x * 8);
+      float t[8][8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < nrank) {
+          const uint32_t remote = dsmem_addr(mine, (uint32_t)r);
+#pragma unroll
+          for (int v = 0; v < 8; ++v) t[r][v] = ld_dsmem_f32(remote + 4u * v);
+        }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { s0[v] = 0.f; s1[v] = 0.f; }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < nrank) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) { s0[v] += t[r][v]; s1[v] += t[r][4 + v]; }
+        }
+    }
+    cluster_arrive();  // peers may leave only after everybody has read their totals; waited for at kernel end
+  }
+}
+// pairs with the trailing cluster_arrive() of block_lane_sum
+__device__ __forceinline__ void block_lane_sum_finish() {
+  if (cluster_nctarank() > 1) cluster_wait();
 }
 
 template <int GPB>  // float4 channel groups per CTA (CB = 4 * GPB channels)
@@ -345,16 +384,20 @@ bn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
                     float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps, int rows,
                     int C) {
   pdl_sync();
-  __shared__ float sm[(kSmallT / 32) * GPB * 8];
-  __shared__ float s_scale[GPB * 4], s_shift[GPB * 4];
+  __shared__ float sm[(kSmallT / 32) * GPB * 8 + GPB * 8];
+  __shared__ float s_scale[GPB * 4], s_shift[GPB * 4], s_mean[GPB * 4];
   const int g = threadIdx.x % GPB, lane = threadIdx.x / GPB;
   constexpr int kLanes = kSmallT / GPB;
-  const int c0 = (blockIdx.x * GPB + g) * 4;
+  // cluster of S CTAs along x: same channel block, rows split S ways
+  const int nrank = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+  const int c0 = (((int)blockIdx.x / nrank) * GPB + g) * 4;
+  const int rows_per = (rows + nrank - 1) / nrank;
+  const int r_lo = rank * rows_per, r_hi = min(rows, r_lo + rows_per);
   const float* xc = x + c0;
   float shift[4], s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-  Vec<4>::get(xc, shift);  // row 0
-  int r = lane;
-  for (; r + 3 * kLanes < rows; r += 4 * kLanes) {
+  Vec<4>::get(xc, shift);  // row 0 (the same shift in every CTA)
+  int r = r_lo + lane;
+  for (; r + 3 * kLanes < r_hi; r += 4 * kLanes) {
     float v[4][4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) Vec<4>::get(xc + (size_t)(r + u * kLanes) * C, v[u]);
@@ -363,7 +406,7 @@ bn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
 #pragma unroll
       for (int q = 0; q < 4; ++q) { float d = v[u][q] - shift[q]; s0[q] += d; s1[q] = fmaf(d, d, s1[q]); }
   }
-  for (; r < rows; r += kLanes) {
+  for (; r < r_hi; r += kLanes) {
     float v[4];
     Vec<4>::get(xc + (size_t)r * C, v);
 #pragma unroll
@@ -379,27 +422,30 @@ bn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
       const float mean = shift[q] + dm;
       const float var = fmaxf(s1[q] / n - dm * dm, 0.f);   // biased, like batchnorm.py:38-42
       const float invstd = 1.0f / sqrtf(var + eps);
-      save_mean[c] = mean;
-      save_invstd[c] = invstd;
-      if (running_mean) running_mean[c] = running_mean[c] * (1.0f - momentum) + mean * momentum;
-      if (running_var) running_var[c] = running_var[c] * (1.0f - momentum) + var * momentum;
-      const float sc = invstd * (gamma ? gamma[c] : 1.0f);
-      s_scale[g * 4 + q] = sc;
-      s_shift[g * 4 + q] = (beta ? beta[c] : 0.0f) - mean * sc;
+      if (rank == 0) {  // every rank holds the same values; one of them publishes
+        save_mean[c] = mean;
+        save_invstd[c] = invstd;
+        if (running_mean) running_mean[c] = running_mean[c] * (1.0f - momentum) + mean * momentum;
+        if (running_var) running_var[c] = running_var[c] * (1.0f - momentum) + var * momentum;
+      }
+      s_scale[g * 4 + q] = invstd * (gamma ? gamma[c] : 1.0f);
+      s_shift[g * 4 + q] = beta ? beta[c] : 0.0f;
+      s_mean[g * 4 + q] = mean;
     }
   }
   __syncthreads();
-  float sc[4], sh[4];
+  float sc[4], sh[4], mu[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { sc[q] = s_scale[g * 4 + q]; sh[q] = s_shift[g * 4 + q]; }
-  // y = (x - mean) * invstd * gamma + beta, evaluated as x * sc + (beta - mean * sc)
-  for (r = lane; r < rows; r += kLanes) {
+  for (int q = 0; q < 4; ++q) { sc[q] = s_scale[g * 4 + q]; sh[q] = s_shift[g * 4 + q]; mu[q] = s_mean[g * 4 + q]; }
+  // y = (x - mean) * (invstd * gamma) + beta; subtracting the mean first keeps the result accurate when |mean| >> std
+  for (r = r_lo + lane; r < r_hi; r += kLanes) {
     float v[4], o[4];
     Vec<4>::get(xc + (size_t)r * C, v);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = fmaf(v[q], sc[q], sh[q]);
+    for (int q = 0; q < 4; ++q) o[q] = fmaf(v[q] - mu[q], sc[q], sh[q]);
     Vec<4>::put(y + c0 + (size_t)r * C, o);
   }
+  block_lane_sum_finish();
 }
 
 template <int GPB>
@@ -408,18 +454,21 @@ bn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, c
                     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dx,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
   pdl_sync();
-  __shared__ float sm[(kSmallT / 32) * GPB * 8];
+  __shared__ float sm[(kSmallT / 32) * GPB * 8 + GPB * 8];
   __shared__ float s_mb[GPB * 4], s_mg[GPB * 4];
   const int g = threadIdx.x % GPB, lane = threadIdx.x / GPB;
   constexpr int kLanes = kSmallT / GPB;
-  const int c0 = (blockIdx.x * GPB + g) * 4;
+  const int nrank = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+  const int c0 = (((int)blockIdx.x / nrank) * GPB + g) * 4;
+  const int rows_per = (rows + nrank - 1) / nrank;
+  const int r_lo = rank * rows_per, r_hi = min(rows, r_lo + rows_per);
   const float* xc = x + c0;
   const float* dc = dy + c0;
   float mu[4], is[4], s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
   Vec<4>::get(mean + c0, mu);
   Vec<4>::get(invstd + c0, is);
-  int r = lane;
-  for (; r + 1 * kLanes < rows; r += 2 * kLanes) {
+  int r = r_lo + lane;
+  for (; r + 1 * kLanes < r_hi; r += 2 * kLanes) {
     float xv[2][4], dv[2][4];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -431,7 +480,7 @@ bn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, c
 #pragma unroll
       for (int q = 0; q < 4; ++q) { s0[q] += dv[u][q]; s1[q] = fmaf(dv[u][q], (xv[u][q] - mu[q]) * is[q], s1[q]); }
   }
-  for (; r < rows; r += kLanes) {
+  for (; r < r_hi; r += kLanes) {
     float xv[4], dv[4];
     Vec<4>::get(xc + (size_t)r * C, xv);
     Vec<4>::get(dc + (size_t)r * C, dv);
@@ -443,14 +492,17 @@ bn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, c
     const float inv_n = 1.0f / (float)rows;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (dbeta) dbeta[c0 + q] = s0[q];
-      if (dgamma) dgamma[c0 + q] = s1[q];
+      if (dbeta && rank == 0) dbeta[c0 + q] = s0[q];
+      if (dgamma && rank == 0) dgamma[c0 + q] = s1[q];
       s_mb[g * 4 + q] = s0[q] * inv_n;
       s_mg[g * 4 + q] = s1[q] * inv_n;
     }
   }
   __syncthreads();
-  if (!dx) return;
+  if (!dx) {
+    block_lane_sum_finish();
+    return;
+  }
   float k1[4], mb[4], mg[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -458,7 +510,7 @@ bn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, c
     mb[q] = s_mb[g * 4 + q];
     mg[q] = s_mg[g * 4 + q];
   }
-  for (r = lane; r < rows; r += kLanes) {
+  for (r = r_lo + lane; r < r_hi; r += kLanes) {
     float xv[4], dv[4], o[4];
     Vec<4>::get(xc + (size_t)r * C, xv);
     Vec<4>::get(dc + (size_t)r * C, dv);
@@ -466,16 +518,27 @@ bn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, c
     for (int q = 0; q < 4; ++q) o[q] = k1[q] * (dv[q] - mb[q] - (xv[q] - mu[q]) * is[q] * mg[q]);
     Vec<4>::put(dx + c0 + (size_t)r * C, o);
   }
+  block_lane_sum_finish();
 }
 
-// channel groups per CTA for the single-kernel path, 0 = use the two-kernel path
-static int bn_small_gpb(size_t rows, int C, const void* a, const void* b = nullptr, const void* c = nullptr) {
-  // Only while a thread sees at most four rows per pass (one batch of loads in flight): with more, the few
-  // CTAs of this path become a chain of dependent-latency loads and the two-kernel path (hundreds of CTAs) wins.
-  if (C % 16 != 0 || rows < 64 || rows > 1024) return 0;
-  if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) != 0) return 0;
-  const int gpb = rows > 512 ? 4 : (rows > 256 ? 2 : 1);   // 256 / 512 / 1024 row lanes per CTA
-  return (C / 4) % gpb == 0 ? gpb : 0;
+// Plan of the single-kernel path: channel groups per CTA (0 = use the two-kernel path) and cluster size S (CTAs
+// that split the rows of one channel block).
+struct SmallBnPlan { int gpb, cluster; };
+static SmallBnPlan bn_small_plan(size_t rows, int C, const void* a, const void* b = nullptr, const void* c = nullptr) {
+  // Only while a thread sees at most four rows per pass (one batch of loads in flight): with more, the CTAs of
+  // this path become chains of dependent-latency loads and the two-kernel path (hundreds of CTAs) wins.
+  if (C % 16 != 0 || rows < 64) return {0, 1};
+  if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) != 0) return {0, 1};
+  const int groups = C / 4;
+  if (rows <= 1024) {
+    const int gpb = rows > 512 ? 4 : (rows > 256 ? 2 : 1);   // 256 / 512 / 1024 row lanes per CTA
+    return {groups % gpb == 0 ? gpb : 0, 1};
+  }
+  // larger: a cluster of 8 CTAs per channel block, about two rows per thread and pass
+  // (16-byte row segments - one channel group per CTA - measured slower than the two-kernel path)
+  for (int gpb = 4; gpb >= 2; gpb >>= 1)
+    if (rows * gpb <= 16384 && groups % gpb == 0) return {gpb, 8};
+  return {0, 1};
 }
 
 // y = (x - mean) * (invstd * gamma) + beta, optionally followed by max(.,0)
@@ -856,11 +919,12 @@ dfb_status dfb_bn_fwd_train(const float* x, const float* gamma, const float* bet
   DFB_INIT();
   DFB_REQUIRE(x && y && save_mean && save_invstd, DFB_ERR_INVALID, "bn_fwd_train: null pointer");
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_fwd_train: empty input");
-  if (const int gpb = bn_small_gpb(rows, C, x, y)) {
-    const unsigned grid = (unsigned)(C / 4 / gpb);
+  const SmallBnPlan sp = bn_small_plan(rows, C, x, y);
+  if (const int gpb = sp.gpb) {
+    const unsigned grid = (unsigned)(C / 4 / gpb) * sp.cluster;
     cudaStream_t s = compute_stream();
-#define DFB_BN_SMALL_FWD(G) launch_k(bn_small_fwd_kernel<G>, grid, kSmallT, 0, s, x, gamma, beta, y, save_mean, save_invstd, running_mean, \
-                                                                          running_var, momentum, eps, (int)rows, C)
+#define DFB_BN_SMALL_FWD(G) launch_k_cluster(bn_small_fwd_kernel<G>, grid, kSmallT, 0, s, sp.cluster, x, gamma, beta, y, save_mean, \
+                                             save_invstd, running_mean, running_var, momentum, eps, (int)rows, C)
     if (gpb == 1) DFB_BN_SMALL_FWD(1);
     else if (gpb == 2) DFB_BN_SMALL_FWD(2);
     else DFB_BN_SMALL_FWD(4);
@@ -899,11 +963,12 @@ dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma, const
   DFB_INIT();
   DFB_REQUIRE(x && dy && save_mean && save_invstd, DFB_ERR_INVALID, "bn_bwd: null pointer");
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_bwd: empty input");
-  if (const int gpb = bn_small_gpb(rows, C, x, dy, dx)) {
-    const unsigned grid = (unsigned)(C / 4 / gpb);
+  const SmallBnPlan sp = bn_small_plan(rows, C, x, dy, dx);
+  if (const int gpb = sp.gpb) {
+    const unsigned grid = (unsigned)(C / 4 / gpb) * sp.cluster;
     cudaStream_t s = compute_stream();
-#define DFB_BN_SMALL_BWD(G) launch_k(bn_small_bwd_kernel<G>, grid, kSmallT, 0, s, x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, \
-                                                                          (int)rows, C)
+#define DFB_BN_SMALL_BWD(G) launch_k_cluster(bn_small_bwd_kernel<G>, grid, kSmallT, 0, s, sp.cluster, x, dy, gamma, save_mean, \
+                                             save_invstd, dx, dgamma, dbeta, (int)rows, C)
     if (gpb == 1) DFB_BN_SMALL_BWD(1);
     else if (gpb == 2) DFB_BN_SMALL_BWD(2);
     else DFB_BN_SMALL_BWD(4);

@@ -255,7 +255,8 @@ def test_batchnorm_against_reference_fixture(cuda_device):
     assert rel_err(from_nhwc(down(m, hy, (n, h, w, c))), g["bn.y_eval"]) < 1e-5
 
 
-@pytest.mark.parametrize("n,c,h,w", [(256, 32, 16, 16), (64, 256, 2, 2), (3, 5, 7, 9), (16, 1024, 3, 3), (2, 3, 2, 2), (1, 4, 1, 1)])
+@pytest.mark.parametrize("n,c,h,w", [(256, 32, 16, 16), (64, 256, 2, 2), (3, 5, 7, 9), (16, 1024, 3, 3), (2, 3, 2, 2), (1, 4, 1, 1),
+                                     (64, 64, 16, 16), (16, 128, 16, 16), (5, 48, 30, 30), (256, 256, 2, 2), (9, 32, 11, 11)])
 def test_batchnorm_against_oracle(cuda_device, n, c, h, w):
     m = cuda_device.mod
     rng = np.random.RandomState(n + c)
@@ -271,7 +272,10 @@ def test_batchnorm_against_oracle(cuda_device, n, c, h, w):
     x64 = x.astype(np.float64)
     mean, var = x64.mean(axis=(0, 2, 3)), x64.var(axis=(0, 2, 3))
     y = (x64 - mean.reshape(1, c, 1, 1)) / np.sqrt(var.reshape(1, c, 1, 1) + 1e-5) * gamma.reshape(1, c, 1, 1) + beta.reshape(1, c, 1, 1)
-    assert np.abs(from_nhwc(down(m, hy, (n, h, w, c))) - y).max() < 2e-5 * max(1.0, np.abs(y).max())
+    # float32 inputs resolve x - mean only to ~0.5 ulp of |mean|: a channel with |mean| >> std (the data above has
+    # some with mean/std > 1e4) carries that into y as ulp(mean) * invstd * gamma whatever the implementation does
+    cond = (np.abs(mean) * gamma / np.sqrt(var + 1e-5)).max()
+    assert np.abs(from_nhwc(down(m, hy, (n, h, w, c))) - y).max() < 2e-5 * max(1.0, np.abs(y).max()) + 4 * 6e-8 * cond
     assert rel_err(down(m, hmean, (c,)), mean) < 1e-6
     assert rel_err(down(m, hrv, (c,)), rv0 * 0.9 + var * 0.1) < 1e-5
     assert rel_err(down(m, hrm, (c,)), rm0 * 0.9 + mean * 0.1) < 1e-5
