@@ -150,3 +150,43 @@ def test_schedulers():
     for _ in range(3):
         st.step()
     assert abs(o3.lr - 0.5) < 1e-12
+
+
+def test_memory_layout_helpers_and_optimizers_follow_parameter_layout(cpu_device):
+    """Conv weights live channels-last (K,R,R,C) behind their logical (K,C,R,R) shape on the B200 device. The host
+    logic that makes this invisible - `with_layout_of`, `flat_storage`, the fused optimizers bringing gradient and
+    state to the parameter's memory layout - is device-independent and checked here on the numpy device."""
+    from DeepFlows import backend_api
+    from DeepFlows.tensor import Tensor
+    from DeepFlows.optim import Adam, SGD
+    rng = np.random.RandomState(3)
+    w = rng.randn(6, 4, 3, 3).astype(F32)
+    g = rng.randn(6, 4, 3, 3).astype(F32)
+    compact = backend_api.Btensor(w, device=cpu_device)
+    cl = compact.channels_last()
+    assert cl.is_channels_last() and cl.is_dense() and not cl.is_compact()
+    assert np.array_equal(cl.numpy(), w)
+    assert np.array_equal(cl.flat_storage().numpy(), w.transpose(0, 2, 3, 1).reshape(-1))      # memory order
+    gt = backend_api.Btensor(g, device=cpu_device)
+    g_cl = gt.with_layout_of(cl)
+    assert g_cl.strides == cl.strides and np.array_equal(g_cl.numpy(), g)
+    assert gt.with_layout_of(compact) is gt and g_cl.with_layout_of(cl) is g_cl              # no copy when layouts agree
+    assert np.array_equal(g_cl.with_layout_of(compact).numpy(), g) and g_cl.with_layout_of(compact).is_compact()
+    sliced = backend_api.Btensor(rng.randn(6, 8, 3, 3).astype(F32), device=cpu_device)[:, 0:8:2, :, :]  # neither compact nor dense
+    assert np.array_equal(sliced.with_layout_of(cl).numpy(), sliced.numpy())
+
+    for make in (lambda ps: Adam(ps, lr=1e-2, weight_decay=1e-3), lambda ps: SGD(ps, lr=0.1, momentum=0.9, nesterov=True)):
+        results = []
+        for layout in ("compact", "channels_last", "switch"):
+            p = Tensor(backend_api.Btensor(w, device=cpu_device), requires_grad=True)
+            if layout == "channels_last":
+                p.data = p.data.channels_last()
+            opt = make([p])
+            for step in range(3):
+                if layout == "switch" and step == 1:       # e.g. a checkpoint was loaded, or the first conv re-laid it out
+                    p.data = p.data.channels_last()
+                p.grad = backend_api.Btensor(g * (step + 1), device=cpu_device)  # gradient arrives compact
+                opt.step()
+            results.append(p.data.numpy().copy())
+            assert all(s.strides == p.data.strides for s in opt.v)
+        assert np.array_equal(results[0], results[1]) and np.array_equal(results[0], results[2])
