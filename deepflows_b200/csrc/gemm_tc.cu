@@ -171,7 +171,9 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32() {
 }
 
 // ---- kernel skeleton ----------------------------------------------------------------------------------
-template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K>   // KR: reduction rows per stage (MN-major operands only: 32 or 128)
+// KR: reduction rows per stage (MN-major operands only: 32 or 128). BSUB: B tiles per stage (the row-halo conv
+// kernel keeps the three taps of one filter column in a stage, with AROWS = 192 halo rows of A)
+template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K, int BSUB = 1>
 struct SmemLayout {
   // What one SM can pull through TMA is bounded by the bytes it keeps in flight (loads take microseconds to
   // return under load), so the ring is as deep as the shared-memory budget allows: ~192 KB for the BN = 128
@@ -179,16 +181,19 @@ struct SmemLayout {
   // output channels) shrinks the A tile to the rows that are really loaded, which buys more stages.
   static constexpr uint32_t kChunk = KR * 128;                 // one [KR k-rows x 128 B] chunk (32 m/n wide)
   static constexpr uint32_t kABytes = (AROWS / 32) * kChunk;
-  static constexpr uint32_t kBBytes = (BN / 32) * kChunk;
+  static constexpr uint32_t kBTile = (BN / 32) * kChunk;
+  static constexpr uint32_t kBBytes = BSUB * kBTile;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kBudget = BN >= 128 ? (BN >= 256 ? (208u << 10) : (192u << 10)) : (100u << 10);
+  static constexpr uint32_t kBudget = BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
+                                               : (BN >= 128 ? (BN >= 256 ? (208u << 10) : (192u << 10)) : (100u << 10));
   static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
-  static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < 3 ? 3 : kStagesFit);
+  static constexpr int kMinStages = BSUB > 1 ? 2 : 3;
+  static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < kMinStages ? kMinStages : kStagesFit);
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   // the M = 128 MMA always addresses four 32-row chunks of A: with AROWS < 128 it reads past the A tile (into the
   // B tile / the next stage: rows that are never stored), so the last stage needs that much slack behind it
   // (AROWS == 32: the A descriptor's chunk stride is 0, all four chunks alias the one that is loaded - no over-read)
-  static constexpr uint32_t kOverRead = AROWS == 32 ? 0 : ((BLOCK_M - AROWS) / 32) * kChunk;
+  static constexpr uint32_t kOverRead = (AROWS == 32 || AROWS >= BLOCK_M) ? 0 : ((BLOCK_M - AROWS) / 32) * kChunk;
   static constexpr uint32_t kTotal = kBarOffset + kOverRead + (2 * kStages + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
   // split-K partial tile staged in the (idle) pipeline stages: 128 rows, padded pitch against bank conflicts
   static constexpr uint32_t kRedPitch = BN + 4;
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap map_b,
                                                       const typename P::Params prm) {
   constexpr int BN = P::BN;
-  using L = SmemLayout<BN, P::AROWS, P::KR>;
+  using L = SmemLayout<BN, P::AROWS, P::KR, P::kSubTiles>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset + L::kOverRead);
@@ -280,10 +285,14 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       const uint32_t b_base = a_base + L::kABytes;
       if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < P::KR / UMMA_K; ++j)
-          umma_tf32(tmem_base, operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_base, j),
-                    operand_desc<P::B_MAJOR, L::kChunk>(b_base, j), idesc,
-                    (kb > kb_begin || j > 0) ? 1u : 0u);
+        for (int t = 0; t < P::kSubTiles; ++t) {  // > 1: several taps share the A halo tile of this stage
+          const uint32_t a_sub = a_base + P::a_sub_offset(prm, t), b_sub = b_base + t * L::kBTile;
+#pragma unroll
+          for (int j = 0; j < P::KR / UMMA_K; ++j)
+            umma_tf32(tmem_base, operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_sub, j),
+                      operand_desc<P::B_MAJOR, L::kChunk>(b_sub, j), idesc,
+                      (kb > kb_begin || t > 0 || j > 0) ? 1u : 0u);
+        }
         umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs have read it
       }
       __syncwarp();
@@ -401,7 +410,7 @@ static bool make_map(CUtensorMap* map, const float* base, int rank, const uint64
 template <class P>
 static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
                          dim3 grid, int splits = 1) {
-  using L = SmemLayout<P::BN, P::AROWS, P::KR>;
+  using L = SmemLayout<P::BN, P::AROWS, P::KR, P::kSubTiles>;
   static bool configured = false;
   if (!configured) {
     DFB_CUDA(cudaFuncSetAttribute(tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
@@ -459,7 +468,8 @@ template <int A_MAJ, int B_MAJ, int BN_>
 struct GemmProblem {
   static constexpr int BN = BN_, A_MAJOR = A_MAJ, B_MAJOR = B_MAJ;
   static constexpr bool kClusterSplit = true;
-  static constexpr int AROWS = BLOCK_M, KR = BLOCK_K;
+  static constexpr int AROWS = BLOCK_M, KR = BLOCK_K, kSubTiles = 1;
+  __device__ static uint32_t a_sub_offset(const GemmParams&, int) { return 0; }
   __device__ static uint32_t tx_bytes(const GemmParams&, const GemmTile&) { return SmemLayout<BN_>::kStageBytes; }
   __device__ static void finish(const GemmParams&, const GemmTile&, int) {}
   using Params = GemmParams;
@@ -587,12 +597,25 @@ struct ConvTile {
 //   W_KRSC_FPROP: the weights themselves, stored channels-last (K,R,R,C): K-major rows Wt[k][tap][c]
 //   W_KRSC_DGRAD: the same buffer read as the MN-major operand Wd[(tap,k)][c] - no copy in either direction
 enum { W_PACKED = 0, W_KRSC_FPROP = 1, W_KRSC_DGRAD = 2 };
-template <int BN_, int WMODE>
+// ROWS: "row halo" variant for 3x3 stride-1 convolutions whose 128-pixel tile is ow_t x oh_t pixels of ONE image
+// (ow_t a multiple of 8). A k-block is (filter column s, 32-channel block): ONE TMA box brings the tile's pixels
+// shifted by s with one halo row above and below ((oh_t + 2) * ow_t rows of 128 bytes), and the three taps
+// (r, s), r = 0..2, are MMAs whose A descriptors start r * ow_t rows into that box - whole multiples of the 1024-byte
+// swizzle atom, so the 128B swizzle stays consistent. The activations cross L2 -> SM 3.75-4.5 times per tile
+// instead of 9 times; these layers (few channels, many pixels) are bound by exactly that traffic.
+template <int BN_, int WMODE, bool ROWS = false>
 struct ConvProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = (WMODE == W_KRSC_DGRAD ? MAJOR_MN : MAJOR_K);
   static constexpr bool kClusterSplit = true;
-  static constexpr int AROWS = BLOCK_M, KR = BLOCK_K;
-  __device__ static uint32_t tx_bytes(const ConvParams&, const ConvTile&) { return SmemLayout<BN_>::kStageBytes; }
+  static constexpr int AROWS = ROWS ? 192 : BLOCK_M, KR = BLOCK_K, kSubTiles = ROWS ? 3 : 1;
+  using LayoutT = SmemLayout<BN_, AROWS, KR, kSubTiles>;
+  __device__ static uint32_t a_sub_offset(const ConvParams& p, int t) {
+    // tap r = t reads input row oh + dh0 + sgn * r; the box starts at the smallest of those rows
+    return ROWS ? (uint32_t)((p.sgn > 0 ? t : 2 - t) * p.ow_t * 128) : 0u;
+  }
+  __device__ static uint32_t tx_bytes(const ConvParams& p, const ConvTile&) {
+    return ROWS ? (uint32_t)((p.oh_t + 2) * p.ow_t * 128) + LayoutT::kBBytes : LayoutT::kStageBytes;
+  }
   __device__ static void finish(const ConvParams&, const ConvTile&, int) {}
   using Params = ConvParams;
   using Tile = ConvTile;
@@ -602,7 +625,7 @@ struct ConvProblem {
     t /= p.tiles_w;
     int th = t % p.tiles_h;
     int tn = t / p.tiles_h;
-    Tile o{tn * p.n_t, th * p.oh_t, tw * p.ow_t, (int)blockIdx.y * BN, 0, p.R * p.R * p.cblks, 0, 0, 0, 0, 0, 0, 0};
+    Tile o{tn * p.n_t, th * p.oh_t, tw * p.ow_t, (int)blockIdx.y * BN, 0, (ROWS ? p.R : p.R * p.R) * p.cblks, 0, 0, 0, 0, 0, 0, 0};
     if (p.par_pad >= 0) {
       const int cls = (int)blockIdx.z / p.splits;  // blockIdx.z = class * splits + split
       o.ph = cls >> 1;
@@ -617,10 +640,12 @@ struct ConvProblem {
     }
     return o;
   }
-  // k-block = (tap, 32-channel block); tap = (i, j): (r, s) of the filter, or the (i, j)-th tap of a parity class
+  // k-block = (tap, 32-channel block); tap = (i, j): (r, s) of the filter, or the (i, j)-th tap of a parity class.
+  // ROWS: k-block = (filter column j, 32-channel block), i unused.
   struct Iter { int i, j, cb, nj; };
   __device__ static Iter iter_init(const Params& p, const Tile& t, int kb) {
     const int tap = kb / p.cblks;
+    if (ROWS) return {0, tap, kb - tap * p.cblks, p.R};
     const int nj = p.par_pad >= 0 ? max(t.ns, 1) : p.R;
     return {tap / nj, tap % nj, kb - tap * p.cblks, nj};
   }
@@ -631,6 +656,11 @@ struct ConvProblem {
     }
   }
   __device__ static void load_a(const Params& p, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
+    if (ROWS) {
+      const int row0 = p.sgn > 0 ? p.dh0 : p.dh0 - 2;  // smallest input-row offset among the three taps
+      tma_load_4d(dst, m, bar, it.cb * 32, t.ow0 + p.dw0 + p.sgn * it.j, t.oh0 + row0, t.n0);
+      return;
+    }
     if (p.par_pad >= 0) {
       tma_load_4d(dst, m, bar, it.cb * 32, t.ow0 + t.d0w - it.j, t.oh0 + t.d0h - it.i, t.n0);
       return;
@@ -643,9 +673,7 @@ struct ConvProblem {
       tma_load_5d(dst, m, bar, (dw & 1) * p.c_red + it.cb * 32, t.ow0 + (dw >> 1), dh & 1, t.oh0 + (dh >> 1), t.n0);
     }
   }
-  __device__ static void load_b(const Params& p, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
-    const int tap = p.par_pad >= 0 ? (t.r0h + 2 * it.i) * p.R + t.r0w + 2 * it.j : it.i * p.R + it.j;
-    const int cb = it.cb;
+  __device__ static void load_b_tap(const Params& p, const Tile& t, int tap, int cb, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
     if (WMODE == W_PACKED) {
       tma_load_2d(dst, m, bar, (tap * p.cblks + cb) * BLOCK_K, t.col0);
     } else if (WMODE == W_KRSC_FPROP) {
@@ -655,6 +683,15 @@ struct ConvProblem {
       for (int j = 0; j < BN / 32; ++j)                          // rows = 32 k (output channels of the conv), 32 c each
         tma_load_3d(dst + j * kChunkBytes, m, bar, t.col0 + j * 32, tap, cb * 32);
     }
+  }
+  __device__ static void load_b(const Params& p, const Tile& t, const Iter& it, const CUtensorMap* m, uint64_t* bar, uint32_t dst) {
+    if (ROWS) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) load_b_tap(p, t, r * p.R + it.j, it.cb, m, bar, dst + r * LayoutT::kBTile);
+      return;
+    }
+    const int tap = p.par_pad >= 0 ? (t.r0h + 2 * it.i) * p.R + t.r0w + 2 * it.j : it.i * p.R + it.j;
+    load_b_tap(p, t, tap, it.cb, m, bar, dst);
   }
   __device__ static float* row_ptr(const Params& p, const Tile& t, int row) {
     const int owi = row % p.ow_t;
@@ -722,6 +759,8 @@ template <int BN_, int AROWS_, int KR_>
 struct WgradProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_MN, B_MAJOR = MAJOR_MN, AROWS = AROWS_, KR = KR_;
   static constexpr uint32_t kChunkW = KR_ * 128;
+  static constexpr int kSubTiles = 1;
+  __device__ static uint32_t a_sub_offset(const WgradParams&, int) { return 0; }
   static constexpr bool kClusterSplit = false;
   __device__ static void store4(const WgradParams&, const WgradTile&, int, int, const float4&) {}
   using Params = WgradParams;
@@ -893,7 +932,7 @@ static bool make_act_map(CUtensorMap* map, const float* base, int N, int H, int 
   return make_map(map, base, 5, d, s, b, major);
 }
 
-template <int BN, int WMODE>
+template <int BN, int WMODE, bool ROWS = false>
 static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float* wt, int n_out, int taps, int cp, int K, int C,
                            ConvParams prm, bool* handled) {
   CUtensorMap mb;
@@ -913,10 +952,26 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
   const int classes = prm.par_pad >= 0 ? 4 : 1;
   dim3 grid((unsigned)(prm.tiles_w * prm.tiles_h * tiles_n), cdiv(n_out, BN), 1);
   // stride-2 dgrad classes hold about a quarter of the taps each
-  const int kblocks = prm.R * prm.R * prm.cblks / (classes == 4 ? 4 : 1);
+  const int kblocks = ROWS ? prm.R * prm.cblks : prm.R * prm.R * prm.cblks / (classes == 4 ? 4 : 1);
   prm.splits = pick_splits((size_t)grid.x * grid.y * classes, kblocks > 0 ? kblocks : 1);
   grid.z = (unsigned)(classes * prm.splits);
-  return launch<ConvProblem<BN, WMODE>>(name, ma, mb, prm, grid, prm.splits);
+  return launch<ConvProblem<BN, WMODE, ROWS>>(name, ma, mb, prm, grid, prm.splits);
+}
+// row-halo variant (ConvProblem<.., ROWS = true>): n_out <= 128
+template <int WMODE>
+static dfb_status run_conv_rows(const char* name, const CUtensorMap& ma, const float* wt, int n_out, int taps, int cp, int K, int C,
+                                const ConvParams& prm, bool* handled) {
+  if (n_out <= 32) return run_conv<32, WMODE, true>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
+  if (n_out <= 64) return run_conv<64, WMODE, true>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
+  return run_conv<128, WMODE, true>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
+}
+static bool conv_rows_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_CONV_ROWS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 template <int WMODE>
 static dfb_status run_conv_bn(const char* name, const CUtensorMap& ma, const float* wt, int n_out, int taps, int cp, int K, int C,
@@ -939,11 +994,25 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
   prm.out = out; prm.n_img = N; prm.OH = OH; prm.OW = OW; prm.n_out = n_out; prm.R = R; prm.cblks = cp / 32;
   prm.dh0 = dh0; prm.dw0 = dh0; prm.sgn = sgn; prm.stride = stride; prm.c_red = actC; prm.par_pad = par_pad;
   pixel_tile(BLOCK_M, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
+  // Row-halo kernel: 3x3, stride 1, at most 128 output channels (beyond that the weights dominate the traffic),
+  // and a 128-pixel tile of ow_t x oh_t pixels inside one image with ow_t in {8, 16, 32}.
+  bool rows = false;
+  if (conv_rows_enabled() && stride == 1 && par_pad < 0 && R == 3 && n_out <= 128) {
+    const int ow_r = std::min(32, pow2_ceil(OW)), oh_r = BLOCK_M / ow_r;
+    if (ow_r >= 8 && pow2_ceil(OH) >= oh_r) {
+      rows = true;
+      prm.ow_t = ow_r; prm.oh_t = oh_r; prm.n_t = 1;
+    }
+  }
   prm.tiles_w = cdiv(OW, prm.ow_t);
   prm.tiles_h = cdiv(OH, prm.oh_t);
   CUtensorMap ma;
-  if (!make_act_map(&ma, act, N, actH, actW, actC, stride, prm.ow_t, prm.oh_t, prm.n_t, MAJOR_K)) return DFB_OK;
+  if (!make_act_map(&ma, act, N, actH, actW, actC, stride, prm.ow_t, rows ? prm.oh_t + 2 : prm.oh_t, prm.n_t, MAJOR_K)) return DFB_OK;
   if (w_layout == DFB_WLAYOUT_KRSC) {  // channels-last weights are consumed in place
+    if (rows) {
+      if (dgrad) return run_conv_rows<W_KRSC_DGRAD>(name, ma, w, n_out, taps, cp, K, C, prm, handled);
+      return run_conv_rows<W_KRSC_FPROP>(name, ma, w, n_out, taps, cp, K, C, prm, handled);
+    }
     if (dgrad) return run_conv_bn<W_KRSC_DGRAD>(name, ma, w, n_out, taps, cp, K, C, prm, handled);
     return run_conv_bn<W_KRSC_FPROP>(name, ma, w, n_out, taps, cp, K, C, prm, handled);
   }
@@ -954,7 +1023,8 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
   if (dgrad) launch_k(weight_transform_kernel<true>, bw_grid(wt_n, 256), 256, 0, compute_stream(), w, wt, K, C, taps, cp);
   else launch_k(weight_transform_kernel<false>, bw_grid(wt_n, 256), 256, 0, compute_stream(), w, wt, K, C, taps, cp);
   DFB_LAUNCH_CHECK("weight_transform");
-  st = run_conv_bn<W_PACKED>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
+  st = rows ? run_conv_rows<W_PACKED>(name, ma, wt, n_out, taps, cp, K, C, prm, handled)
+            : run_conv_bn<W_PACKED>(name, ma, wt, n_out, taps, cp, K, C, prm, handled);
   dfb_free(wt);
   return st;
 }
