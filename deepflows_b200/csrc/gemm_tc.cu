@@ -158,6 +158,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 //             transpose need the 128B swizzle with 32-BYTE atoms (cute: SWIZZLE_128B_BASE32B,
 //             TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), whose pattern repeats every 4 k-rows:
 //             SBO = 512 B between 4-row groups, LBO = bytes between 32-wide m/n chunks.
+// MN-major operand whose 32-wide chunks are `lbo` bytes apart (run-time: the wgrad row-halo kernel addresses the three
+// row-shifted views of one x halo tile as the three chunks of ONE N = 96 operand)
+__device__ __forceinline__ uint64_t operand_desc_mn(uint32_t base, int j, uint32_t lbo) {
+  return smem_desc(base + j * (UMMA_K * 128), lbo, 512, 1);
+}
 template <int MAJOR, uint32_t CHUNK_BYTES = kChunkBytes>
 __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int j) {
   if (MAJOR == MAJOR_K) return smem_desc(base + j * (UMMA_K * 4), 0, 1024, 2);
@@ -173,7 +178,8 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32() {
 // ---- kernel skeleton ----------------------------------------------------------------------------------
 // KR: reduction rows per stage (MN-major operands only: 32 or 128). BSUB: B tiles per stage (the row-halo conv
 // kernel keeps the three taps of one filter column in a stage, with AROWS = 192 halo rows of A)
-template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K, int BSUB = 1>
+// BKR: rows of one B chunk when they differ from KR (wgrad row-halo: 128-pixel A chunks, 192-row B halo chunks).
+template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K, int BSUB = 1, int BKR = KR>
 struct SmemLayout {
   // What one SM can pull through TMA is bounded by the bytes it keeps in flight (loads take microseconds to
   // return under load), so the ring is as deep as the shared-memory budget allows: ~192 KB for the BN = 128
@@ -181,7 +187,8 @@ struct SmemLayout {
   // output channels) shrinks the A tile to the rows that are really loaded, which buys more stages.
   static constexpr uint32_t kChunk = KR * 128;                 // one [KR k-rows x 128 B] chunk (32 m/n wide)
   static constexpr uint32_t kABytes = (AROWS / 32) * kChunk;
-  static constexpr uint32_t kBTile = (BN / 32) * kChunk;
+  static constexpr uint32_t kBChunk = BKR * 128;
+  static constexpr uint32_t kBTile = (BN / 32) * kBChunk;
   static constexpr uint32_t kBBytes = BSUB * kBTile;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kBudget = BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap map_b,
                                                       const typename P::Params prm) {
   constexpr int BN = P::BN;
-  using L = SmemLayout<BN, P::AROWS, P::KR, P::kSubTiles>;
+  using L = SmemLayout<BN, P::AROWS, P::KR, P::kBSub, P::BKR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset + L::kOverRead);
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<P::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   } else if (warp == 1) {
     // ===== MMA issuer: the warp waits convergently, one elected lane (always the same one: tcgen05.commit tracks
     // the MMAs of the thread that executes it) issues =====
-    constexpr uint32_t idesc = instr_desc_tf32<P::A_MAJOR, P::B_MAJOR, BN>();
+    constexpr uint32_t idesc = instr_desc_tf32<P::A_MAJOR, P::B_MAJOR, P::kMmaN>();
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -284,14 +291,19 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
       const uint32_t b_base = a_base + L::kABytes;
       if (elect_one()) {
+        // sub-tiles (taps that share a halo tile of this stage) are the INNER loop: with separate accumulators
+        // (wgrad) consecutive MMAs are then independent and pipeline, instead of each waiting for the previous
+        // one's accumulation into the same TMEM tile
 #pragma unroll
-        for (int t = 0; t < P::kSubTiles; ++t) {  // > 1: several taps share the A halo tile of this stage
-          const uint32_t a_sub = a_base + P::a_sub_offset(prm, t), b_sub = b_base + t * L::kBTile;
+        for (int j = 0; j < P::KR / UMMA_K; ++j) {
 #pragma unroll
-          for (int j = 0; j < P::KR / UMMA_K; ++j)
-            umma_tf32(tmem_base, operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_sub, j),
-                      operand_desc<P::B_MAJOR, L::kChunk>(b_sub, j), idesc,
-                      (kb > kb_begin || t > 0 || j > 0) ? 1u : 0u);
+          for (int t = 0; t < P::kSubTiles; ++t) {
+            const uint32_t a_sub = a_base + P::a_sub_offset(prm, t), b_sub = b_base + P::b_sub_offset(prm, t, L::kBTile);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * P::kAccStride);  // kAccStride == 0: one shared accumulator
+            const uint64_t b_desc = P::kRuntimeLbo ? operand_desc_mn(b_sub, j, P::b_lbo(prm)) : operand_desc<P::B_MAJOR, L::kBChunk>(b_sub, j);
+            umma_tf32(d_tmem, operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_sub, j), b_desc, idesc,
+                      (kb > kb_begin || (P::kAccStride == 0 && t > 0) || j > 0) ? 1u : 0u);
+          }
         }
         umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs have read it
       }
@@ -310,16 +322,17 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     }
     float* red = reinterpret_cast<float*>(smem);  // the pipeline stages are idle once the accumulator is complete
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int cc = 0; cc < P::kAccTiles * BN; cc += 32) {
+      const int acc = cc / BN, c0 = cc - acc * BN;  // accumulator tile (wgrad row-halo: one per tap), column inside it
       float v[32];
       if (kb_end > kb_begin) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc, v);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
       if (nsplit == 1) {
-        P::store(prm, tile, row, c0, v);
+        P::store(prm, tile, row, c0, v, acc);
       } else {
         float* dst = red + (size_t)row * L::kRedPitch + c0;
 #pragma unroll
@@ -361,7 +374,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<P::kTmemCols>(tmem_base);
   }
 }
 
@@ -410,7 +423,7 @@ static bool make_map(CUtensorMap* map, const float* base, int rank, const uint64
 template <class P>
 static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
                          dim3 grid, int splits = 1) {
-  using L = SmemLayout<P::BN, P::AROWS, P::KR, P::kSubTiles>;
+  using L = SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR>;
   static bool configured = false;
   if (!configured) {
     DFB_CUDA(cudaFuncSetAttribute(tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
@@ -468,8 +481,12 @@ template <int A_MAJ, int B_MAJ, int BN_>
 struct GemmProblem {
   static constexpr int BN = BN_, A_MAJOR = A_MAJ, B_MAJOR = B_MAJ;
   static constexpr bool kClusterSplit = true;
-  static constexpr int AROWS = BLOCK_M, KR = BLOCK_K, kSubTiles = 1;
+  static constexpr int AROWS = BLOCK_M, KR = BLOCK_K, BKR = BLOCK_K, kSubTiles = 1, kBSub = 1, kAccStride = 0, kAccTiles = 1, kTmemCols = BN_;
   __device__ static uint32_t a_sub_offset(const GemmParams&, int) { return 0; }
+  __device__ static uint32_t b_sub_offset(const GemmParams&, int, uint32_t) { return 0; }
+  static constexpr int kMmaN = BN_;
+  static constexpr bool kRuntimeLbo = false;
+  __device__ static uint32_t b_lbo(const GemmParams&) { return 0; }
   __device__ static uint32_t tx_bytes(const GemmParams&, const GemmTile&) { return SmemLayout<BN_>::kStageBytes; }
   __device__ static void finish(const GemmParams&, const GemmTile&, int) {}
   using Params = GemmParams;
@@ -512,7 +529,7 @@ struct GemmProblem {
       }
     }
   }
-  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
+  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32], int) {
     const int m = t.m0 + row;
     if (m >= p.M) return;
     float* dst = p.C + (size_t)m * p.ldc + t.n0 + c0;
@@ -607,8 +624,13 @@ template <int BN_, int WMODE, bool ROWS = false>
 struct ConvProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = (WMODE == W_KRSC_DGRAD ? MAJOR_MN : MAJOR_K);
   static constexpr bool kClusterSplit = true;
-  static constexpr int AROWS = ROWS ? 192 : BLOCK_M, KR = BLOCK_K, kSubTiles = ROWS ? 3 : 1;
-  using LayoutT = SmemLayout<BN_, AROWS, KR, kSubTiles>;
+  static constexpr int AROWS = ROWS ? 192 : BLOCK_M, KR = BLOCK_K, BKR = BLOCK_K, kSubTiles = ROWS ? 3 : 1, kBSub = kSubTiles;
+  static constexpr int kAccStride = 0, kAccTiles = 1, kTmemCols = BN_;
+  using LayoutT = SmemLayout<BN_, AROWS, KR, kBSub, BKR>;
+  __device__ static uint32_t b_sub_offset(const ConvParams&, int t, uint32_t b_tile) { return t * b_tile; }
+  static constexpr int kMmaN = BN_;
+  static constexpr bool kRuntimeLbo = false;
+  __device__ static uint32_t b_lbo(const ConvParams&) { return 0; }
   __device__ static uint32_t a_sub_offset(const ConvParams& p, int t) {
     // tap r = t reads input row oh + dh0 + sgn * r; the box starts at the smallest of those rows
     return ROWS ? (uint32_t)((p.sgn > 0 ? t : 2 - t) * p.ow_t * 128) : 0u;
@@ -720,7 +742,7 @@ struct ConvProblem {
         if (col + i < p.n_out) base[col + i] = v[i];
     }
   }
-  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
+  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32], int) {
     float* base = row_ptr(p, t, row);
     if (!base) return;
     const int col = t.col0 + c0;
@@ -745,6 +767,7 @@ struct WgradParams {
   unsigned* tickets;   // one self-resetting arrival counter per output tile (null: separate reduction kernel)
   int krsc;
   int kr;              // output pixels per pipeline stage (32 or 128)
+  int rows;            // row-halo variant: a CTA per filter column, three taps per stage
   int Kout, C, Cp, R, pad, stride;
   int n_img, OH, OW;
   int ow_t, oh_t, n_t, tiles_w, tiles_h, pix_blocks, blocks_per_split, ctiles;
@@ -755,12 +778,28 @@ struct WgradTile {
 };
 // AROWS_: rows of the dy tile that are loaded (32 / 64 / 128 >= output channels of the tile). KR_: output pixels per
 // pipeline stage: 32, or 128 for the small-channel layers, whose 8 KB stages are otherwise all barrier hand-offs
-template <int BN_, int AROWS_, int KR_>
+// ROWS_ (row-halo variant; 3x3, stride 1, KR_ = 128 pixels = ow_t x oh_t of one image, ow_t a multiple of 8): a CTA
+// owns a filter COLUMN s instead of a tap. Per stage ONE TMA box brings the x pixels of the block shifted by s with
+// a halo row above and below, the dy chunk is loaded once, and the three taps (r, s) are MMAs into three
+// accumulators (TMEM columns r * BN) whose B descriptors start r * ow_t rows into the box (multiples of 1024 bytes,
+// a whole number of swizzle periods). Both operands cross L2 -> SM ~2.7 times less often than with a CTA per tap.
+template <int BN_, int AROWS_, int KR_, bool ROWS_ = false>
 struct WgradProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_MN, B_MAJOR = MAJOR_MN, AROWS = AROWS_, KR = KR_;
+  static constexpr int BKR = ROWS_ ? 192 : KR_;       // rows of the x chunk: (oh_t + 2) * ow_t <= 192 with the halo
   static constexpr uint32_t kChunkW = KR_ * 128;
-  static constexpr int kSubTiles = 1;
+  static constexpr uint32_t kChunkB = BKR * 128;
+  // row-halo: the three taps are the three 32-wide chunks of ONE N = 3 * BN operand (chunk stride = ow_t rows), so
+  // a k-step is one MMA, not three (with N = 32 the MMA issue latency, not the math, is what a k-step costs)
+  static constexpr int kSubTiles = 1, kBSub = 1;
+  static constexpr int kAccTiles = ROWS_ ? 3 : 1, kAccStride = 0, kMmaN = ROWS_ ? 3 * BN_ : BN_;
+  static constexpr int kTmemCols = ROWS_ ? (BN_ * 3 <= 128 ? 128 : (BN_ * 3 <= 256 ? 256 : 512)) : BN_;
+  static constexpr bool kRuntimeLbo = ROWS_;
+  static_assert(!ROWS_ || BN_ == 32, "the row-halo wgrad addresses taps as operand chunks: one 32-wide chunk per tap");
+  using LayoutT = SmemLayout<BN_, AROWS_, KR_, kBSub, BKR>;
   __device__ static uint32_t a_sub_offset(const WgradParams&, int) { return 0; }
+  __device__ static uint32_t b_sub_offset(const WgradParams&, int, uint32_t) { return 0; }
+  __device__ static uint32_t b_lbo(const WgradParams& p) { return (uint32_t)(p.ow_t * 128); }
   static constexpr bool kClusterSplit = false;
   __device__ static void store4(const WgradParams&, const WgradTile&, int, int, const float4&) {}
   using Params = WgradParams;
@@ -772,13 +811,16 @@ struct WgradProblem {
     return {m0, tap, ct * BN, b0, min(p.pix_blocks, b0 + p.blocks_per_split), min(AROWS / 32, (p.Kout - m0 + 31) / 32)};
   }
   // rows of the accumulator beyond Kout multiply whatever the idle part of the stage holds; they are never stored
-  __device__ static uint32_t tx_bytes(const Params&, const Tile& t) { return t.a_chunks * kChunkW + SmemLayout<BN_, AROWS_, KR_>::kBBytes; }
+  __device__ static uint32_t tx_bytes(const Params& p, const Tile& t) {
+    return t.a_chunks * kChunkW + (ROWS_ ? (uint32_t)((BN / 32) * (p.oh_t + 2) * p.ow_t * 128) : LayoutT::kBBytes);
+  }
   // k-block = a block of 32 output pixels (tw, th, tn); the tap offset is fixed per CTA
   struct Iter { int tw, th, tn, dh, dw; };
   __device__ static Iter iter_init(const Params& p, const Tile& t, int kb) {
     const int tw = kb % p.tiles_w;
     kb /= p.tiles_w;
     const int r = t.tap / p.R, s = t.tap - r * p.R;
+    if (ROWS_) return {tw, kb % p.tiles_h, kb / p.tiles_h, -p.pad, t.tap - p.pad};  // t.tap is the filter column here
     return {tw, kb % p.tiles_h, kb / p.tiles_h, r - p.pad, s - p.pad};
   }
   __device__ static void iter_next(const Params& p, const Tile&, Iter& it) {
@@ -799,16 +841,18 @@ struct WgradProblem {
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) {
       if (p.stride == 1)
-        tma_load_4d(dst + j * kChunkW, m, bar, t.c0 + j * 32, ow0 + dw, oh0 + dh, n0);
+        tma_load_4d(dst + j * kChunkB, m, bar, t.c0 + j * 32, ow0 + dw, oh0 + dh, n0);
       else
-        tma_load_5d(dst + j * kChunkW, m, bar, (dw & 1) * p.C + t.c0 + j * 32, ow0 + (dw >> 1), dh & 1, oh0 + (dh >> 1), n0);
+        tma_load_5d(dst + j * kChunkB, m, bar, (dw & 1) * p.C + t.c0 + j * 32, ow0 + (dw >> 1), dh & 1, oh0 + (dh >> 1), n0);
     }
   }
-  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32]) {
+  // filter tap an accumulator tile belongs to: the CTA's tap, or (r = acc, s = CTA's column) in the row-halo variant
+  __device__ static int tap_of(const Params& p, const Tile& t, int acc) { return ROWS_ ? acc * p.R + t.tap : t.tap; }
+  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32], int acc) {
     const int k = t.m0 + row;
     if (k >= p.Kout) return;
     const int taps = p.R * p.R;
-    float* dst = p.partial + (((size_t)blockIdx.z * p.Kout + k) * taps + t.tap) * p.Cp + t.c0 + c0;
+    float* dst = p.partial + (((size_t)blockIdx.z * p.Kout + k) * taps + tap_of(p, t, acc)) * p.Cp + t.c0 + c0;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
@@ -833,11 +877,13 @@ struct WgradProblem {
     constexpr int kVec = BN / 4;
     const size_t slab = (size_t)p.Kout * taps * p.Cp;
     const int splits = gridDim.z;
-    for (int idx = tid; idx < rows * kVec; idx += 128) {
-      const int k = t.m0 + idx / kVec;
-      const int c = t.c0 + (idx % kVec) * 4;
+    for (int idx = tid; idx < kAccTiles * rows * kVec; idx += 128) {
+      const int acc_tile = idx / (rows * kVec), rem = idx - acc_tile * rows * kVec;
+      const int tap = tap_of(p, t, acc_tile);
+      const int k = t.m0 + rem / kVec;
+      const int c = t.c0 + (rem % kVec) * 4;
       if (c >= p.C) continue;  // channel padding
-      const float4* src = reinterpret_cast<const float4*>(p.partial + ((size_t)k * taps + t.tap) * p.Cp + c);
+      const float4* src = reinterpret_cast<const float4*>(p.partial + ((size_t)k * taps + tap) * p.Cp + c);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       int z = 0;
       for (; z + 4 <= splits; z += 4) {
@@ -852,9 +898,9 @@ struct WgradProblem {
         acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
       }
       if (p.krsc) {
-        *reinterpret_cast<float4*>(p.dw + ((size_t)k * taps + t.tap) * p.C + c) = acc;
+        *reinterpret_cast<float4*>(p.dw + ((size_t)k * taps + tap) * p.C + c) = acc;
       } else {
-        float* o = p.dw + ((size_t)k * p.C + c) * taps + t.tap;
+        float* o = p.dw + ((size_t)k * p.C + c) * taps + tap;
         o[0] = acc.x; o[taps] = acc.y; o[2 * taps] = acc.z; o[3 * taps] = acc.w;
       }
     }
@@ -1032,6 +1078,10 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
 template <int BN>
 static dfb_status run_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams prm, int splits) {
   dim3 grid(cdiv(prm.Kout, BLOCK_M), (unsigned)(prm.R * prm.R * prm.ctiles), (unsigned)splits);
+  if (prm.rows) {  // a CTA per filter column (BN == 32, Kout <= 32: host)
+    grid.y = (unsigned)(prm.R * prm.ctiles);
+    return launch<WgradProblem<32, 32, 128, true>>("tc_conv_wgrad_rows", ma, mb, prm, grid);
+  }
   if (prm.kr == 128) return launch<WgradProblem<32, 32, 128>>("tc_conv_wgrad", ma, mb, prm, grid);  // BN == 32 (host)
   if (prm.Kout <= 32) return launch<WgradProblem<BN, 32, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
   if (prm.Kout <= 64) return launch<WgradProblem<BN, 64, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
@@ -1106,6 +1156,19 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   // few channels on both sides and many pixels: 128-pixel stages (32 KB) instead of 32-pixel ones (8 KB)
   prm.kr = (K <= 32 && bn == 32 && (size_t)N * OH * OW >= 16384) ? 128 : BLOCK_K;
   pixel_tile(prm.kr, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
+  prm.rows = 0;
+  // Row-halo wgrad (WgradProblem<.., ROWS_ = true>): correct (parity-tested with DFB_WGRAD_ROWS=1) and moves 2.7x
+  // fewer operand bytes, but measured SLOWER than the CTA-per-tap kernel on the layer it targets (40 us vs 26 us for
+  // 256x32x16x16 -> 32): one CTA per SM with three 40 KB stages does not cover the TMA latency that two CTAs per
+  // SM with 32 KB stages do. Off by default until its pipeline is deeper.
+  static const bool wgrad_rows = [] { const char* e = getenv("DFB_WGRAD_ROWS"); return e && e[0] == '1'; }();
+  if (wgrad_rows && prm.kr == 128 && stride == 1 && R == 3) {
+    const int ow_r = std::min(32, pow2_ceil(OW)), oh_r = 128 / ow_r;
+    if (ow_r >= 8 && pow2_ceil(OH) >= oh_r) {
+      prm.rows = 1;
+      prm.ow_t = ow_r; prm.oh_t = oh_r; prm.n_t = 1;
+    }
+  }
   prm.tiles_w = cdiv(OW, prm.ow_t);
   prm.tiles_h = cdiv(OH, prm.oh_t);
   prm.pix_blocks = prm.tiles_w * prm.tiles_h * (int)cdiv(N, prm.n_t);
@@ -1117,10 +1180,11 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
     uint32_t b[4] = {32, (uint32_t)prm.ow_t, (uint32_t)prm.oh_t, (uint32_t)prm.n_t};
     if (!make_map(&ma, dy, 4, d, s, b, MAJOR_MN)) return DFB_OK;
   }
-  if (!make_act_map(&mb, x, N, H, W, C, stride, prm.ow_t, prm.oh_t, prm.n_t, MAJOR_MN)) return DFB_OK;
+  if (!make_act_map(&mb, x, N, H, W, C, stride, prm.ow_t, prm.rows ? prm.oh_t + 2 : prm.oh_t, prm.n_t, MAJOR_MN)) return DFB_OK;
   const int taps = R * R;
-  size_t base_ctas = (size_t)cdiv(K, BLOCK_M) * taps * prm.ctiles;
-  int splits = (int)std::max<size_t>(1, ((size_t)sm_count() * 2 + base_ctas - 1) / base_ctas);
+  size_t base_ctas = (size_t)cdiv(K, BLOCK_M) * (prm.rows ? R : taps) * prm.ctiles;
+  // two CTAs per SM (one for the row-halo variant, whose stages are 40 KB)
+  int splits = (int)std::max<size_t>(1, prm.rows ? (size_t)sm_count() / base_ctas : ((size_t)sm_count() * 2 + base_ctas - 1) / base_ctas);
   splits = std::min(splits, std::max(1, prm.pix_blocks / 8));
   splits = std::min(splits, 128);
   prm.blocks_per_split = (prm.pix_blocks + splits - 1) / splits;
