@@ -194,7 +194,7 @@ struct SmemLayout {
   static constexpr uint32_t kBudget = BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
                                                : (BN >= 128 ? (BN >= 256 ? (208u << 10) : (192u << 10)) : (100u << 10));
   static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
-  static constexpr int kMinStages = BSUB > 1 ? 2 : 3;
+  static constexpr int kMinStages = (BSUB > 1 || BKR != KR) ? 2 : 3;   // halo variants: two CTAs per SM with two stages each
   static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < kMinStages ? kMinStages : kStagesFit);
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   // the M = 128 MMA always addresses four 32-row chunks of A: with AROWS < 128 it reads past the A tile (into the
@@ -1157,12 +1157,10 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   prm.kr = (K <= 32 && bn == 32 && (size_t)N * OH * OW >= 16384) ? 128 : BLOCK_K;
   pixel_tile(prm.kr, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
   prm.rows = 0;
-  // Row-halo wgrad (WgradProblem<.., ROWS_ = true>): correct (parity-tested with DFB_WGRAD_ROWS=1) and moves 2.7x
-  // fewer operand bytes, but measured SLOWER than the CTA-per-tap kernel on the layer it targets (40 us vs 26 us for
-  // 256x32x16x16 -> 32): one CTA per SM with three 40 KB stages does not cover the TMA latency that two CTAs per
-  // SM with 32 KB stages do. Off by default until its pipeline is deeper.
-  static const bool wgrad_rows = [] { const char* e = getenv("DFB_WGRAD_ROWS"); return e && e[0] == '1'; }();
-  if (wgrad_rows && prm.kr == 128 && stride == 1 && R == 3) {
+  // Row-halo wgrad (WgradProblem<.., ROWS_ = true>): 2.7x fewer operand bytes per tile. It needs two CTAs per SM (two
+  // 40 KB stages each): with one CTA per SM and three stages it was SLOWER than the CTA-per-tap kernel (40 us vs 26 us
+  // on 256x32x16x16 -> 32), with two it takes 18 us.
+  if (conv_rows_enabled() && prm.kr == 128 && stride == 1 && R == 3) {
     const int ow_r = std::min(32, pow2_ceil(OW)), oh_r = 128 / ow_r;
     if (ow_r >= 8 && pow2_ceil(OH) >= oh_r) {
       prm.rows = 1;
@@ -1183,8 +1181,7 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   if (!make_act_map(&mb, x, N, H, W, C, stride, prm.ow_t, prm.rows ? prm.oh_t + 2 : prm.oh_t, prm.n_t, MAJOR_MN)) return DFB_OK;
   const int taps = R * R;
   size_t base_ctas = (size_t)cdiv(K, BLOCK_M) * (prm.rows ? R : taps) * prm.ctiles;
-  // two CTAs per SM (one for the row-halo variant, whose stages are 40 KB)
-  int splits = (int)std::max<size_t>(1, prm.rows ? (size_t)sm_count() / base_ctas : ((size_t)sm_count() * 2 + base_ctas - 1) / base_ctas);
+  int splits = (int)std::max<size_t>(1, ((size_t)sm_count() * 2 + base_ctas - 1) / base_ctas);  // two CTAs per SM
   splits = std::min(splits, std::max(1, prm.pix_blocks / 8));
   splits = std::min(splits, 128);
   prm.blocks_per_split = (prm.pix_blocks + splits - 1) / splits;
