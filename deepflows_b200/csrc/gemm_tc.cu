@@ -182,9 +182,11 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32() {
 template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K, int BSUB = 1, int BKR = KR>
 struct SmemLayout {
   // What one SM can pull through TMA is bounded by the bytes it keeps in flight (loads take microseconds to
-  // return under load), so the ring is as deep as the shared-memory budget allows: ~192 KB for the BN = 128
-  // kernels (one CTA per SM), ~96 KB for the narrower ones (two CTAs per SM). AROWS < 128 (wgrad with few
-  // output channels) shrinks the A tile to the rows that are really loaded, which buys more stages.
+  // return under load), and a CTA's prologue / epilogue / split-K reduction are pure latency: TWO CTAs per SM
+  // with ~100 KB of ring each beat one CTA with 192 KB on every layer measured (layer-4 conv 19 -> 14 us,
+  // VGG c2_2 wgrad 504 -> 363 us), so that is the budget up to BN = 128; the 128 x 256 kernels keep one CTA per
+  // SM (208 KB). AROWS < 128 (wgrad with few output channels) shrinks the A tile to the rows that are really
+  // loaded, which buys more stages.
   static constexpr uint32_t kChunk = KR * 128;                 // one [KR k-rows x 128 B] chunk (32 m/n wide)
   static constexpr uint32_t kABytes = (AROWS / 32) * kChunk;
   static constexpr uint32_t kBChunk = BKR * 128;
@@ -192,7 +194,7 @@ struct SmemLayout {
   static constexpr uint32_t kBBytes = BSUB * kBTile;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kBudget = BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
-                                               : (BN >= 128 ? (BN >= 256 ? (208u << 10) : (192u << 10)) : (100u << 10));
+                                               : (BN >= 256 ? (208u << 10) : (100u << 10));
   static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
   static constexpr int kMinStages = (BSUB > 1 || BKR != KR) ? 2 : 3;   // halo variants: two CTAs per SM with two stages each
   static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < kMinStages ? kMinStages : kStagesFit);
