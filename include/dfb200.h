@@ -48,10 +48,10 @@ enum {
 /* GEMM / conv operand precision modes (north star: fp32-accurate, TF32, BF16 operand modes;
  * accumulation is always fp32). */
 enum {
-  DFB_MODE_FP32 = 0,  /* 3xTF32 error-compensated split on tcgen05 (or FFMA for tiny shapes) */
-  DFB_MODE_TF32 = 1,  /* single-pass TF32 operands                                          */
-  DFB_MODE_BF16 = 2,  /* operands rounded to bf16 in shared memory, kind::f16 MMA            */
-  DFB_MODE_SIMT = 3   /* force the FFMA kernel (exact fp32 operands; testing / tiny shapes)  */
+  DFB_MODE_FP32 = 0,  /* exact fp32 operands and FFMA accumulation (parity within 1e-5 of the reference)      */
+  DFB_MODE_TF32 = 1,  /* tcgen05 kind::tf32: fp32 operands read as TF32, fp32 accumulation in TMEM (2e-2)      */
+  DFB_MODE_BF16 = 2,  /* reserved for a bf16-operand tcgen05 path; currently served by the exact FFMA kernels  */
+  DFB_MODE_SIMT = 3   /* force the generic FFMA kernels (no first-layer / tensor-core specialisations; tests)  */
 };
 
 /* ---------------------------------------------------------------------------------------------
