@@ -190,3 +190,73 @@ def test_memory_layout_helpers_and_optimizers_follow_parameter_layout(cpu_device
             results.append(p.data.numpy().copy())
             assert all(s.strides == p.data.strides for s in opt.v)
         assert np.array_equal(results[0], results[1]) and np.array_equal(results[0], results[2])
+
+
+def test_captured_step_protocol_with_a_mock_device():
+    """DeepFlows.cuda_graph.CapturedStep: call 1..warmup run eagerly, the next call captures AND launches (a capture
+    executes nothing), later calls refresh the hyper-parameters of every optimizer that stepped during the capture
+    (in capture order) and replay; a failing capture is torn down and re-raised."""
+    from DeepFlows.cuda_graph import CapturedStep, note_optimizer_step, capturing
+
+    class MockDevice:
+        def __init__(self):
+            self.log = []
+
+        def graph_begin_capture(self):
+            self.log.append("begin")
+
+        def graph_end_capture(self):
+            self.log.append("end")
+            return 42
+
+        def graph_launch(self, g):
+            self.log.append(("launch", g))
+
+        def graph_destroy(self, g):
+            self.log.append(("destroy", g))
+
+        def graph_node_counts(self, g):
+            return (7, 9)
+
+    class MockOpt:
+        def __init__(self, name):
+            self.name, self.t = name, 1
+
+        def step(self):
+            note_optimizer_step(self)
+            self.t += 1
+
+        def _graph_refresh(self, dev, g, index):
+            dev.log.append(("refresh", self.name, index, self.t))
+            self.t += 1
+
+    dev, a, b = MockDevice(), MockOpt("a"), MockOpt("b")
+    calls = []
+
+    def fn():
+        calls.append(capturing())
+        a.step()
+        b.step()
+        return "loss"
+
+    step = CapturedStep(fn, device=dev, warmup=2)
+    assert step() == "loss" and step() == "loss" and not step.captured and dev.log == []
+    assert step() == "loss" and step.captured
+    assert dev.log == ["begin", "end", ("launch", 42)] and calls == [False, False, True]
+    assert step.node_counts() == (7, 9)
+    assert step() == "loss" and step() == "loss"
+    assert dev.log[3:] == [("refresh", "a", 0, 4), ("refresh", "b", 1, 4), ("launch", 42),
+                           ("refresh", "a", 0, 5), ("refresh", "b", 1, 5), ("launch", 42)]
+    assert len(calls) == 3 and a.t == 6                        # replays do not run the Python step
+    step.destroy()
+    assert dev.log[-1] == ("destroy", 42) and not step.captured
+
+    dev2 = MockDevice()
+
+    def bad():
+        raise ValueError("boom")
+
+    failing = CapturedStep(bad, device=dev2, warmup=0)
+    with pytest.raises(ValueError):
+        failing()
+    assert dev2.log == ["begin", "end", ("destroy", 42)] and not capturing() and not failing.captured
