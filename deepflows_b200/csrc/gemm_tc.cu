@@ -11,10 +11,17 @@
 // activations, with the zero padding supplied by TMA's out-of-bounds fill. Stride-2 convolutions read a
 // 5-d parity view (2C, W/2, 2, H/2, N) of the same buffer, so every tap is again a dense box.
 //
-// Pipeline (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma
-// issuer, warps 2-5 = epilogue (tcgen05.ld -> registers -> global). Operands are fp32 in HBM and are
-// consumed as TF32 (kind::tf32, 128-byte swizzled tiles, BLOCK_K = 32 elements per stage, 4 MMAs of K=8 per
-// stage); accumulation is fp32 in TMEM (128 lanes x BLOCK_N columns).
+// Pipeline (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + tcgen05.mma issuer (both run their
+// loops warp-convergently and issue through elect.sync), warps 2-5 = epilogue (tcgen05.ld -> registers ->
+// global). Operands are fp32 in HBM and are consumed as TF32 (kind::tf32, 128-byte swizzled tiles, BLOCK_K = 32
+// elements per stage, 4 MMAs of K=8 per stage); accumulation is fp32 in TMEM (128 lanes x BLOCK_N columns).
+// Tiles are 128 x {32, 64, 128, 256}; up to 128 wide two CTAs share an SM (~100 KB of stage ring each).
+//
+// What the step's small layers need is short latency chains, not math: split-K over a thread-block cluster
+// with the partial tiles summed through distributed shared memory (layers with 8-32 tiles), an incremental
+// k-block iterator in the producer, the "row halo" variants (ConvProblem / WgradProblem with ROWS) that bring
+// a tile's pixels once per filter column and address the three taps of the column by descriptor offsets, and
+// programmatic dependent launch (the prologue below runs while the previous kernel drains).
 //
 // Operand "major-ness": a tile whose reduction index is contiguous in memory is K-major (one TMA box of
 // [rows, 32 k]); a tile whose row/column index is contiguous is MN-major ([32 k, 32 mn] boxes, one per
