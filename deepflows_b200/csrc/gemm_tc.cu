@@ -201,7 +201,7 @@ struct SmemLayout {
   static constexpr uint32_t kBBytes = BSUB * kBTile;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kBudget = BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
-                                               : (BN >= 256 ? (208u << 10) : (100u << 10));
+                                               : (BN >= 256 ? (208u << 10) : (100u << 10));  // (128 x 256 at two CTAs per SM with two stages: measured 7% slower)
   static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
   static constexpr int kMinStages = (BSUB > 1 || BKR != KR) ? 2 : 3;   // halo variants: two CTAs per SM with two stages each
   static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < kMinStages ? kMinStages : kStagesFit);
@@ -213,7 +213,8 @@ struct SmemLayout {
   static constexpr uint32_t kTotal = kBarOffset + kOverRead + (2 * kStages + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
   // split-K partial tile staged in the (idle) pipeline stages: 128 rows, padded pitch against bank conflicts
   static constexpr uint32_t kRedPitch = BN + 4;
-  static_assert(AROWS < BLOCK_M || BLOCK_M * kRedPitch * 4 <= kBarOffset, "partial tile does not fit the pipeline stages");
+  // (the 128 x 256 kernels never split K: they are only chosen for problems with hundreds of tiles)
+  static_assert(AROWS < BLOCK_M || BN >= 256 || BLOCK_M * kRedPitch * 4 <= kBarOffset, "partial tile does not fit the pipeline stages");
 };
 
 template <class P>
@@ -579,7 +580,7 @@ static dfb_status run_gemm(const float* A, const float* B, const GemmParams& prm
   if (!ok) return DFB_OK;  // not representable as a tensor map -> FFMA path
   *handled = true;
   dim3 grid(cdiv(prm.M, BLOCK_M), cdiv(prm.N, BN), 1);
-  const int splits = pick_splits((size_t)grid.x * grid.y, (prm.K + BLOCK_K - 1) / BLOCK_K);
+  const int splits = BN >= 256 ? 1 : pick_splits((size_t)grid.x * grid.y, (prm.K + BLOCK_K - 1) / BLOCK_K);
   grid.z = (unsigned)splits;
   return launch<GemmProblem<A_MAJ, B_MAJ, BN>>("tc_gemm", ma, mb, prm, grid, splits);
 }
@@ -1008,7 +1009,7 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
   dim3 grid((unsigned)(prm.tiles_w * prm.tiles_h * tiles_n), cdiv(n_out, BN), 1);
   // stride-2 dgrad classes hold about a quarter of the taps each
   const int kblocks = ROWS ? prm.R * prm.cblks : prm.R * prm.R * prm.cblks / (classes == 4 ? 4 : 1);
-  prm.splits = pick_splits((size_t)grid.x * grid.y * classes, kblocks > 0 ? kblocks : 1);
+  prm.splits = BN >= 256 ? 1 : pick_splits((size_t)grid.x * grid.y * classes, kblocks > 0 ? kblocks : 1);
   grid.z = (unsigned)(classes * prm.splits);
   return launch<ConvProblem<BN, WMODE, ROWS>>(name, ma, mb, prm, grid, prm.splits);
 }
