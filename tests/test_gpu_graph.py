@@ -140,3 +140,30 @@ def test_graph_pool_keeps_captured_buffers_private(cuda_device):
     assert np.array_equal(y2.numpy(), np.arange(1024, dtype=F32)[::-1] * 3 + 1)
     assert all(np.array_equal(j.numpy(), np.full(1024, -7.0, F32)) for j in junk)
     step.destroy()
+
+
+def test_device_prefetcher_delivers_every_batch(cuda_device):
+    """utils.data.DevicePrefetcher: batches arrive on the device through pinned memory and the copy stream, in
+    order, bit-exact, including a ragged last batch; `into=` refreshes static tensors (the CapturedStep pattern)."""
+    from DeepFlows import backend_api
+    from DeepFlows.tensor import Tensor
+    from DeepFlows.utils.data import data_loader, DevicePrefetcher
+    rng = np.random.RandomState(2)
+    X = rng.randn(70, 3, 8, 8).astype(F32)
+    Y = np.eye(10, dtype=F32)[rng.randint(0, 10, 70)]
+    loader = data_loader(X, Y, batch_size=16)            # 16, 16, 16, 16, 6
+    seen = 0
+    for x, t in DevicePrefetcher(loader, device=cuda_device):
+        n = x.shape[0]
+        junk = backend_api.full((4096,), float(seen), device=cuda_device)  # keep the compute stream busy meanwhile
+        assert np.array_equal(x.numpy(), X[seen:seen + n]) and np.array_equal(t.numpy(), Y[seen:seen + n])
+        assert np.array_equal(junk.numpy(), np.full(4096, float(seen), F32))
+        seen += n
+    assert seen == 70
+    loader = data_loader(X[:64], Y[:64], batch_size=16)
+    xs = Tensor(backend_api.Btensor(np.zeros((16, 3, 8, 8), F32), device=cuda_device))
+    ts = Tensor(backend_api.Btensor(np.zeros((16, 10), F32), device=cuda_device))
+    for i, (x, t) in enumerate(DevicePrefetcher(loader, device=cuda_device, into=(xs, ts))):
+        assert x is xs and t is ts
+        assert np.array_equal(xs.numpy(), X[16 * i:16 * i + 16]) and np.array_equal(ts.numpy(), Y[16 * i:16 * i + 16])
+    assert i == 3
