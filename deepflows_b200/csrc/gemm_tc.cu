@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       tc_fence_after();
     }
     float* red = reinterpret_cast<float*>(smem);  // the pipeline stages are idle once the accumulator is complete
+    constexpr uint32_t kRedPitch = P::kAccTiles * BN + 4;  // == L::kRedPitch with one accumulator tile
 #pragma unroll 1
     for (int cc = 0; cc < P::kAccTiles * BN; cc += 32) {
       const int acc = cc / BN, c0 = cc - acc * BN;  // accumulator tile (wgrad row-halo: one per tap), column inside it
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       if (nsplit == 1) {
         P::store(prm, tile, row, c0, v, acc);
       } else {
-        float* dst = red + (size_t)row * L::kRedPitch + c0;
+        float* dst = red + (size_t)row * kRedPitch + cc;  // cc == c0 with one accumulator tile
 #pragma unroll
         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
@@ -356,14 +357,18 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     cluster_arrive();
     cluster_wait();  // every partial tile is in its CTA's shared memory
     if (warp >= 2) {
-      const int rows_per = BLOCK_M / nsplit;
+      // kDynRedRows (wgrad): only the rows that hold output channels are reduced, spread over all CTAs of the cluster
+      const int red_rows = P::kDynRedRows ? P::red_rows(prm, tile) : BLOCK_M;
+      const int rows_per = P::kDynRedRows ? (red_rows + nsplit - 1) / nsplit : BLOCK_M / nsplit;
       const int t = (warp - 2) * 32 + lane;   // 0..127
-      constexpr int kVecPerRow = BN / 4;
+      constexpr int kVecPerRow = P::kAccTiles * BN / 4;
+      constexpr uint32_t kRedPitch = P::kAccTiles * BN + 4;
       const uint32_t red_base = smem_u32(smem);
       for (int idx = t; idx < rows_per * kVecPerRow; idx += 128) {
         const int r = rank * rows_per + idx / kVecPerRow;
+        if (P::kDynRedRows && r >= red_rows) break;
         const int c = (idx % kVecPerRow) * 4;
-        const uint32_t addr = red_base + (uint32_t)(r * L::kRedPitch + c) * 4u;
+        const uint32_t addr = red_base + (uint32_t)(r * kRedPitch + c) * 4u;
         float4 pv[8];
 #pragma unroll
         for (int s2 = 0; s2 < 8; ++s2)
@@ -378,6 +383,8 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     // nobody leaves while its shared memory may still be read: arrive once this CTA's remote reads have
     // landed in registers (the global stores above only consume registers), wait just before the exit
     cluster_arrive();
+    // two-level split (wgrad): the last cluster that finishes a tile adds the clusters' partial tiles
+    if (P::kClusterFinish && warp >= 2) P::finish_cluster(prm, tile, (warp - 2) * 32 + lane, rank, nsplit);
     cluster_wait();
   } else {
     __syncthreads();
@@ -499,6 +506,9 @@ struct GemmProblem {
   __device__ static uint32_t b_lbo(const GemmParams&) { return 0; }
   __device__ static uint32_t tx_bytes(const GemmParams&, const GemmTile&) { return SmemLayout<BN_>::kStageBytes; }
   __device__ static void finish(const GemmParams&, const GemmTile&, int) {}
+  static constexpr bool kDynRedRows = false, kClusterFinish = false;
+  __device__ static int red_rows(const GemmParams&, const GemmTile&) { return BLOCK_M; }
+  __device__ static void finish_cluster(const GemmParams&, const GemmTile&, int, int, int) {}
   using Params = GemmParams;
   using Tile = GemmTile;
   __device__ static Tile tile(const Params& p) {
@@ -649,6 +659,9 @@ struct ConvProblem {
     return ROWS ? (uint32_t)((p.oh_t + 2) * p.ow_t * 128) + LayoutT::kBBytes : LayoutT::kStageBytes;
   }
   __device__ static void finish(const ConvParams&, const ConvTile&, int) {}
+  static constexpr bool kDynRedRows = false, kClusterFinish = false;
+  __device__ static int red_rows(const ConvParams&, const ConvTile&) { return BLOCK_M; }
+  __device__ static void finish_cluster(const ConvParams&, const ConvTile&, int, int, int) {}
   using Params = ConvParams;
   using Tile = ConvTile;
   __device__ static Tile tile(const Params& p) {
@@ -781,6 +794,7 @@ struct WgradParams {
   int Kout, C, Cp, R, pad, stride;
   int n_img, OH, OW;
   int ow_t, oh_t, n_t, tiles_w, tiles_h, pix_blocks, blocks_per_split, ctiles;
+  int csize, groups;   // WgradClusterProblem: CTAs per cluster (split of one group's pixels), groups of pixels (global partials)
 };
 struct WgradTile {
   int m0, tap, c0, kb_begin, kb_end;
@@ -810,8 +824,10 @@ struct WgradProblem {
   __device__ static uint32_t a_sub_offset(const WgradParams&, int) { return 0; }
   __device__ static uint32_t b_sub_offset(const WgradParams&, int, uint32_t) { return 0; }
   __device__ static uint32_t b_lbo(const WgradParams& p) { return (uint32_t)(p.ow_t * 128); }
-  static constexpr bool kClusterSplit = false;
+  static constexpr bool kClusterSplit = false, kDynRedRows = false, kClusterFinish = false;
   __device__ static void store4(const WgradParams&, const WgradTile&, int, int, const float4&) {}
+  __device__ static int red_rows(const WgradParams&, const WgradTile&) { return BLOCK_M; }
+  __device__ static void finish_cluster(const WgradParams&, const WgradTile&, int, int, int) {}
   using Params = WgradParams;
   using Tile = WgradTile;
   __device__ static Tile tile(const Params& p) {
@@ -913,6 +929,93 @@ struct WgradProblem {
         float* o = p.dw + ((size_t)k * p.C + c) * taps + tap;
         o[0] = acc.x; o[taps] = acc.y; o[2 * taps] = acc.z; o[3 * taps] = acc.w;
       }
+    }
+  }
+};
+
+// Two-level pixel split for wgrad. The pixel blocks are cut into `groups` ranges and each range is shared by the
+// `csize` (2..8) CTAs of a thread-block cluster along z: the cluster sums its CTAs' accumulators through distributed
+// shared memory (the kernel's split-K path) and only ONE partial tile per group reaches global memory - none at all
+// with a single group, where the cluster writes dW directly. With several groups the last cluster to finish a tile adds
+// the groups' partial tiles in group order, each of its CTAs for its own rows (one arrival counter per tile and rank).
+// Against one partial per CTA plus a separate reduction kernel this is `csize` times fewer partial bytes and one
+// launch less on the critical path of the backward pass (the wgrad chain on the side stream).
+template <int BN_, int AROWS_, int KR_, bool ROWS_ = false>
+struct WgradClusterProblem : WgradProblem<BN_, AROWS_, KR_, ROWS_> {
+  using Base = WgradProblem<BN_, AROWS_, KR_, ROWS_>;
+  using Params = WgradParams;
+  using Tile = WgradTile;
+  static constexpr bool kClusterSplit = true, kDynRedRows = true, kClusterFinish = true;
+  static constexpr int kCols = Base::kAccTiles * BN_;
+  static_assert(BN_ < 256, "the 128 x 256 wgrad tiles keep one partial per CTA");
+  static_assert((uint32_t)BLOCK_M * (kCols + 4) * 4 <= Base::LayoutT::kBarOffset, "partial tile does not fit the pipeline stages");
+  __device__ static Tile tile(const Params& p) {
+    const int tap = blockIdx.y / p.ctiles, ct = blockIdx.y - tap * p.ctiles;
+    const int b0 = ((int)blockIdx.z / p.csize) * p.blocks_per_split;  // the kernel cuts [b0, b1) by cluster rank
+    const int m0 = (int)blockIdx.x * BLOCK_M;
+    return {m0, tap, ct * BN_, b0, min(p.pix_blocks, b0 + p.blocks_per_split), min(AROWS_ / 32, (p.Kout - m0 + 31) / 32)};
+  }
+  __device__ static int red_rows(const Params& p, const Tile& t) { return min(BLOCK_M, p.Kout - t.m0); }
+  __device__ static void finish(const Params&, const Tile&, int) {}
+  __device__ static void write_dw(const Params& p, int k, int tap, int c, const float4& q) {
+    const int taps = p.R * p.R;
+    if (p.krsc) {
+      *reinterpret_cast<float4*>(p.dw + ((size_t)k * taps + tap) * p.C + c) = q;
+    } else {
+      float* o = p.dw + ((size_t)k * p.C + c) * taps + tap;
+      o[0] = q.x; o[taps] = q.y; o[2 * taps] = q.z; o[3 * taps] = q.w;
+    }
+  }
+  // `col` counts over the accumulator tiles of the CTA (row-halo: three taps of BN channels each)
+  __device__ static void store4(const Params& p, const Tile& t, int row, int col, const float4& q) {
+    const int acc = col / BN_, c = t.c0 + col - acc * BN_;
+    if (c >= p.C) return;  // channel padding
+    const int k = t.m0 + row, tap = Base::tap_of(p, t, acc);
+    if (p.groups == 1) {
+      write_dw(p, k, tap, c, q);
+    } else {
+      const int g = (int)blockIdx.z / p.csize;
+      *reinterpret_cast<float4*>(p.partial + (((size_t)g * p.Kout + k) * (p.R * p.R) + tap) * p.Cp + c) = q;
+    }
+  }
+  __device__ static void finish_cluster(const Params& p, const Tile& t, int tid, int rank, int nsplit) {
+    if (p.groups == 1) return;
+    __shared__ int s_last_group;
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) {
+      unsigned* ticket = p.tickets + (blockIdx.x + gridDim.x * blockIdx.y) * 8 + rank;
+      const unsigned arrived = atomicAdd(ticket, 1u);
+      s_last_group = arrived == (unsigned)p.groups - 1;
+      if (s_last_group) *ticket = 0;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (!s_last_group) return;
+    __threadfence();
+    const int taps = p.R * p.R;
+    const int rows = red_rows(p, t), rows_per = (rows + nsplit - 1) / nsplit;
+    const int r0 = rank * rows_per, nrows = min(rows, r0 + rows_per) - r0;
+    constexpr int kVec = kCols / 4;
+    const size_t slab4 = (size_t)p.Kout * taps * p.Cp / 4;
+    for (int idx = tid; idx < nrows * kVec; idx += 128) {
+      const int col = (idx % kVec) * 4, acc = col / BN_, c = t.c0 + col - acc * BN_;
+      if (c >= p.C) continue;
+      const int k = t.m0 + r0 + idx / kVec, tap = Base::tap_of(p, t, acc);
+      const float4* src = reinterpret_cast<const float4*>(p.partial + ((size_t)k * taps + tap) * p.Cp + c);
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      int g = 0;
+      for (; g + 4 <= p.groups; g += 4) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = __ldcg(src + (size_t)(g + u) * slab4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sum.x += q[u].x; sum.y += q[u].y; sum.z += q[u].z; sum.w += q[u].w; }
+      }
+      for (; g < p.groups; ++g) {
+        const float4 q = __ldcg(src + (size_t)g * slab4);
+        sum.x += q.x; sum.y += q.y; sum.z += q.z; sum.w += q.w;
+      }
+      write_dw(p, k, tap, c, sum);
     }
   }
 };
@@ -1085,6 +1188,30 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
   return st;
 }
 
+// cluster variant (WgradClusterProblem): grid.z = groups * csize, clusters of csize CTAs along z
+template <int BN>
+static dfb_status run_wgrad_cluster(const CUtensorMap& ma, const CUtensorMap& mb, const WgradParams& prm) {
+  dim3 grid(cdiv(prm.Kout, BLOCK_M), (unsigned)(prm.R * prm.R * prm.ctiles), (unsigned)(prm.groups * prm.csize));
+  if (prm.rows) {
+    grid.y = (unsigned)(prm.R * prm.ctiles);
+    return launch<WgradClusterProblem<32, 32, 128, true>>("tc_conv_wgrad_rows_cl", ma, mb, prm, grid, prm.csize);
+  }
+  if (prm.kr == 128) return launch<WgradClusterProblem<32, 32, 128>>("tc_conv_wgrad_cl", ma, mb, prm, grid, prm.csize);
+  if (prm.Kout <= 32) return launch<WgradClusterProblem<BN, 32, 32>>("tc_conv_wgrad_cl", ma, mb, prm, grid, prm.csize);
+  if (prm.Kout <= 64) return launch<WgradClusterProblem<BN, 64, 32>>("tc_conv_wgrad_cl", ma, mb, prm, grid, prm.csize);
+  return launch<WgradClusterProblem<BN, 128, 32>>("tc_conv_wgrad_cl", ma, mb, prm, grid, prm.csize);
+}
+// DFB_WGRAD_CLUSTER = largest cluster size (2, 4 or 8); 0 / unset: one partial per CTA and the separate reduction
+static int wgrad_cluster_max() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_WGRAD_CLUSTER");
+    const int want = e ? atoi(e) : 0;
+    v = want >= 8 ? 8 : (want >= 4 ? 4 : (want >= 2 ? 2 : 0));
+  }
+  return v;
+}
+
 template <int BN>
 static dfb_status run_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams prm, int splits) {
   dim3 grid(cdiv(prm.Kout, BLOCK_M), (unsigned)(prm.R * prm.R * prm.ctiles), (unsigned)splits);
@@ -1194,6 +1321,33 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   int splits = (int)std::max<size_t>(1, ((size_t)sm_count() * 2 + base_ctas - 1) / base_ctas);  // two CTAs per SM
   splits = std::min(splits, std::max(1, prm.pix_blocks / 8));
   splits = std::min(splits, 128);
+  prm.csize = 1; prm.groups = 1;
+  prm.krsc = w_layout == DFB_WLAYOUT_KRSC ? 1 : 0;
+  prm.dw = dw;
+  // Two-level split (WgradClusterProblem, DFB_WGRAD_CLUSTER=1): clusters of up to 8 CTAs reduce through distributed
+  // shared memory; one partial per cluster, summed by the last cluster of each tile - no separate reduction kernel.
+  if (wgrad_cluster_max() >= 2 && bn < 256 && splits >= 2 && base_ctas * 8 <= (size_t)kTicketWords - 128) {
+    int cs = 2;
+    while (cs * 2 <= std::min(splits, wgrad_cluster_max())) cs *= 2;
+    // a cluster lives inside one GPC (18-20 SMs, two CTAs each): 4 clusters of 8 or 9 of 4 per GPC are co-resident,
+    // and a second wave would double the kernel's time
+    const size_t slots = cs == 8 ? 256 : (cs == 4 ? 288 : (size_t)sm_count() * 2);
+    int groups = (int)std::max<size_t>(1, std::min<size_t>((size_t)(splits / cs), slots / (base_ctas * cs)));
+    prm.blocks_per_split = (prm.pix_blocks + groups - 1) / groups;  // per group; the kernel cuts it by cluster rank
+    groups = (prm.pix_blocks + prm.blocks_per_split - 1) / prm.blocks_per_split;
+    prm.csize = cs; prm.groups = groups;
+    float* partial = nullptr;
+    if (groups > 1) {
+      dfb_status st = dfb_malloc((size_t)groups * K * taps * prm.Cp, &partial);
+      if (st != DFB_OK) return st;
+    }
+    prm.partial = partial;
+    prm.tickets = groups > 1 ? ticket_counter(64) : nullptr;
+    *handled = true;
+    dfb_status st = bn == 128 ? run_wgrad_cluster<128>(ma, mb, prm) : (bn == 64 ? run_wgrad_cluster<64>(ma, mb, prm) : run_wgrad_cluster<32>(ma, mb, prm));
+    if (partial) dfb_free(partial);
+    return st;
+  }
   prm.blocks_per_split = (prm.pix_blocks + splits - 1) / splits;
   splits = (prm.pix_blocks + prm.blocks_per_split - 1) / prm.blocks_per_split;
   float* partial = nullptr;

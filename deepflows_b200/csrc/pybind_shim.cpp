@@ -444,6 +444,16 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
     check(dfb_to_host_async(dptr(src), a.mutable_data(), n));
   });
 
+  // ---- per-batch preparation on the device (augmentation, one-hot + label smoothing) ----------------------
+  m.attr("AUGMENT_FIELDS") = DFB_AUGMENT_FIELDS;
+  m.def("augment_batch", [](const py::object& x, const py::object& y, const py::object& table, int N, int C, int H, int W, int pad,
+                            bool clip, float lo, float hi) {
+    check(dfb_augment_batch(dptr(x), dptr(y), dptr(table), N, C, H, W, pad, clip ? 1 : 0, lo, hi));
+  });
+  m.def("onehot_smooth", [](const py::object& labels, const py::object& y, size_t n, int classes, float on_value, float off_value) {
+    check(dfb_onehot_smooth(dptr(labels), dptr(y), n, classes, on_value, off_value));
+  });
+
   // ---- data parallel ---------------------------------------------------------------------------------
   m.def("comm_unique_id", []() {
     unsigned char id[128];

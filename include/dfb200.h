@@ -108,6 +108,23 @@ DFB_API dfb_status dfb_copy(const float* src, float* dst, size_t n); /* device t
  * dfb_prefetch_wait makes the compute stream wait for the prefetches issued so far. */
 DFB_API dfb_status dfb_prefetch_from_host(const float* pinned_src, float* dst, size_t n);
 DFB_API dfb_status dfb_prefetch_wait(void);
+/* Per-batch preparation that the reference's training scripts do in numpy on the host before every step, here as
+ * one pass on the device over the batch that the prefetch delivered; bit-identical to the numpy code.
+ * dfb_augment_batch: augment_batch of test/ResNet_CIFAR10_cuda.py:129-148 on x, y = (N, C, H, W):
+ *   reflect-pad by `pad` (numpy mode='reflect', pad < H, W), crop H x W at (crop_y, crop_x) of the padded image,
+ *   mirror the crop horizontally where flip != 0, zero the rectangle [erase_y, +erase_h) x [erase_x, +erase_w) of
+ *   the result (erase_h = 0 or erase_w = 0: none), then clip to [clip_lo, clip_hi] if `clip` (NaN stays NaN).
+ *   `table` is a device array of N rows of DFB_AUGMENT_FIELDS floats holding the host's random draws as exact small
+ *   integers: {crop_y, crop_x, flip, erase_y, erase_x, erase_h, erase_w, unused}. y must not alias x.
+ * dfb_onehot_smooth: y[i][j] = (j == labels[i] ? 1 : 0) * on_value + off_value, the product and the sum rounded
+ *   separately (test/ResNet_CIFAR10_cuda.py:181-183 with on_value = 1 - eps, off_value = eps / classes, both rounded
+ *   to float as numpy rounds the Python scalars; 1, 0 gives the plain one-hot of the other scripts). labels are class
+ *   indices stored as floats (the reference's buffers are float-only, cu:48-83). */
+#define DFB_AUGMENT_FIELDS 8
+DFB_API dfb_status dfb_augment_batch(const float* x, float* y, const float* table, int N, int C, int H, int W,
+                                     int pad, int clip, float clip_lo, float clip_hi);
+DFB_API dfb_status dfb_onehot_smooth(const float* labels, float* y, size_t n, int classes, float on_value,
+                                     float off_value);
 
 /* Side stream: work enqueued between dfb_side_begin() and dfb_side_end() runs on a second stream that is
  * ordered after everything enqueued on the compute stream so far, concurrently with what the compute

@@ -308,3 +308,47 @@ def sgd_step(p, g, vel, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
     else:
         upd = g
     return (p + (upd * F32(lr)) * F32(-1)).astype(F32), vel
+
+
+# ------------------------------------------------------------------------------------------------
+# per-batch preparation of the training scripts (host numpy in the reference):
+# augment_batch, test/ResNet_CIFAR10_cuda.py:129-148, and the smoothed one-hot targets, :181-183
+# ------------------------------------------------------------------------------------------------
+def _reflect_index(i, n):
+    """Index into an axis of length n for position i of its numpy 'reflect' padding (edge not repeated)."""
+    i = np.abs(i)
+    return np.where(i >= n, 2 * (n - 1) - i, i)
+
+
+def augment_batch(inputs, epoch, num_epochs, pad=4):
+    """Same draws from numpy's global generator, in the same order, as the reference function [131-143]; the
+    crop / flip of the reflect-padded batch is written as one gather instead of the reference's per-sample slices.
+    Pinned against the reference function itself in tests/golden/pipeline.npz (oracle/make_golden_pipeline.py)."""
+    n, c, h, w = inputs.shape
+    span = 2 * pad + 1
+    cy = np.random.randint(0, span, size=n)
+    cx = np.random.randint(0, span, size=n)
+    flip = np.random.rand(n) < 0.5
+    rect = None
+    if epoch < num_epochs - 5 and np.random.rand() < 0.2:
+        eh = max(1, int(h * np.random.uniform(0.1, 0.2)))
+        ew = max(1, int(w * np.random.uniform(0.1, 0.2)))
+        rect = (np.random.randint(0, h - eh + 1, size=n), np.random.randint(0, w - ew + 1, size=n), eh, ew)
+    hh, ww = np.arange(h), np.arange(w)
+    src_h = _reflect_index(cy[:, None] + hh[None, :] - pad, h)                       # (n, h)
+    col = np.where(flip[:, None], w - 1 - ww[None, :], ww[None, :])                  # the flip mirrors the crop
+    src_w = _reflect_index(cx[:, None] + col - pad, w)                               # (n, w)
+    out = inputs[np.arange(n)[:, None, None, None], np.arange(c)[None, :, None, None],
+                 src_h[:, None, :, None], src_w[:, None, None, :]]
+    if rect is not None:
+        ey, ex, eh, ew = rect
+        inside = (((hh[None, :] >= ey[:, None]) & (hh[None, :] < ey[:, None] + eh))[:, None, :, None] &
+                  ((ww[None, :] >= ex[:, None]) & (ww[None, :] < ex[:, None] + ew))[:, None, None, :])
+        out = np.where(inside, inputs.dtype.type(0), out)
+    return np.clip(out, -1.0, 1.0)
+
+
+def smooth_one_hot(labels, num_classes, eps):
+    """float32 one-hot rows * (1 - eps) + eps / num_classes, each step rounded to float32 [181-183]."""
+    hot = (np.asarray(labels).reshape(-1, 1) == np.arange(num_classes)[None, :]).astype(F32)
+    return hot * F32(1 - eps) + F32(eps / num_classes)
