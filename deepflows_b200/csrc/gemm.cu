@@ -95,6 +95,11 @@ dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float
   DFB_REQUIRE(x_layout == DFB_LAYOUT_NCHW || x_layout == DFB_LAYOUT_NHWC, DFB_ERR_INVALID, "conv2d_wgrad: bad layout");
   dfb_status st = check_mode("conv2d_wgrad", mode);
   if (st != DFB_OK) return st;
+  if (want_tc(mode)) {  // first layer at training batch sizes: column matrix + tcgen05 (gemm_tc.cu: tc_stem_wgrad)
+    bool handled = false;
+    st = tc_stem_wgrad(x, x_layout, dy, dw, w_layout, N, C, H, W, K, R, pad, stride, mode, &handled);
+    if (st != DFB_OK || handled) return st;
+  }
   if (mode != DFB_MODE_SIMT) {
     bool handled = false;
     st = direct_conv_wgrad(x, x_layout, dy, dw, w_layout, N, C, H, W, K, R, pad, stride, &handled);

@@ -1201,12 +1201,13 @@ static dfb_status run_wgrad_cluster(const CUtensorMap& ma, const CUtensorMap& mb
   if (prm.Kout <= 64) return launch<WgradClusterProblem<BN, 64, 32>>("tc_conv_wgrad_cl", ma, mb, prm, grid, prm.csize);
   return launch<WgradClusterProblem<BN, 128, 32>>("tc_conv_wgrad_cl", ma, mb, prm, grid, prm.csize);
 }
-// DFB_WGRAD_CLUSTER = largest cluster size (2, 4 or 8); 0 / unset: one partial per CTA and the separate reduction
+// DFB_WGRAD_CLUSTER = largest cluster size (2, 4 or 8; default 8); 0: one partial per CTA and the separate reduction.
+// Measured on the ResNet-18 step (batch 256): 1.368 ms without, 1.353 ms with clusters of 4, 1.351 ms with clusters of 8.
 static int wgrad_cluster_max() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DFB_WGRAD_CLUSTER");
-    const int want = e ? atoi(e) : 0;
+    const int want = e ? atoi(e) : 8;
     v = want >= 8 ? 8 : (want >= 4 ? 4 : (want >= 2 ? 2 : 0));
   }
   return v;
@@ -1279,14 +1280,17 @@ dfb_status tc_conv_dgrad(const float* dy, const float* w, int w_layout, float* d
   return tc::conv_like("tc_conv_dgrad_s2", dy, w, w_layout, dx, true, N, K, OH, OW, C, R, H / 2, W / 2, 1, 0, 0, K, C, handled, pad);
 }
 
-dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K, int R, int pad,
-                         int stride, int mode, float*, size_t, bool* handled) {
+// c_valid <= C: channels of x that belong to the gradient (the first-layer path pads its column matrix to 32 channels);
+// dW then has c_valid channels. The in-kernel reductions store float4s, so they need c_valid % 4 == 0.
+static dfb_status wgrad_impl(const float* x, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K, int R, int pad,
+                             int stride, int mode, int c_valid, bool* handled) {
   using namespace tc;
   *handled = false;
   if (!conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
+  const bool vec_ok = (c_valid & 3) == 0;
   WgradParams prm;
-  prm.Kout = K; prm.C = C; prm.Cp = (C + 31) / 32 * 32; prm.R = R; prm.pad = pad; prm.stride = stride;
+  prm.Kout = K; prm.C = c_valid; prm.Cp = (C + 31) / 32 * 32; prm.R = R; prm.pad = pad; prm.stride = stride;
   prm.n_img = N; prm.OH = OH; prm.OW = OW;
   int bn = prm.Cp % 128 == 0 ? 128 : (prm.Cp % 64 == 0 ? 64 : 32);
   if (prm.Cp % 256 == 0 && (size_t)N * OH * OW >= 16384) bn = 256;  // big layers: 128 x 256 tiles (see run_gemm_bn)
@@ -1324,9 +1328,9 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   prm.csize = 1; prm.groups = 1;
   prm.krsc = w_layout == DFB_WLAYOUT_KRSC ? 1 : 0;
   prm.dw = dw;
-  // Two-level split (WgradClusterProblem, DFB_WGRAD_CLUSTER=1): clusters of up to 8 CTAs reduce through distributed
+  // Two-level split (WgradClusterProblem): clusters of up to 8 CTAs reduce through distributed
   // shared memory; one partial per cluster, summed by the last cluster of each tile - no separate reduction kernel.
-  if (wgrad_cluster_max() >= 2 && bn < 256 && splits >= 2 && base_ctas * 8 <= (size_t)kTicketWords - 128) {
+  if (wgrad_cluster_max() >= 2 && vec_ok && bn < 256 && splits >= 2 && base_ctas * 8 <= (size_t)kTicketWords - 128) {
     int cs = 2;
     while (cs * 2 <= std::min(splits, wgrad_cluster_max())) cs *= 2;
     // a cluster lives inside one GPC (18-20 SMs, two CTAs each): 4 clusters of 8 or 9 of 4 per GPC are co-resident,
@@ -1360,14 +1364,14 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
   // The in-kernel reduction is done by ONE CTA per tile: worth it (one launch less) while a tile's partials are
   // small; beyond that the separate reduction kernel, which spreads over the machine, is faster.
   const size_t tile_partial_bytes = (size_t)splits * std::min(K, BLOCK_M) * bn * sizeof(float);
-  prm.tickets = (base_ctas <= (size_t)kTicketWords - 64 && tile_partial_bytes <= (192u << 10)) ? ticket_counter(64) : nullptr;
+  prm.tickets = (vec_ok && base_ctas <= (size_t)kTicketWords - 64 && tile_partial_bytes <= (192u << 10)) ? ticket_counter(64) : nullptr;
   *handled = true;
   if (bn == 256) st = run_wgrad<256>(ma, mb, prm, splits);
   else if (bn == 128) st = run_wgrad<128>(ma, mb, prm, splits);
   else if (bn == 64) st = run_wgrad<64>(ma, mb, prm, splits);
   else st = run_wgrad<32>(ma, mb, prm, splits);
   if (st == DFB_OK && !prm.tickets) {
-    launch_k(wgrad_reduce_kernel, bw_grid((size_t)K * C * taps, 256), 256, 0, compute_stream(), partial, dw, splits, K, C, prm.Cp, taps,
+    launch_k(wgrad_reduce_kernel, bw_grid((size_t)K * c_valid * taps, 256), 256, 0, compute_stream(), partial, dw, splits, K, c_valid, prm.Cp, taps,
                                                                                           w_layout == DFB_WLAYOUT_KRSC ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1377,6 +1381,82 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
     }
   }
   dfb_free(partial);
+  return st;
+}
+
+dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K, int R, int pad,
+                         int stride, int mode, float*, size_t, bool* handled) {
+  return wgrad_impl(x, dy, dw, w_layout, N, C, H, W, K, R, pad, stride, mode, C, handled);
+}
+
+// ---- first layer (image input, C <= 4) on the tensor pipe ------------------------------------------------------
+// The weight gradient of the first layer is a [K x C*R*R] = [32 x 27] matrix summed over a quarter of a million
+// pixels: as a gather kernel on the FFMA pipe it is latency bound (74 us for the ResNet stem at batch 256, 8 % of the
+// HBM roofline). Here the receptive fields are first written out as a [pixels x 32] column matrix (C*R*R <= 32 columns,
+// zero padded; one coalesced 128-byte row per pixel, the 3 MB image stays in L1/L2), and the gradient becomes the
+// weight gradient of a 1x1 convolution over 32 "channels": the tcgen05 wgrad kernel with 128-pixel stages. The column
+// order is the gradient's own memory order (tap-major for channels-last weights, channel-major for (K,C,R,R)), so a
+// row of the GEMM result is a row of dW.
+__global__ void __launch_bounds__(256) stem_cols_kernel(const float* __restrict__ x, int nchw, float* __restrict__ col, int N, int C,
+                                                        int H, int W, int R, int pad, int stride, int OH, int OW, int krsc) {
+  pdl_sync();
+  const int taps = R * R, cols = C * taps;
+  const size_t total = (size_t)N * OH * OW * 8;  // a float4 (four columns) per thread
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int q = (int)(i & 7);
+    size_t t = i >> 3;
+    const int ow = (int)(t % OW);
+    t /= OW;
+    const int oh = (int)(t % OH), n = (int)(t / OH);
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = q * 4 + u;
+      v[u] = 0.f;
+      if (j < cols) {
+        const int tap = krsc ? j / C : j % taps, c = krsc ? j % C : j / taps;
+        const int ih = oh * stride + tap / R - pad, iw = ow * stride + tap % R - pad;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+          v[u] = __ldg(x + (nchw ? (((size_t)n * C + c) * H + ih) * W + iw : (((size_t)n * H + ih) * W + iw) * C + c));
+      }
+    }
+    reinterpret_cast<float4*>(col)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+// on by default (DFB_STEM_TC=0: the gather kernel in every mode). ResNet stem at batch 256: 74 us -> the column pass plus
+// the tensor-core kernel; the training step 1.349 -> 1.308 ms.
+static bool stem_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_STEM_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+dfb_status tc_stem_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K, int R,
+                         int pad, int stride, int mode, bool* handled) {
+  *handled = false;
+  if (!stem_tc_enabled() || tc_disabled() || mode != DFB_MODE_TF32) return DFB_OK;
+  const int cols = C * R * R;
+  if (C > 4 || cols > 32 || (K & 3) || stride < 1 || H + 2 * pad < R || W + 2 * pad < R) return DFB_OK;
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
+  const size_t pixels = (size_t)N * OH * OW;
+  if (pixels < 16384) return DFB_OK;  // small batches: the gather kernel is a single short launch
+  float* col = nullptr;
+  dfb_status st = dfb_malloc(pixels * 32, &col);
+  if (st != DFB_OK) return st;
+  launch_k(stem_cols_kernel, bw_grid(pixels * 8, 256), 256, 0, compute_stream(), x, x_layout == DFB_LAYOUT_NCHW ? 1 : 0, col, N, C, H, W, R,
+           pad, stride, OH, OW, w_layout == DFB_WLAYOUT_KRSC ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) {
+    dfb_free(col);
+    DFB_FAIL(DFB_ERR_RUNTIME, "stem_cols launch failed: %s", cudaGetErrorString(e));
+  }
+  // the column matrix is an (N, OH, OW, 32) channels-last activation; its 1x1 wgrad has cols valid channels
+  st = wgrad_impl(col, dy, dw, w_layout, N, 32, OH, OW, K, 1, 0, 1, mode, cols, handled);
+  dfb_free(col);
   return st;
 }
 

@@ -34,6 +34,9 @@ dfb_status tc_conv_dgrad(const float* dy, const float* w, int w_layout, float* d
 dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K,
                          int R, int pad, int stride, int mode, float* workspace, size_t workspace_floats,
                          bool* handled);
+// first-layer weight gradient (C <= 4, C*R*R <= 32) as a column matrix + the tcgen05 1x1 wgrad (TF32 mode, large batches)
+dfb_status tc_stem_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H, int W,
+                         int K, int R, int pad, int stride, int mode, bool* handled);
 size_t tc_conv_workspace_floats(int N, int C, int H, int W, int K, int R, int pad, int stride);
 
 }  // namespace dfb

@@ -135,6 +135,36 @@ def test_conv_channels_last_weights(cuda_device, shape, mode):
         assert tc_launches == 3  # fprop, exact dgrad, wgrad all on tcgen05 (the reference-mode dgrad is a gather kernel)
 
 
+STEM_SHAPES = [  # first layers at training batch sizes (>= 16384 output pixels): image input, C * R * R <= 32
+    (16, 3, 32, 32, 32, 3, 1, 1),    # ResNet stem
+    (16, 3, 32, 32, 64, 3, 1, 1),    # VGG first layer
+    (24, 1, 28, 28, 32, 5, 2, 1),    # CNN-MNIST conv1 (25 taps)
+    (72, 2, 31, 33, 16, 3, 0, 2),    # stride 2, odd image, no padding
+]
+
+
+@pytest.mark.parametrize("krsc", [False, True])
+@pytest.mark.parametrize("nchw", [False, True])
+@pytest.mark.parametrize("shape", STEM_SHAPES)
+def test_first_layer_wgrad_at_training_batch(cuda_device, shape, nchw, krsc):
+    """TF32 mode, image input from either layout, weights in either layout: the gradient is a column matrix + the
+    tcgen05 1x1 wgrad (one tensor-core launch); with DFB_STEM_TC=0 the exact-fp32 gather kernel."""
+    import os
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = shape
+    rng = np.random.RandomState(sum(shape))
+    x = rng.randn(n, c, h, w).astype(F32)
+    wt = (rng.randn(k, c, r, r) / np.sqrt(c * r * r)).astype(F32)
+    oh, ow = ops.out_size(h, r, p, s), ops.out_size(w, r, p, s)
+    gy = rng.randn(n, k, oh, ow).astype(F32)
+    t0 = m.tc_launch_count()
+    y, _, _, dw = run_conv(m, x, wt, gy, p, s, 1, x_layout_nchw=nchw, krsc=krsc)
+    tc_launches = m.tc_launch_count() - t0
+    assert rel_err(y, ops.conv2d_fprop(x, wt, p, s)) < TOL[1]
+    assert rel_err(dw, ops.conv2d_wgrad(x, gy, wt.shape, p, s)) < TOL[1]
+    assert tc_launches == (0 if os.environ.get("DFB_STEM_TC", "1") == "0" else 1)
+
+
 TC_SHAPES = [  # N, C, H, W, K, R, pad, stride - all TMA-eligible (C, K multiples of 4; stride 2 needs even H, W)
     (8, 32, 16, 16, 32, 3, 1, 1), (8, 32, 16, 16, 64, 3, 1, 2), (8, 32, 16, 16, 64, 1, 0, 2), (16, 128, 4, 4, 128, 3, 1, 1),
     (32, 256, 2, 2, 256, 3, 1, 1), (2, 64, 14, 14, 64, 3, 1, 1), (3, 20, 11, 13, 36, 3, 1, 1), (2, 64, 56, 56, 64, 3, 1, 1),
