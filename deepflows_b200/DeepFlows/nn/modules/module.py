@@ -244,6 +244,10 @@ class Module:
         return out
 
     def load_state_dict(self, state_dict: Dict[str, Any], strict: bool = True):
+        """Reference: nn/modules/module.py:471-537 (same assignment rules and error text). One deliberate
+        difference: BatchNorm running statistics are registered buffers here (so they are saved and loaded),
+        plain attributes in the reference; a dict without them - anything the reference wrote - therefore
+        still loads under strict=True, i.e. missing *buffers* are not an error."""
         missing, unexpected = [], set(state_dict.keys())
 
         def assign(target, value):
@@ -262,7 +266,7 @@ class Module:
                     if key in state_dict:
                         assign(t, state_dict[key])
                         unexpected.discard(key)
-                    else:
+                    elif registry is mod._parameters:
                         missing.append(key)
         if strict:
             errors = []

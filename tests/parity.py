@@ -96,3 +96,71 @@ def check_training_case(name, device_name, tol_param=1e-4, tol_out=1e-4):
         if k in g:
             assert rel_err(v, g[k]) < tol_stats, k
     return worst
+
+
+# ---- transfer learning: fixture from oracle/make_golden_transfer.py -------------------------
+FROZEN_PREFIXES = ("conv1.", "bn1.", "layer1_0.")
+
+
+def run_transfer(device_name):
+    from DeepFlows import backend_api, nn, tensor
+    from DeepFlows.tensor import Tensor
+    g = golden("train_transfer")
+    df = df_namespace()
+    dev = backend_api.Device(device_name)
+    tensor.Graph.free_graph_all()
+    np.random.seed(32)
+    model = workloads.resnet_cifar(df, device_name, widths=(4, 8, 8, 16), layers=(1, 1, 1, 1))
+    for k, p in model.named_parameters():                      # the fixture's own initial values (host RNG streams differ)
+        p.data = backend_api.Btensor(g["init." + k], device=dev)
+    weights = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
+    model.load_weights(weights)
+    frozen = []
+    for k, p in model.named_parameters():
+        if k.startswith(FROZEN_PREFIXES):
+            p.requires_grad = False
+            frozen.append(k)
+    p0 = {k: p.data.numpy().copy() for k, p in model.named_parameters()}
+    opt = df.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-3, weight_decay=5e-4)
+    crit = nn.CrossEntropyLoss()
+    losses, logits = [], []
+    np.random.seed(23)
+    model.train()
+    for it in range(g["x"].shape[0]):
+        x, t = Tensor(g["x"][it], device=dev), Tensor(g["target"][it], device=dev)
+        out = model(x)
+        loss = crit(out, t)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.data.numpy().item())
+        logits.append(out.data.numpy().copy())
+        tensor.Graph.free_graph()
+    return g, model, weights, frozen, p0, np.array(losses, np.float32), np.stack(logits), opt
+
+
+def check_transfer(device_name, tol=1e-4):
+    g, model, weights, frozen, p0, losses, logits, opt = run_transfer(device_name)
+    assert frozen == g["frozen"].tolist()
+    ill = set(g["ill_conditioned"].tolist())
+    for k in weights:
+        assert np.array_equal(p0[k], weights[k]), k             # load_weights took every offered tensor ...
+    assert np.array_equal(p0["fc.weight"], g["init.fc.weight"])  # ... and left the rest alone
+    assert len(opt.params) == len(p0) - len(frozen)
+    assert rel_err(losses, g["losses"]) < tol and rel_err(logits, g["logits"]) < tol
+    for k, p in model.named_parameters():
+        got = p.data.numpy()
+        if k in frozen:
+            assert np.array_equal(got, p0[k]), "frozen parameter %s moved" % k
+            assert p.grad is None, "frozen parameter %s received a gradient" % k
+        elif k in ill:  # Adam-normalised step on a gradient that is ~0 analytically: bounded by the step size only
+            assert np.abs(got - p0[k]).max() <= 1.01 * 1e-3 * g["x"].shape[0] * (1 + np.abs(p0[k]).max()) + 1e-6, k
+        else:
+            assert not np.array_equal(got, p0[k]), "trainable parameter %s did not move" % k
+            assert rel_err(got, g["p1." + k]) < tol, k
+    tol_stats = tol if not ill else 2e-2  # second-step activations see the ill-conditioned first steps at the lr level
+    for mod_name, mod in model.named_modules():
+        if hasattr(mod, "num_features") and mod.running_mean is not None:
+            assert rel_err(mod.running_mean.numpy(), g["rm." + mod_name]) < tol_stats, mod_name
+            assert rel_err(mod.running_var.numpy(), g["rv." + mod_name]) < tol_stats, mod_name
+    return model, weights, g

@@ -145,3 +145,12 @@ def test_checkpoint_roundtrip_on_cuda(cuda_device, tmp_path):
     load_checkpoint(model, opt, save_path=path)
     for k, v in model.state_dict().items():
         assert np.array_equal(v, saved[k])
+
+
+def test_transfer_learning_matches_reference_on_cuda(cuda_device):
+    """SURVEY 8f rank 3 on the device: `load_weights` of a partial dict, frozen stem / first stage (their conv
+    weights still get the channels-last layout on first use, no wgrad is launched for them), Adam over the trainable
+    subset; same fixture and bounds as tests/test_transfer_cpu.py."""
+    from DeepFlows import backend_api
+    backend_api.set_precision("fp32")
+    parity.check_transfer("cuda")
