@@ -1,8 +1,10 @@
+"""Map-style dataset protocol (reference: DeepFlows/utils/data/dataset.py): subclasses provide indexing and a length;
+`DataLoader` needs nothing else."""
+
+
 class Dataset:
-    """Map-style dataset protocol (reference: DeepFlows/utils/data/dataset.py)."""
+    def __len__(self):
+        raise NotImplementedError("%s must define __len__" % type(self).__name__)
 
     def __getitem__(self, index):
-        raise NotImplementedError
-
-    def __len__(self):
-        raise NotImplementedError
+        raise NotImplementedError("%s must define __getitem__" % type(self).__name__)

@@ -260,3 +260,44 @@ def test_captured_step_protocol_with_a_mock_device():
     with pytest.raises(ValueError):
         failing()
     assert dev2.log == ["begin", "end", ("destroy", 42)] and not capturing() and not failing.captured
+
+
+def test_lr_schedulers_closed_form():
+    """optim/scheduler.py against the formulas of the reference (scheduler.py:14-59), values worked out by hand."""
+    import math
+    from DeepFlows.optim.scheduler import StepLR, CosineAnnealingLR, WarmupCosineLR
+
+    class Opt:
+        def __init__(self, lr):
+            self.lr = lr
+
+    o = Opt(0.1)
+    s = StepLR(o, step_size=2, gamma=0.5)
+    seen = []
+    for _ in range(5):
+        s.step()
+        seen.append(o.lr)
+    assert seen == [0.1, 0.1, 0.05, 0.05, 0.025]          # epoch 0 never decays
+    o = Opt(1.0)
+    s = CosineAnnealingLR(o, T_max=4, eta_min=0.0)
+    seen = []
+    for _ in range(6):
+        s.step()
+        seen.append(o.lr)
+    want = [(1 + math.cos(math.pi * (e % 4) / 4)) / 2 for e in range(6)]
+    assert seen == want and seen[4] == 1.0                   # restarts at T_max
+    o = Opt(1e-3)
+    s = WarmupCosineLR(o, warmup_epochs=5, T_max=20, eta_min=1e-5)   # the ResNet script's schedule
+    seen = []
+    for _ in range(8):
+        s.step()
+        seen.append(o.lr)
+    assert seen[0] == 0.0 and seen[5] == 1e-3 and abs(seen[2] - 4e-4) < 1e-18
+    assert seen[7] == 1e-5 + (1e-3 - 1e-5) * (1 + math.cos(math.pi * 2 / 20)) / 2
+
+    class NoLr:
+        pass
+    n = NoLr()
+    CosineAnnealingLR(n, 3).step()
+    StepLR(n, 1).step()
+    assert not hasattr(n, "lr")
