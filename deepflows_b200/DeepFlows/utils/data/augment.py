@@ -85,9 +85,9 @@ class BatchAugment:
         n, c, h, w = xb.shape
         if tuple(tb.shape) != (n, FIELDS):
             raise ValueError("BatchAugment: the table must have shape (%d, %d), got %s" % (n, FIELDS, tuple(tb.shape)))
-        if not dev.has("augment_batch"):
+        if dev.name != "cuda":  # the numpy device: the reference's own host code path
             out = BackendTensor(self.apply_host(xb.numpy(), tb.numpy()), device=dev)
-        else:
+        else:                   # no host fallback on the GPU: a missing extension raises in the device wrapper
             xb, tb = xb.compact(), tb.compact()
             out = BackendTensor.make((n, c, h, w), device=dev)
             lo, hi = self.clip if self.clip is not None else (0.0, 0.0)
@@ -104,7 +104,7 @@ def smooth_one_hot(labels, num_classes, eps=0.0, device=None):
     lb = _backend(labels)
     if isinstance(lb, BackendTensor):
         device = lb.device
-    if device is None or not device.has("onehot_smooth"):
+    if device is None or device.name != "cuda":  # host arrays / the numpy device; on the GPU there is no host fallback
         idx = np.asarray(lb.numpy() if isinstance(lb, BackendTensor) else labels).reshape(-1).astype(np.int64)
         hot = (idx[:, None] == np.arange(num_classes)[None, :]).astype(np.float32)
         out = hot * on + off
