@@ -113,6 +113,32 @@ void ewise_unary(const py::object& a, const py::object& out) {
   check(F(A.ptr, O.ptr, O.size));
 }
 
+// Int32Vector / SizeTVector: the two helper containers the reference module exports for shapes and strides
+// (ndarray_backend_cuda.cu:526-556: default constructor, push_back, size(), indexing with negative indices, clear).
+// backend_tensor.py passes tuples, so they are only here for scripts that build the containers by hand; every entry
+// point that takes a shape accepts them because they are Python sequences.
+template <typename T>
+struct PyVector {
+  std::vector<T> items;
+};
+template <typename T>
+void bind_vector(py::module_& m, const char* name, const char* doc) {
+  py::class_<PyVector<T>>(m, name, doc)
+      .def(py::init<>())
+      .def("push_back", [](PyVector<T>& v, T value) { v.items.push_back(value); }, py::arg("value"))
+      .def("size", [](const PyVector<T>& v) { return v.items.size(); })
+      .def("__len__", [](const PyVector<T>& v) { return v.items.size(); })
+      .def("__getitem__",
+           [name](const PyVector<T>& v, long long i) {
+             const long long n = (long long)v.items.size();
+             if (i < 0) i += n;
+             if (i < 0 || i >= n) throw py::index_error(std::string(name) + " index out of range: " + std::to_string(i));
+             return v.items[(size_t)i];
+           },
+           py::arg("index"))
+      .def("clear", [](PyVector<T>& v) { v.items.clear(); });
+}
+
 }  // namespace
 
 PYBIND11_MODULE(CUDA_BACKEND, m) {
@@ -131,6 +157,9 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
   m.attr("WLAYOUT_KRSC") = (int)DFB_WLAYOUT_KRSC;
   m.attr("DGRAD_REFERENCE") = (int)DFB_DGRAD_REFERENCE;
   m.attr("DGRAD_EXACT") = (int)DFB_DGRAD_EXACT;
+
+  bind_vector<int32_t>(m, "Int32Vector", "Vector of int32 (shape / stride arguments)");
+  bind_vector<size_t>(m, "SizeTVector", "Vector of size_t (numpy shape / stride arguments)");
 
   py::class_<Array>(m, "Array")
       .def(py::init<size_t>(), py::return_value_policy::take_ownership)

@@ -42,6 +42,25 @@ def test_shim_imports_at_the_reference_path():
                  "ewise_tanh", "matmul", "reduce_sum", "reduce_max"):
         assert hasattr(m, name), name
     assert m.__max_dimensions__ == 8
+    assert m.__device__name__ == "cuda" and isinstance(m.__tile_size__, int) and isinstance(m.__version__, str)
+    # the helper containers of the reference module (cu:526-556)
+    for cls, bad in ((m.Int32Vector, 2 ** 40), (m.SizeTVector, -1)):
+        v = cls()
+        for x in (3, 1, 4):
+            v.push_back(x)
+        assert v.size() == 3 and len(v) == 3 and v[0] == 3 and v[-1] == 4 and list(v) == [3, 1, 4] and tuple(v) == (3, 1, 4)
+        with pytest.raises(IndexError):
+            v[3]
+        with pytest.raises(IndexError):
+            v[-4]
+        with pytest.raises(TypeError):
+            v.push_back(bad)
+        v.clear()
+        assert v.size() == 0
+    shape = m.Int32Vector()
+    shape.push_back(2)
+    with pytest.raises(ValueError, match="cannot be null"):   # accepted as a shape: the call gets as far as the null check
+        m.compact(None, None, shape, shape, 0)
 
 
 def test_no_cpu_fallback_without_a_gpu():
