@@ -4,7 +4,9 @@
 //   GemmProblem   C[M,N] (+)= op(A)[M,K] . op(B)[K,N]     Linear forward / backward, L0 matmul
 //   ConvProblem   y[pix, Kout] = sum_taps x[pix + tap, :] . Wt[Kout, tap, :]    conv fprop, and dgrad
 //                 for stride 1 (the same contraction over dy with the taps mirrored)
-//   WgradProblem  dWt[Kout, tap, C] = sum_pix dy[pix, Kout] * x[pix + tap, C]   (split over pixel ranges)
+//   WgradProblem  dWt[Kout, tap, C] = sum_pix dy[pix, Kout] * x[pix + tap, C]   (split over pixel ranges;
+//                 WgradClusterProblem: the ranges of one group are summed by a cluster through DSMEM)
+// plus the first-layer weight gradient as a column matrix + 1x1 WgradProblem (tc_stem_wgrad),
 // replacing the reference's pad + k*k strided setitems + permute/compact + one-thread-per-output matmul
 // (DeepFlows/nn/functional.py:249-344, ndarray_backend_cuda.cu:443-466). Nothing is materialised: the
 // im2col gather is expressed as TMA box coordinates on a 4-d (C,W,H,N) view of the channels-last
