@@ -19,7 +19,6 @@ algorithm: oracle/numpy_device.py under the same host code) on the host cores, o
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys

@@ -13,7 +13,6 @@ the CUDA module). Differences that matter for speed, none for results:
 * the only device shipped is `cuda` (libdfb200.so). `cpu` exists only when a test registers a
   numpy device module with `register_numpy_device` - this package never computes on the host.
 """
-import math
 import operator
 import os
 from functools import reduce

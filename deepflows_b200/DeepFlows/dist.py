@@ -11,12 +11,11 @@ The transport is pluggable so the bucketing logic can be tested on CPU: `NcclTra
 dfb_comm_*) for GPUs, `TorchGlooTransport` (torch.distributed, tests only) for the numpy device.
 """
 import os
-import pickle
 import socket
 import struct
 import time
 
-from .tensor import Tensor, Graph
+from .tensor import Tensor
 from .backend.backend_tensor import BackendTensor
 
 _ctx = None

@@ -16,8 +16,6 @@ also the physical order the reference's conv output has before its final transpo
 """
 from typing import Optional
 
-import numpy as np
-
 from .. import tensor
 from ..tensor import Tensor, FusedOperator, UnaryOperator, BinaryOperator
 from .. import backend_api

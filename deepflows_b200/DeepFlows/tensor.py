@@ -14,7 +14,6 @@ gradient arrives instead of a zero-fill per node [134]; `FusedOperator` lets one
 batch-norm, pooling, cross-entropy in nn/functional.py) return the gradients of all its inputs from a
 single fused backward kernel.
 """
-import builtins
 from typing import Optional, Tuple
 
 import numpy as np

@@ -8,7 +8,6 @@ import numpy as np
 import pytest
 
 from conftest import golden, rel_err, ROOT
-from oracle import numpy_ops as ops
 
 pytestmark = pytest.mark.gpu
 F32 = np.float32

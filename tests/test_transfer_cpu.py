@@ -4,7 +4,6 @@ trainable parameters only, two steps."""
 import numpy as np
 import pytest
 
-from conftest import golden, rel_err
 import parity
 import workloads
 

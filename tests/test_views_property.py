@@ -2,7 +2,6 @@
 permute / slice / broadcast / flip / reshape / setitem / reductions must agree with numpy on the same data. These are
 the strided views that every device kernel call is built from (reference: backend_tensor.py:320-528)."""
 import numpy as np
-import pytest
 from hypothesis import given, settings, strategies as st, HealthCheck
 
 F32 = np.float32
