@@ -44,7 +44,6 @@ struct ConvGeom {
   int krsc;  // weights (and dW) stored channels-last (K,R,R,C) instead of (K,C,R,R)
 };
 __device__ __forceinline__ size_t weight_index(const ConvGeom& g, int kout, int c, int tap) {
-  const int RR = g.R * g.R;
   return g.krsc ? ((size_t)kout * RR + tap) * g.C + c : ((size_t)kout * g.C + c) * RR + tap;
 }
 
@@ -410,7 +409,6 @@ dgrad_lastwriter_kernel(const float* __restrict__ dy, const float* __restrict__ 
   pdl_sync();
   size_t total = (size_t)g.N * g.H * g.W * g.C;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int RR = g.R * g.R;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     int c = (int)(i % g.C);
     size_t pix = i / g.C;
