@@ -1,5 +1,5 @@
-"""Data-parallel host logic (bucketing, gradient averaging, parameter broadcast) with world_size 2 on CPU:
-two processes, torch.distributed `gloo` as the transport, the oracle's numpy device as the compute device.
+"""Data-parallel host logic (bucketing, gradient averaging, parameter broadcast) with world_size 2 and 3 on CPU:
+one process per replica, torch.distributed `gloo` as the transport, the oracle's numpy device as the compute device.
 Parity definition: replica r's pre-all-reduce gradients equal single-process gradients on shard
 r, and the applied update equals the update from the mean of the shard gradients."""
 import os
@@ -8,6 +8,7 @@ import sys
 import textwrap
 
 import numpy as np
+import pytest
 
 from conftest import ROOT
 
@@ -51,8 +52,8 @@ WORKER = textwrap.dedent('''
     ctx = dist.init(model.parameters(), transport=GlooTransport(), bucket_mb=0.002)   # tiny buckets: several of them
     w0 = {k: p.data.numpy().copy() for k, p in model.named_parameters()}
     rng = np.random.RandomState(7)
-    X = rng.randn(8, 3, 16, 16).astype(np.float32)
-    T = np.eye(10, dtype=np.float32)[rng.randint(0, 10, 8)]
+    X = rng.randn(4 * world, 3, 16, 16).astype(np.float32)
+    T = np.eye(10, dtype=np.float32)[rng.randint(0, 10, 4 * world)]
     xs, ts = X[rank * 4:(rank + 1) * 4], T[rank * 4:(rank + 1) * 4]
     opt = df.optim.SGD(model.parameters(), lr=0.1)
     dev = backend_api.Device("cpu")
@@ -69,24 +70,27 @@ WORKER = textwrap.dedent('''
 ''')
 
 
-def test_two_replicas_average_gradients(tmp_path, cpu_device):
+@pytest.mark.parametrize("world", [2, 3])
+def test_replicas_average_gradients(tmp_path, cpu_device, world):
     out = str(tmp_path / "rank")
     script = tmp_path / "worker.py"
-    port = 29000 + os.getpid() % 1000
+    port = 29000 + (os.getpid() * 7 + world) % 1000
     script.write_text(WORKER % dict(root=ROOT, port=port, out=out))
     procs = []
-    for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), OMP_NUM_THREADS="1")
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     logs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
-    r0, r1 = dict(np.load(out + "_0.npz")), dict(np.load(out + "_1.npz"))
+    ranks = [dict(np.load(out + "_%d.npz" % r)) for r in range(world)]
+    r0 = ranks[0]
     assert int(r0["nbuckets"]) > 1
     keys = [k[3:] for k in r0 if k.startswith("w0.")]
-    for k in keys:  # broadcast: both replicas start from rank 0's weights; all-reduce: identical summed gradients
-        assert np.array_equal(r0["w0." + k], r1["w0." + k]), k
-        assert np.array_equal(r0["g." + k], r1["g." + k]), k
-        assert np.array_equal(r0["w1." + k], r1["w1." + k]), k
+    for k in keys:  # broadcast: every replica starts from rank 0's weights; all-reduce: identical summed gradients
+        for rr in ranks[1:]:
+            assert np.array_equal(r0["w0." + k], rr["w0." + k]), k
+            assert np.array_equal(r0["g." + k], rr["g." + k]), k
+            assert np.array_equal(r0["w1." + k], rr["w1." + k]), k
 
     # single-process reference: gradient of each shard, averaged, applied with the same SGD step
     import DeepFlows
@@ -97,10 +101,10 @@ def test_two_replicas_average_gradients(tmp_path, cpu_device):
     try:
         df = workloads.namespace(DeepFlows)
         rng = np.random.RandomState(7)
-        X = rng.randn(8, 3, 16, 16).astype(np.float32)
-        T = np.eye(10, dtype=np.float32)[rng.randint(0, 10, 8)]
+        X = rng.randn(4 * world, 3, 16, 16).astype(np.float32)
+        T = np.eye(10, dtype=np.float32)[rng.randint(0, 10, 4 * world)]
         shard_grads = []
-        for r in range(2):
+        for r in range(world):
             tensor.Graph.free_graph_all()
             model = workloads.cnn_cifar10(df, "cpu", widths=(4, 8, 8), in_hw=16, dropout=0.0)
             for k, p in model.named_parameters():
@@ -110,9 +114,11 @@ def test_two_replicas_average_gradients(tmp_path, cpu_device):
             loss.backward()
             shard_grads.append({k: p.grad.numpy().copy() for k, p in model.named_parameters()})
         for k in keys:
-            total = shard_grads[0][k] + shard_grads[1][k]
+            total = shard_grads[0][k].copy()
+            for g in shard_grads[1:]:
+                total = total + g[k]
             assert np.abs(r0["g." + k] - total).max() <= 1e-6 * max(1.0, np.abs(total).max()), k
-            want = r0["w0." + k] - np.float32(0.1) * (total * np.float32(0.5))
+            want = r0["w0." + k] - np.float32(0.1) * (total * np.float32(1.0 / world))
             assert np.abs(r0["w1." + k] - want).max() <= 1e-6 * max(1.0, np.abs(want).max()), k
     finally:
         backend_api.set_dgrad_mode("reference")
