@@ -19,8 +19,9 @@ echo "== bench --impl reference"
 timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_reference_arm.json 2> $out/${tag}_bench_reference_arm.err
 tail -c 400 $out/${tag}_bench_reference_arm.json
 echo "== ncu launch list of one eager step (numbers under ncu are never bench values)"
-# 3 warm-up + 2 timed eager steps, then the profile pass; one step is ~160 launches: capture a window that is sure to
-# hold a whole steady-state step and let the summary take the last 160
-timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 330 --csv --log-file $out/${tag}_launches.csv \
+# bench --mode eager runs ~10 identical eager steps of ~160 launches each (warm-up, timed, end-to-end) after ~80 start-up
+# launches: a window of 320 launches starting at 900 is two whole steady-state steps (check "n=" in the summary: every
+# per-step count doubled)
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 320 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --mode eager > $out/${tag}_launches_bench.log 2>&1
-python scripts/summarize_launches.py $out/${tag}_launches.csv 0.5 | tee $out/${tag}_launch_summary.txt | head -30
+python scripts/summarize_launches.py $out/${tag}_launches.csv 1.0 | tee $out/${tag}_launch_summary.txt | head -30
