@@ -5,7 +5,7 @@ import numpy as np
 from hypothesis import given, settings, strategies as st, HealthCheck
 
 F32 = np.float32
-SET = dict(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+SET = dict(max_examples=120, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 
 
 def _array(shape, seed):
