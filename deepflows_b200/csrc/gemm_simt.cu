@@ -44,6 +44,7 @@ struct ConvGeom {
   int krsc;  // weights (and dW) stored channels-last (K,R,R,C) instead of (K,C,R,R)
 };
 __device__ __forceinline__ size_t weight_index(const ConvGeom& g, int kout, int c, int tap) {
+  const int RR = g.R * g.R;
   return g.krsc ? ((size_t)kout * RR + tap) * g.C + c : ((size_t)kout * g.C + c) * RR + tap;
 }
 
