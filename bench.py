@@ -1,21 +1,29 @@
 #!/usr/bin/env python
-"""bench.py - the headline benchmark: ResNet-18 (CIFAR-10 shape) training throughput through the unchanged
-DeepFlows API on deepflows_b200's `cuda` device (BASELINE.json: configs[3], batch 256 per GPU, BatchNorm +
-Adam, data-parallel over N GPUs of one node).
+"""bench.py - training throughput through the unchanged DeepFlows API on deepflows_b200's `cuda` device.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision tf32|fp32|bf16] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4] [--precision tf32|fp32|bf16]
+                    [--mode graph|eager] [--impl ours|reference]
 
-One JSON line on stdout (rank 0). A "step" = host batch -> forward -> softmax-CE -> backward ->
-(gradient all-reduce) -> Adam step.
-  value  : images/s with the batch already resident in HBM (device-timed with CUDA events on the compute
-           stream, max over ranks), whole job (all N GPUs).
-  e2e    : the same metric through the public API with HOST inputs: every step's batch is copied from pinned
-           host memory (prefetched on a copy stream while the previous step computes, then moved into the
-           step's input buffers) and every step's loss is read back to the host (async copy into pinned
-           memory, picked up one step later); all inside the timed region.
-  roofline / cpu_baseline : see DESIGN.md "Measurement".
-`--impl reference` times the reference's CPU path for the same workload (the oracle port of the reference
-algorithm: oracle/numpy_device.py under the same host code) on the host cores, on a bounded sample.
+Default workload = the headline: ResNet-18 (CIFAR-10 shape, BASELINE.json configs[3]), batch 256 per GPU, BatchNorm +
+Adam, data-parallel over the N GPUs of one node. `--config c2|c3|c5-vgg16|c5-resnet` selects the other BASELINE configs
+(CNN-MNIST, CNN-CIFAR10, VGG-16+BN / ResNet[3,4,6,3] at 224x224, batch 128 per GPU).
+
+One JSON line on stdout (rank 0). A "step" = batch -> forward -> softmax-CE -> backward -> (gradient all-reduce) ->
+optimizer step.
+  value   : images/s with the batch already resident in HBM: K steps bracketed by barrier + synchronize and CUDA events on
+            the library's compute stream, max over ranks. The K-step block is repeated until >= 1 s has been timed and the
+            MEDIAN block is reported (`blocks` lists how many, `block_ms` their spread): 20 steps of 1 ms on a cold GPU at
+            boost clocks is a burst, not a throughput.
+  e2e     : the same metric through the public API with HOST inputs: every step's batch is copied from pinned host memory
+            (prefetched on a copy stream while the previous step computes, then moved into the step's input buffers) and
+            every step's loss is read back to the host; all inside the timed region.
+  roofline: the fused call that costs the step most device time, re-timed over rotating argument sets (> 256 MB of
+            distinct buffers, i.e. out of L2 like inside the step), algorithmic bytes / FLOPs over that time,
+            against MEASURED_PEAKS.json (HBM) or profiles/measured_tf32_peak.json (tensor pipe).
+  parity  : the same model / weights / batch stepped once on the oracle's numpy device and on cuda (loss, logits).
+  cpu_baseline / --impl reference : the reference algorithm (oracle numpy device under the same host code) on the host
+            cores, on a bounded sample.
+  extra   : the same step launched eagerly from Python, and in fp32 mode (N = 1 only).
 """
 import argparse
 import json
@@ -36,16 +44,47 @@ import workloads  # noqa: E402
 F32 = np.float32
 WIDTHS, LAYERS, HW, CLASSES = (32, 64, 128, 256), (2, 2, 2, 2), 32, 10
 
+# name -> model builder, input shape, batch per GPU, optimizer, target smoothing, bounded CPU sample (batch, steps, warm-up)
+CONFIGS = {
+    "c2": dict(metric="CNN-MNIST train img/s",
+               workload="CNN-MNIST (test/CNN_MNIST_cuda.py:72-96: 2 x (conv5x5-ReLU-pool) + FC), Adam lr 1e-3, one-hot targets",
+               build=lambda df, d: workloads.cnn_mnist(df, d), shape=(1, 28, 28), batch=256, smooth=0.0,
+               opt=lambda optim, ps: optim.Adam(ps, lr=1e-3), cpu=(256, 3, 1)),
+    "c3": dict(metric="CNN-CIFAR10 train img/s",
+               workload="CNN-CIFAR10 (test/CNN_CIFAR10_cuda.py:61-114: 3 x (conv-BN-ReLU-pool), Dropout(.5), FC), Adam lr 5e-3 wd 5e-4, "
+                        "one-hot targets, host-RNG dropout masks uploaded every step",
+               build=lambda df, d: workloads.cnn_cifar10(df, d), shape=(3, 32, 32), batch=256, smooth=0.0,
+               opt=lambda optim, ps: optim.Adam(ps, lr=5e-3, weight_decay=5e-4), cpu=(256, 3, 1)),
+    "c4": dict(metric="ResNet-18 CIFAR-10 train img/s",
+               workload="ResNet-18 CIFAR-10 shape (test/ResNet_CIFAR10_cuda.py, widths 32-64-128-256, all blocks registered), "
+                        "Adam lr 1e-3 wd 5e-4, label-smoothed dense targets, exact dgrad",
+               build=lambda df, d: workloads.resnet_cifar(df, d, widths=WIDTHS, layers=LAYERS, num_classes=CLASSES, registered=True),
+               shape=(3, HW, HW), batch=256, smooth=0.05,
+               opt=lambda optim, ps: optim.Adam(ps, lr=1e-3, weight_decay=5e-4), cpu=(256, 3, 1)),
+    "c5-vgg16": dict(metric="VGG-16 224x224 train img/s",
+                     workload="VGG-16 + BatchNorm at 224x224 (test/VGG.py:7-138, 13 conv3x3 + FC 25088-4096-4096-10), Adam lr 1e-3 wd 1e-4, "
+                              "one-hot targets, host-RNG dropout masks",
+                     build=lambda df, d: workloads.vgg16_bn(df, d, img=224), shape=(3, 224, 224), batch=128, smooth=0.0,
+                     opt=lambda optim, ps: optim.Adam(ps, lr=1e-3, weight_decay=1e-4), cpu=(2, 1, 0)),
+    "c5-resnet": dict(metric="ResNet[3,4,6,3] 224x224 train img/s",
+                      workload="ResNet basic blocks [3,4,6,3], widths 64-512, stride-1 stem, no max-pool (test/ResNet.py:24-150, what "
+                               "pretrained_models.py:455-460 builds for 'ResNet-50'), all blocks registered, SGD lr 0.01 momentum 0.9 wd 5e-4",
+                      build=lambda df, d: workloads.resnet_imagenet(df, d), shape=(3, 224, 224), batch=128, smooth=0.0,
+                      opt=lambda optim, ps: optim.SGD(ps, lr=0.01, momentum=0.9, weight_decay=5e-4), cpu=(2, 1, 0)),
+}
 
-def synthetic_batch(batch, seed):
+
+def synthetic_batch(batch, seed, shape=(3, HW, HW), smooth=0.05):
     rng = np.random.RandomState(seed)
-    x = np.clip(rng.randn(batch, 3, HW, HW), -1, 1).astype(F32)  # test/ResNet_CIFAR10_cuda.py:147
-    t = (np.eye(CLASSES, dtype=F32)[rng.randint(0, CLASSES, batch)] * (1 - 0.05) + 0.05 / CLASSES).astype(F32)  # :181-183
+    x = np.clip(rng.randn(batch, *shape), -1, 1).astype(F32)  # test/ResNet_CIFAR10_cuda.py:147
+    t = np.eye(CLASSES, dtype=F32)[rng.randint(0, CLASSES, batch)]
+    if smooth:
+        t = (t * (1 - smooth) + smooth / CLASSES).astype(F32)  # :181-183
     return x, t
 
 
 def conv_layers(batch):
-    """(name, N, C, H, W, K, R, pad, stride, count) of every conv in the model, for FLOP / byte accounting."""
+    """(name, N, C, H, W, K, R, pad, stride, count) of every conv of the C4 model (scripts/opbench.py)."""
     out = [("stem", batch, 3, HW, HW, WIDTHS[0], 3, 1, 1, 1)]
     h, cin = HW // 2, WIDTHS[0]
     for si, (wd, nb) in enumerate(zip(WIDTHS, LAYERS)):
@@ -59,16 +98,6 @@ def conv_layers(batch):
                 out.append(("l%d.b%d.down" % (si + 1, b), batch, cin, h, h, wd, 1, 0, s, 1))
             h, cin = h2, wd
     return out
-
-
-def gemm_flops_per_step(batch):
-    total = 0
-    for i, (_, n, c, h, w, k, r, p, s, _) in enumerate(conv_layers(batch)):
-        oh = (h + 2 * p - r) // s + 1
-        f = 2.0 * n * oh * oh * k * c * r * r
-        total += f * (2 if i == 0 else 3)  # the stem has no dgrad
-    total += 3 * 2.0 * batch * WIDTHS[-1] * CLASSES
-    return total
 
 
 class ClockSampler:
@@ -102,13 +131,14 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = self.rows[first:last] or self.rows[max(0, first - 1):]  # at least the sample that straddles the region
         for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
+                power.append(float(r[3]))
                 for nm, val in zip(names, r[5:9]):
                     if val.lower().startswith("active"):
                         reasons.add(nm)
@@ -116,10 +146,10 @@ class ClockSampler:
                 pass
         busy = sorted(v for v in sm if mx is None or v > 0.3 * mx) or sorted(sm)
         return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def build_training(device_name, batch, precision, seed=0):
+def build_training(device_name, cfg, precision, seed=0):
     import DeepFlows
     from DeepFlows import backend_api, nn
     df = workloads.namespace(DeepFlows)
@@ -127,8 +157,8 @@ def build_training(device_name, batch, precision, seed=0):
         backend_api.set_precision(precision)
     backend_api.set_dgrad_mode("exact")
     np.random.seed(seed)
-    model = workloads.resnet_cifar(df, device_name, widths=WIDTHS, layers=LAYERS, num_classes=CLASSES, registered=True)
-    opt = df.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    model = cfg["build"](df, device_name)
+    opt = cfg["opt"](df.optim, model.parameters())
     return df, model, opt, nn.CrossEntropyLoss()
 
 
@@ -138,32 +168,68 @@ def train_step(df, model, opt, crit, x, t):
     opt.zero_grad()
     loss.backward()
     opt.step()
-    return loss
+    return loss, out
 
 
 # ------------------------------------------------------------------------------------------------
-def run_cpu(args, batch, steps, warmup):
-    """The reference algorithm on the host cores: same host code on the oracle's numpy device."""
+def run_cpu(cfg, batch, steps, warmup, keep_first=False):
+    """The reference algorithm on the host cores: same host code on the oracle's numpy device. With `keep_first` the loss
+    and logits of the first step (fresh seed-0 weights, batch seed 1) are returned for the parity block."""
     from oracle import numpy_device
     from DeepFlows import backend_api
     from DeepFlows.tensor import Tensor, Graph
     backend_api.register_numpy_device(numpy_device)
-    df, model, opt, crit = build_training("cpu", batch, "fp32")
+    df, model, opt, crit = build_training("cpu", cfg, "fp32")
     dev = backend_api.Device("cpu")
-    x, t = synthetic_batch(batch, 1)
-    times = []
+    x, t = synthetic_batch(batch, 1, cfg["shape"], cfg["smooth"])
+    times, first = [], None
+    np.random.seed(1234)  # dropout masks
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        loss = train_step(df, model, opt, crit, Tensor(x, device=dev), Tensor(t, device=dev))
-        float(loss.data.numpy()[0])
+        loss, out = train_step(df, model, opt, crit, Tensor(x, device=dev), Tensor(t, device=dev))
+        lv = float(loss.data.numpy()[0])
+        if it == 0 and keep_first:
+            first = (lv, out.data.numpy().copy())
         Graph.free_graph()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     backend_api.register_numpy_device(None)
+    Graph.free_graph_all()
     sec = sum(times) / len(times)
     return {"value": batch / sec, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "%d steps (+%d warm-up) of ResNet-18/CIFAR at batch %d on the oracle numpy device (reference algorithm: "
-                      "im2col + sgemm, numpy/OpenBLAS threads)" % (steps, warmup, batch), "ms_per_step": sec * 1e3}
+            "sample": "%d steps (+%d warm-up) of the workload at batch %d on the oracle numpy device (reference algorithm: "
+                      "im2col + sgemm, numpy/OpenBLAS threads)" % (steps, warmup, batch), "ms_per_step": sec * 1e3}, first
+
+
+def gpu_first_step(cfg, batch, precision, dev):
+    """One eager training step of a FRESH seed-0 model on cuda at the CPU sample's batch (for the parity block)."""
+    from DeepFlows import backend_api
+    from DeepFlows.tensor import Tensor, Graph
+    df, model, opt, crit = build_training("cuda", cfg, precision)
+    x, t = synthetic_batch(batch, 1, cfg["shape"], cfg["smooth"])
+    np.random.seed(1234)
+    loss, out = train_step(df, model, opt, crit, Tensor(x, device=dev), Tensor(t, device=dev))
+    res = (float(loss.data.numpy()[0]), out.data.numpy().copy())
+    Graph.free_graph_all()
+    return res
+
+
+def load_peaks():
+    peaks = {}
+    for name in ("MEASURED_PEAKS.json", os.path.join("profiles", "measured_tf32_peak.json")):
+        try:
+            peaks.update(json.load(open(os.path.join(ROOT, name))))
+        except (OSError, ValueError):
+            pass
+    hbm = (peaks.get("hbm_gbs"), "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else \
+        (6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)")
+    if peaks.get("tf32_tflops"):
+        tc = (peaks["tf32_tflops"], "measured cuBLAS TF32 8192^3 burst (profiles/measured_tf32_peak.json)")
+    elif peaks.get("bf16_tflops"):
+        tc = (peaks["bf16_tflops"] / 2, "half the measured bf16 burst (MEASURED_PEAKS.json); TF32 itself not measured")
+    else:
+        tc = (795.0, "half the fallback bf16 1.59 PF (B200_PROFILING.md)")
+    return hbm, tc
 
 
 def main():
@@ -171,34 +237,41 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's)")
     ap.add_argument("--precision", default=os.environ.get("DEEPFLOWS_PRECISION", "tf32"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: the step is captured once and replayed as one CUDA graph; eager: every kernel launched from Python")
-    ap.add_argument("--cpu-batch", type=int, default=256)
+    ap.add_argument("--cpu-batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the eager-mode and fp32-mode extra measurements")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="repeat the K-step block until this much has been timed")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "ResNet-18 CIFAR-10 shape (test/ResNet_CIFAR10_cuda.py, widths 32-64-128-256, all blocks registered), "
-                          "Adam lr 1e-3 wd 5e-4, label-smoothed dense targets, exact dgrad",
-              "batch_per_gpu": args.batch, "global_batch": args.batch * world,
-              "image": "3x32x32", "parallelism": "dp%d" % world,
+    B = args.batch or cfg["batch"]
+    cpu_batch, cpu_steps, cpu_warm = cfg["cpu"]
+    if args.cpu_batch:
+        cpu_batch = args.cpu_batch
+    config = {"workload": cfg["workload"], "name": args.config,
+              "batch_per_gpu": B, "global_batch": B * world,
+              "image": "x".join(str(v) for v in cfg["shape"]), "parallelism": "dp%d" % world,
               "launch": "one CUDA graph per step (captured from the unchanged DeepFlows step)" if args.mode == "graph"
                         else "eager (every kernel launched from Python)",
-              "l2": "per-step activation working set (~1.5 GB at batch 256) exceeds the 126 MB L2; no explicit flush"}
+              "l2": "per-step activation working set far exceeds the 126 MB L2 (C4: ~1.5 GB at batch 256); no explicit flush"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-        base = run_cpu(args, args.cpu_batch, max(1, steps), warmup)
-        line = {"impl": "reference", "metric": "ResNet-18 CIFAR-10 train img/s", "value": base["value"], "unit": "img/s",
-                "n_gpus": args.gpus, "steps": max(1, steps), "warmup": warmup, "ms_per_step": base["ms_per_step"],
+        steps, warmup = max(1, min(args.steps, cpu_steps)), min(args.warmup, cpu_warm)
+        base, _ = run_cpu(cfg, cpu_batch, steps, warmup)
+        line = {"impl": "reference", "metric": cfg["metric"], "value": base["value"], "unit": "img/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, batch_per_gpu=args.cpu_batch, global_batch=args.cpu_batch),
+                "config": dict(config, batch_per_gpu=cpu_batch, global_batch=cpu_batch, launch="numpy on the host cores"),
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
@@ -211,11 +284,27 @@ def main():
     if not dev.enabled():
         raise SystemExit("CUDA_BACKEND extension is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
     dev.set_device(local_rank)
-    df, model, opt, crit = build_training("cuda", args.batch, args.precision)
+
+    # ---- parity block (N = 1): fresh model, one eager step at the CPU sample's batch, against the oracle -------------
+    parity = None
+    base = None
+    if not args.no_cpu_baseline and world == 1:
+        got_loss, got_logits = gpu_first_step(cfg, cpu_batch, args.precision, dev)
+        base, (want_loss, want_logits) = run_cpu(cfg, cpu_batch, cpu_steps, cpu_warm, keep_first=True)
+        parity = {"batch": cpu_batch, "loss_gpu": got_loss, "loss_cpu": want_loss,
+                  "rel": abs(got_loss - want_loss) / max(abs(want_loss), 1e-30),
+                  "logits_rel": float(np.abs(got_logits - want_logits).max() / max(np.abs(want_logits).max(), 1e-30)),
+                  "tolerance": 2e-2 if args.precision != "fp32" else 1e-4,
+                  "what": "first training step of the same seed-0 model on the same batch: cuda (%s, eager) vs the oracle numpy device"
+                          % args.precision}
+        parity["ok"] = bool(parity["rel"] <= parity["tolerance"] and parity["logits_rel"] <= parity["tolerance"])
+        if not parity["ok"]:
+            raise SystemExit("bench: parity check failed: %s" % json.dumps(parity))
+
+    df, model, opt, crit = build_training("cuda", cfg, args.precision)
     if world > 1:
         dist.init(model.parameters())
-    B = args.batch
-    x_host, t_host = synthetic_batch(B, 100 + rank)
+    x_host, t_host = synthetic_batch(B, 100 + rank, cfg["shape"], cfg["smooth"])
     px, pt = dev.pinned_empty(x_host.size), dev.pinned_empty(t_host.size)
     px[:], pt[:] = x_host.reshape(-1), t_host.reshape(-1)
     x_dev = Tensor(backend_api.Btensor(x_host, device=dev))
@@ -231,15 +320,18 @@ def main():
             dev.synchronize()
 
     def eager_step():
-        loss = train_step(df, model, opt, crit, x_dev, t_dev)
+        loss, _ = train_step(df, model, opt, crit, x_dev, t_dev)
         Graph.free_graph()
         return loss
 
-    captured = None
-    if args.mode == "graph":
-        from DeepFlows.cuda_graph import CapturedStep
-        captured = CapturedStep(eager_step, device=dev, warmup=1)  # call 1 eager, call 2 captures, then replays
-    resident_step = captured if captured is not None else eager_step
+    def make_step(mode):
+        if mode == "graph":
+            from DeepFlows.cuda_graph import CapturedStep
+            return CapturedStep(eager_step, device=dev, warmup=1)  # call 1 eager, call 2 captures, then replays
+        return eager_step
+
+    resident_step = make_step(args.mode)
+    captured = resident_step if args.mode == "graph" else None
 
     # End-to-end step: every step's batch travels from pinned host memory to the device and the loss travels
     # back. The copy of batch i+1 goes to a staging buffer on the copy stream while step i computes (double
@@ -274,7 +366,7 @@ def main():
         e2e["i"] = i + 1
         return e2e["last"]
 
-    def timed(fn, steps):
+    def timed(fn, steps, cap=None):
         ev0, ev1 = dev.event_create(), dev.event_create()
         barrier()
         l0 = dev.launch_count()
@@ -286,23 +378,37 @@ def main():
         barrier()
         ms = dev.event_elapsed_ms(ev0, ev1)
         launches = dev.launch_count() - l0
-        if captured is not None and captured.captured:
-            launches += captured.node_counts()[0] * steps  # kernel nodes replayed by the graph launches
+        if cap is not None and cap.captured:
+            launches += cap.node_counts()[0] * steps  # kernel nodes replayed by the graph launches
         dev.event_destroy(ev0)
         dev.event_destroy(ev1)
         return ms, launches
 
-    def max_over_ranks(ms):
+    def max_over_ranks(values):
+        """Element-wise max over ranks of a list of floats (a sum all-reduce of a one-hot [rank][i] table)."""
         if world == 1:
-            return ms
-        v = np.zeros(world, F32)
-        v[rank] = ms
-        buf = backend_api.Btensor(v, device=dev)
-        dev.comm_allreduce_async(buf._handle, world)
+            return list(values)
+        v = np.zeros((world, len(values)), F32)
+        v[rank] = values
+        buf = backend_api.Btensor(v.reshape(-1), device=dev)
+        dev.comm_allreduce_async(buf._handle, v.size)
         dev.comm_wait()
-        return float(buf.numpy().max())
+        return [float(m) for m in buf.numpy().reshape(world, -1).max(axis=0)]
 
-    for _ in range(max(3, args.warmup)):
+    def timed_blocks(fn, steps, cap):
+        """Blocks of `steps` steps until >= min_seconds has been timed (same count on every rank); median block."""
+        ms0, launches = timed(fn, steps, cap)
+        ms0 = max_over_ranks([ms0])[0]
+        n_blocks = int(min(200, max(1, np.ceil(args.min_seconds * 1e3 / max(ms0, 1e-3)))))
+        blocks = [ms0]
+        for _ in range(n_blocks - 1):
+            ms, _ = timed(fn, steps, cap)
+            blocks.append(ms)
+        blocks = max_over_ranks(blocks)
+        return float(np.median(blocks)), blocks, launches
+
+    W = max(3, args.warmup)
+    for _ in range(W):
         resident_step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -310,19 +416,59 @@ def main():
     for _ in range(3):
         resident_step()      # every rank (the step holds collectives): the GPU is under load when timing starts
     s0 = sampler.mark()
-    ms_res, launches = timed(resident_step, args.steps)
-    ms_res = max_over_ranks(ms_res)
+    ms_res, blocks_res, launches = timed_blocks(resident_step, args.steps, captured)
     prefetch_batch()
     for _ in range(2):
         e2e_step()
-    ms_e2e, _ = timed(e2e_step, args.steps)
-    ms_e2e = max_over_ranks(ms_e2e)
+    ms_e2e, blocks_e2e, _ = timed_blocks(e2e_step, args.steps, captured)
     s1 = sampler.mark()
     clocks = sampler.stop(s0, s1) if rank == 0 else None
 
+    # ---- data-parallel check: replicas must hold bit-identical parameters after the timed steps ------------------------
+    dp_check = None
+    if world > 1:
+        dev.synchronize()
+        checksum = float(sum(float(p.data.numpy().astype(np.float64).sum()) for p in model.parameters()))
+        v = np.zeros(world, np.float64)
+        v[rank] = checksum
+        hi, lo = v.astype(F32), (v - v.astype(F32).astype(np.float64)).astype(F32)  # two float32 words per rank
+        buf = backend_api.Btensor(np.concatenate([hi, lo]), device=dev)
+        dev.comm_allreduce_async(buf._handle, 2 * world)
+        dev.comm_wait()
+        got = buf.numpy()
+        sums = got[:world].astype(np.float64) + got[world:].astype(np.float64)
+        agree = bool(np.all(sums == sums[0]))
+        dp_check = {"param_checksum": checksum, "ranks_agree": agree}
+        if not agree:
+            raise SystemExit("bench: data-parallel replicas diverged: per-rank parameter checksums %s" % sums.tolist())
+
+    # ---- extras (N = 1): the same step launched eagerly, and in fp32 mode ---------------------------------------------
+    extra = {}
+    if world == 1 and not args.no_extra:
+        if args.mode == "graph":
+            for _ in range(3):
+                eager_step()
+            ms, _ = timed(eager_step, args.steps)
+            extra["eager"] = {"ms_per_step": ms / args.steps, "value": B * args.steps / (ms / 1e3), "unit": "img/s",
+                              "what": "same step, every kernel launched from Python (what an unchanged script gets)"}
+        if args.precision != "fp32":
+            backend_api.set_precision("fp32")
+            try:
+                step32 = make_step(args.mode)
+                for _ in range(4):
+                    step32()
+                ms, _ = timed(step32, args.steps, step32 if args.mode == "graph" else None)
+                extra["fp32"] = {"ms_per_step": ms / args.steps, "value": B * args.steps / (ms / 1e3), "unit": "img/s",
+                                 "what": "same step in fp32 mode (1e-5 parity), launch mode as the headline"}
+                if args.mode == "graph":
+                    step32.destroy()
+            finally:
+                backend_api.set_precision(args.precision)
+
     # ---- per-kernel profile pass: CUDA events around every fused conv call, same steps ----------------
     # every rank runs it: the steps contain the data-parallel all-reduces, so the ranks must stay in lockstep
-    roofline = profile_dominant_kernel(dev, eager_step, args, B)
+    hbm, tc = load_peaks()
+    roofline, flops = profile_dominant_kernel(dev, eager_step, hbm, tc)
 
     if world > 1:
         barrier()
@@ -331,38 +477,27 @@ def main():
         if world > 1:
             os._exit(0)
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
     total_imgs = B * world * args.steps
     value = total_imgs / (ms_res / 1e3)
-    flops = gemm_flops_per_step(B)
     line = {
-        "metric": "ResNet-18 CIFAR-10 train img/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": cfg["metric"], "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"tf32": "tf32 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate"}.get(args.precision, "f32"),
         "data": "synthetic", "config": config,
+        "blocks": len(blocks_res), "block_ms": {"min": min(blocks_res), "median": ms_res, "max": max(blocks_res)},
         "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(4 * (x_host.size + t_host.size)), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(4 * (x_host.size + t_host.size)), "d2h_bytes_per_step": 4, "blocks": len(blocks_e2e)},
         "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
-        "gemm_tflops_per_gpu": flops / (ms_res / args.steps / 1e3) / 1e12,
+        "gemm_tflops_per_gpu": flops / (ms_res / args.steps / 1e3) / 1e12 if flops else None,
         "clocks": clocks, "roofline": roofline,
     }
-    if roofline is not None:
-        if roofline["bound"] == "hbm":
-            peak, which = peaks.get("hbm_gbs"), "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"
-            if peak is None:
-                peak, which = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        else:
-            peak, which = peaks.get("bf16_tflops_sustained"), "measured sustained bf16 cuBLAS (MEASURED_PEAKS.json)"
-            if peak is None:
-                peak, which = 1400.0, "fallback sustained 1.4 PF (B200_PROFILING.md)"
-        roofline["peak"], roofline["peak_source"] = peak, which
-        roofline["frac"] = roofline["achieved"] / peak
-    if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
-        base = run_cpu(args, args.cpu_batch, 3, 1)
+    if parity is not None:
+        line["parity"] = parity
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+    if extra:
+        line["extra"] = extra
+    if base is not None:
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -371,15 +506,16 @@ def main():
         os._exit(0)
 
 
-def profile_dominant_kernel(dev, step_fn, args, batch):
-    """Find the fused op + geometry that costs the step most device time and report it against its roofline.
+def profile_dominant_kernel(dev, step_fn, hbm, tc):
+    """Find the fused call + geometry that costs the step most device time and report it against its roofline.
 
-    Pass 1 (eager, CUDA events around every conv2d_fprop / dgrad / wgrad / BatchNorm call of a few identical
-    steps) finds the distinct (op, geometry) pairs, how often each runs per step, and keeps one set of live
-    arguments for each. Pass 2 times each pair the way it runs inside the captured step: 16 back-to-back calls
-    replayed from a CUDA graph (no host launch cost), CUDA events around three replays. The pair with the
-    largest per-step total is the dominant kernel; `achieved` = its algorithmic bytes or FLOPs
-    over that duration."""
+    Pass 1 (eager, CUDA events around every conv2d_fprop / dgrad / wgrad / gemm / BatchNorm call of two identical steps)
+    finds the distinct (op, geometry) pairs, how often each runs per step, and keeps one set of live arguments for each.
+    Pass 2 re-times each pair the way it runs inside the captured step: R calls replayed from a CUDA graph (no host launch
+    cost), each call on its OWN copy of every array argument with R chosen so that the copies exceed 256 MB - twice the L2 -
+    so operands come from HBM as they do inside the step (back-to-back calls on one argument set would be served by the
+    126 MB L2). The pair with the largest per-step total is the dominant kernel; `achieved` = its algorithmic bytes or FLOPs
+     over that duration. Also returns the GEMM FLOPs of one step (sum over the recorded conv / gemm calls)."""
     pending = []
     for _ in range(2):  # un-instrumented eager steps: refill the allocator pool after the graph capture
         step_fn()
@@ -396,8 +532,12 @@ def profile_dominant_kernel(dev, step_fn, args, batch):
 
     conv_geom = lambda off: (lambda a: tuple(int(v) for v in a[off:off + 8]))  # noqa: E731
     saved = {}
-    for name, geom in (("conv2d_fprop", conv_geom(4)), ("conv2d_dgrad", conv_geom(3)), ("conv2d_wgrad", conv_geom(4)),
-                       ("bn_fwd_train", lambda a: (int(a[10]), int(a[11]))), ("bn_bwd", lambda a: (int(a[8]), int(a[9])))):
+    specs = [("conv2d_fprop", conv_geom(4)), ("conv2d_dgrad", conv_geom(3)), ("conv2d_wgrad", conv_geom(4)),
+             ("gemm", lambda a: tuple(int(v) for v in a[3:8])),
+             ("bn_fwd_train", lambda a: (int(a[10]), int(a[11]))), ("bn_bwd", lambda a: (int(a[8]), int(a[9])))]
+    for name, geom in specs:
+        if not dev.has(name):
+            continue
         orig = getattr(dev, name)
         saved[name] = orig
         dev.__dict__[name] = wrap(name, geom, orig)
@@ -418,18 +558,46 @@ def profile_dominant_kernel(dev, step_fn, args, batch):
         r["count"] += 1
         r["eager_ms"] += eager_ms
     if not pairs:
-        return None
-    # pass 2: graph-replayed timing of every distinct pair
-    reps = 16
+        return None, 0.0
+
+    def conv_work(geom):
+        n, c, h, w, k, rr, p, s = geom
+        oh, ow = (h + 2 * p - rr) // s + 1, (w + 2 * p - rr) // s + 1
+        return 2.0 * n * oh * ow * k * c * rr * rr, 4.0 * (n * c * h * w + k * c * rr * rr + n * oh * ow * k)
+
+    flops_step = 0.0
+    for (name, geom), r in pairs.items():
+        if name.startswith("conv2d"):
+            flops_step += conv_work(geom)[0] * r["count"] / steps
+        elif name == "gemm":
+            flops_step += 2.0 * geom[0] * geom[1] * geom[2] * r["count"] / steps
+
+    is_array = lambda v: hasattr(v, "size") and hasattr(v, "ptr")  # noqa: E731  (the shim's Array)
+
+    def clone_args(a):
+        out = []
+        for v in a:
+            if is_array(v):
+                c = dev.Array(v.size)
+                dev.copy(v, c, v.size)
+                out.append(c)
+            else:
+                out.append(v)
+        return out
+
+    # pass 2: graph-replayed timing of every distinct pair over rotating (L2-cold) argument sets
     for (name, geom), r in pairs.items():
         fn, a = saved[name], r["args"]
-        if dev.has("side_begin") and name == "conv2d_wgrad":
-            pass  # timed on the compute stream here; inside the step it overlaps dgrad on the side stream
-        for _ in range(2):
-            fn(*a)
+        per_set = 4 * sum(v.size for v in a if is_array(v))
+        reps = int(max(4, min(48, np.ceil((256 << 20) / max(per_set, 1)))))
+        if per_set * reps > (8 << 30):   # the 224x224 layers: a few sets are already far beyond L2
+            reps = max(2, int((8 << 30) // per_set))
+        sets = [list(a)] + [clone_args(a) for _ in range(reps - 1)]
+        for s_ in sets[:2]:
+            fn(*s_)
         dev.graph_begin_capture()
-        for _ in range(reps):
-            fn(*a)
+        for s_ in sets:
+            fn(*s_)
         g = dev.graph_end_capture()
         dev.graph_launch(g)
         e0, e1 = dev.event_create(), dev.event_create()
@@ -440,28 +608,32 @@ def profile_dominant_kernel(dev, step_fn, args, batch):
         dev.event_synchronize(e1)
         r["us"] = dev.event_elapsed_ms(e0, e1) / (3 * reps) * 1e3
         r["per_step"] = r["count"] / steps
+        r["sets"] = reps
         dev.event_destroy(e0)
         dev.event_destroy(e1)
         dev.graph_destroy(g)
         r["args"] = None
+        del sets
     by_op = {}
     for (name, geom), r in pairs.items():
         by_op[name] = by_op.get(name, 0.0) + r["us"] * r["per_step"] / 1e3
     (name, geom), r = max(pairs.items(), key=lambda kv: kv[1]["us"] * kv[1]["per_step"])
     avg_s = r["us"] * 1e-6
-    if name.startswith("conv2d"):
-        n, c, h, w, k, rr, p, s = geom
-        oh, ow = (h + 2 * p - rr) // s + 1, (w + 2 * p - rr) // s + 1
-        flops = 2.0 * n * oh * ow * k * c * rr * rr
-        bytes_min = 4.0 * (n * c * h * w + k * c * rr * rr + n * oh * ow * k)
-        t_tc_us = flops / 700e12 * 1e6   # TF32 dense ~ half of sustained bf16
-        t_hbm_us = bytes_min / 6.5456e12 * 1e6
+    if name.startswith("conv2d") or name == "gemm":
+        if name == "gemm":
+            m_, n_, k_ = geom[:3]
+            flops, bytes_min = 2.0 * m_ * n_ * k_, 4.0 * (m_ * k_ + k_ * n_ + m_ * n_)
+            desc = "gemm M=%d N=%d K=%d ta=%d tb=%d" % geom
+        else:
+            flops, bytes_min = conv_work(geom)
+            desc = "%s N=%d C=%d H=%d W=%d K=%d R=%d pad=%d stride=%d" % ((name,) + geom)
+        t_tc_us = flops / (tc[0] * 1e12) * 1e6
+        t_hbm_us = bytes_min / (hbm[0] * 1e9) * 1e6
         bound = "tensor" if t_tc_us > t_hbm_us else "hbm"
         achieved = flops / avg_s / 1e12 if bound == "tensor" else bytes_min / avg_s / 1e9
         unit = "TFLOP/s" if bound == "tensor" else "GB/s"
-        desc = "%s N=%d C=%d H=%d W=%d K=%d R=%d pad=%d stride=%d" % ((name,) + geom)
         extra = {"flops_per_launch": flops, "bytes_per_launch": bytes_min, "tflops": flops / avg_s / 1e12,
-                 "gbs": bytes_min / avg_s / 1e9}
+                 "gbs": bytes_min / avg_s / 1e9, "t_hbm_us": t_hbm_us, "t_tensor_us": t_tc_us}
     else:
         rows, c = geom
         per_elem = 12.0 if name == "bn_fwd_train" else 20.0
@@ -469,19 +641,23 @@ def profile_dominant_kernel(dev, step_fn, args, batch):
         bound, achieved, unit = "hbm", bytes_min / avg_s / 1e9, "GB/s"
         desc = "%s rows=%d C=%d" % (name, rows, c)
         extra = {"bytes_per_launch": bytes_min}
+    peak, which = (tc if bound == "tensor" else hbm)
     traffic = None
     try:  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture, when there is one
         table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic = table.get(desc, {}).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
-    return dict({"kernel": desc, "bound": bound, "achieved": achieved, "peak": None, "unit": unit, "frac": None,
-                 "traffic": traffic, "avg_launch_us": r["us"], "launches_per_step": r["per_step"],
+    worst = sorted(((kv[1]["us"] * kv[1]["per_step"], kv[0][0], kv[0][1], kv[1]["us"]) for kv in pairs.items()), reverse=True)[:6]
+    return dict({"kernel": desc, "bound": bound, "achieved": achieved, "peak": peak, "peak_source": which, "unit": unit,
+                 "frac": achieved / peak, "traffic": traffic, "avg_launch_us": r["us"], "launches_per_step": r["per_step"],
+                 "argument_sets": r["sets"],
                  "share_of_step_ms": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])},
+                 "top_calls": [{"us_per_step": round(t, 2), "op": n_, "geom": list(g_), "us": round(u, 2)} for t, n_, g_, u in worst],
                  "how": "each distinct fused call of the step (found with CUDA events around the calls of eager steps) is "
-                        "re-timed as 16 back-to-back calls replayed from a CUDA graph, CUDA events on the compute stream "
-                        "around 3 replays - the cost it has inside the captured step, free of host launch latency"},
-                **extra)
+                        "re-timed as R calls replayed from one CUDA graph, each call on its own copy of the arguments (R sets "
+                        "> 256 MB, so nothing is served from L2), CUDA events on the compute stream around 3 replays"},
+                **extra), flops_step
 
 
 if __name__ == "__main__":

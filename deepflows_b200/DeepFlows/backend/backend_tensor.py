@@ -24,7 +24,7 @@ __all__ = [
     "all_devices", "Device", "Btensor", "empty", "full", "zeros", "ones", "zeros_like", "ones_like",
     "broadcast_to", "reshape", "maximum", "max", "log", "exp", "tanh", "flip", "summation", "mean", "pad",
     "expand_dims", "register_numpy_device", "set_precision", "get_precision", "set_dgrad_mode",
-    "get_dgrad_mode",
+    "get_dgrad_mode", "set_fix_mean", "get_fix_mean",
 ]
 
 
@@ -66,6 +66,12 @@ class BackendDevice:
 
     def enabled(self):
         return self.mod is not None
+
+    def __deepcopy__(self, memo):
+        return self  # a device is a process-wide singleton (its module object cannot be copied)
+
+    def __reduce__(self):
+        return (Device, (self.name,))
 
     def has(self, attr):
         """True when the device module implements the (fused, L1) entry point `attr`."""
@@ -160,7 +166,9 @@ def Device(device_name=None):
 # ---- numerics switches (new; the reference has a single fp32 path) ---------------------------------
 _PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2, "simt": 3}
 _precision = os.environ.get("DEEPFLOWS_PRECISION", "fp32").lower()
-_dgrad_mode = os.environ.get("DEEPFLOWS_DGRAD", "reference").lower()
+# 'exact' (the true transposed convolution) is the default; 'reference' reproduces the upstream last-writer-wins
+# im2col backward bit for bit and is what the golden-parity tests select explicitly.
+_dgrad_mode = os.environ.get("DEEPFLOWS_DGRAD", "exact").lower()
 
 
 def set_precision(name):
@@ -184,8 +192,9 @@ def precision_mode():
 
 
 def set_dgrad_mode(name):
-    """'reference': the last-writer-wins input gradient of the reference's im2col backward
-    (DeepFlows/nn/functional.py:285-294); 'exact': the true transposed convolution."""
+    """'exact' (default): the true transposed convolution. 'reference': the last-writer-wins input gradient of
+    the reference's im2col backward (DeepFlows/nn/functional.py:285-294) - mathematically wrong for
+    overlapping windows, kept as an opt-in bug-parity mode (also DEEPFLOWS_DGRAD=reference)."""
     global _dgrad_mode
     name = name.lower()
     if name not in ("reference", "exact"):
@@ -195,6 +204,21 @@ def set_dgrad_mode(name):
 
 def get_dgrad_mode():
     return _dgrad_mode
+
+
+# `mean(axis)` of the reference divides by the TOTAL element count (backend_tensor.py:659-662), so the
+# scripts' two-step global average pool returns true_mean / (N^2 C^2 W). That is kept by default (script parity);
+# DEEPFLOWS_FIX_MEAN=1 / set_fix_mean(True) divides by the length of the reduced axis instead.
+_fix_mean = os.environ.get("DEEPFLOWS_FIX_MEAN", "0") == "1"
+
+
+def set_fix_mean(enabled):
+    global _fix_mean
+    _fix_mean = bool(enabled)
+
+
+def get_fix_mean():
+    return _fix_mean
 
 
 # ------------------------------------------------------------------------------------------------
@@ -251,6 +275,13 @@ class BackendTensor:
         t._dense = None
         return t
 
+    def __deepcopy__(self, memo):
+        """Same values, same layout, a buffer of its own on the same device (used by Module.to / copy.deepcopy)."""
+        src = self if self.is_dense() else self.compact()
+        out = src._like()
+        src._device.scalar_add(src._handle, 0.0, out._handle)
+        return out
+
     # ---- properties ---------------------------------------------------------------------------------
     @property
     def shape(self):
@@ -306,6 +337,16 @@ class BackendTensor:
             self._dense = d
         return d
 
+    def _dense_within_view(self):
+        """The strides are a permutation of a compact layout of this shape (offset and handle size not considered):
+        the elements occupy one contiguous run of prod(shape) floats starting at `_offset`."""
+        expect = 1
+        for st, sh in sorted(((st, sh) for st, sh in zip(self._strides, self._shape) if sh != 1)):
+            if st != expect:
+                return False
+            expect *= sh
+        return True
+
     def is_channels_last(self):
         """4-d (N,C,H,W) view whose memory order is N,H,W,C and which covers its handle."""
         if len(self._shape) != 4 or self._offset != 0:
@@ -329,8 +370,8 @@ class BackendTensor:
         agree, otherwise copied into a new buffer with ref's strides. `ref` must be dense. Used wherever two
         tensors are walked as flat buffers side by side (fused optimizer steps, gradient buckets)."""
         assert self._shape == ref._shape, (self._shape, ref._shape)
-        if self._strides == ref._strides and self._offset == 0 and self.is_dense():
-            return self
+        if self._strides == ref._strides and (self.is_dense() or self._dense_within_view()):
+            return self  # may start at an offset inside a larger buffer (a gradient that aliases its all-reduce bucket)
         if ref.is_compact():
             return self.compact()
         if ref.is_channels_last():
@@ -599,6 +640,9 @@ class BackendTensor:
 
     def mean(self, axis=None, keepdims=False):
         # reference quirk Q3 (lines 659-662): divides by the TOTAL element count, also for one axis
+        if _fix_mean and axis is not None:
+            ax = axis[0] if isinstance(axis, (tuple, list)) else axis
+            return self.sum(axis, keepdims=keepdims) / self._shape[ax]
         return self.sum(axis, keepdims=keepdims) / prod(self._shape)
 
     def flip(self, axes):

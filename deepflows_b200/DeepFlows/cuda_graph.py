@@ -13,7 +13,9 @@ buffers they touched, and `libdfb200` keeps those buffers reserved for the graph
   * the contents of tensors that existed before the capture (inputs, targets, parameters, optimizer state);
   * optimizer hyper-parameters (`optimizer.lr` set by a scheduler, Adam's step counter): optimizers that
     stepped during the capture are refreshed through `dfb_graph_set_adam` / `dfb_graph_set_sgd`.
-What may not: shapes, control flow, host<->device copies or `.numpy()` inside the callable (they raise).
+  * host-drawn tensors registered with `note_host_refill` (Dropout masks): their buffers are refilled from the host
+    before every launch, in registration order, so a seeded run draws the same masks as an eager run.
+What may not: shapes, control flow, other host<->device copies or `.numpy()` inside the callable (they raise).
 """
 from . import backend_api
 
@@ -30,6 +32,13 @@ def note_optimizer_step(optimizer):
         _active._optimizers.append(optimizer)
 
 
+def note_host_refill(buffer, draw):
+    """Called from inside a capture: `buffer` (a BackendTensor allocated during the capture) must hold `draw()` (a
+    float32 numpy array of its shape) before every launch of the captured graph."""
+    assert _active is not None, "note_host_refill outside a capture"
+    _active._refills.append((buffer, draw))
+
+
 class CapturedStep:
     def __init__(self, fn, device=None, warmup=1):
         self.fn = fn
@@ -39,6 +48,11 @@ class CapturedStep:
         self.result = None
         self._exec = None
         self._optimizers = []
+        self._refills = []
+
+    def _refill(self):
+        for buf, draw in self._refills:
+            self.device.from_numpy(draw(), buf._handle)
 
     @property
     def captured(self):
@@ -64,10 +78,12 @@ class CapturedStep:
                 raise
             _active = None
             self._exec = dev.graph_end_capture()
+            self._refill()
             dev.graph_launch(self._exec)  # the capture itself executed nothing
             return self.result
         for i, opt in enumerate(self._optimizers):
             opt._graph_refresh(self.device, self._exec, i)
+        self._refill()
         self.device.graph_launch(self._exec)
         return self.result
 

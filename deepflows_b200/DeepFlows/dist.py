@@ -4,11 +4,15 @@ One process per GPU (the autograd tape and the grad switch are process-global). 
 its shard of the global batch; after `backward()` the gradients of all parameters are packed into
 flat buckets and sum-all-reduced with NCCL on the communication stream while the host goes on;
 `Optimizer.step()` waits for the communication stream and folds the 1/world_size average into the
-fused optimizer kernel's `grad_scale`. Scripts stay unchanged: `init_from_env()` is called by the
-launcher shim (or explicitly), `backward()` and `step()` consult this module's context.
+fused optimizer kernel's `grad_scale`. Scripts stay unchanged apart from one `dist.init(model.parameters())`
+call (which reads RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT from the launcher's environment); `backward()`
+and `step()` consult this module's context.
 
 The transport is pluggable so the bucketing logic can be tested on CPU: `NcclTransport` (libdfb200
-dfb_comm_*) for GPUs, `TorchGlooTransport` (torch.distributed, tests only) for the numpy device.
+dfb_comm_*) for GPUs; tests/test_dist_gloo.py supplies a torch.distributed (gloo) transport for the numpy device.
+
+Gradient accumulation over several `backward()` calls before one `step()` is not supported: after a backward the
+gradients alias their (already summed) buckets, and a second backward raises instead of reducing them twice.
 """
 import os
 import socket
@@ -168,6 +172,13 @@ class DataParallel:
         if self._plan is None:
             self._build_plan()
         if self._open is None:
+            if self._pending:
+                # a second backward() before optimizer.step(): param.grad aliases a bucket whose all-reduce may still
+                # be in flight, and re-reducing the summed values would scale them by the world size
+                self.transport.wait()
+                self._pending = False
+                raise RuntimeError("data parallel: backward() was called again before optimizer.step(); gradient "
+                                   "accumulation across backward passes is not supported (call step() / zero_grad())")
             self._open = {b: len(slots) for b, (_, slots) in enumerate(self._plan)}
         seen = self._arrived.get(i, 0) + 1
         self._arrived[i] = seen
@@ -199,7 +210,8 @@ class DataParallel:
         if sizes:
             dev.multi_copy(srcs, dsts, sizes)
         self.transport.allreduce_sum(flat)
-        # gradients now alias the bucket: the optimizer reads the reduced values in place
+        # gradients now alias the bucket: the optimizer reads the reduced values in place (with_layout_of accepts a
+        # dense view at an offset, the fused steps take (handle, offset) pairs)
         for i, off, n in slots:
             p = self.params[i]
             if p.grad is not None:

@@ -15,9 +15,15 @@ class Dropout(Module):
     def forward(self, x):
         if not self.training:
             return x * (1 - self.p)
-        host = np.random.binomial(1, 1 - self.p, x.shape).astype(np.float32)
         mask = x.device.empty(x.shape, dtype="float32")
-        x.device.from_numpy(host, mask._handle)
+        from ... import cuda_graph
+        if cuda_graph.capturing():
+            # Inside a captured step nothing may be copied from the host: the mask buffer belongs to the graph and is
+            # refilled from the host RNG (same call, same order as an eager step) before every launch of the graph.
+            cuda_graph.note_host_refill(mask, lambda shape=x.shape, p=self.p: np.random.binomial(1, 1 - p, shape).astype(np.float32))
+        else:
+            host = np.random.binomial(1, 1 - self.p, x.shape).astype(np.float32)
+            x.device.from_numpy(host, mask._handle)
         return x * mask / (1 - self.p)
 
     def __repr__(self):

@@ -309,23 +309,30 @@ class Module:
 
     # ---- device moves ---------------------------------------------------------------------------------
     def to(self, device):
+        """A copy of this module on `device` (self when every parameter and buffer already lives there); the
+        reference deep-copies and re-homes the copy [806-818]. Tensors are rebuilt through numpy on the target
+        device, parameters stay Parameters, registered buffers (BatchNorm running statistics) move too."""
         name = device if isinstance(device, str) else device.name
-        own = getattr(self, "device", None)
-        own_name = own if isinstance(own, str) else getattr(own, "name", None)
-        if own_name == name:
+        tensors = [t for t in list(self.parameters()) + list(self.buffers()) if t is not None]
+        if all(t.device.name == name for t in tensors):
+            object.__setattr__(self, "device", backend_api.Device(name))
             return self
         module = deepcopy(self)
         module.move(name)
         return module
 
     def move(self, device):
-        object.__setattr__(self, "device", backend_api.Device(device))
+        name = device if isinstance(device, str) else device.name
+        object.__setattr__(self, "device", backend_api.Device(name))
         for key, p in list(self._parameters.items()):
             if p is not None:
-                self._parameters[key] = p.to(device)
+                self._parameters[key] = p.to(name)
+        for key, b in list(self._buffers.items()):
+            if b is not None:
+                self._buffers[key] = b.to(name)
         for module in self._modules.values():
             if isinstance(module, Module):
-                module.move(device)
+                module.move(name)
 
     def cuda(self):
         return self.to("cuda")

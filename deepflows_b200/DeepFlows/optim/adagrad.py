@@ -12,7 +12,11 @@ class Adagrad(Optimizer):
         self.s = [backend_api.zeros_like(p.data) for p in self.params]
 
     def step(self):
+        # data parallel: wait for the bucketed all-reduces on the compute stream and average (1/world_size)
+        grad_scale = self._grad_scale()
         for i, p, g in self._active():
+            if grad_scale != 1.0:
+                g = g * grad_scale
             if self.weight_decay:
                 g = g + p.data * self.weight_decay
             self.s[i] = self.s[i] + g * g

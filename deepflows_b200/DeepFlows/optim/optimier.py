@@ -13,6 +13,8 @@ class Optimizer:
         raise NotImplementedError
 
     def zero_grad(self):
+        from .. import dist
+        dist.pre_step()  # data parallel: gradients may alias buckets whose all-reduce is still in flight
         for param in self.params:
             param.zero_grad()
 

@@ -184,6 +184,19 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32() {
          ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+// ---- optional in-kernel timeline (build with -DDFB_TC_TIMING: scripts/tc_timing_probe.cu) -------------------------
+// The first and the last CTA of a launch record clock64() at the hand-over points of the pipeline; off in the shipped
+// library (the macro expands to nothing).
+#ifdef DFB_TC_TIMING
+__device__ unsigned long long g_tc_stamp[2][16];
+#define TC_STAMP(i)                                                                                         \
+  do {                                                                                                      \
+    if (stamp_slot >= 0 && (threadIdx.x & 31) == 0) g_tc_stamp[stamp_slot][i] = (unsigned long long)clock64(); \
+  } while (0)
+#else
+#define TC_STAMP(i)
+#endif
+
 // ---- kernel skeleton ----------------------------------------------------------------------------------
 // KR: reduction rows per stage (MN-major operands only: 32 or 128). BSUB: B tiles per stage (the row-halo conv
 // kernel keeps the three taps of one filter column in a stage, with AROWS = 192 halo rows of A)
@@ -234,6 +247,12 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef DFB_TC_TIMING
+  const bool first_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool last_cta = blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1;
+  const int stamp_slot = first_cta ? 0 : (last_cta ? 1 : -1);
+  if (warp == 0) TC_STAMP(0);
+#endif
   typename P::Tile tile = P::tile(prm);
   // Split-K: the CTAs of a cluster (cluster dims (1,1,S), P::kClusterSplit) share one output tile; CTA `rank`
   // takes the rank-th slice of the k-blocks, accumulates it in its own TMEM, and the S partial tiles are
@@ -262,9 +281,11 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) TC_STAMP(1);
   // everything above (barrier init, descriptor prefetch, TMEM allocation) overlapped the previous kernel's tail;
   // global memory is touched only from here on
   pdl_sync();
+  if (warp == 0) TC_STAMP(2);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -288,9 +309,11 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
         P::load_b(prm, tile, it, &map_b, full_bar + stage, b_dst);
       }
       __syncwarp();
+      if (kb == kb_begin) TC_STAMP(3);
       P::iter_next(prm, tile, it);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
+    TC_STAMP(4);
   } else if (warp == 1) {
     // ===== MMA issuer: the warp waits convergently, one elected lane (always the same one: tcgen05.commit tracks
     // the MMAs of the thread that executes it) issues =====
@@ -300,6 +323,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(full_bar + stage, phase);
       tc_fence_after();
+      if (kb == kb_begin) TC_STAMP(5);
       const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
       const uint32_t b_base = a_base + L::kABytes;
       if (elect_one()) {
@@ -324,6 +348,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     }
     if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
     __syncwarp();
+    TC_STAMP(6);
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int quarter = warp & 3;
@@ -332,6 +357,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
+    if (warp == 2) TC_STAMP(7);
     float* red = reinterpret_cast<float*>(smem);  // the pipeline stages are idle once the accumulator is complete
     constexpr uint32_t kRedPitch = P::kAccTiles * BN + 4;  // == L::kRedPitch with one accumulator tile
 #pragma unroll 1
@@ -353,11 +379,14 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       }
     }
     tc_fence_before();
+    if (warp == 2) TC_STAMP(8);
     P::finish(prm, tile, (warp - 2) * 32 + lane);  // the 128 epilogue threads (wgrad: last CTA of a tile sums the splits)
+    if (warp == 2) TC_STAMP(9);
   }
   if (P::kClusterSplit && nsplit > 1) {
     cluster_arrive();
     cluster_wait();  // every partial tile is in its CTA's shared memory
+    if (warp == 2) TC_STAMP(10);
     if (warp >= 2) {
       // kDynRedRows (wgrad): only the rows that hold output channels are reduced, spread over all CTAs of the cluster
       const int red_rows = P::kDynRedRows ? P::red_rows(prm, tile) : BLOCK_M;
@@ -384,6 +413,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     }
     // nobody leaves while its shared memory may still be read: arrive once this CTA's remote reads have
     // landed in registers (the global stores above only consume registers), wait just before the exit
+    if (warp == 2) TC_STAMP(11);
     cluster_arrive();
     // two-level split (wgrad): the last cluster that finishes a tile adds the clusters' partial tiles
     if (P::kClusterFinish && warp >= 2) P::finish_cluster(prm, tile, (warp - 2) * 32 + lane, rank, nsplit);
@@ -391,9 +421,11 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   } else {
     __syncthreads();
   }
+  if (warp == 2) TC_STAMP(12);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<P::kTmemCols>(tmem_base);
+    TC_STAMP(13);
   }
 }
 
@@ -1463,5 +1495,11 @@ dfb_status tc_stem_wgrad(const float* x, int x_layout, const float* dy, float* d
 }
 
 size_t tc_conv_workspace_floats(int, int, int, int, int, int, int, int) { return 0; }
+
+#ifdef DFB_TC_TIMING
+extern "C" __attribute__((visibility("default"))) int dfb_debug_tc_stamps(unsigned long long* out32) {
+  return (int)cudaMemcpyFromSymbol(out32, tc::g_tc_stamp, sizeof(unsigned long long) * 32);
+}
+#endif
 
 }  // namespace dfb

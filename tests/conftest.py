@@ -46,9 +46,11 @@ def cuda_device():
 
 @pytest.fixture(autouse=True)
 def _fresh_graph():
-    from DeepFlows import tensor, autograd
+    from DeepFlows import tensor, autograd, backend_api
     tensor.Graph.free_graph_all()
     autograd.set_grad_enabled(True)
+    backend_api.set_dgrad_mode("exact")  # the package default; fixture-parity tests select "reference" themselves
     yield
     tensor.Graph.free_graph_all()
     autograd.set_grad_enabled(True)
+    backend_api.set_dgrad_mode("exact")

@@ -20,6 +20,13 @@ TRAIN_CASES = {
     "resnet_script": dict(build=lambda df, d: workloads.resnet_cifar(df, d, widths=(4, 8, 8, 16), layers=(1, 1, 1, 1),
                                                                     registered=False),
                           opt=lambda optim, ps: optim.Adam(ps, lr=1e-3, weight_decay=5e-4), lr=1e-3),
+    # the reference with its mean(axis) repaired (oracle/make_golden_fixmean.py; DEEPFLOWS_FIX_MEAN=1 here): every block's
+    # gradient is O(1), so these are the fixtures that see conv dgrad / wgrad / BatchNorm backward inside a real graph
+    "resnet_fixmean": dict(build=lambda df, d: workloads.resnet_cifar(df, d, widths=(4, 8, 8, 16), layers=(1, 1, 1, 1)),
+                           opt=lambda optim, ps: optim.Adam(ps, lr=1e-3, weight_decay=5e-4), lr=1e-3, fix_mean=True),
+    "resnet_fixmean_sgd": dict(build=lambda df, d: workloads.resnet_cifar(df, d, widths=(4, 8, 8, 16), layers=(1, 1, 1, 1)),
+                               opt=lambda optim, ps: optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=5e-4), lr=0.05,
+                               fix_mean=True),
 }
 
 
@@ -35,38 +42,45 @@ def run_training_case(name, device_name):
     from DeepFlows import backend_api, tensor, nn
     from DeepFlows.tensor import Tensor
     g = golden("train_" + name)
+    backend_api.set_dgrad_mode("reference")  # the fixtures hold the reference's last-writer-wins dgrad (conftest restores the default)
     df = df_namespace()
     case = TRAIN_CASES[name]
     dev = backend_api.Device(device_name)
-    np.random.seed(11)
-    model = case["build"](df, device_name)
-    for k, p in workloads.all_parameters(model):
-        p.data = backend_api.Btensor(g["p0." + k], device=dev)
-    opt = case["opt"](df.optim, model.parameters())
-    crit = nn.CrossEntropyLoss()
-    losses, logits = [], []
-    np.random.seed(23)
-    model.train()
-    for it in range(g["x"].shape[0]):
-        x, t = Tensor(g["x"][it], device=dev), Tensor(g["target"][it], device=dev)
-        out = model(x)
-        loss = crit(out, t)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        losses.append(loss.data.numpy().item())
-        logits.append(out.data.numpy().copy())
-        tensor.Graph.free_graph()
+    backend_api.set_fix_mean(bool(case.get("fix_mean")))
+    try:
+        np.random.seed(11)
+        model = case["build"](df, device_name)
+        for k, p in workloads.all_parameters(model):
+            p.data = backend_api.Btensor(g["p0." + k], device=dev)
+        opt = case["opt"](df.optim, model.parameters())
+        crit = nn.CrossEntropyLoss()
+        losses, logits, grads0 = [], [], {}
+        np.random.seed(23)
+        model.train()
+        for it in range(g["x"].shape[0]):
+            x, t = Tensor(g["x"][it], device=dev), Tensor(g["target"][it], device=dev)
+            out = model(x)
+            loss = crit(out, t)
+            opt.zero_grad()
+            loss.backward()
+            if it == 0:
+                grads0 = {k: p.grad.numpy().copy() for k, p in workloads.all_parameters(model) if p.grad is not None}
+            opt.step()
+            losses.append(loss.data.numpy().item())
+            logits.append(out.data.numpy().copy())
+            tensor.Graph.free_graph()
+    finally:
+        backend_api.set_fix_mean(False)
     params = {k: p.data.numpy() for k, p in workloads.all_parameters(model)}
     stats = {}
     for mod_name, mod in model.named_modules():
         if hasattr(mod, "num_features") and mod.running_mean is not None:
             stats["rm." + mod_name] = mod.running_mean.numpy()
             stats["rv." + mod_name] = mod.running_var.numpy()
-    return dict(losses=np.array(losses, F32), logits=np.stack(logits), params=params, stats=stats), g
+    return dict(losses=np.array(losses, F32), logits=np.stack(logits), params=params, stats=stats, grads0=grads0), g
 
 
-def check_training_case(name, device_name, tol_param=1e-4, tol_out=1e-4):
+def check_training_case(name, device_name, tol_param=1e-4, tol_out=1e-4, tol_grad=1e-4):
     """north_star: one training step's parameter update within 1e-4 (relative to max |param|).
 
     Parameters listed in the fixture's `ill_conditioned` array are those whose update the REFERENCE ITSELF
@@ -78,6 +92,18 @@ def check_training_case(name, device_name, tol_param=1e-4, tol_out=1e-4):
     res, g = run_training_case(name, device_name)
     assert rel_err(res["losses"], g["losses"]) < tol_out, (res["losses"], g["losses"])
     assert rel_err(res["logits"], g["logits"]) < 5 * tol_out
+    # first-step gradients (fixtures that hold them): each within tol of the reference, relative to its own magnitude
+    # (floored at 1e-3 of the largest gradient of the net: below that a gradient is rounding noise of the others)
+    g0 = {k[3:]: v for k, v in g.items() if k.startswith("g0.")}
+    if g0:
+        gmax = max(np.abs(v).max() for v in g0.values())
+        ill0 = set(g.get("ill_conditioned", np.array([], dtype="U1")).tolist())
+        for k, v in g0.items():
+            # an analytically-zero gradient (a BatchNorm bias that the next BatchNorm removes) is rounding noise in the
+            # reference itself: those are judged against the largest gradient of the net
+            floor = gmax if k in ill0 else 1e-3 * gmax
+            err = np.abs(res["grads0"][k].astype(np.float64) - v).max() / max(np.abs(v).max(), floor)
+            assert err < tol_grad, "gradient of %s differs from the reference by %.3g" % (k, err)
     worst = 0.0
     case = TRAIN_CASES[name]
     for k, v in res["params"].items():
@@ -106,6 +132,7 @@ def run_transfer(device_name):
     from DeepFlows import backend_api, nn, tensor
     from DeepFlows.tensor import Tensor
     g = golden("train_transfer")
+    backend_api.set_dgrad_mode("reference")  # fixture from the reference (last-writer-wins dgrad)
     df = df_namespace()
     dev = backend_api.Device(device_name)
     tensor.Graph.free_graph_all()

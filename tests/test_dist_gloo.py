@@ -121,4 +121,4 @@ def test_replicas_average_gradients(tmp_path, cpu_device, world):
             want = r0["w0." + k] - np.float32(0.1) * (total * np.float32(1.0 / world))
             assert np.abs(r0["w1." + k] - want).max() <= 1e-6 * max(1.0, np.abs(want).max()), k
     finally:
-        backend_api.set_dgrad_mode("reference")
+        backend_api.set_dgrad_mode("exact")

@@ -94,7 +94,7 @@ def test_graph_replay_is_bit_identical_to_eager(cuda_device, opt_name, precision
             assert e_opt.t == g_opt.t
     finally:
         backend_api.set_precision("fp32")
-        backend_api.set_dgrad_mode("reference")
+        backend_api.set_dgrad_mode("exact")
 
 
 def test_capture_rejects_host_copies(cuda_device):

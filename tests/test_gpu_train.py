@@ -70,7 +70,7 @@ def test_cuda_matches_numpy_device_on_resnet18_shapes(cuda_device, cpu_device):
             # SGD-level comparison: gradient error relative to the largest gradient in the net
             assert np.abs(results["cuda"][2][k] - v).max() <= 1e-4 * max(np.abs(v).max(), 1e-3 * gmax), k
     finally:
-        backend_api.set_dgrad_mode("reference")
+        backend_api.set_dgrad_mode("exact")
 
 
 def test_full_size_properties_resnet18_batch256(cuda_device):
@@ -127,7 +127,7 @@ def test_full_size_properties_resnet18_batch256(cuda_device):
         moved = [np.abs(p.data.numpy() - before[k]).max() for k, p in model.named_parameters()]
         assert all(np.isfinite(mv) for mv in moved) and max(moved) > 0 and max(moved) <= 1.01e-3 * 1.5
     finally:
-        backend_api.set_dgrad_mode("reference")
+        backend_api.set_dgrad_mode("exact")
 
 
 def test_checkpoint_roundtrip_on_cuda(cuda_device, tmp_path):

@@ -189,3 +189,111 @@ def all_parameters(model):
 
     visit(model, "")
     return out
+
+
+def vgg16_bn(df, device, img=224, num_classes=10, widths=(64, 128, 256, 512, 512), fc=4096, dropout=0.5):
+    """test/VGG.py:7-138: 13 bias-free 3x3 convs (2-2-3-3-3 per stage), each followed by BatchNorm and ReLU, a 2x2
+    max-pool after every stage, then Linear(512 * (img/32)^2, 4096) - ReLU - Dropout - Linear(4096, 4096) - ReLU -
+    Dropout - Linear(4096, classes)."""
+    nn = df.nn
+    depth = (2, 2, 3, 3, 3)
+
+    class VGG16Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            cin = 3
+            self.plan = []
+            for si, (wd, nconv) in enumerate(zip(widths, depth)):
+                for ci in range(nconv):
+                    cname, bname = "conv%d_%d" % (si + 1, ci + 1), "bn%d_%d" % (si + 1, ci + 1)
+                    setattr(self, cname, nn.Conv2d(cin, wd, kernel_size=3, stride=1, padding=1, bias=False, device=device))
+                    setattr(self, bname, nn.BatchNorm2d(wd, device=device))
+                    self.plan.append((cname, bname))
+                    cin = wd
+                setattr(self, "pool%d" % (si + 1), nn.MaxPool2d(kernel_size=2, stride=2))
+                self.plan.append(("pool%d" % (si + 1), None))
+            side = img // 32
+            self.fc1 = nn.Linear(widths[-1] * side * side, fc, device=device)
+            self.fc2 = nn.Linear(fc, fc, device=device)
+            self.fc3 = nn.Linear(fc, num_classes, device=device)
+            self.relu = nn.ReLU()
+            self.dropout = nn.Dropout(dropout)
+
+        def forward(self, x):
+            for a, b in self.plan:
+                if b is None:
+                    x = getattr(self, a)(x)
+                else:
+                    x = self.relu(getattr(self, b)(getattr(self, a)(x)))
+            x = x.reshape(x.shape[0], -1)
+            x = self.dropout(self.relu(self.fc1(x)))
+            x = self.dropout(self.relu(self.fc2(x)))
+            return self.fc3(x)
+
+    return VGG16Model()
+
+
+def resnet_imagenet(df, device, layers=(3, 4, 6, 3), widths=(64, 128, 256, 512), num_classes=10, registered=True):
+    """test/ResNet.py:24-150 (the model `pretrained_models.py:455-460` falls back to for "ResNet-50": basic blocks,
+    [3,4,6,3]): stem conv3x3(3->64, stride 1)-BN-ReLU with NO max-pool, basic blocks conv-bn-conv-bn (+ 1x1 conv-bn
+    shortcut) + identity followed by ReLU, mean(2), mean(2), Linear(512, classes). As in the CIFAR script the blocks
+    live in Python lists; `registered=True` also sets them as attributes so that all of them train."""
+    nn, tensor = df.nn, df.tensor
+
+    class ResidualBlock(nn.Module):
+        def __init__(self, cin, cout, stride=1, downsample=None):
+            super().__init__()
+            self.conv1 = nn.Conv2d(cin, cout, kernel_size=3, stride=stride, padding=1, bias=False, device=device)
+            self.bn1 = nn.BatchNorm2d(cout, device=device)
+            self.conv2 = nn.Conv2d(cout, cout, kernel_size=3, stride=1, padding=1, bias=False, device=device)
+            self.bn2 = nn.BatchNorm2d(cout, device=device)
+            self.downsample = downsample
+            self.relu = nn.ReLU()
+            if registered and downsample is not None:
+                self.ds_conv, self.ds_bn = downsample
+
+        def forward(self, x):
+            identity = x
+            out = self.bn2(self.conv2(self.bn1(self.conv1(x))))
+            if self.downsample is not None:
+                for layer in self.downsample:
+                    identity = layer(identity)
+            return self.relu(out + identity)
+
+    class ResNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.in_channels = widths[0]
+            self.conv1 = nn.Conv2d(3, widths[0], kernel_size=3, stride=1, padding=1, bias=False, device=device)
+            self.bn1 = nn.BatchNorm2d(widths[0], device=device)
+            self.relu = nn.ReLU()
+            self.stages = []
+            for si, (wd, nb) in enumerate(zip(widths, layers)):
+                stage = self._make_layer(wd, nb, stride=1 if si == 0 else 2)
+                self.stages.append(stage)
+                if registered:
+                    for bi, block in enumerate(stage):
+                        setattr(self, "layer%d_%d" % (si + 1, bi), block)
+            self.fc = nn.Linear(widths[-1], num_classes, device=device)
+
+        def _make_layer(self, cout, blocks, stride):
+            downsample = None
+            if stride != 1 or self.in_channels != cout:
+                downsample = [nn.Conv2d(self.in_channels, cout, kernel_size=1, stride=stride, bias=False, device=device),
+                              nn.BatchNorm2d(cout, device=device)]
+            out = [ResidualBlock(self.in_channels, cout, stride, downsample)]
+            self.in_channels = cout
+            for _ in range(1, blocks):
+                out.append(ResidualBlock(cout, cout))
+            return out
+
+        def forward(self, x):
+            x = self.relu(self.bn1(self.conv1(x)))
+            for stage in self.stages:
+                for block in stage:
+                    x = block(x)
+            x = tensor.mean(x, axis=2)
+            x = tensor.mean(x, axis=2)
+            return self.fc(x)
+
+    return ResNet()
