@@ -24,7 +24,7 @@ __all__ = [
     "all_devices", "Device", "Btensor", "empty", "full", "zeros", "ones", "zeros_like", "ones_like",
     "broadcast_to", "reshape", "maximum", "max", "log", "exp", "tanh", "flip", "summation", "mean", "pad",
     "expand_dims", "register_numpy_device", "set_precision", "get_precision", "set_dgrad_mode",
-    "get_dgrad_mode", "set_fix_mean", "get_fix_mean",
+    "get_dgrad_mode", "set_fix_mean", "get_fix_mean", "set_fusion", "get_fusion", "PendingTensor", "BnApply",
 ]
 
 
@@ -221,6 +221,23 @@ def get_fix_mean():
     return _fix_mean
 
 
+# Cross-op fusion on the cuda device (new): convolutions hand the per-channel statistics of their output to the
+# BatchNorm that follows, BatchNorm produces its output lazily so that `bn(x) + identity`, `bn(x) + bn_ds(x2)` and
+# `relu(...)` of it become ONE kernel, conv dgrad adds the identity branch's gradient in its epilogue and computes the
+# BatchNorm-backward reductions of the gradient it writes. DEEPFLOWS_FUSE=0 / set_fusion(False) runs every op on its own
+# (what round 1 did; same results to rounding).
+_fusion = os.environ.get("DEEPFLOWS_FUSE", "1") != "0"
+
+
+def set_fusion(enabled):
+    global _fusion
+    _fusion = bool(enabled)
+
+
+def get_fusion():
+    return _fusion
+
+
 # ------------------------------------------------------------------------------------------------
 # BackendTensor
 # ------------------------------------------------------------------------------------------------
@@ -234,7 +251,9 @@ def _compact_strides(shape):
 class BackendTensor:
     """N-d float32 array = (shape, strides, offset) view over a flat device handle."""
 
-    __slots__ = ("_shape", "_strides", "_offset", "_device", "_handle", "_dense")
+    # `_aux`: what a producer attached for the next consumer (fusion): ("colstats", mean_var Array) on a convolution's
+    # output, ("bn_sums", sums Array, {id(record): row}) on a gradient whose BatchNorm-backward reductions exist
+    __slots__ = ("_shape", "_strides", "_offset", "_device", "_handle", "_dense", "_aux")
 
     def __init__(self, other, device=None):
         if isinstance(other, BackendTensor):
@@ -255,6 +274,7 @@ class BackendTensor:
         self._device = src._device
         self._handle = src._handle
         self._dense = src._dense
+        self._aux = None
 
     # reference name for the same thing
     _init = _adopt
@@ -273,6 +293,7 @@ class BackendTensor:
         t._device = device if device is not None else default_device()
         t._handle = t._device.Array(prod(t._shape)) if handle is None else handle
         t._dense = None
+        t._aux = None
         return t
 
     def __deepcopy__(self, memo):
@@ -524,6 +545,10 @@ class BackendTensor:
         return None
 
     def __add__(self, other):
+        if isinstance(self, PendingTensor) or isinstance(other, PendingTensor):
+            fused = PendingTensor.try_add(self, other)
+            if fused is not None:
+                return fused
         rv = self._rowvec_operand(other)
         if rv is not None:
             out = self._like()
@@ -660,6 +685,110 @@ class BackendTensor:
         out = self._device.full(new_shape, 0)
         out[tuple(slice(lo, lo + n) for (lo, _), n in zip(axes, self._shape))] = self
         return out
+
+
+class BnApply:
+    """One training-mode BatchNorm whose statistics exist (mean_var: the producing convolution's epilogue) and whose
+    output has not been written yet. `launch` happens at most a few times (a fused sum does not materialise the plain
+    output); the running statistics are updated by the first one only."""
+    __slots__ = ("x", "mean_var", "gamma", "beta", "save_mean", "save_invstd", "rmean", "rvar", "momentum", "eps", "applied")
+
+    def __init__(self, x, mean_var, gamma, beta, rmean, rvar, momentum, eps):
+        dev = x.device
+        c = x.shape[1]
+        self.x, self.mean_var, self.gamma, self.beta = x, mean_var, gamma, beta
+        self.save_mean, self.save_invstd = dev.Array(c), dev.Array(c)
+        self.rmean, self.rvar, self.momentum, self.eps = rmean, rvar, float(momentum), float(eps)
+        self.applied = False
+
+    def fwd_tuple(self):
+        first = not self.applied
+        self.applied = True
+        h = lambda t: t._handle if t is not None else None  # noqa: E731
+        return (self.x._handle, self.mean_var, h(self.gamma), h(self.beta), self.save_mean, self.save_invstd,
+                h(self.rmean) if first else None, h(self.rvar) if first else None, self.momentum, self.eps)
+
+    def bwd_tuple(self):
+        h = lambda t: t._handle if t is not None else None  # noqa: E731
+        return (self.x._handle, self.save_mean, self.save_invstd, h(self.gamma), h(self.beta))
+
+
+class PendingTensor(BackendTensor):
+    """A channels-last activation that is still an expression: relu?( bn_a(x_a) [+ bn_b(x_b)] [+ residual] ), written by
+    ONE dfb_bn_fwd_apply launch when somebody needs the values (`_handle`). `a + b` and relu of a pending tensor extend
+    the expression instead of launching, so a residual block's `bn2(...) + identity` (+ ReLU) costs one pass."""
+    __slots__ = ("_real", "sides", "residual", "relu")
+
+    def __init__(self, *args, **kwargs):
+        raise TypeError("use PendingTensor.defer(...)")
+
+    @staticmethod
+    def defer(shape, strides, device, sides, residual=None, relu=False):
+        t = BackendTensor.__new__(PendingTensor)
+        t._shape = tuple(int(v) for v in shape)
+        t._strides = tuple(int(v) for v in strides)
+        t._offset = 0
+        t._device = device
+        t._dense = True
+        t._aux = None
+        t._real = None
+        t.sides, t.residual, t.relu = list(sides), residual, bool(relu)
+        return t
+
+    @property
+    def _handle(self):
+        if self._real is None:
+            n, c, h, w = self._shape
+            y = self._device.Array(n * c * h * w)
+            self._device.bn_fwd_apply(self.sides[0].fwd_tuple(), self.sides[1].fwd_tuple() if len(self.sides) > 1 else None,
+                                      self.residual._handle if self.residual is not None else None, y, n * h * w, c, self.relu)
+            self._real = y
+        return self._real
+
+    @_handle.setter
+    def _handle(self, value):
+        self._real = value
+
+    @property
+    def pending(self):
+        return self._real is None
+
+    # layout questions are answered from the strides: asking must not launch anything
+    def is_dense(self):
+        return True
+
+    def is_compact(self):
+        return self._strides == _compact_strides(self._shape)
+
+    def is_channels_last(self):
+        return True
+
+    def with_relu(self):
+        """relu(self) as a new pending tensor, or None when the expression cannot take it."""
+        if self._real is not None or self.relu:
+            return None
+        return PendingTensor.defer(self._shape, self._strides, self._device, self.sides, self.residual, True)
+
+    @staticmethod
+    def try_add(a, b):
+        """a + b as a (still pending) extension of a pending operand's expression, or None."""
+        if not (isinstance(a, BackendTensor) and isinstance(b, BackendTensor)):
+            return None
+        if a._device != b._device or a._shape != b._shape or a._strides != b._strides:
+            return None
+        pa = isinstance(a, PendingTensor) and a.pending and not a.relu and a.residual is None
+        pb = isinstance(b, PendingTensor) and b.pending and not b.relu and b.residual is None
+        if pa and pb and len(a.sides) == 1 and len(b.sides) == 1:
+            return PendingTensor.defer(a._shape, a._strides, a._device, [a.sides[0], b.sides[0]])
+        if pb and not pa:
+            a, b, pa, pb = b, a, pb, pa   # addition commutes bit for bit
+        if pa and not pb:
+            if isinstance(b, PendingTensor) and b.pending:
+                return None               # b is an expression that cannot be merged: let it materialise first
+            if not b.is_dense() or b._offset != 0:
+                return None
+            return PendingTensor.defer(a._shape, a._strides, a._device, a.sides, b)
+        return None
 
 
 def _gemm_operand(t):

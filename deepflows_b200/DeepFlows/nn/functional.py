@@ -19,7 +19,7 @@ from typing import Optional
 from .. import tensor
 from ..tensor import Tensor, FusedOperator, UnaryOperator, BinaryOperator
 from .. import backend_api
-from ..backend.backend_tensor import BackendTensor, precision_mode, get_dgrad_mode
+from ..backend.backend_tensor import (BackendTensor, PendingTensor, BnApply, precision_mode, get_dgrad_mode, get_fusion)
 
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 WLAYOUT_KCRS, WLAYOUT_KRSC = 0, 1
@@ -40,13 +40,30 @@ def linear(input: Tensor, weight: Tensor, bias: Optional[Tensor] = None):
 
 class _relu(UnaryOperator):
     def forward(self, x: Tensor):
-        src = x.data if x.data.is_dense() else x.data.compact()
+        self._expr = None
+        xd = x.data
+        if isinstance(xd, PendingTensor) and xd.pending and xd.device.has("relu_bwd_bn"):
+            fused = xd.with_relu()  # relu(bn(..) [+ ..]) written by the BatchNorm's own pass
+            if fused is not None:
+                self._expr, self._x = fused, None
+                return fused
+        src = xd if xd.is_dense() else xd.compact()
         self._x = src
         out = src._like()
         src.device.scalar_maximum(src._handle, 0.0, out._handle)
         return out
 
     def grad_fn(self, x: Tensor, grad):
+        if self._expr is not None:
+            # the pre-activation was never stored: the backward kernel recomputes it exactly as the forward pass did
+            e = self._expr
+            n, c, h, w = e.shape
+            dev = e.device
+            gy = grad.channels_last()
+            dx = dev.Array(n * c * h * w)
+            dev.relu_bwd_bn(e.sides[0].bwd_tuple(), e.sides[1].bwd_tuple() if len(e.sides) > 1 else None,
+                            e.residual._handle if e.residual is not None else None, gy._handle, dx, n * h * w, c)
+            return _nhwc_view(dx, n, c, h, w, dev)
         src = self._x
         dev = src.device
         if not dev.has("relu_bwd"):
@@ -177,8 +194,9 @@ def cross_entropy(input: Tensor, target: Tensor, reduction: str = "mean", dim: i
 # convolution
 # ------------------------------------------------------------------------------------------------
 class _conv2d(FusedOperator):
-    def __init__(self, x: Tensor, kernel: Tensor, padding: int, stride: int):
+    def __init__(self, x: Tensor, kernel: Tensor, padding: int, stride: int, want_stats: bool = False):
         self.padding, self.stride = int(padding), int(stride)
+        self._want_stats = bool(want_stats)
         super().__init__(x, kernel)
 
     def forward(self, x, kernel):
@@ -212,6 +230,13 @@ class _conv2d(FusedOperator):
         self._x, self._layout, self._w, self._mode = xd, layout, wd, mode
         self._wl = (w_layout,) if w_layout else ()  # trailing argument only when it is not the default
         y = dev.Array(n * oh * ow * k)
+        if self._want_stats and get_fusion() and dev.has("conv2d_fprop_stats") and tensor.is_grad_enable():
+            # the BatchNorm that follows gets the per-channel mean / variance of y from this kernel's epilogue
+            mean_var = dev.Array(2 * k)
+            dev.conv2d_fprop_stats(xd._handle, layout, wd._handle, w_layout, y, n, c, h, w, k, r, p, s, mode, mean_var)
+            out = _nhwc_view(y, n, k, oh, ow, dev)
+            out._aux = ("colstats", mean_var)
+            return out
         ws, ws_n = self._workspace(dev)
         dev.conv2d_fprop(xd._handle, layout, wd._handle, y, n, c, h, w, k, r, p, s, mode, ws, ws_n, *self._wl)
         return _nhwc_view(y, n, k, oh, ow, dev)
@@ -244,23 +269,68 @@ class _conv2d(FusedOperator):
         if needs[0]:
             buf = dev.Array(n * h * w * c)
             dmode = 0 if get_dgrad_mode() == "reference" else 1
-            dev.conv2d_dgrad(gy._handle, self._w._handle, buf, n, c, h, w, k, r, p, s, self._mode, dmode, ws, ws_n,
-                             *self._wl)
-            dx = _nhwc_view(buf, n, c, h, w, dev)
+            fuse = self._dgrad_fusion(dev, n, c, h, w) if (dmode == 1 and get_fusion() and dev.has("conv2d_dgrad_fused")) else None
+            if fuse is not None:
+                addend, recs, sums = fuse
+                b0 = recs[0].bwd_tuple() if len(recs) > 0 else (None,) * 5
+                b1 = recs[1].bwd_tuple() if len(recs) > 1 else (None,) * 5
+                dev.conv2d_dgrad_fused(gy._handle, self._w._handle, self._wl[0] if self._wl else WLAYOUT_KCRS, buf, n, c, h, w, k, r, p,
+                                       s, self._mode, dmode, addend._handle if addend is not None else None, len(recs),
+                                       b0[0], b0[1], b0[2], b1[0], b1[1], b1[2], sums)
+                dx = _nhwc_view(buf, n, c, h, w, dev)
+                if recs:
+                    dx._aux = ("bn_sums", sums, {id(rec): 1 + i for i, rec in enumerate(recs)})
+                if addend is not None:
+                    dx = tensor.ReplacesGrad(dx)   # already holds (existing gradient of x) + dgrad
+            else:
+                dev.conv2d_dgrad(gy._handle, self._w._handle, buf, n, c, h, w, k, r, p, s, self._mode, dmode, ws, ws_n,
+                                 *self._wl)
+                dx = _nhwc_view(buf, n, c, h, w, dev)
         if both:
             dev.side_join()
         return dx, dw
+
+    def _dgrad_fusion(self, dev, n, c, h, w):
+        """What the dgrad epilogue can take over for the input tensor x of this convolution:
+          * the sum with the gradient x already holds (the other branch of a residual block, processed earlier);
+          * when this contribution COMPLETES x's gradient: the two reductions of BatchNorm backward for the BatchNorm(s)
+            that will receive exactly this gradient - x itself (conv -> bn -> conv), or the two terms of the residual sum
+            x = bn2(..) + bn_ds(..) / bn2(..) + identity (`add` hands its gradient to both parents unchanged).
+        Returns (addend BackendTensor | None, [BnApply records], sums Array | None) or None."""
+        x = self.inputs[0]
+        addend = None
+        if x.grad is not None:
+            g = x.grad.data if isinstance(x.grad, Tensor) else x.grad
+            if g.shape == (n, c, h, w) and g.is_channels_last():
+                addend = g
+            else:
+                return None
+        recs = []
+        if x._ngrads + 1 == len(x.children):   # nothing else will arrive after this
+            cand = []
+            if isinstance(x, _batch_norm_train):
+                cand = [x]
+            elif isinstance(x, tensor.add) and all(isinstance(q, Tensor) for q in x.parents):
+                cand = [q for q in x.parents if isinstance(q, _batch_norm_train) and len(q.children) == 1 and q._ngrads == 0]
+            for node in cand:
+                rec = getattr(node, "_rec", None)
+                if rec is not None and rec.applied and rec.x.shape == (n, c, h, w):
+                    recs.append(rec)
+        if addend is None and not recs:
+            return None
+        return addend, recs[:2], (dev.Array(3 * c) if recs else None)
 
     def release(self):
         self._x = self._w = None
 
 
-def conv2d(x: Tensor, kernel: Tensor, padding: int = 0, stride: int = 1):
+def conv2d(x: Tensor, kernel: Tensor, padding: int = 0, stride: int = 1, want_stats: bool = False):
     """2-d convolution, x (N,C,H,W), kernel (K,C,R,R); square kernel, symmetric zero padding, scalar
-    stride, no dilation/groups - the reference's contract [316-335]."""
+    stride, no dilation/groups - the reference's contract [316-335]. `want_stats` (new, optional): also produce the
+    per-channel statistics of the output for a BatchNorm that follows (Conv2d sets it for bias-free convolutions)."""
     if not isinstance(x, Tensor):
         x = Tensor(x, device=kernel.device)
-    return _conv2d(x, kernel, padding, stride)
+    return _conv2d(x, kernel, padding, stride, want_stats)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -328,6 +398,7 @@ class _batch_norm_train(FusedOperator):
         self._rm, self._rv = running_mean, running_var
         self.momentum, self.eps = float(momentum), float(eps)
         self._affine = weight is not None
+        self._rec = None
         super().__init__(*([x, weight, bias] if self._affine else [x]))
 
     def forward(self, x, weight=None, bias=None):
@@ -337,17 +408,24 @@ class _batch_norm_train(FusedOperator):
         rows = n * h * w
         g = weight.data.compact() if weight is not None else None
         b = bias.data.compact() if bias is not None else None
-        y = dev.Array(rows * c)
-        self._mean, self._invstd = dev.Array(c), dev.Array(c)
         rm = self._rm.data.compact() if self._rm is not None else None
         rv = self._rv.data.compact() if self._rv is not None else None
-        dev.bn_fwd_train(xd._handle, g._handle if g is not None else None, b._handle if b is not None else None, y,
-                         self._mean, self._invstd, rm._handle if rm is not None else None,
-                         rv._handle if rv is not None else None, self.momentum, self.eps, rows, c)
         if rm is not None and rm is not self._rm.data:  # running stats were non-compact views: write back
             self._rm.data, self._rv.data = rm, rv
         self._x, self._g = xd, g
         self._rm = self._rv = None
+        aux = getattr(xd, "_aux", None)
+        if aux is not None and aux[0] == "colstats" and get_fusion() and dev.has("bn_fwd_apply"):
+            # statistics came with the convolution's output: the BatchNorm is one elementwise pass, launched when its
+            # output is first needed - by then `+ identity` / a second BatchNorm / ReLU may have joined the expression
+            self._rec = BnApply(xd, aux[1], g, b, rm, rv, self.momentum, self.eps)
+            self._mean, self._invstd = self._rec.save_mean, self._rec.save_invstd
+            return PendingTensor.defer((n, c, h, w), (h * w * c, 1, w * c, c), dev, [self._rec])
+        y = dev.Array(rows * c)
+        self._mean, self._invstd = dev.Array(c), dev.Array(c)
+        dev.bn_fwd_train(xd._handle, g._handle if g is not None else None, b._handle if b is not None else None, y,
+                         self._mean, self._invstd, rm._handle if rm is not None else None,
+                         rv._handle if rv is not None else None, self.momentum, self.eps, rows, c)
         return _nhwc_view(y, n, c, h, w, dev)
 
     def backward_all(self, grad, needs):
@@ -355,18 +433,33 @@ class _batch_norm_train(FusedOperator):
         n, c, h, w = xd.shape
         dev = xd.device
         gy = grad.channels_last()
-        dx = dev.Array(n * h * w * c) if needs[0] else None
+        rows = n * h * w
+        dx = dev.Array(rows * c) if needs[0] else None
+        gh = self._g._handle if self._g is not None else None
+        aux = getattr(gy, "_aux", None)
+        if (aux is not None and aux[0] == "bn_sums" and self._rec is not None and id(self._rec) in aux[2]
+                and dev.has("bn_bwd_apply")):
+            # the convolution that produced this gradient also reduced it: sum(dy) and sum(dy * x_hat) are there
+            sums, row = aux[1], aux[2][id(self._rec)]
+            db = BackendTensor.make((1, c, 1, 1), None, dev, sums, 0)
+            dg = BackendTensor.make((1, c, 1, 1), None, dev, sums, row * c)
+            if dx is not None:
+                dev.bn_bwd_apply(xd._handle, gy._handle, gh, self._mean, self._invstd, (sums, 0), (sums, row * c), dx, rows, c)
+            out = [_nhwc_view(dx, n, c, h, w, dev) if dx is not None else None]
+            if self._affine:
+                out += [dg if needs[1] else None, db if needs[2] else None]
+            return out
         dg = BackendTensor.make((1, c, 1, 1), device=dev) if self._affine and needs[1] else None
         db = BackendTensor.make((1, c, 1, 1), device=dev) if self._affine and needs[2] else None
-        dev.bn_bwd(xd._handle, gy._handle, self._g._handle if self._g is not None else None, self._mean, self._invstd,
-                   dx, dg._handle if dg is not None else None, db._handle if db is not None else None, n * h * w, c)
+        dev.bn_bwd(xd._handle, gy._handle, gh, self._mean, self._invstd,
+                   dx, dg._handle if dg is not None else None, db._handle if db is not None else None, rows, c)
         out = [_nhwc_view(dx, n, c, h, w, dev) if dx is not None else None]
         if self._affine:
             out += [dg, db]
         return out
 
     def release(self):
-        self._x = self._g = self._mean = self._invstd = None
+        self._x = self._g = self._mean = self._invstd = self._rec = None
 
 
 def batch_norm(x: Tensor, weight, bias, running_mean, running_var, training: bool, momentum: float, eps: float):

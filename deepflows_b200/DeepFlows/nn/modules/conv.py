@@ -62,5 +62,7 @@ class Conv2d(_ConvNd):
                           device, dtype)
 
     def forward(self, x):
-        out = F.conv2d(x, self.weight, self.padding, self.stride)
+        # a bias-free convolution in training mode is (in every script) followed by BatchNorm: its epilogue also emits the
+        # per-channel statistics of the output, which BatchNorm then does not have to compute (F.batch_norm)
+        out = F.conv2d(x, self.weight, self.padding, self.stride, want_stats=self.bias is None and self.training)
         return out + self.bias if self.bias is not None else out

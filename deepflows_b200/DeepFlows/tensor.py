@@ -63,6 +63,16 @@ class Graph:
 _tensor_count = 0
 
 
+class ReplacesGrad:
+    """Returned by a fused backward (conv dgrad with the `addend` epilogue) instead of a plain gradient: `value`
+    already contains the gradient its input had accumulated so far PLUS this contribution - it replaces the input's
+    gradient instead of being added to it."""
+    __slots__ = ("value",)
+
+    def __init__(self, value):
+        self.value = value
+
+
 def _reduce_broadcast_grad(g: BackendTensor, shape) -> BackendTensor:
     """Sum `g` down to `shape` (the inverse of the forward broadcast) on the device."""
     shape = tuple(shape)
@@ -108,6 +118,7 @@ class Tensor:
 
         self.requires_grad = bool(requires_grad) and is_grad_enable()
         self.grad = None  # BackendTensor once a gradient has arrived
+        self._ngrads = 0  # gradient contributions received in the current backward pass
         self.children = []
         self.parents = []
         if self.requires_grad:
@@ -289,11 +300,15 @@ class Tensor:
 
     # ---- reverse pass ---------------------------------------------------------------------------------
     def _accumulate_grad(self, g):
-        if isinstance(g, Tensor):
-            g = g.data
-        if g.shape != self.data.shape:
-            g = _reduce_broadcast_grad(g, self.data.shape)
-        self.grad = g if self.grad is None else self.grad + g
+        if isinstance(g, ReplacesGrad):
+            self.grad = g.value  # the producing kernel already added what was there
+        else:
+            if isinstance(g, Tensor):
+                g = g.data
+            if g.shape != self.data.shape:
+                g = _reduce_broadcast_grad(g, self.data.shape)
+            self.grad = g if self.grad is None else self.grad + g
+        self._ngrads += 1
         hook = Tensor._grad_ready_hook
         if hook is not None and not self.parents:
             hook(self)
@@ -329,6 +344,7 @@ class Tensor:
                         for parent in node.parents:
                             if parent.requires_grad:
                                 parent._accumulate_grad(node.grad_fn(parent, g))
+                node._ngrads = 0
                 if not node.is_leaf:
                     node.grad = None
         hook = Tensor._post_backward_hook
@@ -342,6 +358,7 @@ class Tensor:
 
     def zero_grad(self):
         self.grad = None
+        self._ngrads = 0
 
     def to(self, device):
         name = device if isinstance(device, str) else device.name

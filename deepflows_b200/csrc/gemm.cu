@@ -113,4 +113,88 @@ dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float
   return simt_conv_wgrad(x, x_layout, dy, dw, w_layout, N, C, H, W, K, R, pad, stride);
 }
 
+// ---- convolutions with fused epilogue work ---------------------------------------------------------------------------
+// Same contractions as above; the tensor-core kernels do the extra work in their epilogue (gemm_tc.cu: RowEpi), every
+// other path (exact-fp32 FFMA kernels, the first-layer kernels) runs it as separate passes with the same results.
+
+// y = conv(x, w) and mean_var[2][K] = per-channel mean / biased variance of y over (N, OH, OW): what the BatchNorm that
+// follows needs (DeepFlows/nn/modules/batchnorm.py:33-42), without a pass of its own over y
+dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H,
+                                  int W, int K, int R, int pad, int stride, int mode, float* mean_var) {
+  DFB_INIT();
+  DFB_REQUIRE(x && w && y && mean_var, DFB_ERR_INVALID, "conv2d_fprop_stats: null pointer");
+  DFB_REQUIRE(x_layout == DFB_LAYOUT_NCHW || x_layout == DFB_LAYOUT_NHWC, DFB_ERR_INVALID, "conv2d_fprop_stats: bad layout");
+  dfb_status st = check_mode("conv2d_fprop_stats", mode);
+  if (st != DFB_OK) return st;
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
+  DFB_REQUIRE(OH > 0 && OW > 0 && N > 0, DFB_ERR_INVALID, "conv2d_fprop_stats: empty output");
+  bool handled = false;
+  if (mode != DFB_MODE_SIMT) {
+    st = direct_conv_fprop(x, x_layout, w, w_layout, y, N, C, H, W, K, R, pad, stride, &handled);
+    if (st != DFB_OK) return st;
+  }
+  if (!handled && want_tc(mode) && x_layout == DFB_LAYOUT_NHWC) {
+    ConvFuse f{};
+    f.kind = FUSE_STATS;
+    f.stats_out = mean_var;
+    st = tc_conv_fprop(x, w, w_layout, y, N, C, H, W, K, R, pad, stride, mode, nullptr, 0, &handled, &f);
+    if (st != DFB_OK || handled) return st;
+  }
+  if (!handled) {
+    st = simt_conv_fprop(x, x_layout, w, w_layout, y, N, C, H, W, K, R, pad, stride);
+    if (st != DFB_OK) return st;
+  }
+  return dfb_colstats_mean_var(y, (size_t)N * OH * OW, K, mean_var);
+}
+
+// dx = dgrad(dy, w) [+ addend], and for n_bn (0..2) BatchNorms whose OUTPUT gradient dx is: sums[0][C] = sum(dx),
+// sums[1 + i][C] = sum(dx * x_hat_i) with x_hat_i = (bn_x_i - bn_mean_i) * bn_invstd_i - the two reductions of the
+// BatchNorm backward (dbeta, dgamma), so that it only needs its elementwise pass (dfb_bn_bwd_apply)
+dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
+                                  int R, int pad, int stride, int mode, int dgrad_mode, const float* addend, int n_bn,
+                                  const float* bn_x0, const float* bn_mean0, const float* bn_invstd0, const float* bn_x1,
+                                  const float* bn_mean1, const float* bn_invstd1, float* sums) {
+  DFB_INIT();
+  DFB_REQUIRE(dy && w && dx, DFB_ERR_INVALID, "conv2d_dgrad_fused: null pointer");
+  DFB_REQUIRE(n_bn >= 0 && n_bn <= 2, DFB_ERR_INVALID, "conv2d_dgrad_fused: n_bn must be 0, 1 or 2");
+  DFB_REQUIRE(n_bn == 0 || (sums && bn_x0 && bn_mean0 && bn_invstd0), DFB_ERR_INVALID, "conv2d_dgrad_fused: BatchNorm 0 incomplete");
+  DFB_REQUIRE(n_bn < 2 || (bn_x1 && bn_mean1 && bn_invstd1), DFB_ERR_INVALID, "conv2d_dgrad_fused: BatchNorm 1 incomplete");
+  DFB_REQUIRE(dgrad_mode == DFB_DGRAD_REFERENCE || dgrad_mode == DFB_DGRAD_EXACT, DFB_ERR_INVALID,
+              "conv2d_dgrad_fused: bad dgrad_mode %d", dgrad_mode);
+  dfb_status st = check_mode("conv2d_dgrad_fused", mode);
+  if (st != DFB_OK) return st;
+  if (want_tc(mode) && dgrad_mode == DFB_DGRAD_EXACT) {
+    ConvFuse f{};
+    f.addend = addend;
+    f.kind = n_bn ? FUSE_BNBWD : FUSE_NONE;
+    f.n_sets = n_bn;
+    f.stats_out = sums;
+    f.bn_x[0] = bn_x0; f.bn_mean[0] = bn_mean0; f.bn_invstd[0] = bn_invstd0;
+    f.bn_x[1] = bn_x1; f.bn_mean[1] = bn_mean1; f.bn_invstd[1] = bn_invstd1;
+    bool handled = false;
+    st = tc_conv_dgrad(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, mode, nullptr, 0, &handled, &f);
+    if (st != DFB_OK || handled) return st;
+  }
+  st = simt_conv_dgrad(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, dgrad_mode);
+  if (st != DFB_OK) return st;
+  const size_t n = (size_t)N * C * H * W;
+  if (addend) {
+    st = dfb_ewise_add(dx, addend, dx, n);
+    if (st != DFB_OK) return st;
+  }
+  if (n_bn >= 1) {
+    st = dfb_bn_bwd_sums(bn_x0, dx, bn_mean0, bn_invstd0, sums, sums + C, (size_t)N * H * W, C);
+    if (st != DFB_OK) return st;
+  }
+  if (n_bn >= 2) {  // the first row (sum dx) is the same for both; it is written twice with the same values
+    float* tmp = nullptr;
+    st = dfb_malloc((size_t)C, &tmp);
+    if (st != DFB_OK) return st;
+    st = dfb_bn_bwd_sums(bn_x1, dx, bn_mean1, bn_invstd1, tmp, sums + 2 * (size_t)C, (size_t)N * H * W, C);
+    dfb_free(tmp);
+    if (st != DFB_OK) return st;
+  }
+  return DFB_OK;
+}
+
 }  // extern "C"

@@ -197,6 +197,233 @@ __device__ unsigned long long g_tc_stamp[2][16];
 #define TC_STAMP(i)
 #endif
 
+
+// ---- fused epilogue of the row-major problems (conv fprop / dgrad) ------------------------------------------------------
+// The accumulator tile leaves TMEM through shared memory (the pipeline stages are idle by then) and is written out
+// with whole rows per warp instruction - 128-bit stores, lanes along the channel dimension - instead of one row per
+// thread. On the way out the same pass can
+//   * add a tensor of the output's shape (`addend`: the identity branch's gradient in a residual block's backward),
+//   * produce per-channel statistics of what it writes, so that the BatchNorm that follows needs no pass of its own:
+//       EPI_STATS  mean / biased variance of the output (forward: conv -> BatchNorm)
+//       EPI_BNBWD  sum(d) and sum(d * x_hat) for up to two BatchNorms whose output gradient d is being written
+//                  (backward: dgrad -> BatchNorm backward; two when a residual block's shortcut has its own BatchNorm)
+// Every lane owns fixed columns, so the sums accumulate in registers; lanes, warps and CTAs are merged in a fixed order
+// (deterministic), one partial per CTA goes to global memory, and the last CTA of the launch (ticket) reduces the
+// partials. Variance uses shifted sums (shift = the first value a lane sees, re-based at every merge): no cancellation
+// when |mean| >> std, no divisions in the loops.
+enum { EPI_NONE = 0, EPI_STATS = 1, EPI_BNBWD = 2 };
+struct EpiArgs {
+  const float* addend;       // same shape / layout as the output, or null
+  int stat_kind;             // EPI_*
+  int n_sets;                // EPI_BNBWD: 1 or 2 BatchNorms
+  float* stat_part;          // [partials][3][n_out]
+  float* stat_cnt;           // [partials] rows behind each partial (EPI_STATS)
+  float* stat_out;           // [3][n_out]: EPI_STATS mean, var, -; EPI_BNBWD sum d, sum d*x_hat(set 0), sum d*x_hat(set 1)
+  unsigned* stat_ticket;
+  const float* bn_x[2];      // EPI_BNBWD: inputs of the BatchNorms (shape of the output)
+  const float* bn_mean[2];
+  const float* bn_invstd[2];
+};
+// (shift, sum of (v - shift), sum of (v - shift)^2, count) of one column over some rows
+struct Moments {
+  float s, m1, m2, n;
+  __device__ __forceinline__ void merge(const Moments& o) {
+    if (o.n > 0.f) {
+      if (n > 0.f) {
+        const float d = o.s - s;
+        m2 += o.m2 + 2.f * d * o.m1 + o.n * d * d;
+        m1 += o.m1 + o.n * d;
+        n += o.n;
+      } else {
+        *this = o;
+      }
+    }
+  }
+};
+template <int BN>
+struct RowEpi {
+  static constexpr int LPR = (BN / 4 < 32) ? BN / 4 : 32;    // lanes per output row
+  static constexpr int RPI = 32 / LPR;                        // rows per warp instruction
+  static constexpr int NCG = (BN / 4 <= 32) ? 1 : BN / 128;   // float4 column groups per lane
+  float a[NCG][4], b[NCG][4], c[NCG][4];                      // EPI_STATS: shift, m1, m2; EPI_BNBWD: sum d, sum d*xh0, sum d*xh1
+  float n;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int g = 0; g < NCG; ++g)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[g][q] = 0.f; b[g][q] = 0.f; c[g][q] = 0.f; }
+    n = 0.f;
+  }
+  // What one float4 of the output needs from global memory besides the accumulator: loaded ahead of the stores of a
+  // batch of rows, so that the loads of the whole batch are in flight together.
+  struct Extras { float4 add, x0, x1; };
+  __device__ __forceinline__ static Extras load_extras(const EpiArgs& e, const float* out, const float* row_out, int col, int n_out) {
+    Extras x;
+    x.add = x.x0 = x.x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_out == nullptr || col + 4 > n_out) return x;
+    const size_t off = (size_t)(row_out - out) + col;
+    if (e.addend) x.add = __ldg(reinterpret_cast<const float4*>(e.addend + off));
+    if (e.stat_kind == EPI_BNBWD) {
+      x.x0 = __ldg(reinterpret_cast<const float4*>(e.bn_x[0] + off));
+      if (e.n_sets > 1) x.x1 = __ldg(reinterpret_cast<const float4*>(e.bn_x[1] + off));
+    }
+    return x;
+  }
+  // one float4 of the output: row base pointer `row_out` (inside e's output tensor), absolute column `col`.
+  // The caller adds 1 to `n` after the last column group of a row.
+  __device__ __forceinline__ void emit(const EpiArgs& e, float* row_out, int col, int g, float4 v, const Extras& x, int n_out) {
+    if (col + 4 > n_out) return;
+    if (e.addend) { v.x += x.add.x; v.y += x.add.y; v.z += x.add.z; v.w += x.add.w; }
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    if (e.stat_kind == EPI_STATS) {
+      if (n == 0.f) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[g][q] = vv[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float d = vv[q] - a[g][q]; b[g][q] += d; c[g][q] = fmaf(d, d, c[g][q]); }
+    } else if (e.stat_kind == EPI_BNBWD) {
+      const float4 mu0 = __ldg(reinterpret_cast<const float4*>(e.bn_mean[0] + col)), is0 = __ldg(reinterpret_cast<const float4*>(e.bn_invstd[0] + col));
+      const float xh0[4] = {(x.x0.x - mu0.x) * is0.x, (x.x0.y - mu0.y) * is0.y, (x.x0.z - mu0.z) * is0.z, (x.x0.w - mu0.w) * is0.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[g][q] += vv[q]; b[g][q] = fmaf(vv[q], xh0[q], b[g][q]); }
+      if (e.n_sets > 1) {
+        const float4 mu1 = __ldg(reinterpret_cast<const float4*>(e.bn_mean[1] + col)), is1 = __ldg(reinterpret_cast<const float4*>(e.bn_invstd[1] + col));
+        const float xh1[4] = {(x.x1.x - mu1.x) * is1.x, (x.x1.y - mu1.y) * is1.y, (x.x1.z - mu1.z) * is1.z, (x.x1.w - mu1.w) * is1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[g][q] = fmaf(vv[q], xh1[q], c[g][q]);
+      }
+    }
+    *reinterpret_cast<float4*>(row_out + col) = v;
+  }
+  // Merge lanes -> warps -> CTA, write this CTA's partial, and let the last CTA of the launch reduce all partials.
+  // Called by the 128 epilogue threads (t = 0..127, warp ew = t / 32); `wstat` is the CTA's [4][4][BN] scratch.
+  __device__ void finish(const EpiArgs& e, float* wstat, int t, int col0, int n_out, int pidx, int n_partials, unsigned total_ctas) {
+    if (e.stat_kind == EPI_NONE) return;
+    const int lane = t & 31, ew = t >> 5;
+    const bool stats = e.stat_kind == EPI_STATS;
+    // lanes that share columns (different rows of one warp instruction)
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+      const float on = __shfl_xor_sync(0xffffffffu, n, off);
+#pragma unroll
+      for (int g = 0; g < NCG; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float oa = __shfl_xor_sync(0xffffffffu, a[g][q], off), ob = __shfl_xor_sync(0xffffffffu, b[g][q], off),
+                      oc = __shfl_xor_sync(0xffffffffu, c[g][q], off);
+          if (stats) {
+            Moments m{a[g][q], b[g][q], c[g][q], n};
+            // both partners must end with the same bits: merge in lane order (lower lane first)
+            Moments o{oa, ob, oc, on};
+            if (lane & off) { o.merge(m); m = o; } else { m.merge(o); }
+            a[g][q] = m.s; b[g][q] = m.m1; c[g][q] = m.m2;
+          } else {
+            a[g][q] += oa; b[g][q] += ob; c[g][q] += oc;
+          }
+        }
+      n += on;
+    }
+    if (lane < LPR) {
+#pragma unroll
+      for (int g = 0; g < NCG; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cl = (g * 32 + lane) * 4 + q;
+          wstat[(ew * 4 + 0) * BN + cl] = a[g][q];
+          wstat[(ew * 4 + 1) * BN + cl] = b[g][q];
+          wstat[(ew * 4 + 2) * BN + cl] = c[g][q];
+          wstat[(ew * 4 + 3) * BN + cl] = n;
+        }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int cl = t; cl < BN; cl += 128) {
+      const int col = col0 + cl;
+      if (col >= n_out) continue;
+      float r0, r1, r2, rn;
+      if (stats) {
+        Moments m{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) m.merge(Moments{wstat[(w * 4 + 0) * BN + cl], wstat[(w * 4 + 1) * BN + cl], wstat[(w * 4 + 2) * BN + cl], wstat[(w * 4 + 3) * BN + cl]});
+        r0 = m.s; r1 = m.m1; r2 = m.m2; rn = m.n;
+      } else {
+        r0 = r1 = r2 = 0.f; rn = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { r0 += wstat[(w * 4 + 0) * BN + cl]; r1 += wstat[(w * 4 + 1) * BN + cl]; r2 += wstat[(w * 4 + 2) * BN + cl]; }
+      }
+      float* dst = e.stat_part + (size_t)pidx * 3 * n_out + col;
+      dst[0] = r0; dst[n_out] = r1; dst[2 * n_out] = r2;
+      if (stats && cl == 0 && col0 == 0) e.stat_cnt[pidx] = rn;
+    }
+    // ---- last CTA of the launch: reduce the partials ----
+    __shared__ int s_last_cta;
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t == 0) {
+      const unsigned arrived = atomicAdd(e.stat_ticket, 1u);
+      s_last_cta = arrived == total_ctas - 1;
+      if (s_last_cta) *e.stat_ticket = 0;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (!s_last_cta) return;
+    __threadfence();
+    int cpp = 4;                                   // columns per pass: power of two, <= 128
+    while (cpp < n_out && cpp < 128) cpp <<= 1;
+    const int groups = 128 / cpp, cq = t % cpp, gq = t / cpp;
+    for (int cbase = 0; cbase < n_out; cbase += cpp) {
+      const int col = cbase + cq;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, tn = 0.f, sref = 0.f;
+      if (col < n_out) {
+        if (stats) sref = __ldcg(e.stat_part + col);   // partial 0 always holds rows (pixel 0 is in it)
+        for (int p0 = gq; p0 < n_partials; p0 += 4 * groups) {
+          float pa[4], pb[4], pc[4], pn[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int pp = p0 + u * groups;
+            const bool ok = pp < n_partials;
+            const float* src = e.stat_part + (size_t)(ok ? pp : 0) * 3 * n_out + col;
+            pa[u] = ok ? __ldcg(src) : 0.f;
+            pb[u] = ok ? __ldcg(src + n_out) : 0.f;
+            pc[u] = ok ? __ldcg(src + 2 * n_out) : 0.f;
+            pn[u] = (ok && stats) ? __ldcg(e.stat_cnt + pp) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (stats) {
+              const float d = pa[u] - sref;
+              t1 += pb[u] + pn[u] * d;
+              t2 += pc[u] + 2.f * d * pb[u] + pn[u] * d * d;
+              tn += pn[u];
+            } else {
+              t0 += pa[u]; t1 += pb[u]; t2 += pc[u];
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // wstat is free again (every group is past its previous read)
+      wstat[(gq * 4 + 0) * cpp + cq] = t0;
+      wstat[(gq * 4 + 1) * cpp + cq] = t1;
+      wstat[(gq * 4 + 2) * cpp + cq] = t2;
+      wstat[(gq * 4 + 3) * cpp + cq] = tn;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (gq == 0 && col < n_out) {
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, rn = 0.f;
+        for (int g2 = 0; g2 < groups; ++g2) {   // fixed order
+          r0 += wstat[(g2 * 4 + 0) * cpp + cq]; r1 += wstat[(g2 * 4 + 1) * cpp + cq];
+          r2 += wstat[(g2 * 4 + 2) * cpp + cq]; rn += wstat[(g2 * 4 + 3) * cpp + cq];
+        }
+        if (stats) {
+          const float dm = r1 / rn;
+          e.stat_out[col] = sref + dm;                                   // mean
+          e.stat_out[n_out + col] = fmaxf(r2 / rn - dm * dm, 0.f);       // biased variance (batchnorm.py:38-42)
+        } else {
+          e.stat_out[col] = r0; e.stat_out[n_out + col] = r1; e.stat_out[2 * n_out + col] = r2;
+        }
+      }
+    }
+  }
+};
+
 // ---- kernel skeleton ----------------------------------------------------------------------------------
 // KR: reduction rows per stage (MN-major operands only: 32 or 128). BSUB: B tiles per stage (the row-halo conv
 // kernel keeps the three taps of one filter column in a stage, with AROWS = 192 halo rows of A)
@@ -216,7 +443,7 @@ struct SmemLayout {
   static constexpr uint32_t kBBytes = BSUB * kBTile;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kBudget = BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
-                                               : (BN >= 256 ? (208u << 10) : (100u << 10));  // (128 x 256 at two CTAs per SM with two stages: measured 7% slower)
+                                               : (BN >= 256 ? (192u << 10) : (100u << 10));  // (128 x 256 at two CTAs per SM with two stages: measured 7% slower)
   static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
   static constexpr int kMinStages = (BSUB > 1 || BKR != KR) ? 2 : 3;   // halo variants: two CTAs per SM with two stages each
   static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < kMinStages ? kMinStages : kStagesFit);
@@ -225,11 +452,16 @@ struct SmemLayout {
   // B tile / the next stage: rows that are never stored), so the last stage needs that much slack behind it
   // (AROWS == 32: the A descriptor's chunk stride is 0, all four chunks alias the one that is loaded - no over-read)
   static constexpr uint32_t kOverRead = (AROWS == 32 || AROWS >= BLOCK_M) ? 0 : ((BLOCK_M - AROWS) / 32) * kChunk;
-  static constexpr uint32_t kTotal = kBarOffset + kOverRead + (2 * kStages + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
+  // fused-epilogue scratch behind the barriers (row-major problems): 128 row pointers + per-warp column statistics
+  // [4 warps][4 values][BN columns]
+  static constexpr uint32_t kEpiOffset = kBarOffset + kOverRead + (2 * kStages + 1) * 8 + 16;
+  static constexpr uint32_t kEpiBytes = 1024 + 64 * BN;
+  static constexpr uint32_t kTotal = kEpiOffset + 16 + kEpiBytes + 1024;  // +1024 for manual alignment
   // split-K partial tile staged in the (idle) pipeline stages: 128 rows, padded pitch against bank conflicts
   static constexpr uint32_t kRedPitch = BN + 4;
   // (the 128 x 256 kernels never split K: they are only chosen for problems with hundreds of tiles)
-  static_assert(AROWS < BLOCK_M || BN >= 256 || BLOCK_M * kRedPitch * 4 <= kBarOffset, "partial tile does not fit the pipeline stages");
+  static_assert(AROWS < BLOCK_M || BLOCK_M * kRedPitch * 4 <= kBarOffset, "output tile does not fit the pipeline stages");
+  static_assert(kTotal <= 227u * 1024u, "more shared memory than a CTA can have");
 };
 
 template <class P>
@@ -245,6 +477,10 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  // fused-epilogue scratch: output row pointers of the tile, per-warp column statistics
+  float** row_tab = reinterpret_cast<float**>(smem + ((L::kEpiOffset + 15) & ~15u));
+  float* wstat = reinterpret_cast<float*>(row_tab + BLOCK_M);
+  (void)row_tab; (void)wstat;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef DFB_TC_TIMING
@@ -358,8 +594,12 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       tc_fence_after();
     }
     if (warp == 2) TC_STAMP(7);
-    float* red = reinterpret_cast<float*>(smem);  // the pipeline stages are idle once the accumulator is complete
-    constexpr uint32_t kRedPitch = P::kAccTiles * BN + 4;  // == L::kRedPitch with one accumulator tile
+    float* stage = reinterpret_cast<float*>(smem);  // the pipeline stages are idle once the accumulator is complete
+    constexpr uint32_t kPitch = P::kAccTiles * BN + 4;  // == L::kRedPitch with one accumulator tile
+    // row-major problems leave through shared memory (coalesced write-out); the weight-gradient tiles of an unsplit
+    // launch go from registers to their partial slab as 128-byte runs per thread
+    constexpr bool kStaged = P::kRowMajor;
+    if constexpr (P::kRowMajor) row_tab[row] = P::row_ptr(prm, tile, row);
 #pragma unroll 1
     for (int cc = 0; cc < P::kAccTiles * BN; cc += 32) {
       const int acc = cc / BN, c0 = cc - acc * BN;  // accumulator tile (wgrad row-halo: one per tap), column inside it
@@ -370,23 +610,68 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      if (nsplit == 1) {
-        P::store(prm, tile, row, c0, v, acc);
-      } else {
-        float* dst = red + (size_t)row * kRedPitch + cc;  // cc == c0 with one accumulator tile
+      if constexpr (!kStaged) {
+        if (nsplit == 1) {
+          P::store(prm, tile, row, c0, v, acc);
+          continue;
+        }
+      }
+      {
+        float* dst = stage + (size_t)row * kPitch + cc;  // cc == c0 with one accumulator tile
 #pragma unroll
         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
     }
     tc_fence_before();
     if (warp == 2) TC_STAMP(8);
-    P::finish(prm, tile, (warp - 2) * 32 + lane);  // the 128 epilogue threads (wgrad: last CTA of a tile sums the splits)
+    if constexpr (P::kRowMajor) {
+      if (nsplit == 1) {
+        // each warp writes out the 32 rows it staged itself: no cross-warp synchronisation. Rows go in batches: all
+        // shared-memory and global loads of a batch are issued before its first store (a store to a generic pointer
+        // would otherwise fence the loads of the next row behind it: measured 3.6 us for a 64 KB tile)
+        __syncwarp();
+        RowEpi<BN> epi;
+        epi.init();
+        constexpr int LPR = RowEpi<BN>::LPR, RPI = RowEpi<BN>::RPI, NCG = RowEpi<BN>::NCG;
+        constexpr int U = NCG == 1 ? 4 : 2;   // rows in flight per lane
+        const int lr = lane / LPR, lc = lane % LPR;
+#pragma unroll 1
+        for (int rr = 0; rr < 32; rr += RPI * U) {
+          float* rp[U];
+          float4 val[U][NCG];
+          typename P::Extras ex[U][NCG];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = quarter * 32 + rr + u * RPI + lr;
+            rp[u] = row_tab[r];
+#pragma unroll
+            for (int g = 0; g < NCG; ++g) val[u][g] = *reinterpret_cast<const float4*>(stage + (size_t)r * kPitch + (g * 32 + lc) * 4);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int g = 0; g < NCG; ++g) ex[u][g] = P::load_extras(prm, tile, rp[u], (g * 32 + lc) * 4);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (rp[u]) {
+#pragma unroll
+              for (int g = 0; g < NCG; ++g) P::emit4(prm, tile, epi, rp[u], (g * 32 + lc) * 4, g, val[u][g], ex[u][g]);
+              epi.n += 1.f;
+            }
+          }
+        }
+        P::epi_finish(prm, tile, epi, wstat, (warp - 2) * 32 + lane);
+      }
+    }
+    if (nsplit == 1) P::finish(prm, tile, (warp - 2) * 32 + lane);  // the 128 epilogue threads (wgrad: last CTA of a tile sums the splits)
     if (warp == 2) TC_STAMP(9);
   }
   if (P::kClusterSplit && nsplit > 1) {
     cluster_arrive();
     cluster_wait();  // every partial tile is in its CTA's shared memory
     if (warp == 2) TC_STAMP(10);
+    RowEpi<BN> epi;
+    epi.init();
     if (warp >= 2) {
       // kDynRedRows (wgrad): only the rows that hold output channels are reduced, spread over all CTAs of the cluster
       const int red_rows = P::kDynRedRows ? P::red_rows(prm, tile) : BLOCK_M;
@@ -400,6 +685,12 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
         if (P::kDynRedRows && r >= red_rows) break;
         const int c = (idx % kVecPerRow) * 4;
         const uint32_t addr = red_base + (uint32_t)(r * kRedPitch + c) * 4u;
+        float* row_out = nullptr;
+        typename P::Extras ex{};
+        if constexpr (P::kRowMajor) {
+          row_out = row_tab[r];
+          ex = P::load_extras(prm, tile, row_out, c);   // in flight together with the remote loads below
+        }
         float4 pv[8];
 #pragma unroll
         for (int s2 = 0; s2 < 8; ++s2)
@@ -408,13 +699,24 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int s2 = 1; s2 < 8; ++s2)  // fixed order: deterministic
           if (s2 < nsplit) { acc.x += pv[s2].x; acc.y += pv[s2].y; acc.z += pv[s2].z; acc.w += pv[s2].w; }
-        P::store4(prm, tile, r, c, acc);
+        if constexpr (P::kRowMajor) {
+          // (a split launch has at most 128 columns: one float4 column group per lane, every row seen once per lane)
+          if (row_out) {
+            P::emit4(prm, tile, epi, row_out, c, 0, acc, ex);
+            epi.n += 1.f;
+          }
+        } else {
+          P::store4(prm, tile, r, c, acc);
+        }
       }
     }
     // nobody leaves while its shared memory may still be read: arrive once this CTA's remote reads have
     // landed in registers (the global stores above only consume registers), wait just before the exit
     if (warp == 2) TC_STAMP(11);
     cluster_arrive();
+    if constexpr (P::kRowMajor) {
+      if (warp >= 2) P::epi_finish(prm, tile, epi, wstat, (warp - 2) * 32 + lane);
+    }
     // two-level split (wgrad): the last cluster that finishes a tile adds the clusters' partial tiles
     if (P::kClusterFinish && warp >= 2) P::finish_cluster(prm, tile, (warp - 2) * 32 + lane, rank, nsplit);
     cluster_wait();
@@ -524,6 +826,7 @@ struct GemmParams {
   float* C;
   const float* bias;
   int M, N, K, ldc, accumulate;
+  int vec_ok;   // C and ldc allow 128-bit accesses
 };
 struct GemmTile {
   int m0, n0, kb_begin, kb_end;
@@ -545,6 +848,41 @@ struct GemmProblem {
   __device__ static void finish_cluster(const GemmParams&, const GemmTile&, int, int, int) {}
   using Params = GemmParams;
   using Tile = GemmTile;
+  static constexpr bool kRowMajor = true;
+  __device__ static float* row_ptr(const Params& p, const Tile& t, int row) {
+    const int m = t.m0 + row;
+    return m < p.M ? p.C + (size_t)m * p.ldc : nullptr;
+  }
+  struct Extras { float4 old; };   // C's previous values when accumulating
+  __device__ static Extras load_extras(const Params& p, const Tile& t, const float* row_out, int c) {
+    Extras x;
+    x.old = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = t.n0 + c;
+    if (row_out && p.accumulate && p.vec_ok && n + 4 <= p.N) x.old = *reinterpret_cast<const float4*>(row_out + n);
+    return x;
+  }
+  // four consecutive columns starting at tile column c of the row that starts at row_out
+  __device__ static void emit4(const Params& p, const Tile& t, RowEpi<BN_>&, float* row_out, int c, int, float4 q, const Extras& x) {
+    const int n = t.n0 + c;
+    if (n >= p.N) return;
+    float* dst = row_out + n;
+    if (p.vec_ok && n + 4 <= p.N) {
+      if (p.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n)); q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w; }
+      if (p.accumulate) { q.x += x.old.x; q.y += x.old.y; q.z += x.old.z; q.w += x.old.w; }
+      *reinterpret_cast<float4*>(dst) = q;
+      return;
+    }
+    const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (n + i < p.N) {
+        float x = v[i];
+        if (p.bias) x += __ldg(p.bias + n + i);
+        dst[i] = p.accumulate ? dst[i] + x : x;
+      }
+    }
+  }
+  __device__ static void epi_finish(const Params&, const Tile&, RowEpi<BN_>&, float*, int) {}
   __device__ static Tile tile(const Params& p) {
     return {(int)blockIdx.x * BLOCK_M, (int)blockIdx.y * BN, 0, (p.K + BLOCK_K - 1) / BLOCK_K};
   }
@@ -567,34 +905,6 @@ struct GemmProblem {
     } else {
 #pragma unroll
       for (int j = 0; j < BN / 32; ++j) tma_load_2d(dst + j * kChunkBytes, m, bar, t.n0 + j * 32, kb * BLOCK_K);
-    }
-  }
-  __device__ static void store4(const Params& p, const Tile& t, int row, int c, const float4& q) {
-    const int m = t.m0 + row;
-    if (m >= p.M) return;
-    const float v[4] = {q.x, q.y, q.z, q.w};
-    float* dst = p.C + (size_t)m * p.ldc + t.n0 + c;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (t.n0 + c + i < p.N) {
-        float x = v[i];
-        if (p.bias) x += __ldg(p.bias + t.n0 + c + i);
-        dst[i] = p.accumulate ? dst[i] + x : x;
-      }
-    }
-  }
-  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32], int) {
-    const int m = t.m0 + row;
-    if (m >= p.M) return;
-    float* dst = p.C + (size_t)m * p.ldc + t.n0 + c0;
-    const int ncols = min(32, p.N - (t.n0 + c0));
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < ncols) {
-        float x = v[i];
-        if (p.bias) x += __ldg(p.bias + t.n0 + c0 + i);
-        dst[i] = p.accumulate ? dst[i] + x : x;
-      }
     }
   }
 };
@@ -658,6 +968,7 @@ struct ConvParams {
   // of an image with 2*OH x 2*OW pixels.
   int par_pad;
   int splits;          // split-K cluster size along z
+  EpiArgs epi;         // fused epilogue: addend, per-channel statistics (see RowEpi)
 };
 struct ConvTile {
   int n0, oh0, ow0, col0, kb_begin, kb_end;
@@ -786,32 +1097,17 @@ struct ConvProblem {
     }
     return p.out + (((size_t)n * OHf + oh) * OWf + ow) * p.n_out;
   }
-  __device__ static void store4(const Params& p, const Tile& t, int row, int c, const float4& q) {
-    float* base = row_ptr(p, t, row);
-    if (!base) return;
-    const int col = t.col0 + c;
-    if ((p.n_out & 3) == 0 && col + 4 <= p.n_out) {
-      *reinterpret_cast<float4*>(base + col) = q;
-    } else {
-      const float v[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (col + i < p.n_out) base[col + i] = v[i];
-    }
+  static constexpr bool kRowMajor = true;
+  using Extras = typename RowEpi<BN_>::Extras;
+  __device__ static Extras load_extras(const Params& p, const Tile& t, const float* row_out, int c) {
+    return RowEpi<BN_>::load_extras(p.epi, p.out, row_out, t.col0 + c, p.n_out);
   }
-  __device__ static void store(const Params& p, const Tile& t, int row, int c0, const float (&v)[32], int) {
-    float* base = row_ptr(p, t, row);
-    if (!base) return;
-    const int col = t.col0 + c0;
-    float* dst = base + col;
-    if ((p.n_out & 3) == 0 && col + 32 <= p.n_out) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (col + i < p.n_out) dst[i] = v[i];
-    }
+  __device__ static void emit4(const Params& p, const Tile& t, RowEpi<BN_>& epi, float* row_out, int c, int g, const float4& q, const Extras& x) {
+    epi.emit(p.epi, row_out, t.col0 + c, g, q, x, p.n_out);
+  }
+  __device__ static void epi_finish(const Params& p, const Tile& t, RowEpi<BN_>& epi, float* wstat, int tid) {
+    epi.finish(p.epi, wstat, tid, t.col0, p.n_out, (int)(blockIdx.x * gridDim.z + blockIdx.z), (int)(gridDim.x * gridDim.z),
+               gridDim.x * gridDim.y * gridDim.z);
   }
 };
 
@@ -858,8 +1154,13 @@ struct WgradProblem {
   __device__ static uint32_t a_sub_offset(const WgradParams&, int) { return 0; }
   __device__ static uint32_t b_sub_offset(const WgradParams&, int, uint32_t) { return 0; }
   __device__ static uint32_t b_lbo(const WgradParams& p) { return (uint32_t)(p.ow_t * 128); }
-  static constexpr bool kClusterSplit = false, kDynRedRows = false, kClusterFinish = false;
+  static constexpr bool kClusterSplit = false, kDynRedRows = false, kClusterFinish = false, kRowMajor = false;
   __device__ static void store4(const WgradParams&, const WgradTile&, int, int, const float4&) {}
+  __device__ static float* row_ptr(const WgradParams&, const WgradTile&, int) { return nullptr; }
+  struct Extras {};
+  __device__ static Extras load_extras(const WgradParams&, const WgradTile&, const float*, int) { return Extras{}; }
+  __device__ static void emit4(const WgradParams&, const WgradTile&, RowEpi<BN_>&, float*, int, int, const float4&, const Extras&) {}
+  __device__ static void epi_finish(const WgradParams&, const WgradTile&, RowEpi<BN_>&, float*, int) {}
   __device__ static int red_rows(const WgradParams&, const WgradTile&) { return BLOCK_M; }
   __device__ static void finish_cluster(const WgradParams&, const WgradTile&, int, int, int) {}
   using Params = WgradParams;
@@ -1148,7 +1449,18 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
   const int kblocks = ROWS ? prm.R * prm.cblks : prm.R * prm.R * prm.cblks / (classes == 4 ? 4 : 1);
   prm.splits = BN >= 256 ? 1 : pick_splits((size_t)grid.x * grid.y * classes, kblocks > 0 ? kblocks : 1);
   grid.z = (unsigned)(classes * prm.splits);
-  return launch<ConvProblem<BN, WMODE, ROWS>>(name, ma, mb, prm, grid, prm.splits);
+  float* part = nullptr;
+  if (prm.epi.stat_kind != EPI_NONE) {  // one partial per (pixel tile, class / split rank) + its row count
+    const size_t partials = (size_t)grid.x * grid.z;
+    dfb_status st = dfb_malloc(partials * 3 * n_out + partials, &part);
+    if (st != DFB_OK) return st;
+    prm.epi.stat_part = part;
+    prm.epi.stat_cnt = part + partials * 3 * n_out;
+    prm.epi.stat_ticket = ticket_counter(3);
+  }
+  dfb_status st = launch<ConvProblem<BN, WMODE, ROWS>>(name, ma, mb, prm, grid, prm.splits);
+  if (part) dfb_free(part);  // stream-ordered
+  return st;
 }
 // row-halo variant (ConvProblem<.., ROWS = true>): n_out <= 128
 template <int WMODE>
@@ -1180,10 +1492,18 @@ static dfb_status run_conv_bn(const char* name, const CUtensorMap& ma, const flo
 // y[pix, n_out] = sum_{taps, c} act[pix*stride + off(tap), c] * Wt[n_out][tap][c]
 static dfb_status conv_like(const char* name, const float* act, const float* w, int w_layout, float* out, bool dgrad, int N,
                             int actC, int actH, int actW, int n_out, int R, int OH, int OW, int stride, int dh0, int sgn, int K,
-                            int C, bool* handled, int par_pad = -1) {
+                            int C, bool* handled, int par_pad = -1, const ConvFuse* fuse = nullptr) {
   const int taps = R * R;
   const int cp = (actC + 31) / 32 * 32;
   ConvParams prm;
+  prm.epi = EpiArgs{};
+  if (fuse) {  // the partial buffers depend on the grid: run_conv fills them in
+    prm.epi.addend = fuse->addend;
+    prm.epi.stat_kind = fuse->kind;
+    prm.epi.n_sets = fuse->n_sets;
+    prm.epi.stat_out = fuse->stats_out;
+    for (int i = 0; i < 2; ++i) { prm.epi.bn_x[i] = fuse->bn_x[i]; prm.epi.bn_mean[i] = fuse->bn_mean[i]; prm.epi.bn_invstd[i] = fuse->bn_invstd[i]; }
+  }
   prm.out = out; prm.n_img = N; prm.OH = OH; prm.OW = OW; prm.n_out = n_out; prm.R = R; prm.cblks = cp / 32;
   prm.dh0 = dh0; prm.dw0 = dh0; prm.sgn = sgn; prm.stride = stride; prm.c_red = actC; prm.par_pad = par_pad;
   pixel_tile(BLOCK_M, OH, OW, &prm.ow_t, &prm.oh_t, &prm.n_t);
@@ -1277,7 +1597,8 @@ dfb_status tc_gemm(const float* A, const float* B, float* C, int M, int N, int K
   if (tc_disabled() || mode != DFB_MODE_TF32) return DFB_OK;
   if (K <= 0 || (lda & 3) || (ldb & 3)) return DFB_OK;
   if ((size_t)M * N < 4096 || K < 16) return DFB_OK;  // launch-latency territory: FFMA kernel is as fast
-  GemmParams prm{C, bias, M, N, K, ldc, accumulate};
+  const int vec_ok = ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) ? 1 : 0;
+  GemmParams prm{C, bias, M, N, K, ldc, accumulate, vec_ok};
   if (!trans_a && !trans_b) return run_gemm_bn<MAJOR_K, MAJOR_MN>(A, B, prm, lda, ldb, handled);
   if (!trans_a && trans_b) return run_gemm_bn<MAJOR_K, MAJOR_K>(A, B, prm, lda, ldb, handled);
   if (trans_a && !trans_b) return run_gemm_bn<MAJOR_MN, MAJOR_MN>(A, B, prm, lda, ldb, handled);
@@ -1293,25 +1614,25 @@ static bool conv_tc_ok(int N, int C, int H, int W, int K, int R, int pad, int st
 }
 
 dfb_status tc_conv_fprop(const float* x, const float* w, int w_layout, float* y, int N, int C, int H, int W, int K, int R, int pad,
-                         int stride, int mode, float*, size_t, bool* handled) {
+                         int stride, int mode, float*, size_t, bool* handled, const ConvFuse* fuse) {
   *handled = false;
   if (!conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
-  return tc::conv_like("tc_conv_fprop", x, w, w_layout, y, false, N, C, H, W, K, R, OH, OW, stride, -pad, +1, K, C, handled);
+  return tc::conv_like("tc_conv_fprop", x, w, w_layout, y, false, N, C, H, W, K, R, OH, OW, stride, -pad, +1, K, C, handled, -1, fuse);
 }
 
 dfb_status tc_conv_dgrad(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K, int R, int pad,
-                         int stride, int mode, float*, size_t, bool* handled) {
+                         int stride, int mode, float*, size_t, bool* handled, const ConvFuse* fuse) {
   *handled = false;
   if (!conv_tc_ok(N, C, H, W, K, R, pad, stride, mode)) return DFB_OK;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
   if (stride == 1) {
     // dx[n,h,w,c] = sum_{r,s,k} dy[n, h + pad - r, w + pad - s, k] * w[k][c][r][s]
-    return tc::conv_like("tc_conv_dgrad", dy, w, w_layout, dx, true, N, K, OH, OW, C, R, H, W, 1, pad, -1, K, C, handled);
+    return tc::conv_like("tc_conv_dgrad", dy, w, w_layout, dx, true, N, K, OH, OW, C, R, H, W, 1, pad, -1, K, C, handled, -1, fuse);
   }
   // stride 2: four output-parity classes of dx, each a stride-1 contraction over dy with every other tap
   // (ConvParams::par_pad); one launch, blockIdx.z = class. H and W are even (conv_tc_ok).
-  return tc::conv_like("tc_conv_dgrad_s2", dy, w, w_layout, dx, true, N, K, OH, OW, C, R, H / 2, W / 2, 1, 0, 0, K, C, handled, pad);
+  return tc::conv_like("tc_conv_dgrad_s2", dy, w, w_layout, dx, true, N, K, OH, OW, C, R, H / 2, W / 2, 1, 0, 0, K, C, handled, pad, fuse);
 }
 
 // c_valid <= C: channels of x that belong to the gradient (the first-layer path pads its column matrix to 32 channels);

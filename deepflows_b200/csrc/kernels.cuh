@@ -20,6 +20,22 @@ dfb_status direct_conv_fprop(const float* x, int x_layout, const float* w, int w
 dfb_status direct_conv_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H, int W,
                              int K, int R, int pad, int stride, bool* handled);
 
+// Optional work fused into the epilogue of a convolution (gemm_tc.cu: RowEpi; gemm.cu runs the same work as separate
+// kernels when the tensor-core path does not take the problem):
+//   addend    : out += addend (tensor of the output's shape)
+//   stats     : FUSE_STATS -> stats_out[2][n_out] = per-channel mean / biased variance of the output
+//               FUSE_BNBWD -> stats_out[3][n_out] = sum(out), sum(out * x_hat_0), sum(out * x_hat_1) with
+//                             x_hat_i = (bn_x[i] - bn_mean[i]) * bn_invstd[i]  (n_sets of them, 1 or 2)
+enum { FUSE_NONE = 0, FUSE_STATS = 1, FUSE_BNBWD = 2 };
+struct ConvFuse {
+  const float* addend;
+  int kind, n_sets;
+  float* stats_out;
+  const float* bn_x[2];
+  const float* bn_mean[2];
+  const float* bn_invstd[2];
+};
+
 // gemm_tc.cu — TMA + tcgen05/TMEM path. Each returns DFB_OK and sets *handled = true when it ran
 // the problem, leaves *handled = false when the shape is outside what the tensor-core kernels
 // take (the dispatcher then uses the SIMT path), or returns an error status.
@@ -27,10 +43,10 @@ dfb_status tc_gemm(const float* A, const float* B, float* C, int M, int N, int K
                    int lda, int ldb, int ldc, int accumulate, const float* bias, int mode, bool* handled);
 dfb_status tc_conv_fprop(const float* x, const float* w, int w_layout, float* y, int N, int C, int H, int W, int K, int R,
                          int pad, int stride, int mode, float* workspace, size_t workspace_floats,
-                         bool* handled);
+                         bool* handled, const ConvFuse* fuse = nullptr);
 dfb_status tc_conv_dgrad(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
                          int R, int pad, int stride, int mode, float* workspace, size_t workspace_floats,
-                         bool* handled);
+                         bool* handled, const ConvFuse* fuse = nullptr);
 dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K,
                          int R, int pad, int stride, int mode, float* workspace, size_t workspace_floats,
                          bool* handled);

@@ -116,6 +116,7 @@ struct SumsArgs {
   float* running_mean;   // STATS
   float* running_var;    // STATS
   float eps, momentum;
+  int raw_var;           // STATS: out1 = biased variance instead of 1/sqrt(var + eps); running statistics untouched
 };
 
 // Pairwise (tree) sum over the row lanes of a CTA through shared memory; the result lands in lane 0. A tree
@@ -265,7 +266,7 @@ col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
           const float mean = a.x[c] + dm;
           const float var = fmaxf(s1[v] / n - dm * dm, 0.f);
           a.out0[c] = mean;
-          a.out1[c] = 1.0f / sqrtf(var + a.eps);
+          a.out1[c] = a.raw_var ? var : 1.0f / sqrtf(var + a.eps);
           if (a.running_mean) a.running_mean[c] = a.running_mean[c] * (1.0f - a.momentum) + mean * a.momentum;
           if (a.running_var) a.running_var[c] = a.running_var[c] * (1.0f - a.momentum) + var * a.momentum;
         } else {
@@ -851,6 +852,111 @@ softmax_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict_
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// BatchNorm forward from statistics that already exist (the producing convolution's epilogue, or
+// dfb_colstats_mean_var): ONE pass that normalises, and - when the host saw them coming - also adds the
+// other branch of a residual block (a plain tensor, or a second BatchNorm applied on the fly: the shortcut's
+// conv + BatchNorm) and applies ReLU. Replaces bn_stats + bn_apply (+ binary add) (+ scalar_maximum).
+// CTA 0 additionally publishes mean / invstd for the backward pass and updates the running statistics.
+// -------------------------------------------------------------------------------------------------
+struct BnSide {
+  const float* x;
+  const float* mean_var;   // [2][C]: batch mean, biased batch variance
+  const float* gamma;
+  const float* beta;
+  float* save_mean;
+  float* save_invstd;
+  float* running_mean;
+  float* running_var;
+  float momentum, eps;
+};
+__device__ __forceinline__ void bn_side_prologue(const BnSide& s, int C, float* s_mean, float* s_scale, float* s_shift) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = s.mean_var[c], var = s.mean_var[C + c];
+    const float invstd = 1.0f / sqrtf(var + s.eps);
+    s_mean[c] = mean;
+    s_scale[c] = invstd * (s.gamma ? s.gamma[c] : 1.0f);
+    s_shift[c] = s.beta ? s.beta[c] : 0.0f;
+    if (blockIdx.x == 0) {
+      s.save_mean[c] = mean;
+      s.save_invstd[c] = invstd;
+      if (s.running_mean) s.running_mean[c] = s.running_mean[c] * (1.0f - s.momentum) + mean * s.momentum;
+      if (s.running_var) s.running_var[c] = s.running_var[c] * (1.0f - s.momentum) + var * s.momentum;
+    }
+  }
+}
+template <int V, bool RELU, bool DUAL, bool RES>
+__global__ void __launch_bounds__(kT)
+bn_apply_fused_kernel(BnSide a, BnSide b, const float* __restrict__ res, float* __restrict__ y, size_t rows, int C) {
+  pdl_sync();
+  extern __shared__ float sm[];  // mean, scale, shift per side
+  float* am = sm; float* as = sm + C; float* ah = sm + 2 * C;
+  float* bm = sm + 3 * C; float* bs = sm + 4 * C; float* bh = sm + 5 * C;
+  bn_side_prologue(a, C, am, as, ah);
+  if (DUAL) bn_side_prologue(b, C, bm, bs, bh);
+  __syncthreads();
+  const int G = C / V;
+  const size_t total = rows * G;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int g = (int)(i % G);
+    float xv[V], x2[V], rv[V], o[V];
+    Vec<V>::get(a.x + i * V, xv);
+    if (DUAL) Vec<V>::get(b.x + i * V, x2);
+    if (RES) Vec<V>::get(res + i * V, rv);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = g * V + v;
+      float t = fmaf(xv[v] - am[c], as[c], ah[c]);
+      if (DUAL) t = t + fmaf(x2[v] - bm[c], bs[c], bh[c]);
+      if (RES) t = t + rv[v];
+      o[v] = RELU ? fmaxf(t, 0.f) : t;
+    }
+    Vec<V>::put(y + i * V, o);
+  }
+}
+
+// ReLU backward through a fused BatchNorm(+residual)+ReLU: the pre-activation z is recomputed exactly as the forward
+// kernel computed it (same operations, same operands), dx = z >= 0 ? dy : 0 (maximum.grad_fn, tensor.py:872-877)
+template <int V, bool DUAL, bool RES>
+__global__ void __launch_bounds__(kT)
+relu_bwd_bn_kernel(const float* __restrict__ xa, const float* __restrict__ mean_a, const float* __restrict__ invstd_a,
+                   const float* __restrict__ gamma_a, const float* __restrict__ beta_a, const float* __restrict__ xb,
+                   const float* __restrict__ mean_b, const float* __restrict__ invstd_b, const float* __restrict__ gamma_b,
+                   const float* __restrict__ beta_b, const float* __restrict__ res, const float* __restrict__ dy,
+                   float* __restrict__ dx, size_t rows, int C) {
+  pdl_sync();
+  extern __shared__ float sm[];
+  float* am = sm; float* as = sm + C; float* ah = sm + 2 * C;
+  float* bm = sm + 3 * C; float* bs = sm + 4 * C; float* bh = sm + 5 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    am[c] = mean_a[c]; as[c] = invstd_a[c] * (gamma_a ? gamma_a[c] : 1.0f); ah[c] = beta_a ? beta_a[c] : 0.0f;
+    if (DUAL) { bm[c] = mean_b[c]; bs[c] = invstd_b[c] * (gamma_b ? gamma_b[c] : 1.0f); bh[c] = beta_b ? beta_b[c] : 0.0f; }
+  }
+  __syncthreads();
+  const int G = C / V;
+  const size_t total = rows * G;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int g = (int)(i % G);
+    float xv[V], x2[V], rv[V], dv[V], o[V];
+    Vec<V>::get(xa + i * V, xv);
+    if (DUAL) Vec<V>::get(xb + i * V, x2);
+    if (RES) Vec<V>::get(res + i * V, rv);
+    Vec<V>::get(dy + i * V, dv);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = g * V + v;
+      float t = fmaf(xv[v] - am[c], as[c], ah[c]);
+      if (DUAL) t = t + fmaf(x2[v] - bm[c], bs[c], bh[c]);
+      if (RES) t = t + rv[v];
+      o[v] = t >= 0.f ? dv[v] : 0.f;
+    }
+    Vec<V>::put(dx + i * V, o);
+  }
+}
+
 static unsigned ew_grid(size_t items) { return bw_grid(items, kT, 8); }
 
 }  // namespace dfb
@@ -1007,6 +1113,117 @@ dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma, const
     DFB_LAUNCH_CHECK("bn_bwd_apply");
   }
   dfb_free(scratch);
+  return DFB_OK;
+}
+
+dfb_status dfb_colstats_mean_var(const float* x, size_t rows, int C, float* mean_var) {
+  DFB_INIT();
+  DFB_REQUIRE(x && mean_var, DFB_ERR_INVALID, "colstats_mean_var: null pointer");
+  DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "colstats_mean_var: empty input");
+  SumsArgs a{};
+  a.x = x;
+  a.out0 = mean_var;
+  a.out1 = mean_var + C;
+  a.raw_var = 1;
+  return launch_col_sums<SUMS_STATS>("colstats_mean_var", a, rows, C, x);
+}
+
+dfb_status dfb_bn_fwd_apply(const float* x, const float* mean_var, const float* gamma, const float* beta, float* save_mean,
+                            float* save_invstd, float* running_mean, float* running_var, float momentum, float eps,
+                            const float* x2, const float* mean_var2, const float* gamma2, const float* beta2, float* save_mean2,
+                            float* save_invstd2, float* running_mean2, float* running_var2, float momentum2, float eps2,
+                            const float* residual, float* y, size_t rows, int C, int relu) {
+  DFB_INIT();
+  DFB_REQUIRE(x && mean_var && save_mean && save_invstd && y, DFB_ERR_INVALID, "bn_fwd_apply: null pointer");
+  DFB_REQUIRE(!x2 || (mean_var2 && save_mean2 && save_invstd2), DFB_ERR_INVALID, "bn_fwd_apply: second BatchNorm incomplete");
+  DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_fwd_apply: empty input");
+  const size_t smem = (size_t)(x2 ? 6 : 3) * C * sizeof(float);
+  DFB_REQUIRE(smem <= 48 * 1024, DFB_ERR_INVALID, "bn_fwd_apply: too many channels (%d)", C);
+  BnSide a{x, mean_var, gamma, beta, save_mean, save_invstd, running_mean, running_var, momentum, eps};
+  BnSide b{x2, mean_var2, gamma2, beta2, save_mean2, save_invstd2, running_mean2, running_var2, momentum2, eps2};
+  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(residual) |
+                                   reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  cudaStream_t s = compute_stream();
+  const unsigned grid = vec ? ew_grid(rows * (C / 4)) : ew_grid(rows * C);
+  const int sel = (relu ? 4 : 0) | (x2 ? 2 : 0) | (residual ? 1 : 0);
+#define DFB_BN_APPLY(R, D, S)                                                                                         \
+  do {                                                                                                                \
+    if (vec) launch_k(bn_apply_fused_kernel<4, R, D, S>, grid, kT, smem, s, a, b, residual, y, rows, C);              \
+    else launch_k(bn_apply_fused_kernel<1, R, D, S>, grid, kT, smem, s, a, b, residual, y, rows, C);                  \
+  } while (0)
+  switch (sel) {
+    case 0: DFB_BN_APPLY(false, false, false); break;
+    case 1: DFB_BN_APPLY(false, false, true); break;
+    case 2: DFB_BN_APPLY(false, true, false); break;
+    case 3: DFB_BN_APPLY(false, true, true); break;
+    case 4: DFB_BN_APPLY(true, false, false); break;
+    case 5: DFB_BN_APPLY(true, false, true); break;
+    case 6: DFB_BN_APPLY(true, true, false); break;
+    default: DFB_BN_APPLY(true, true, true); break;
+  }
+#undef DFB_BN_APPLY
+  DFB_LAUNCH_CHECK("bn_fwd_apply");
+  return DFB_OK;
+}
+
+dfb_status dfb_relu_bwd_bn(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                           const float* x2, const float* mean2, const float* invstd2, const float* gamma2, const float* beta2,
+                           const float* residual, const float* dy, float* dx, size_t rows, int C) {
+  DFB_INIT();
+  DFB_REQUIRE(x && mean && invstd && dy && dx, DFB_ERR_INVALID, "relu_bwd_bn: null pointer");
+  DFB_REQUIRE(!x2 || (mean2 && invstd2), DFB_ERR_INVALID, "relu_bwd_bn: second BatchNorm incomplete");
+  if (rows == 0) return DFB_OK;
+  const size_t smem = (size_t)(x2 ? 6 : 3) * C * sizeof(float);
+  DFB_REQUIRE(smem <= 48 * 1024, DFB_ERR_INVALID, "relu_bwd_bn: too many channels (%d)", C);
+  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(residual) |
+                                   reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  cudaStream_t s = compute_stream();
+  const unsigned grid = vec ? ew_grid(rows * (C / 4)) : ew_grid(rows * C);
+#define DFB_RELU_BN(D, S)                                                                                                          \
+  do {                                                                                                                             \
+    if (vec) launch_k(relu_bwd_bn_kernel<4, D, S>, grid, kT, smem, s, x, mean, invstd, gamma, beta, x2, mean2, invstd2, gamma2, beta2, \
+                      residual, dy, dx, rows, C);                                                                                  \
+    else launch_k(relu_bwd_bn_kernel<1, D, S>, grid, kT, smem, s, x, mean, invstd, gamma, beta, x2, mean2, invstd2, gamma2, beta2,  \
+                  residual, dy, dx, rows, C);                                                                                      \
+  } while (0)
+  if (x2 && residual) DFB_RELU_BN(true, true);
+  else if (x2) DFB_RELU_BN(true, false);
+  else if (residual) DFB_RELU_BN(false, true);
+  else DFB_RELU_BN(false, false);
+#undef DFB_RELU_BN
+  DFB_LAUNCH_CHECK("relu_bwd_bn");
+  return DFB_OK;
+}
+
+// BatchNorm backward in two explicit halves, for callers whose sums come from somewhere else (the dgrad epilogue)
+dfb_status dfb_bn_bwd_sums(const float* x, const float* dy, const float* save_mean, const float* save_invstd, float* dbeta,
+                           float* dgamma, size_t rows, int C) {
+  DFB_INIT();
+  DFB_REQUIRE(x && dy && save_mean && save_invstd && dbeta && dgamma, DFB_ERR_INVALID, "bn_bwd_sums: null pointer");
+  DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_bwd_sums: empty input");
+  SumsArgs a{};
+  a.x = x;
+  a.dy = dy;
+  a.mean = save_mean;
+  a.invstd = save_invstd;
+  a.out0 = dbeta;
+  a.out1 = dgamma;
+  return launch_col_sums<SUMS_BNBWD>("bn_bwd_sums", a, rows, C, x, dy);
+}
+dfb_status dfb_bn_bwd_apply(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
+                            const float* dbeta, const float* dgamma, float* dx, size_t rows, int C) {
+  DFB_INIT();
+  DFB_REQUIRE(x && dy && save_mean && save_invstd && dbeta && dgamma && dx, DFB_ERR_INVALID, "bn_bwd_apply: null pointer");
+  DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_bwd_apply: empty input");
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  const size_t sm2 = (size_t)5 * C * sizeof(float);
+  DFB_REQUIRE(sm2 <= 48 * 1024, DFB_ERR_INVALID, "bn_bwd_apply: too many channels (%d)", C);
+  cudaStream_t s = compute_stream();
+  if (C % 4 == 0 && al)
+    launch_k(bn_bwd_apply_kernel<4>, ew_grid(rows * (C / 4)), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, dbeta, dgamma);
+  else
+    launch_k(bn_bwd_apply_kernel<1>, ew_grid(rows * C), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, dbeta, dgamma);
+  DFB_LAUNCH_CHECK("bn_bwd_apply");
   return DFB_OK;
 }
 

@@ -375,6 +375,62 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
     check(dfb_bn_bwd(dptr(x), dptr(dy), dptr(gamma), dptr(save_mean), dptr(save_invstd), dptr(dx), dptr(dgamma), dptr(dbeta),
                      rows, C));
   });
+  // ---- fused epilogue / BatchNorm halves (include/dfb200.h: dfb_conv2d_fprop_stats ... dfb_bn_bwd_apply) ----
+  m.def("conv2d_fprop_stats", [](const py::object& x, int x_layout, const py::object& w, int w_layout, const py::object& y, int N,
+                                 int C, int H, int W, int K, int R, int pad, int stride, int mode, const py::object& mean_var) {
+    check(dfb_conv2d_fprop_stats(dptr(x), x_layout, dptr(w), w_layout, dptr(y), N, C, H, W, K, R, pad, stride, mode, dptr(mean_var)));
+  });
+  m.def("conv2d_dgrad_fused", [](const py::object& dy, const py::object& w, int w_layout, const py::object& dx, int N, int C, int H,
+                                 int W, int K, int R, int pad, int stride, int mode, int dgrad_mode, const py::object& addend,
+                                 int n_bn, const py::object& x0, const py::object& mean0, const py::object& invstd0,
+                                 const py::object& x1, const py::object& mean1, const py::object& invstd1, const py::object& sums) {
+    check(dfb_conv2d_dgrad_fused(dptr(dy), dptr(w), w_layout, dptr(dx), N, C, H, W, K, R, pad, stride, mode, dgrad_mode, dptr(addend),
+                                 n_bn, dptr(x0), dptr(mean0), dptr(invstd0), dptr(x1), dptr(mean1), dptr(invstd1), dptr(sums)));
+  });
+  m.def("colstats_mean_var", [](const py::object& x, size_t rows, int C, const py::object& mean_var) {
+    check(dfb_colstats_mean_var(dptr(x), rows, C, dptr(mean_var)));
+  });
+  // each BatchNorm is the tuple (x, mean_var, gamma, beta, save_mean, save_invstd, running_mean, running_var, momentum, eps)
+  m.def("bn_fwd_apply", [](const py::tuple& a, const py::object& b_or_none, const py::object& residual, const py::object& y,
+                           size_t rows, int C, bool relu) {
+    auto f = [](const py::tuple& t, int i) { return dptr(t[i]); };
+    if (a.size() != 10) throw py::value_error("bn_fwd_apply: a BatchNorm is a 10-tuple");
+    if (b_or_none.is_none()) {
+      check(dfb_bn_fwd_apply(f(a, 0), f(a, 1), f(a, 2), f(a, 3), f(a, 4), f(a, 5), f(a, 6), f(a, 7), a[8].cast<float>(), a[9].cast<float>(),
+                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, dptr(residual), dptr(y),
+                             rows, C, relu ? 1 : 0));
+    } else {
+      py::tuple b = b_or_none.cast<py::tuple>();
+      if (b.size() != 10) throw py::value_error("bn_fwd_apply: a BatchNorm is a 10-tuple");
+      check(dfb_bn_fwd_apply(f(a, 0), f(a, 1), f(a, 2), f(a, 3), f(a, 4), f(a, 5), f(a, 6), f(a, 7), a[8].cast<float>(), a[9].cast<float>(),
+                             f(b, 0), f(b, 1), f(b, 2), f(b, 3), f(b, 4), f(b, 5), f(b, 6), f(b, 7), b[8].cast<float>(), b[9].cast<float>(),
+                             dptr(residual), dptr(y), rows, C, relu ? 1 : 0));
+    }
+  });
+  // each BatchNorm is the tuple (x, save_mean, save_invstd, gamma, beta)
+  m.def("relu_bwd_bn", [](const py::tuple& a, const py::object& b_or_none, const py::object& residual, const py::object& dy,
+                          const py::object& dx, size_t rows, int C) {
+    auto f = [](const py::tuple& t, int i) { return dptr(t[i]); };
+    if (a.size() != 5) throw py::value_error("relu_bwd_bn: a BatchNorm is a 5-tuple");
+    if (b_or_none.is_none()) {
+      check(dfb_relu_bwd_bn(f(a, 0), f(a, 1), f(a, 2), f(a, 3), f(a, 4), nullptr, nullptr, nullptr, nullptr, nullptr, dptr(residual),
+                            dptr(dy), dptr(dx), rows, C));
+    } else {
+      py::tuple b = b_or_none.cast<py::tuple>();
+      if (b.size() != 5) throw py::value_error("relu_bwd_bn: a BatchNorm is a 5-tuple");
+      check(dfb_relu_bwd_bn(f(a, 0), f(a, 1), f(a, 2), f(a, 3), f(a, 4), f(b, 0), f(b, 1), f(b, 2), f(b, 3), f(b, 4), dptr(residual),
+                            dptr(dy), dptr(dx), rows, C));
+    }
+  });
+  m.def("bn_bwd_sums", [](const py::object& x, const py::object& dy, const py::object& save_mean, const py::object& save_invstd,
+                          const py::object& dbeta, const py::object& dgamma, size_t rows, int C) {
+    check(dfb_bn_bwd_sums(dptr(x), dptr(dy), dptr(save_mean), dptr(save_invstd), dptr(dbeta), dptr(dgamma), rows, C));
+  });
+  m.def("bn_bwd_apply", [](const py::object& x, const py::object& dy, const py::object& gamma, const py::object& save_mean,
+                           const py::object& save_invstd, const py::object& dbeta, const py::object& dgamma, const py::object& dx,
+                           size_t rows, int C) {
+    check(dfb_bn_bwd_apply(dptr(x), dptr(dy), dptr(gamma), dptr(save_mean), dptr(save_invstd), dptr(dbeta), dptr(dgamma), dptr(dx), rows, C));
+  });
   m.def("relu_fwd", [](const py::object& x, const py::object& y, size_t n) { check(dfb_relu_fwd(dptr(x), dptr(y), n)); });
   m.def("relu_bwd", [](const py::object& x, const py::object& dy, const py::object& dx, size_t n) {
     check(dfb_relu_bwd(dptr(x), dptr(dy), dptr(dx), n));

@@ -242,6 +242,24 @@ DFB_API dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* d
                                     int w_layout, int N, int C, int H, int W, int K, int R, int pad,
                                     int stride, int mode, float* workspace, size_t workspace_floats);
 
+/* Convolutions with fused epilogue work (new; the reference has no equivalent - its BatchNorm is 16 tensor ops of
+ * its own, DeepFlows/nn/modules/batchnorm.py:30-55, and residual gradients are summed by Tensor.backward,
+ * DeepFlows/tensor.py:484-494). The tensor-core kernels do the extra work while the output tile leaves the SM; every
+ * other path runs it as separate passes with the same results.
+ *   dfb_conv2d_fprop_stats : y = conv(x, w) and mean_var[2][K] = per-channel mean / biased variance of y, what the
+ *                            BatchNorm that follows needs (dfb_bn_fwd_apply), without a statistics pass over y.
+ *   dfb_conv2d_dgrad_fused : dx = dgrad(dy, w) [+ addend], and for n_bn (0, 1, 2) BatchNorms whose OUTPUT gradient dx
+ *                            is: sums[0][C] = sum(dx), sums[1+i][C] = sum(dx * x_hat_i), x_hat_i = (bn_x_i - mean_i) *
+ *                            invstd_i - the two reductions of BatchNorm backward (dfb_bn_bwd_apply does the rest). */
+DFB_API dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, int w_layout, float* y, int N,
+                                          int C, int H, int W, int K, int R, int pad, int stride, int mode,
+                                          float* mean_var);
+DFB_API dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H,
+                                          int W, int K, int R, int pad, int stride, int mode, int dgrad_mode,
+                                          const float* addend, int n_bn, const float* bn_x0, const float* bn_mean0,
+                                          const float* bn_invstd0, const float* bn_x1, const float* bn_mean1,
+                                          const float* bn_invstd1, float* sums);
+
 /* y[r, c] = x[r, c] + v[c]   (conv bias (1,K,1,1) on channels-last, Linear bias (1,out);
  * replaces broadcast_to + compact + ewise_add, backend_tensor.py:533-542) */
 DFB_API dfb_status dfb_add_rowvec(const float* x, const float* v, float* y, size_t rows, int cols);
@@ -268,6 +286,32 @@ DFB_API dfb_status dfb_bn_fwd_eval(const float* x, const float* gamma, const flo
 DFB_API dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma,
                               const float* save_mean, const float* save_invstd, float* dx,
                               float* dgamma, float* dbeta, size_t rows, int C);
+
+/* BatchNorm in explicit halves, for callers that already hold the reductions (the convolution epilogues above):
+ *   dfb_colstats_mean_var : mean_var[2][C] = per-channel mean / biased variance of x[rows, C] (one pass)
+ *   dfb_bn_fwd_apply      : y = [relu]( bn(x) [+ bn2(x2)] [+ residual] ) from given statistics, ONE pass; publishes
+ *                           save_mean / save_invstd and updates the running statistics of each BatchNorm like
+ *                           dfb_bn_fwd_train. x2 == NULL: no second BatchNorm (the 1x1-conv shortcut of a residual block).
+ *                           Replaces batchnorm.py:30-55 + the block's `out + identity` (+ F.relu) as one kernel.
+ *   dfb_relu_bwd_bn       : dx = z >= 0 ? dy : 0 with z = bn(x) [+ bn2(x2)] [+ residual] recomputed exactly as
+ *                           dfb_bn_fwd_apply computed it (the fused forward never stores z)
+ *   dfb_bn_bwd_sums / dfb_bn_bwd_apply : the reduction half and the elementwise half of dfb_bn_bwd */
+DFB_API dfb_status dfb_colstats_mean_var(const float* x, size_t rows, int C, float* mean_var);
+DFB_API dfb_status dfb_bn_fwd_apply(const float* x, const float* mean_var, const float* gamma, const float* beta,
+                                    float* save_mean, float* save_invstd, float* running_mean, float* running_var,
+                                    float momentum, float eps, const float* x2, const float* mean_var2,
+                                    const float* gamma2, const float* beta2, float* save_mean2, float* save_invstd2,
+                                    float* running_mean2, float* running_var2, float momentum2, float eps2,
+                                    const float* residual, float* y, size_t rows, int C, int relu);
+DFB_API dfb_status dfb_relu_bwd_bn(const float* x, const float* mean, const float* invstd, const float* gamma,
+                                   const float* beta, const float* x2, const float* mean2, const float* invstd2,
+                                   const float* gamma2, const float* beta2, const float* residual, const float* dy,
+                                   float* dx, size_t rows, int C);
+DFB_API dfb_status dfb_bn_bwd_sums(const float* x, const float* dy, const float* save_mean, const float* save_invstd,
+                                   float* dbeta, float* dgamma, size_t rows, int C);
+DFB_API dfb_status dfb_bn_bwd_apply(const float* x, const float* dy, const float* gamma, const float* save_mean,
+                                    const float* save_invstd, const float* dbeta, const float* dgamma, float* dx,
+                                    size_t rows, int C);
 
 /* ReLU (F.relu = maximum(x, 0), functional.py:15-16). Backward follows maximum.grad_fn
  * (tensor.py:872-877): dx = (y == x) * dy, i.e. the gradient passes where x >= 0. */

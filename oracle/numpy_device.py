@@ -334,6 +334,100 @@ def bn_bwd(x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, rows, C):
         _flat(dbeta)[:C] = db.astype(F32)
 
 
+# ---- the fused halves (include/dfb200.h: dfb_conv2d_fprop_stats ... dfb_bn_bwd_apply), restated from the ops above:
+# statistics = the BatchNorm's own (batchnorm.py:33-42), apply = x_hat * gamma + beta (+ the other branch of the block), ---
+def colstats_mean_var(x, rows, C, mean_var):
+    _count("colstats_mean_var")
+    xa = _flat(x)[: rows * C].reshape(rows, C).astype(np.float64)
+    mv = _flat(mean_var)
+    mv[:C] = xa.mean(axis=0).astype(F32)
+    mv[C:2 * C] = xa.var(axis=0).astype(F32)
+
+
+def conv2d_fprop_stats(x, x_layout, w, w_layout, y, N, C, H, W, K, R, pad, stride, mode, mean_var):
+    _count("conv2d_fprop_stats")
+    out = ops.conv2d_fprop(_nchw(_flat(x), N, C, H, W, x_layout), _kcrs(w, K, C, R, w_layout), pad, stride)
+    _store_nhwc(_flat(y), out)
+    colstats_mean_var(y, out.size // K, K, mean_var)
+
+
+def _bn_side_apply(side, rows, C):
+    x, mean_var, gamma, beta, save_mean, save_invstd, rmean, rvar, momentum, eps = side
+    xa = _flat(x)[: rows * C].reshape(rows, C)
+    mean, var = _flat(mean_var)[:C].copy(), _flat(mean_var)[C:2 * C].copy()
+    invstd = (F32(1) / np.sqrt(var + F32(eps))).astype(F32)
+    _flat(save_mean)[:C] = mean
+    _flat(save_invstd)[:C] = invstd
+    if rmean is not None:
+        rm, rv = _flat(rmean), _flat(rvar)
+        rm[:C] = rm[:C] * F32(1 - momentum) + mean * F32(momentum)
+        rv[:C] = rv[:C] * F32(1 - momentum) + var * F32(momentum)
+    g = _flat(gamma)[:C] if gamma is not None else F32(1)
+    b = _flat(beta)[:C] if beta is not None else F32(0)
+    return ((xa - mean) * (invstd * g) + b).astype(F32)
+
+
+def bn_fwd_apply(a, b, residual, y, rows, C, relu):
+    _count("bn_fwd_apply")
+    out = _bn_side_apply(a, rows, C)
+    if b is not None:
+        out = out + _bn_side_apply(b, rows, C)
+    if residual is not None:
+        out = out + _flat(residual)[: rows * C].reshape(rows, C)
+    if relu:
+        out = np.maximum(out, F32(0))
+    _flat(y)[: rows * C] = out.astype(F32).reshape(-1)
+
+
+def _bn_side_value(side, rows, C):
+    x, mean, invstd, gamma, beta = side
+    g = _flat(gamma)[:C] if gamma is not None else F32(1)
+    b = _flat(beta)[:C] if beta is not None else F32(0)
+    return ((_flat(x)[: rows * C].reshape(rows, C) - _flat(mean)[:C]) * (_flat(invstd)[:C] * g) + b).astype(F32)
+
+
+def relu_bwd_bn(a, b, residual, dy, dx, rows, C):
+    _count("relu_bwd_bn")
+    z = _bn_side_value(a, rows, C)
+    if b is not None:
+        z = z + _bn_side_value(b, rows, C)
+    if residual is not None:
+        z = z + _flat(residual)[: rows * C].reshape(rows, C)
+    g = _flat(dy)[: rows * C].reshape(rows, C)
+    _flat(dx)[: rows * C] = np.where(z >= 0, g, F32(0)).astype(F32).reshape(-1)
+
+
+def bn_bwd_sums(x, dy, save_mean, save_invstd, dbeta, dgamma, rows, C):
+    _count("bn_bwd_sums")
+    bn_bwd(x, dy, None, save_mean, save_invstd, None, dgamma, dbeta, rows, C)
+
+
+def bn_bwd_apply(x, dy, gamma, save_mean, save_invstd, dbeta, dgamma, dx, rows, C):
+    _count("bn_bwd_apply")
+    xa = _flat(x)[: rows * C].reshape(rows, C).astype(np.float64)
+    ga = _flat(dy)[: rows * C].reshape(rows, C).astype(np.float64)
+    mean, invstd = _flat(save_mean)[:C].astype(np.float64), _flat(save_invstd)[:C].astype(np.float64)
+    db, dg = _flat(dbeta)[:C].astype(np.float64), _flat(dgamma)[:C].astype(np.float64)
+    g = _flat(gamma)[:C].astype(np.float64) if gamma is not None else 1.0
+    _flat(dx)[: rows * C] = (g * invstd * (ga - db / rows - (xa - mean) * invstd * dg / rows)).astype(F32).reshape(-1)
+
+
+def conv2d_dgrad_fused(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, addend, n_bn, x0, mean0, invstd0,
+                       x1, mean1, invstd1, sums):
+    _count("conv2d_dgrad_fused")
+    conv2d_dgrad(dy, w, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, None, 0, w_layout)
+    n = N * C * H * W
+    if addend is not None:
+        _flat(dx)[:n] = _flat(dx)[:n] + _flat(addend)[:n]
+    rows = N * H * W
+    for i, (bx, bm, bi) in enumerate(((x0, mean0, invstd0), (x1, mean1, invstd1))[:n_bn]):
+        bn_bwd_sums(bx, dx, bm, bi, (sums, 0) if not isinstance(sums, tuple) else sums, _off(sums, (1 + i) * C), rows, C)
+
+
+def _off(h, k):
+    return (h[0], h[1] + k) if isinstance(h, tuple) else (h, k)
+
+
 def relu_fwd(x, y, n):
     _count("relu_fwd"); _flat(y)[:n] = ops.relu_fwd(_flat(x)[:n])
 

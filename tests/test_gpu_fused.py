@@ -1,0 +1,191 @@
+"""Fused epilogues on a B200 (include/dfb200.h: dfb_conv2d_fprop_stats, dfb_conv2d_dgrad_fused, dfb_bn_fwd_apply,
+dfb_relu_bwd_bn, dfb_bn_bwd_sums / dfb_bn_bwd_apply) against the unfused entry points and numpy.
+
+The convolution shapes are the ResNet-18/CIFAR layers of the benchmark (row-halo 32-channel tiles, 64-wide tiles, the
+cluster split-K tiles of layers 3-4, stride-2 dgrad with its four parity classes) plus ragged ones (pixel counts that do
+not fill a tile, several column tiles)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+CONV_SHAPES = [  # N, C, H, W, K, R, pad, stride
+    (64, 32, 16, 16, 32, 3, 1, 1),     # layer 1: row-halo kernel, 32-wide tile
+    (64, 32, 16, 16, 64, 3, 1, 2),     # layer 2 entry, stride 2
+    (64, 64, 8, 8, 64, 3, 1, 1),       # layer 2
+    (64, 32, 16, 16, 64, 1, 0, 2),     # 1x1 stride-2 shortcut
+    (256, 128, 4, 4, 128, 3, 1, 1),    # layer 3: cluster split-K
+    (256, 256, 2, 2, 256, 3, 1, 1),    # layer 4: two column tiles, split 8
+    (256, 128, 4, 4, 256, 3, 1, 2),    # layer 4 entry
+    (3, 8, 7, 9, 12, 3, 1, 1),         # ragged: 189 pixels, 12 output channels
+    (10, 16, 20, 20, 272, 3, 1, 1),    # three column tiles, last one partial
+]
+
+
+def _dev(m, a):
+    h = m.Array(a.size)
+    m.from_numpy(np.ascontiguousarray(a, dtype=F32).reshape(-1), h)
+    return h
+
+
+def _host(m, h, shape):
+    strides = [1] * len(shape)
+    for i in range(len(shape) - 2, -1, -1):
+        strides[i] = strides[i + 1] * shape[i + 1]
+    return m.to_numpy(h, list(shape), strides, 0)
+
+
+@pytest.mark.parametrize("mode_name", ["tf32", "fp32"])
+@pytest.mark.parametrize("geom", CONV_SHAPES)
+def test_conv_fprop_stats(cuda_device, geom, mode_name):
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = geom
+    mode = m.MODE_TF32 if mode_name == "tf32" else m.MODE_FP32
+    oh, ow = (h + 2 * p - r) // s + 1, (w + 2 * p - r) // s + 1
+    rng = np.random.RandomState(1)
+    x = (rng.randn(n, h, w, c) + 0.5).astype(F32)              # channels-last, non-zero mean
+    wt = (rng.randn(k, r, r, c) / np.sqrt(c * r * r)).astype(F32)
+    wt[0] += 0.3                                                # one channel with |mean| >> std
+    hx, hw = _dev(m, x), _dev(m, wt)
+    y0, y1, mv = m.Array(n * oh * ow * k), m.Array(n * oh * ow * k), m.Array(2 * k)
+    m.conv2d_fprop(hx, m.LAYOUT_NHWC, hw, y0, n, c, h, w, k, r, p, s, mode, None, 0, m.WLAYOUT_KRSC)
+    m.conv2d_fprop_stats(hx, m.LAYOUT_NHWC, hw, m.WLAYOUT_KRSC, y1, n, c, h, w, k, r, p, s, mode, mv)
+    a0, a1 = _host(m, y0, (n * oh * ow, k)), _host(m, y1, (n * oh * ow, k))
+    assert np.array_equal(a0, a1), "the fused epilogue changed the convolution's output"
+    got = _host(m, mv, (2, k))
+    a64 = a1.astype(np.float64)
+    assert np.abs(got[0] - a64.mean(0)).max() <= 2e-6 * max(1.0, np.abs(a64.mean(0)).max())
+    assert rel_err(got[1], a64.var(0)) < 2e-5
+
+
+@pytest.mark.parametrize("n_bn", [0, 1, 2])
+@pytest.mark.parametrize("mode_name", ["tf32", "fp32"])
+@pytest.mark.parametrize("geom", CONV_SHAPES)
+def test_conv_dgrad_fused(cuda_device, geom, mode_name, n_bn):
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = geom
+    if s == 2 and (h % 2 or w % 2):
+        pytest.skip("odd stride-2 geometry")
+    mode = m.MODE_TF32 if mode_name == "tf32" else m.MODE_FP32
+    oh, ow = (h + 2 * p - r) // s + 1, (w + 2 * p - r) // s + 1
+    rng = np.random.RandomState(2)
+    dy = rng.randn(n, oh, ow, k).astype(F32)
+    wt = (rng.randn(k, r, r, c) / np.sqrt(c * r * r)).astype(F32)
+    addend = rng.randn(n, h, w, c).astype(F32)
+    bx = [(rng.randn(n, h, w, c) * (1 + i) + i).astype(F32) for i in range(2)]
+    mean = [b.reshape(-1, c).mean(0).astype(F32) for b in bx]
+    invstd = [(1.0 / np.sqrt(b.reshape(-1, c).var(0) + 1e-5)).astype(F32) for b in bx]
+    hdy, hw, hadd = _dev(m, dy), _dev(m, wt), _dev(m, addend)
+    hbx, hmean, hinv = [_dev(m, b) for b in bx], [_dev(m, v) for v in mean], [_dev(m, v) for v in invstd]
+    dx0, dx1, sums = m.Array(n * h * w * c), m.Array(n * h * w * c), m.Array(3 * c)
+    m.conv2d_dgrad(hdy, hw, dx0, n, c, h, w, k, r, p, s, mode, m.DGRAD_EXACT, None, 0, m.WLAYOUT_KRSC)
+    m.conv2d_dgrad_fused(hdy, hw, m.WLAYOUT_KRSC, dx1, n, c, h, w, k, r, p, s, mode, m.DGRAD_EXACT, hadd, n_bn,
+                         hbx[0] if n_bn > 0 else None, hmean[0] if n_bn > 0 else None, hinv[0] if n_bn > 0 else None,
+                         hbx[1] if n_bn > 1 else None, hmean[1] if n_bn > 1 else None, hinv[1] if n_bn > 1 else None,
+                         sums if n_bn else None)
+    plain = _host(m, dx0, (n * h * w, c))
+    got = _host(m, dx1, (n * h * w, c))
+    want = plain + addend.reshape(-1, c)
+    assert np.array_equal(got, want), "dgrad + addend must equal the separate add bit for bit"
+    if n_bn:
+        sm = _host(m, sums, (3, c))
+        g64 = got.astype(np.float64)
+        scale = np.abs(g64).sum(0).max()
+        assert np.abs(sm[0] - g64.sum(0)).max() <= 2e-6 * scale
+        for i in range(n_bn):
+            xh = (bx[i].reshape(-1, c).astype(np.float64) - mean[i]) * invstd[i]
+            ref = (g64 * xh).sum(0)
+            assert np.abs(sm[1 + i] - ref).max() <= 4e-6 * np.abs(g64 * xh).sum(0).max(), i
+
+
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("dual", [False, True])
+@pytest.mark.parametrize("res", [False, True])
+@pytest.mark.parametrize("rows,c", [(4096, 32), (1000, 12), (256, 256), (77, 5)])
+def test_bn_fwd_apply_and_relu_bwd(cuda_device, rows, c, res, dual, relu):
+    m = cuda_device.mod
+    rng = np.random.RandomState(3)
+    xs = [(rng.randn(rows, c) * 2 + 1).astype(F32) for _ in range(2)]
+    gam = [(rng.rand(c) + 0.5).astype(F32) for _ in range(2)]
+    bet = [rng.randn(c).astype(F32) for _ in range(2)]
+    r = rng.randn(rows, c).astype(F32)
+    eps, mom = 1e-5, 0.1
+    y_ref = np.zeros((rows, c))
+    sides, keep = [], []
+    for i in range(2 if dual else 1):
+        hx = _dev(m, xs[i])
+        mv = m.Array(2 * c)
+        m.colstats_mean_var(hx, rows, c, mv)
+        mvh = _host(m, mv, (2, c))
+        x64 = xs[i].astype(np.float64)
+        assert np.abs(mvh[0] - x64.mean(0)).max() < 1e-5 and rel_err(mvh[1], x64.var(0)) < 2e-5
+        sm_, si_, rm, rv = m.Array(c), m.Array(c), _dev(m, np.zeros(c, F32)), _dev(m, np.ones(c, F32))
+        sides.append((hx, mv, _dev(m, gam[i]), _dev(m, bet[i]), sm_, si_, rm, rv, mom, eps))
+        keep.append((sm_, si_, rm, rv))
+        y_ref += (x64 - x64.mean(0)) / np.sqrt(x64.var(0) + eps) * gam[i] + bet[i]
+    if res:
+        y_ref += r
+    if relu:
+        y_ref = np.maximum(y_ref, 0)
+    hy, hr = m.Array(rows * c), _dev(m, r)
+    m.bn_fwd_apply(sides[0], sides[1] if dual else None, hr if res else None, hy, rows, c, relu)
+    y = _host(m, hy, (rows, c))
+    assert np.abs(y - y_ref).max() <= 2e-5 * max(1.0, np.abs(y_ref).max())
+    for i, (sm_, si_, rm, rv) in enumerate(keep):
+        x64 = xs[i].astype(np.float64)
+        assert np.abs(_host(m, sm_, (c,)) - x64.mean(0)).max() < 1e-5
+        assert rel_err(_host(m, si_, (c,)), 1 / np.sqrt(x64.var(0) + eps)) < 2e-5
+        assert np.abs(_host(m, rm, (c,)) - mom * x64.mean(0)).max() < 1e-5
+        assert rel_err(_host(m, rv, (c,)), (1 - mom) + mom * x64.var(0)) < 2e-5
+    if relu:
+        dy = rng.randn(rows, c).astype(F32)
+        hdy, hdx = _dev(m, dy), m.Array(rows * c)
+        five = [(s[0], s[4], s[5], s[2], s[3]) for s in sides]
+        m.relu_bwd_bn(five[0], five[1] if dual else None, hr if res else None, hdy, hdx, rows, c)
+        dx = _host(m, hdx, (rows, c))
+        # the mask is the one the forward kernel applied: wherever it wrote a positive value the gradient passes
+        assert np.array_equal(dx[y > 0], dy[y > 0])
+        assert np.all((dx == 0) | (dx == dy))
+        undecided = np.abs(y_ref) < 1e-4      # pre-activations at rounding distance from 0
+        assert np.array_equal(dx[(y == 0) & ~undecided], np.zeros_like(dx)[(y == 0) & ~undecided])
+
+
+@pytest.mark.parametrize("rows,c", [(4096, 32), (1000, 12), (256, 256)])
+def test_bn_bwd_halves_equal_whole(cuda_device, rows, c):
+    m = cuda_device.mod
+    rng = np.random.RandomState(4)
+    x, dy = (rng.randn(rows, c) + 2).astype(F32), rng.randn(rows, c).astype(F32)
+    g = (rng.rand(c) + 0.5).astype(F32)
+    mean, invstd = x.mean(0).astype(F32), (1 / np.sqrt(x.astype(np.float64).var(0) + 1e-5)).astype(F32)
+    hx, hdy, hg, hm, hi = _dev(m, x), _dev(m, dy), _dev(m, g), _dev(m, mean), _dev(m, invstd)
+    dx0, dg0, db0 = m.Array(rows * c), m.Array(c), m.Array(c)
+    m.bn_bwd(hx, hdy, hg, hm, hi, dx0, dg0, db0, rows, c)
+    dx1, sums = m.Array(rows * c), m.Array(2 * c)
+    m.bn_bwd_sums(hx, hdy, hm, hi, (sums, 0), (sums, c), rows, c)
+    m.bn_bwd_apply(hx, hdy, hg, hm, hi, (sums, 0), (sums, c), dx1, rows, c)
+    s = _host(m, sums, (2, c))
+    assert rel_err(s[0], _host(m, db0, (c,))) < 1e-5 and rel_err(s[1], _host(m, dg0, (c,))) < 1e-5
+    assert rel_err(_host(m, dx1, (rows, c)), _host(m, dx0, (rows, c))) < 1e-5
+
+
+@pytest.mark.parametrize("mnk", [(1024, 256, 32), (300, 10, 64), (130, 70, 96), (4096, 128, 1152), (128, 4097, 64), (64, 64, 2304)])
+@pytest.mark.parametrize("bias,acc", [(False, False), (True, False), (True, True)])
+def test_gemm_epilogue(cuda_device, mnk, bias, acc):
+    """The coalesced GEMM write-out: row / column tails, bias, accumulate, unaligned leading dimension."""
+    m = cuda_device.mod
+    M, N, K = mnk
+    rng = np.random.RandomState(5)
+    A, B = rng.randn(M, K).astype(F32), rng.randn(N, K).astype(F32)
+    C0 = rng.randn(M, N).astype(F32)
+    b = rng.randn(N).astype(F32)
+    hA, hB, hC, hb = _dev(m, A), _dev(m, B), _dev(m, C0), _dev(m, b)
+    l0 = m.tc_launch_count()
+    m.gemm(hA, hB, hC, M, N, K, 0, 1, K, K, N, 1 if acc else 0, hb if bias else None, m.MODE_TF32)
+    if M * N >= 4096:
+        assert m.tc_launch_count() > l0
+    want = A.astype(np.float64) @ B.astype(np.float64).T + (b if bias else 0) + (C0 if acc else 0)
+    got = _host(m, hC, (M, N))
+    assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max()
