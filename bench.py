@@ -533,8 +533,11 @@ def profile_dominant_kernel(dev, step_fn, hbm, tc):
     conv_geom = lambda off: (lambda a: tuple(int(v) for v in a[off:off + 8]))  # noqa: E731
     saved = {}
     specs = [("conv2d_fprop", conv_geom(4)), ("conv2d_dgrad", conv_geom(3)), ("conv2d_wgrad", conv_geom(4)),
+             ("conv2d_fprop_stats", conv_geom(5)), ("conv2d_dgrad_fused", lambda a: tuple(int(v) for v in a[4:12]) + (int(a[14] is not None), int(a[15]))),
              ("gemm", lambda a: tuple(int(v) for v in a[3:8])),
-             ("bn_fwd_train", lambda a: (int(a[10]), int(a[11]))), ("bn_bwd", lambda a: (int(a[8]), int(a[9])))]
+             ("bn_fwd_train", lambda a: (int(a[10]), int(a[11]))), ("bn_bwd", lambda a: (int(a[8]), int(a[9]))),
+             ("bn_fwd_apply", lambda a: (int(a[4]), int(a[5]), int(a[1] is not None), int(a[2] is not None), int(bool(a[6])))),
+             ("bn_bwd_apply", lambda a: (int(a[8]), int(a[9]))), ("relu_bwd_bn", lambda a: (int(a[5]), int(a[6])))]
     for name, geom in specs:
         if not dev.has(name):
             continue
@@ -568,7 +571,7 @@ def profile_dominant_kernel(dev, step_fn, hbm, tc):
     flops_step = 0.0
     for (name, geom), r in pairs.items():
         if name.startswith("conv2d"):
-            flops_step += conv_work(geom)[0] * r["count"] / steps
+            flops_step += conv_work(geom[:8])[0] * r["count"] / steps
         elif name == "gemm":
             flops_step += 2.0 * geom[0] * geom[1] * geom[2] * r["count"] / steps
 
@@ -581,14 +584,19 @@ def profile_dominant_kernel(dev, step_fn, hbm, tc):
                 c = dev.Array(v.size)
                 dev.copy(v, c, v.size)
                 out.append(c)
+            elif isinstance(v, tuple) and not (len(v) == 2 and is_array(v[0]) and isinstance(v[1], int)):
+                out.append(tuple(clone_args(v)))   # a BatchNorm record: (x, statistics, gamma, ...)
             else:
                 out.append(v)
         return out
 
+    def arg_floats(a):
+        return sum(v.size if is_array(v) else (arg_floats(v) if isinstance(v, tuple) else 0) for v in a)
+
     # pass 2: graph-replayed timing of every distinct pair over rotating (L2-cold) argument sets
     for (name, geom), r in pairs.items():
         fn, a = saved[name], r["args"]
-        per_set = 4 * sum(v.size for v in a if is_array(v))
+        per_set = 4 * arg_floats(a)
         reps = int(max(4, min(48, np.ceil((256 << 20) / max(per_set, 1)))))
         if per_set * reps > (8 << 30):   # the 224x224 layers: a few sets are already far beyond L2
             reps = max(2, int((8 << 30) // per_set))
@@ -625,8 +633,13 @@ def profile_dominant_kernel(dev, step_fn, hbm, tc):
             flops, bytes_min = 2.0 * m_ * n_ * k_, 4.0 * (m_ * k_ + k_ * n_ + m_ * n_)
             desc = "gemm M=%d N=%d K=%d ta=%d tb=%d" % geom
         else:
-            flops, bytes_min = conv_work(geom)
-            desc = "%s N=%d C=%d H=%d W=%d K=%d R=%d pad=%d stride=%d" % ((name,) + geom)
+            flops, bytes_min = conv_work(geom[:8])
+            if name == "conv2d_dgrad_fused":   # + the addend and the BatchNorm inputs it reads, all of the output's size
+                n_, c_, h_, w_ = geom[:4]
+                bytes_min += 4.0 * n_ * c_ * h_ * w_ * (geom[8] + geom[9])
+            desc = "%s N=%d C=%d H=%d W=%d K=%d R=%d pad=%d stride=%d" % ((name,) + geom[:8])
+            if len(geom) > 8:
+                desc += " addend=%d bn=%d" % geom[8:10]
         t_tc_us = flops / (tc[0] * 1e12) * 1e6
         t_hbm_us = bytes_min / (hbm[0] * 1e9) * 1e6
         bound = "tensor" if t_tc_us > t_hbm_us else "hbm"
@@ -635,11 +648,17 @@ def profile_dominant_kernel(dev, step_fn, hbm, tc):
         extra = {"flops_per_launch": flops, "bytes_per_launch": bytes_min, "tflops": flops / avg_s / 1e12,
                  "gbs": bytes_min / avg_s / 1e9, "t_hbm_us": t_hbm_us, "t_tensor_us": t_tc_us}
     else:
-        rows, c = geom
-        per_elem = 12.0 if name == "bn_fwd_train" else 20.0
+        rows, c = geom[:2]
+        # bytes per element: two-pass BatchNorm forward 12, backward 20; the one-pass halves of the fused
+        # path: apply = read each input + write (8 + 4 per extra input), backward apply / ReLU-through-BN 12 (+ 4 per extra)
+        per_elem = {"bn_fwd_train": 12.0, "bn_bwd": 20.0, "bn_bwd_apply": 12.0}.get(name)
+        if name == "bn_fwd_apply":
+            per_elem = 8.0 + 4.0 * (geom[2] + geom[3])
+        if name == "relu_bwd_bn":
+            per_elem = 12.0
         bytes_min = per_elem * rows * c
         bound, achieved, unit = "hbm", bytes_min / avg_s / 1e9, "GB/s"
-        desc = "%s rows=%d C=%d" % (name, rows, c)
+        desc = "%s rows=%d C=%d" % (name, rows, c) + ("" if len(geom) == 2 else " " + ",".join(str(v) for v in geom[2:]))
         extra = {"bytes_per_launch": bytes_min}
     peak, which = (tc if bound == "tensor" else hbm)
     traffic = None
@@ -648,7 +667,7 @@ def profile_dominant_kernel(dev, step_fn, hbm, tc):
         traffic = table.get(desc, {}).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
-    worst = sorted(((kv[1]["us"] * kv[1]["per_step"], kv[0][0], kv[0][1], kv[1]["us"]) for kv in pairs.items()), reverse=True)[:6]
+    worst = sorted(((kv[1]["us"] * kv[1]["per_step"], kv[0][0], kv[0][1], kv[1]["us"]) for kv in pairs.items()), reverse=True)[:12]
     return dict({"kernel": desc, "bound": bound, "achieved": achieved, "peak": peak, "peak_source": which, "unit": unit,
                  "frac": achieved / peak, "traffic": traffic, "avg_launch_us": r["us"], "launches_per_step": r["per_step"],
                  "argument_sets": r["sets"],

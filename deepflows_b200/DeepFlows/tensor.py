@@ -14,8 +14,9 @@ gradient arrives instead of a zero-fill per node [134]; `FusedOperator` lets one
 batch-norm, pooling, cross-entropy in nn/functional.py) return the gradients of all its inputs from a
 single fused backward kernel.
 """
-from typing import Optional, Tuple
+from typing import Any, List, Optional, Tuple, Type, Union  # noqa: F401  (re-exported: the scripts star-import this module)
 
+import numpy  # noqa: F401
 import numpy as np
 
 from .autograd import is_grad_enable, no_grad
@@ -25,6 +26,9 @@ __all__ = [
     "Graph", "Tensor", "UnaryOperator", "BinaryOperator", "FusedOperator", "add", "sub", "mul", "div", "pow",
     "matmul", "sum", "mean", "max", "exp", "log", "maximum", "sqrt", "square", "Reshape", "transpose",
     "get_slice", "empty", "zeros", "ones", "randn", "rand", "uniform",
+    # what `from DeepFlows.tensor import *` also brings into a script with the reference (it defines no __all__)
+    "np", "numpy", "is_grad_enable", "no_grad", "Device", "backend_api", "BackendTensor", "default_device",
+    "Any", "List", "Optional", "Tuple", "Type", "Union",
 ]
 
 

@@ -198,6 +198,21 @@ __device__ unsigned long long g_tc_stamp[2][16];
 #endif
 
 
+// shared-space accesses by 32-bit shared address (generic-pointer LD/ST to shared memory cost more per access)
+__device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float* lds_ptr(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return reinterpret_cast<float*>(v);
+}
+
 // ---- fused epilogue of the row-major problems (conv fprop / dgrad) ------------------------------------------------------
 // The accumulator tile leaves TMEM through shared memory (the pipeline stages are idle by then) and is written out
 // with whole rows per warp instruction - 128-bit stores, lanes along the channel dimension - instead of one row per
@@ -212,6 +227,9 @@ __device__ unsigned long long g_tc_stamp[2][16];
 // partials. Variance uses shifted sums (shift = the first value a lane sees, re-based at every merge): no cancellation
 // when |mean| >> std, no divisions in the loops.
 enum { EPI_NONE = 0, EPI_STATS = 1, EPI_BNBWD = 2 };
+// compile-time selection of the epilogue work (template parameter EPI of ConvProblem): the write-out loop is
+// instruction-bound, a run-time switch per float4 costs more than the work itself
+enum { EF_NONE = 0, EF_STATS = 1, EF_ADDEND = 2, EF_BNBWD = 4 };
 struct EpiArgs {
   const float* addend;       // same shape / layout as the output, or null
   int stat_kind;             // EPI_*
@@ -257,13 +275,15 @@ struct RowEpi {
   // What one float4 of the output needs from global memory besides the accumulator: loaded ahead of the stores of a
   // batch of rows, so that the loads of the whole batch are in flight together.
   struct Extras { float4 add, x0, x1; };
+  template <int EF>
   __device__ __forceinline__ static Extras load_extras(const EpiArgs& e, const float* out, const float* row_out, int col, int n_out) {
     Extras x;
+    if constexpr (EF == EF_NONE || EF == EF_STATS) return x;
     x.add = x.x0 = x.x1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row_out == nullptr || col + 4 > n_out) return x;
     const size_t off = (size_t)(row_out - out) + col;
-    if (e.addend) x.add = __ldg(reinterpret_cast<const float4*>(e.addend + off));
-    if (e.stat_kind == EPI_BNBWD) {
+    if constexpr ((EF & EF_ADDEND) != 0) x.add = __ldg(reinterpret_cast<const float4*>(e.addend + off));
+    if constexpr ((EF & EF_BNBWD) != 0) {
       x.x0 = __ldg(reinterpret_cast<const float4*>(e.bn_x[0] + off));
       if (e.n_sets > 1) x.x1 = __ldg(reinterpret_cast<const float4*>(e.bn_x[1] + off));
     }
@@ -271,18 +291,19 @@ struct RowEpi {
   }
   // one float4 of the output: row base pointer `row_out` (inside e's output tensor), absolute column `col`.
   // The caller adds 1 to `n` after the last column group of a row.
+  template <int EF>
   __device__ __forceinline__ void emit(const EpiArgs& e, float* row_out, int col, int g, float4 v, const Extras& x, int n_out) {
     if (col + 4 > n_out) return;
-    if (e.addend) { v.x += x.add.x; v.y += x.add.y; v.z += x.add.z; v.w += x.add.w; }
+    if constexpr ((EF & EF_ADDEND) != 0) { v.x += x.add.x; v.y += x.add.y; v.z += x.add.z; v.w += x.add.w; }
     const float vv[4] = {v.x, v.y, v.z, v.w};
-    if (e.stat_kind == EPI_STATS) {
+    if constexpr ((EF & EF_STATS) != 0) {
       if (n == 0.f) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) a[g][q] = vv[q];
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) { const float d = vv[q] - a[g][q]; b[g][q] += d; c[g][q] = fmaf(d, d, c[g][q]); }
-    } else if (e.stat_kind == EPI_BNBWD) {
+    } else if constexpr ((EF & EF_BNBWD) != 0) {
       const float4 mu0 = __ldg(reinterpret_cast<const float4*>(e.bn_mean[0] + col)), is0 = __ldg(reinterpret_cast<const float4*>(e.bn_invstd[0] + col));
       const float xh0[4] = {(x.x0.x - mu0.x) * is0.x, (x.x0.y - mu0.y) * is0.y, (x.x0.z - mu0.z) * is0.z, (x.x0.w - mu0.w) * is0.w};
 #pragma unroll
@@ -298,7 +319,8 @@ struct RowEpi {
   }
   // Merge lanes -> warps -> CTA, write this CTA's partial, and let the last CTA of the launch reduce all partials.
   // Called by the 128 epilogue threads (t = 0..127, warp ew = t / 32); `wstat` is the CTA's [4][4][BN] scratch.
-  __device__ void finish(const EpiArgs& e, float* wstat, int t, int col0, int n_out, int pidx, int n_partials, unsigned total_ctas) {
+  // `scratch`: 8 KB of shared memory nobody else touches any more (the idle pipeline stages).
+  __device__ void finish(const EpiArgs& e, float* wstat, float* scratch, int t, int col0, int n_out, int pidx, int n_partials, unsigned total_ctas) {
     if (e.stat_kind == EPI_NONE) return;
     const int lane = t & 31, ew = t >> 5;
     const bool stats = e.stat_kind == EPI_STATS;
@@ -355,74 +377,81 @@ struct RowEpi {
       dst[0] = r0; dst[n_out] = r1; dst[2 * n_out] = r2;
       if (stats && cl == 0 && col0 == 0) e.stat_cnt[pidx] = rn;
     }
-    // ---- last CTA of the launch: reduce the partials ----
-    __shared__ int s_last_cta;
-    __threadfence();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (t == 0) {
-      const unsigned arrived = atomicAdd(e.stat_ticket, 1u);
-      s_last_cta = arrived == total_ctas - 1;
-      if (s_last_cta) *e.stat_ticket = 0;
+  }
+};
+
+// The partials of one launch -> per-channel results, one CTA per float4 column group: 128 threads walk the partials
+// (four 128-bit loads per array in flight), a fixed-order shuffle / shared-memory tree adds them. A separate, tiny,
+// fully parallel kernel behind the convolution: letting the convolution's last CTA do this (ticket + __threadfence)
+// put a serial chain of L2 round trips at the end of every fused launch (+8 us per convolution, measured).
+__global__ void __launch_bounds__(128) epi_finalize_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int n_partials,
+                                                          int n_out, int stats, float* __restrict__ out) {
+  pdl_sync();
+  const int ncol4 = n_out >> 2, c4 = blockIdx.x, t = threadIdx.x;
+  const float4* part4 = reinterpret_cast<const float4*>(part);
+  float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0, sref = t0;
+  float tn = 0.f;
+  if (stats) sref = __ldcg(part4 + c4);   // partial 0 always holds rows (pixel 0 is in it)
+  for (int p0 = t; p0 < n_partials; p0 += 4 * 128) {
+    float4 pa[4], pb[4], pc[4];
+    float pn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = p0 + u * 128;
+      const bool ok = pp < n_partials;
+      const float4* src = part4 + (size_t)(ok ? pp : 0) * 3 * ncol4 + c4;
+      pa[u] = __ldcg(src);
+      pb[u] = __ldcg(src + ncol4);
+      pc[u] = __ldcg(src + 2 * ncol4);
+      pn[u] = stats ? __ldcg(cnt + (ok ? pp : 0)) : 0.f;
+      if (!ok) { pa[u] = sref; pb[u] = pc[u] = make_float4(0.f, 0.f, 0.f, 0.f); pn[u] = 0.f; }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (!s_last_cta) return;
-    __threadfence();
-    int cpp = 4;                                   // columns per pass: power of two, <= 128
-    while (cpp < n_out && cpp < 128) cpp <<= 1;
-    const int groups = 128 / cpp, cq = t % cpp, gq = t / cpp;
-    for (int cbase = 0; cbase < n_out; cbase += cpp) {
-      const int col = cbase + cq;
-      float t0 = 0.f, t1 = 0.f, t2 = 0.f, tn = 0.f, sref = 0.f;
-      if (col < n_out) {
-        if (stats) sref = __ldcg(e.stat_part + col);   // partial 0 always holds rows (pixel 0 is in it)
-        for (int p0 = gq; p0 < n_partials; p0 += 4 * groups) {
-          float pa[4], pb[4], pc[4], pn[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int pp = p0 + u * groups;
-            const bool ok = pp < n_partials;
-            const float* src = e.stat_part + (size_t)(ok ? pp : 0) * 3 * n_out + col;
-            pa[u] = ok ? __ldcg(src) : 0.f;
-            pb[u] = ok ? __ldcg(src + n_out) : 0.f;
-            pc[u] = ok ? __ldcg(src + 2 * n_out) : 0.f;
-            pn[u] = (ok && stats) ? __ldcg(e.stat_cnt + pp) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (stats) {
-              const float d = pa[u] - sref;
-              t1 += pb[u] + pn[u] * d;
-              t2 += pc[u] + 2.f * d * pb[u] + pn[u] * d * d;
-              tn += pn[u];
-            } else {
-              t0 += pa[u]; t1 += pb[u]; t2 += pc[u];
-            }
-          }
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // wstat is free again (every group is past its previous read)
-      wstat[(gq * 4 + 0) * cpp + cq] = t0;
-      wstat[(gq * 4 + 1) * cpp + cq] = t1;
-      wstat[(gq * 4 + 2) * cpp + cq] = t2;
-      wstat[(gq * 4 + 3) * cpp + cq] = tn;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (gq == 0 && col < n_out) {
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, rn = 0.f;
-        for (int g2 = 0; g2 < groups; ++g2) {   // fixed order
-          r0 += wstat[(g2 * 4 + 0) * cpp + cq]; r1 += wstat[(g2 * 4 + 1) * cpp + cq];
-          r2 += wstat[(g2 * 4 + 2) * cpp + cq]; rn += wstat[(g2 * 4 + 3) * cpp + cq];
-        }
-        if (stats) {
-          const float dm = r1 / rn;
-          e.stat_out[col] = sref + dm;                                   // mean
-          e.stat_out[n_out + col] = fmaxf(r2 / rn - dm * dm, 0.f);       // biased variance (batchnorm.py:38-42)
-        } else {
-          e.stat_out[col] = r0; e.stat_out[n_out + col] = r1; e.stat_out[2 * n_out + col] = r2;
-        }
+    for (int u = 0; u < 4; ++u) {
+      if (stats) {
+        const float n_ = pn[u];
+        float d;
+        d = pa[u].x - sref.x; t1.x += pb[u].x + n_ * d; t2.x += pc[u].x + 2.f * d * pb[u].x + n_ * d * d;
+        d = pa[u].y - sref.y; t1.y += pb[u].y + n_ * d; t2.y += pc[u].y + 2.f * d * pb[u].y + n_ * d * d;
+        d = pa[u].z - sref.z; t1.z += pb[u].z + n_ * d; t2.z += pc[u].z + 2.f * d * pb[u].z + n_ * d * d;
+        d = pa[u].w - sref.w; t1.w += pb[u].w + n_ * d; t2.w += pc[u].w + 2.f * d * pb[u].w + n_ * d * d;
+        tn += n_;
+      } else {
+        t0.x += pa[u].x; t0.y += pa[u].y; t0.z += pa[u].z; t0.w += pa[u].w;
+        t1.x += pb[u].x; t1.y += pb[u].y; t1.z += pb[u].z; t1.w += pb[u].w;
+        t2.x += pc[u].x; t2.y += pc[u].y; t2.z += pc[u].z; t2.w += pc[u].w;
       }
     }
   }
-};
+  float v[13] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, tn};
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int i = 0; i < 13; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+  __shared__ float red[4][13];
+  if ((t & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < 13; ++i) red[t >> 5][i] = v[i];
+  }
+  __syncthreads();
+  if (t == 0) {
+    float r[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) r[i] = ((red[0][i] + red[1][i]) + red[2][i]) + red[3][i];
+    float4* out4 = reinterpret_cast<float4*>(out);
+    if (stats) {
+      const float inv = 1.f / r[12];
+      const float4 dm = make_float4(r[4] * inv, r[5] * inv, r[6] * inv, r[7] * inv);
+      out4[c4] = make_float4(sref.x + dm.x, sref.y + dm.y, sref.z + dm.z, sref.w + dm.w);   // mean
+      out4[ncol4 + c4] = make_float4(fmaxf(r[8] * inv - dm.x * dm.x, 0.f), fmaxf(r[9] * inv - dm.y * dm.y, 0.f),
+                                     fmaxf(r[10] * inv - dm.z * dm.z, 0.f), fmaxf(r[11] * inv - dm.w * dm.w, 0.f));  // biased variance (batchnorm.py:38-42)
+    } else {
+      out4[c4] = make_float4(r[0], r[1], r[2], r[3]);
+      out4[ncol4 + c4] = make_float4(r[4], r[5], r[6], r[7]);
+      out4[2 * ncol4 + c4] = make_float4(r[8], r[9], r[10], r[11]);
+    }
+  }
+}
 
 // ---- kernel skeleton ----------------------------------------------------------------------------------
 // KR: reduction rows per stage (MN-major operands only: 32 or 128). BSUB: B tiles per stage (the row-halo conv
@@ -594,7 +623,8 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       tc_fence_after();
     }
     if (warp == 2) TC_STAMP(7);
-    float* stage = reinterpret_cast<float*>(smem);  // the pipeline stages are idle once the accumulator is complete
+    const uint32_t stage_u32 = smem_u32(smem);  // the pipeline stages are idle once the accumulator is complete
+    const uint32_t rowtab_u32 = smem_u32(row_tab);
     constexpr uint32_t kPitch = P::kAccTiles * BN + 4;  // == L::kRedPitch with one accumulator tile
     // row-major problems leave through shared memory (coalesced write-out); the weight-gradient tiles of an unsplit
     // launch go from registers to their partial slab as 128-byte runs per thread
@@ -617,9 +647,9 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
         }
       }
       {
-        float* dst = stage + (size_t)row * kPitch + cc;  // cc == c0 with one accumulator tile
+        const uint32_t dst = stage_u32 + (uint32_t)(row * kPitch + cc) * 4u;  // cc == c0 with one accumulator tile
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 32; i += 4) sts_f4(dst + i * 4, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
       }
     }
     tc_fence_before();
@@ -643,9 +673,9 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int r = quarter * 32 + rr + u * RPI + lr;
-            rp[u] = row_tab[r];
+            rp[u] = lds_ptr(rowtab_u32 + r * 8);
 #pragma unroll
-            for (int g = 0; g < NCG; ++g) val[u][g] = *reinterpret_cast<const float4*>(stage + (size_t)r * kPitch + (g * 32 + lc) * 4);
+            for (int g = 0; g < NCG; ++g) val[u][g] = lds_f4(stage_u32 + (uint32_t)(r * kPitch + (g * 32 + lc) * 4) * 4u);
           }
 #pragma unroll
           for (int u = 0; u < U; ++u)
@@ -660,7 +690,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
             }
           }
         }
-        P::epi_finish(prm, tile, epi, wstat, (warp - 2) * 32 + lane);
+        P::epi_finish(prm, tile, epi, wstat, reinterpret_cast<float*>(smem), (warp - 2) * 32 + lane);
       }
     }
     if (nsplit == 1) P::finish(prm, tile, (warp - 2) * 32 + lane);  // the 128 epilogue threads (wgrad: last CTA of a tile sums the splits)
@@ -688,7 +718,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
         float* row_out = nullptr;
         typename P::Extras ex{};
         if constexpr (P::kRowMajor) {
-          row_out = row_tab[r];
+          row_out = lds_ptr(smem_u32(row_tab) + r * 8);
           ex = P::load_extras(prm, tile, row_out, c);   // in flight together with the remote loads below
         }
         float4 pv[8];
@@ -714,12 +744,13 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     // landed in registers (the global stores above only consume registers), wait just before the exit
     if (warp == 2) TC_STAMP(11);
     cluster_arrive();
-    if constexpr (P::kRowMajor) {
-      if (warp >= 2) P::epi_finish(prm, tile, epi, wstat, (warp - 2) * 32 + lane);
-    }
     // two-level split (wgrad): the last cluster that finishes a tile adds the clusters' partial tiles
     if (P::kClusterFinish && warp >= 2) P::finish_cluster(prm, tile, (warp - 2) * 32 + lane, rank, nsplit);
     cluster_wait();
+    // column statistics: after the wait nobody reads this CTA's staging tile any more (the last CTA's reduction uses it as scratch)
+    if constexpr (P::kRowMajor) {
+      if (warp >= 2) P::epi_finish(prm, tile, epi, wstat, reinterpret_cast<float*>(smem), (warp - 2) * 32 + lane);
+    }
   } else {
     __syncthreads();
   }
@@ -882,7 +913,7 @@ struct GemmProblem {
       }
     }
   }
-  __device__ static void epi_finish(const Params&, const Tile&, RowEpi<BN_>&, float*, int) {}
+  __device__ static void epi_finish(const Params&, const Tile&, RowEpi<BN_>&, float*, float*, int) {}
   __device__ static Tile tile(const Params& p) {
     return {(int)blockIdx.x * BLOCK_M, (int)blockIdx.y * BN, 0, (p.K + BLOCK_K - 1) / BLOCK_K};
   }
@@ -985,7 +1016,7 @@ enum { W_PACKED = 0, W_KRSC_FPROP = 1, W_KRSC_DGRAD = 2 };
 // (r, s), r = 0..2, are MMAs whose A descriptors start r * ow_t rows into that box - whole multiples of the 1024-byte
 // swizzle atom, so the 128B swizzle stays consistent. The activations cross L2 -> SM 3.75-4.5 times per tile
 // instead of 9 times; these layers (few channels, many pixels) are bound by exactly that traffic.
-template <int BN_, int WMODE, bool ROWS = false>
+template <int BN_, int WMODE, bool ROWS = false, int EF = EF_NONE>
 struct ConvProblem {
   static constexpr int BN = BN_, A_MAJOR = MAJOR_K, B_MAJOR = (WMODE == W_KRSC_DGRAD ? MAJOR_MN : MAJOR_K);
   static constexpr bool kClusterSplit = true;
@@ -1100,14 +1131,15 @@ struct ConvProblem {
   static constexpr bool kRowMajor = true;
   using Extras = typename RowEpi<BN_>::Extras;
   __device__ static Extras load_extras(const Params& p, const Tile& t, const float* row_out, int c) {
-    return RowEpi<BN_>::load_extras(p.epi, p.out, row_out, t.col0 + c, p.n_out);
+    return RowEpi<BN_>::template load_extras<EF>(p.epi, p.out, row_out, t.col0 + c, p.n_out);
   }
   __device__ static void emit4(const Params& p, const Tile& t, RowEpi<BN_>& epi, float* row_out, int c, int g, const float4& q, const Extras& x) {
-    epi.emit(p.epi, row_out, t.col0 + c, g, q, x, p.n_out);
+    epi.template emit<EF>(p.epi, row_out, t.col0 + c, g, q, x, p.n_out);
   }
-  __device__ static void epi_finish(const Params& p, const Tile& t, RowEpi<BN_>& epi, float* wstat, int tid) {
-    epi.finish(p.epi, wstat, tid, t.col0, p.n_out, (int)(blockIdx.x * gridDim.z + blockIdx.z), (int)(gridDim.x * gridDim.z),
-               gridDim.x * gridDim.y * gridDim.z);
+  __device__ static void epi_finish(const Params& p, const Tile& t, RowEpi<BN_>& epi, float* wstat, float* scratch, int tid) {
+    if constexpr ((EF & (EF_STATS | EF_BNBWD)) != 0)
+      epi.finish(p.epi, wstat, scratch, tid, t.col0, p.n_out, (int)(blockIdx.x * gridDim.z + blockIdx.z), (int)(gridDim.x * gridDim.z),
+                 gridDim.x * gridDim.y * gridDim.z);
   }
 };
 
@@ -1160,7 +1192,7 @@ struct WgradProblem {
   struct Extras {};
   __device__ static Extras load_extras(const WgradParams&, const WgradTile&, const float*, int) { return Extras{}; }
   __device__ static void emit4(const WgradParams&, const WgradTile&, RowEpi<BN_>&, float*, int, int, const float4&, const Extras&) {}
-  __device__ static void epi_finish(const WgradParams&, const WgradTile&, RowEpi<BN_>&, float*, int) {}
+  __device__ static void epi_finish(const WgradParams&, const WgradTile&, RowEpi<BN_>&, float*, float*, int) {}
   __device__ static int red_rows(const WgradParams&, const WgradTile&) { return BLOCK_M; }
   __device__ static void finish_cluster(const WgradParams&, const WgradTile&, int, int, int) {}
   using Params = WgradParams;
@@ -1456,9 +1488,31 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
     if (st != DFB_OK) return st;
     prm.epi.stat_part = part;
     prm.epi.stat_cnt = part + partials * 3 * n_out;
-    prm.epi.stat_ticket = ticket_counter(3);
   }
-  dfb_status st = launch<ConvProblem<BN, WMODE, ROWS>>(name, ma, mb, prm, grid, prm.splits);
+  // the epilogue work is a template parameter; only the combinations the host asks for exist: fprop + statistics,
+  // dgrad + addend / BatchNorm-backward sums / both (channels-last weights; conv_like refuses the rest)
+  const bool add = prm.epi.addend != nullptr;
+  dfb_status st = DFB_OK;
+  bool launched = false;
+  if constexpr (WMODE == W_KRSC_FPROP) {
+    if (prm.epi.stat_kind == EPI_STATS) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_STATS>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+  }
+  if constexpr (WMODE == W_KRSC_DGRAD) {
+    if (prm.epi.stat_kind == EPI_BNBWD && add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+    else if (prm.epi.stat_kind == EPI_BNBWD) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+    else if (add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+  }
+  if (!launched) st = launch<ConvProblem<BN, WMODE, ROWS, EF_NONE>>(name, ma, mb, prm, grid, prm.splits);
+  if (st == DFB_OK && part) {
+    launch_k(epi_finalize_kernel, (unsigned)(n_out / 4), 128, 0, compute_stream(), (const float*)prm.epi.stat_part, (const float*)prm.epi.stat_cnt,
+             (int)(grid.x * grid.z), n_out, prm.epi.stat_kind == EPI_STATS ? 1 : 0, prm.epi.stat_out);
+    cudaError_t e = cudaGetLastError();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) {
+      dfb_free(part);
+      DFB_FAIL(DFB_ERR_RUNTIME, "epi_finalize launch failed: %s", cudaGetErrorString(e));
+    }
+  }
   if (part) dfb_free(part);  // stream-ordered
   return st;
 }
@@ -1497,6 +1551,11 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
   const int cp = (actC + 31) / 32 * 32;
   ConvParams prm;
   prm.epi = EpiArgs{};
+  if (fuse && (fuse->addend || fuse->kind != FUSE_NONE)) {
+    // fused epilogues exist for channels-last weights: statistics on fprop, addend / BatchNorm sums on dgrad
+    if (w_layout != DFB_WLAYOUT_KRSC || (dgrad && fuse->kind == FUSE_STATS) || (!dgrad && (fuse->addend || fuse->kind == FUSE_BNBWD)))
+      return DFB_OK;  // not handled: the dispatcher runs the work as separate kernels
+  }
   if (fuse) {  // the partial buffers depend on the grid: run_conv fills them in
     prm.epi.addend = fuse->addend;
     prm.epi.stat_kind = fuse->kind;
