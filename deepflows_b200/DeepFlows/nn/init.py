@@ -105,7 +105,9 @@ def _kaiming_std(tensor, a, mode, nonlinearity):
     return calculate_gain(nonlinearity, a) / math.sqrt(_calculate_correct_fan(tensor, mode))
 
 
-def kaiming_uniform_(tensor: Tensor, a: float = 0, mode: str = "fan_in", nonlinearity: str = "leaky_relu"):
+def kaiming_uniform_(tensor: Tensor, a: float = 0, mode: str = "fan_in", nonlinearity: str = "relu"):
+    # the reference's default here is "relu" (init.py:140-153), not torch's "leaky_relu": Conv2d / Linear call it with
+    # a=sqrt(5) and get gain sqrt(2) (kaiming_normal_ below does default to "leaky_relu", init.py:156-168)
     if 0 in tensor.shape:
         warnings.warn("Initializing zero-element tensors is a no-op")
         return tensor

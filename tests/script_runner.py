@@ -65,7 +65,7 @@ def _stub_modules(samples):
         def fetch_openml(name, version=1, return_X_y=True, **kw):
             rng = np.random.RandomState(7)
             x = pd.DataFrame(rng.randint(0, 256, (max(5000, samples), 784)).astype(np.float64))
-            y = pd.Series(rng.randint(0, 10, max(5000, samples)).astype(str))
+            y = pd.Series(rng.randint(0, 10, max(5000, samples)).astype(np.int64))   # (the real set has string categories)
             return x, y
         skd.fetch_openml = fetch_openml
     except ImportError:
@@ -81,7 +81,7 @@ def _idx_bytes(arr):
 def _synthetic_file(path, samples):
     """Bytes of a small seeded dataset file for the basenames the scripts open, else None."""
     base = os.path.basename(str(path).replace("\\", "/"))
-    rng = np.random.RandomState(abs(hash(base)) % (2 ** 31) if False else sum(base.encode()))
+    rng = np.random.RandomState(sum(base.encode()))
     if base in ("train-images-idx3-ubyte", "t10k-images-idx3-ubyte"):
         return _idx_bytes(rng.randint(0, 256, (samples, 28, 28)))
     if base in ("train-labels-idx1-ubyte", "t10k-labels-idx1-ubyte"):
