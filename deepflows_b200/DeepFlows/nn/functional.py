@@ -372,22 +372,93 @@ class _pool2d(FusedOperator):
         self._x = self._y = None
 
 
-def _check_pool(name, kernel_size, stride, padding):
-    stride = kernel_size if not stride else stride
-    if stride != kernel_size or padding != 0:
-        raise NotImplementedError(
-            "%s: only non-overlapping windows without padding are implemented (kernel_size == stride, padding == 0);"
-            " got kernel_size=%s stride=%s padding=%s" % (name, kernel_size, stride, padding))
+class _pad_spatial(UnaryOperator):
+    """Zero padding of the trailing spatial axes (reference: __pad1d / __pad2d, functional.py:153-164,297-313)."""
+
+    def __init__(self, x: Tensor, p: int):
+        self.p = int(p)
+        super().__init__(x)
+
+    def forward(self, x: Tensor):
+        if self.p == 0:
+            return x.data
+        return x.data.compact().pad([(0, 0), (0, 0)] + [(self.p, self.p)] * (x.ndim - 2))
+
+    def grad_fn(self, x: Tensor, grad):
+        if self.p == 0:
+            return grad
+        p = self.p
+        return grad[(slice(None), slice(None)) + (slice(p, -p),) * (x.ndim - 2)].compact()
+
+
+class _im2col(UnaryOperator):
+    """Sliding windows as an explicit tensor, built from k (1-d) or k*k (2-d) strided slice copies like the reference's
+    __im2col1d / __im2col2d (functional.py:118-145,249-294): (N,C,L) -> (N,C,k,Lo), (N,C,H,W) -> (N,C,k,k,OH,OW).
+    Only the shapes the fused kernels do not take come through here (pooling with stride != kernel or padding, 1-d ops).
+    Backward scatters the windows back: summed where windows overlap (`exact`), or - 2-d, dgrad mode `reference` - the
+    reference's last-writer-wins assignment."""
+
+    def __init__(self, x: Tensor, kernel_size: int, stride: int):
+        self.k, self.s = int(kernel_size), int(stride)
+        super().__init__(x)
+
+    def _windows(self, shape):
+        k, s = self.k, self.s
+        if len(shape) == 3:
+            lo = (shape[2] - k) // s + 1
+            return [((i,), (slice(i, i + lo * s, s),)) for i in range(k)], (lo,)
+        oh, ow = (shape[2] - k) // s + 1, (shape[3] - k) // s + 1
+        return [((i, j), (slice(i, i + oh * s, s), slice(j, j + ow * s, s))) for i in range(k) for j in range(k)], (oh, ow)
+
+    def forward(self, x: Tensor):
+        xd = x.data.compact()
+        n, c = xd.shape[:2]
+        wins, out_sp = self._windows(xd.shape)
+        col = backend_api.zeros((n, c) + (self.k,) * len(out_sp) + out_sp, device=xd.device)
+        both, tail = (slice(None), slice(None)), (slice(None),) * len(out_sp)
+        for pos, sl in wins:
+            col[both + pos + tail] = xd[both + sl]
+        return col
+
+    def grad_fn(self, x: Tensor, grad):
+        g = grad.compact()
+        n, c = x.shape[:2]
+        wins, out_sp = self._windows(x.shape)
+        gx = backend_api.zeros(x.shape, device=x.device)
+        both, tail = (slice(None), slice(None)), (slice(None),) * len(out_sp)
+        overwrite = len(out_sp) == 2 and get_dgrad_mode() == "reference"
+        for pos, sl in wins:
+            piece = g[both + pos + tail].compact().reshape((n, c) + out_sp)
+            if not overwrite:
+                piece = gx[both + sl].compact() + piece
+            gx[both + sl] = piece
+        return gx
+
+
+def _pool2d_general(x: Tensor, kernel_size: int, stride: int, padding: int, is_max: bool):
+    """Pooling for any stride / zero padding, composed like the reference composes it [347-374]: pad with ZEROS (not
+    -inf), windows, row maximum with the equality-mask gradient (every tied maximum receives it) / row average."""
+    n, c = x.shape[:2]
+    col = _im2col(_pad_spatial(x, padding), kernel_size, stride)
+    oh, ow = col.shape[-2:]
+    rows = col.transpose(0, 4, 5, 1, 2, 3).reshape(-1, kernel_size * kernel_size)
+    # (keepdims: the reference's non-keepdims sum back-propagates by left-aligned broadcasting, SURVEY Q12)
+    out = tensor.max(rows, 1, True) if is_max else tensor.sum(rows, 1, True) * (1.0 / (kernel_size * kernel_size))
+    return out.reshape(n, oh, ow, c).transpose(0, 3, 1, 2)
 
 
 def max_pool2d(x: Tensor, kernel_size: int, stride: int, padding=0):
-    _check_pool("max_pool2d", kernel_size, stride, padding)
-    return _pool2d(x, kernel_size, True)
+    stride = kernel_size if not stride else stride
+    if stride == kernel_size and padding == 0:
+        return _pool2d(x, kernel_size, True)      # the fused kernels: every configuration of the scripts
+    return _pool2d_general(x, kernel_size, stride, padding, True)
 
 
 def avg_pool2d(x: Tensor, kernel_size: int, stride: int, padding=0):
-    _check_pool("avg_pool2d", kernel_size, stride, padding)
-    return _pool2d(x, kernel_size, False)
+    stride = kernel_size if not stride else stride
+    if stride == kernel_size and padding == 0:
+        return _pool2d(x, kernel_size, False)
+    return _pool2d_general(x, kernel_size, stride, padding, False)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -489,14 +560,29 @@ def batch_norm(x: Tensor, weight, bias, running_mean, running_var, training: boo
 # 1-d ops (composed from tensor ops; not on the accelerated path)
 # ------------------------------------------------------------------------------------------------
 def conv1d(input: Tensor, kernel: Tensor, padding: int = 0, stride: int = 1):
-    """Not implemented: the reference's own conv1d calls a non-existent `.swapaxes` [166-191], so no
-    script can depend on it; 1-d ops are listed as a later widening step."""
-    raise NotImplementedError("conv1d is outside the accelerated path (SURVEY 8f rank 4)")
+    """1-d convolution, input (N,C,L), kernel (K,C,k) -> (N,K,Lo). The reference's version cannot run (it indexes the
+    window tensor with too few axes and calls a non-existent `.swapaxes`, functional.py:118-191); this is the operation
+    it documents, composed the way it intended: pad, windows, one matmul."""
+    k_out, c, k = kernel.shape
+    n = input.shape[0]
+    col = _im2col(_pad_spatial(input, padding), k, stride)             # (N, C, k, Lo)
+    lo = col.shape[-1]
+    rows = col.transpose(0, 3, 1, 2).reshape(n * lo, c * k)            # (N*Lo, C*k)
+    out = rows @ kernel.reshape(k_out, c * k).transpose(1, 0)          # (N*Lo, K)
+    return out.reshape(n, lo, k_out).transpose(0, 2, 1)
 
 
 def max_pool1d(x: Tensor, kernel_size: int, stride: int, padding: int = 0):
-    raise NotImplementedError("max_pool1d is outside the accelerated path (SURVEY 8f rank 4)")
+    """(N,C,L) -> (N,C,Lo): zero padding, window maximum, equality-mask gradient [193-218]."""
+    n, c = x.shape[:2]
+    col = _im2col(_pad_spatial(x, padding), kernel_size, stride)       # (N, C, k, Lo)
+    lo = col.shape[-1]
+    return tensor.max(col.transpose(0, 1, 3, 2).reshape(n * c * lo, kernel_size), 1, True).reshape(n, c, lo)
 
 
 def avg_pool1d(x: Tensor, kernel_size: int, stride: int, padding: int = 0):
-    raise NotImplementedError("avg_pool1d is outside the accelerated path (SURVEY 8f rank 4)")
+    """(N,C,L) -> (N,C,Lo): zero padding, window average (padding zeros count, like the 2-d version) [221-246]."""
+    n, c = x.shape[:2]
+    col = _im2col(_pad_spatial(x, padding), kernel_size, stride)
+    lo = col.shape[-1]
+    return (tensor.sum(col.transpose(0, 1, 3, 2).reshape(n * c * lo, kernel_size), 1, True) * (1.0 / kernel_size)).reshape(n, c, lo)

@@ -147,6 +147,14 @@ def test_checkpoint_roundtrip_on_cuda(cuda_device, tmp_path):
         assert np.array_equal(v, saved[k])
 
 
+def test_checkpoint_resume_equals_uninterrupted_on_cuda(cuda_device, tmp_path):
+    """Adam's v / s / t and BatchNorm's running statistics after REAL steps round-trip through the reference's format."""
+    import ckpt_checks
+    from DeepFlows import backend_api
+    backend_api.set_precision("fp32")
+    ckpt_checks.resume_equals_uninterrupted("cuda", tmp_path)
+
+
 def test_transfer_learning_matches_reference_on_cuda(cuda_device):
     """SURVEY 8f rank 3 on the device: `load_weights` of a partial dict, frozen stem / first stage (their conv
     weights still get the channels-last layout on first use, no wgrad is launched for them), Adam over the trainable
