@@ -55,6 +55,9 @@ class _relu(UnaryOperator):
 
     def grad_fn(self, x: Tensor, grad):
         if self._expr is not None:
+            aux = getattr(grad, "_aux", None)
+            if aux is not None and aux[0] == "bn_sums" and len(aux) > 3 and aux[3] == id(self._expr):
+                return grad   # the convolution that produced this gradient applied the mask in its epilogue
             # the pre-activation was never stored: the backward kernel recomputes it exactly as the forward pass did
             e = self._expr
             n, c, h, w = e.shape
@@ -229,7 +232,22 @@ class _conv2d(FusedOperator):
         self._geom = (n, c, h, w, k, r, p, s)
         self._x, self._layout, self._w, self._mode = xd, layout, wd, mode
         self._wl = (w_layout,) if w_layout else ()  # trailing argument only when it is not the default
+        self._col = None
         y = dev.Array(n * oh * ow * k)
+        if (c <= 4 and c * r * r <= 32 and k % 4 == 0 and mode == 1 and n * oh * ow >= 16384 and self._want_stats and get_fusion()
+                and w_layout == WLAYOUT_KRSC and dev.has("stem_cols") and tensor.is_grad_enable()):
+            # First layer (image input) at training batch sizes in TF32 mode: the receptive fields are written once as a
+            # [pixels x 32] column matrix; the convolution is its 1x1 convolution with the padded weights on the tensor
+            # pipe (statistics for the BatchNorm included), and the matrix is kept for the weight gradient.
+            cols = c * r * r
+            col, wp, mean_var = dev.Array(n * oh * ow * 32), dev.Array(k * 32), dev.Array(2 * k)
+            dev.stem_cols(xd._handle, layout, col, n, c, h, w, r, p, s, w_layout)
+            dev.stem_pad_weights(wd._handle, wp, k, cols)
+            dev.conv2d_fprop_stats(col, LAYOUT_NHWC, wp, WLAYOUT_KRSC, y, n, 32, oh, ow, k, 1, 0, 1, mode, mean_var)
+            self._col = (col, oh, ow, cols)
+            out = _nhwc_view(y, n, k, oh, ow, dev)
+            out._aux = ("colstats", mean_var)
+            return out
         if self._want_stats and get_fusion() and dev.has("conv2d_fprop_stats") and tensor.is_grad_enable():
             # the BatchNorm that follows gets the per-channel mean / variance of y from this kernel's epilogue
             mean_var = dev.Array(2 * k)
@@ -261,8 +279,13 @@ class _conv2d(FusedOperator):
             if both:
                 dev.side_begin()
             try:
-                dev.conv2d_wgrad(self._x._handle, self._layout, gy._handle, dw._handle, n, c, h, w, k, r, p, s,
-                                 self._mode, ws, ws_n, *self._wl)
+                if self._col is not None:   # first layer: the column matrix of the forward pass is still there
+                    col, oh, ow, cols = self._col
+                    dev.conv2d_wgrad_cols(col, gy._handle, dw._handle, self._wl[0] if self._wl else WLAYOUT_KCRS, n, oh, ow, k, cols,
+                                          self._mode)
+                else:
+                    dev.conv2d_wgrad(self._x._handle, self._layout, gy._handle, dw._handle, n, c, h, w, k, r, p, s,
+                                     self._mode, ws, ws_n, *self._wl)
             finally:
                 if both:
                     dev.side_end()
@@ -271,15 +294,16 @@ class _conv2d(FusedOperator):
             dmode = 0 if get_dgrad_mode() == "reference" else 1
             fuse = self._dgrad_fusion(dev, n, c, h, w) if (dmode == 1 and get_fusion() and dev.has("conv2d_dgrad_fused")) else None
             if fuse is not None:
-                addend, recs, sums = fuse
-                b0 = recs[0].bwd_tuple() if len(recs) > 0 else (None,) * 5
-                b1 = recs[1].bwd_tuple() if len(recs) > 1 else (None,) * 5
+                addend, recs, sums, relu_expr = fuse
+                res = relu_expr.residual if relu_expr is not None else None
                 dev.conv2d_dgrad_fused(gy._handle, self._w._handle, self._wl[0] if self._wl else WLAYOUT_KCRS, buf, n, c, h, w, k, r, p,
-                                       s, self._mode, dmode, addend._handle if addend is not None else None, len(recs),
-                                       b0[0], b0[1], b0[2], b1[0], b1[1], b1[2], sums)
+                                       s, self._mode, dmode, addend._handle if addend is not None else None,
+                                       recs[0].bwd_tuple() if len(recs) > 0 else None, recs[1].bwd_tuple() if len(recs) > 1 else None,
+                                       sums, relu_expr is not None, res._handle if res is not None else None)
                 dx = _nhwc_view(buf, n, c, h, w, dev)
                 if recs:
-                    dx._aux = ("bn_sums", sums, {id(rec): 1 + i for i, rec in enumerate(recs)})
+                    # (the 4th entry tells the ReLU node between this convolution and the BatchNorm(s) that its mask is applied)
+                    dx._aux = ("bn_sums", sums, {id(rec): 1 + i for i, rec in enumerate(recs)}, id(relu_expr) if relu_expr is not None else None)
                 if addend is not None:
                     dx = tensor.ReplacesGrad(dx)   # already holds (existing gradient of x) + dgrad
             else:
@@ -305,23 +329,34 @@ class _conv2d(FusedOperator):
                 addend = g
             else:
                 return None
-        recs = []
+        recs, relu_expr = [], None
         if x._ngrads + 1 == len(x.children):   # nothing else will arrive after this
+            node = x
+            if isinstance(node, _relu) and node._expr is not None and len(node.parents) == 1 and dev.has("relu_bwd_bn"):
+                # x = relu(expression of BatchNorms): the epilogue applies the ReLU's backward too, if the node under the
+                # ReLU feeds nothing else (its gradient is then exactly the masked one)
+                below = node.parents[0]
+                if isinstance(below, Tensor) and len(below.children) == 1 and below._ngrads == 0:
+                    relu_expr, node = node._expr, below
             cand = []
-            if isinstance(x, _batch_norm_train):
-                cand = [x]
-            elif isinstance(x, tensor.add) and all(isinstance(q, Tensor) for q in x.parents):
-                cand = [q for q in x.parents if isinstance(q, _batch_norm_train) and len(q.children) == 1 and q._ngrads == 0]
-            for node in cand:
-                rec = getattr(node, "_rec", None)
+            if isinstance(node, _batch_norm_train):
+                cand = [node]
+            elif isinstance(node, tensor.add) and all(isinstance(q, Tensor) for q in node.parents):
+                cand = [q for q in node.parents if isinstance(q, _batch_norm_train) and len(q.children) == 1 and q._ngrads == 0]
+            for bn in cand:
+                rec = getattr(bn, "_rec", None)
                 if rec is not None and rec.applied and rec.x.shape == (n, c, h, w):
                     recs.append(rec)
+            if relu_expr is not None:
+                # the mask needs every term of the pre-activation: all BatchNorms of the expression must be the ones found
+                if [id(r_) for r_ in relu_expr.sides] != [id(r_) for r_ in recs]:
+                    recs, relu_expr = [], None
         if addend is None and not recs:
             return None
-        return addend, recs[:2], (dev.Array(3 * c) if recs else None)
+        return addend, recs[:2], (dev.Array(3 * c) if recs else None), relu_expr
 
     def release(self):
-        self._x = self._w = None
+        self._x = self._w = self._col = None
 
 
 def conv2d(x: Tensor, kernel: Tensor, padding: int = 0, stride: int = 1, want_stats: bool = False):

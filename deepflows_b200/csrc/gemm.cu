@@ -153,12 +153,14 @@ dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, 
 dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
                                   int R, int pad, int stride, int mode, int dgrad_mode, const float* addend, int n_bn,
                                   const float* bn_x0, const float* bn_mean0, const float* bn_invstd0, const float* bn_x1,
-                                  const float* bn_mean1, const float* bn_invstd1, float* sums) {
+                                  const float* bn_mean1, const float* bn_invstd1, float* sums, int relu, const float* gamma0,
+                                  const float* beta0, const float* gamma1, const float* beta1, const float* relu_res) {
   DFB_INIT();
   DFB_REQUIRE(dy && w && dx, DFB_ERR_INVALID, "conv2d_dgrad_fused: null pointer");
   DFB_REQUIRE(n_bn >= 0 && n_bn <= 2, DFB_ERR_INVALID, "conv2d_dgrad_fused: n_bn must be 0, 1 or 2");
   DFB_REQUIRE(n_bn == 0 || (sums && bn_x0 && bn_mean0 && bn_invstd0), DFB_ERR_INVALID, "conv2d_dgrad_fused: BatchNorm 0 incomplete");
   DFB_REQUIRE(n_bn < 2 || (bn_x1 && bn_mean1 && bn_invstd1), DFB_ERR_INVALID, "conv2d_dgrad_fused: BatchNorm 1 incomplete");
+  DFB_REQUIRE(!relu || n_bn >= 1, DFB_ERR_INVALID, "conv2d_dgrad_fused: the ReLU mask needs the BatchNorm(s) behind it");
   DFB_REQUIRE(dgrad_mode == DFB_DGRAD_REFERENCE || dgrad_mode == DFB_DGRAD_EXACT, DFB_ERR_INVALID,
               "conv2d_dgrad_fused: bad dgrad_mode %d", dgrad_mode);
   dfb_status st = check_mode("conv2d_dgrad_fused", mode);
@@ -171,6 +173,9 @@ dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout,
     f.stats_out = sums;
     f.bn_x[0] = bn_x0; f.bn_mean[0] = bn_mean0; f.bn_invstd[0] = bn_invstd0;
     f.bn_x[1] = bn_x1; f.bn_mean[1] = bn_mean1; f.bn_invstd[1] = bn_invstd1;
+    f.relu = relu;
+    f.bn_gamma[0] = gamma0; f.bn_beta[0] = beta0; f.bn_gamma[1] = gamma1; f.bn_beta[1] = beta1;
+    f.relu_res = relu_res;
     bool handled = false;
     st = tc_conv_dgrad(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, mode, nullptr, 0, &handled, &f);
     if (st != DFB_OK || handled) return st;
@@ -180,6 +185,11 @@ dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout,
   const size_t n = (size_t)N * C * H * W;
   if (addend) {
     st = dfb_ewise_add(dx, addend, dx, n);
+    if (st != DFB_OK) return st;
+  }
+  if (relu) {
+    st = dfb_relu_bwd_bn(bn_x0, bn_mean0, bn_invstd0, gamma0, beta0, n_bn > 1 ? bn_x1 : nullptr, bn_mean1, bn_invstd1, gamma1, beta1,
+                         relu_res, dx, dx, (size_t)N * H * W, C);
     if (st != DFB_OK) return st;
   }
   if (n_bn >= 1) {
@@ -195,6 +205,45 @@ dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout,
     if (st != DFB_OK) return st;
   }
   return DFB_OK;
+}
+
+// ---- first layer (image input) through its column matrix ---------------------------------------------------------------
+dfb_status dfb_stem_cols(const float* x, int x_layout, float* col, int N, int C, int H, int W, int R, int pad, int stride,
+                         int w_layout) {
+  DFB_INIT();
+  DFB_REQUIRE(x && col, DFB_ERR_INVALID, "stem_cols: null pointer");
+  DFB_REQUIRE(C >= 1 && R >= 1 && C * R * R <= 32 && stride >= 1 && H + 2 * pad >= R && W + 2 * pad >= R, DFB_ERR_INVALID,
+              "stem_cols: needs C*R*R <= 32 (got C=%d R=%d)", C, R);
+  DFB_REQUIRE((reinterpret_cast<uintptr_t>(col) & 15) == 0, DFB_ERR_INVALID, "stem_cols: col must be 16-byte aligned");
+  return tc_stem_cols(x, x_layout, col, N, C, H, W, R, pad, stride, w_layout);
+}
+dfb_status dfb_stem_pad_weights(const float* w, float* wp, int K, int cols) {
+  DFB_INIT();
+  DFB_REQUIRE(w && wp && K > 0 && cols > 0 && cols <= 32, DFB_ERR_INVALID, "stem_pad_weights: bad arguments");
+  return tc_stem_pad_weights(w, wp, K, cols);
+}
+dfb_status dfb_conv2d_wgrad_cols(const float* col, const float* dy, float* dw, int w_layout, int N, int OH, int OW, int K, int cols,
+                                 int mode) {
+  DFB_INIT();
+  DFB_REQUIRE(col && dy && dw, DFB_ERR_INVALID, "conv2d_wgrad_cols: null pointer");
+  DFB_REQUIRE(cols > 0 && cols <= 32, DFB_ERR_INVALID, "conv2d_wgrad_cols: cols must be in 1..32");
+  bool handled = false;
+  dfb_status st = DFB_OK;
+  if (want_tc(mode)) {
+    st = tc_wgrad_cols(col, dy, dw, w_layout, N, OH, OW, K, cols, mode, &handled);
+    if (st != DFB_OK || handled) return st;
+  }
+  // exact path: dW[k][j] = sum_pix dy[pix][k] * col[pix][j], a GEMM with both operands read transposed
+  float* full = nullptr;
+  st = dfb_malloc((size_t)K * 32, &full);
+  if (st != DFB_OK) return st;
+  st = simt_gemm(dy, col, full, K, 32, N * OH * OW, 1, 0, K, 32, 32, 0, nullptr);
+  if (st == DFB_OK) {  // keep the first `cols` of every 32-wide row
+    const int32_t shape[2] = {K, cols}, strides[2] = {32, 1};
+    st = dfb_compact(full, dw, (size_t)K * cols, 2, shape, strides, 0);
+  }
+  dfb_free(full);
+  return st;
 }
 
 }  // extern "C"

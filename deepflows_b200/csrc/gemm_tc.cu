@@ -229,7 +229,10 @@ __device__ __forceinline__ float* lds_ptr(uint32_t addr) {
 enum { EPI_NONE = 0, EPI_STATS = 1, EPI_BNBWD = 2 };
 // compile-time selection of the epilogue work (template parameter EPI of ConvProblem): the write-out loop is
 // instruction-bound, a run-time switch per float4 costs more than the work itself
-enum { EF_NONE = 0, EF_STATS = 1, EF_ADDEND = 2, EF_BNBWD = 4 };
+// EF_RELU (with EF_BNBWD): the gradient being written belongs to relu(bn_0(x_0) [+ bn_1(x_1)] [+ residual]); the ReLU's
+// backward is applied first (the pre-activation is recomputed exactly as dfb_bn_fwd_apply computed it), the sums are
+// taken of the masked gradient
+enum { EF_NONE = 0, EF_STATS = 1, EF_ADDEND = 2, EF_BNBWD = 4, EF_RELU = 8 };
 struct EpiArgs {
   const float* addend;       // same shape / layout as the output, or null
   int stat_kind;             // EPI_*
@@ -241,6 +244,10 @@ struct EpiArgs {
   const float* bn_x[2];      // EPI_BNBWD: inputs of the BatchNorms (shape of the output)
   const float* bn_mean[2];
   const float* bn_invstd[2];
+  const float* bn_gamma[2];  // EF_RELU: affine parameters (null: 1 / 0) and the residual term of the pre-activation
+  const float* bn_beta[2];
+  const float* relu_res;
+  int relu;
 };
 // (shift, sum of (v - shift), sum of (v - shift)^2, count) of one column over some rows
 struct Moments {
@@ -274,7 +281,7 @@ struct RowEpi {
   }
   // What one float4 of the output needs from global memory besides the accumulator: loaded ahead of the stores of a
   // batch of rows, so that the loads of the whole batch are in flight together.
-  struct Extras { float4 add, x0, x1; };
+  struct Extras { float4 add, x0, x1, res; };
   template <int EF>
   __device__ __forceinline__ static Extras load_extras(const EpiArgs& e, const float* out, const float* row_out, int col, int n_out) {
     Extras x;
@@ -287,6 +294,10 @@ struct RowEpi {
       x.x0 = __ldg(reinterpret_cast<const float4*>(e.bn_x[0] + off));
       if (e.n_sets > 1) x.x1 = __ldg(reinterpret_cast<const float4*>(e.bn_x[1] + off));
     }
+    if constexpr ((EF & EF_RELU) != 0) {
+      x.res = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.relu_res) x.res = __ldg(reinterpret_cast<const float4*>(e.relu_res + off));
+    }
     return x;
   }
   // one float4 of the output: row base pointer `row_out` (inside e's output tensor), absolute column `col`.
@@ -295,6 +306,24 @@ struct RowEpi {
   __device__ __forceinline__ void emit(const EpiArgs& e, float* row_out, int col, int g, float4 v, const Extras& x, int n_out) {
     if (col + 4 > n_out) return;
     if constexpr ((EF & EF_ADDEND) != 0) { v.x += x.add.x; v.y += x.add.y; v.z += x.add.z; v.w += x.add.w; }
+    if constexpr ((EF & EF_RELU) != 0) {
+      // z = fmaf(x - mean, invstd * gamma, beta) [+ the same of the second BatchNorm] [+ residual]: dfb_bn_fwd_apply's
+      // operations in its order, so the mask is the one the forward pass applied; the gradient passes where z >= 0
+      const float xa[4] = {x.x0.x, x.x0.y, x.x0.z, x.x0.w}, xb[4] = {x.x1.x, x.x1.y, x.x1.z, x.x1.w}, rr[4] = {x.res.x, x.res.y, x.res.z, x.res.w};
+      float d[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cq = col + q;
+        float z = fmaf(xa[q] - __ldg(e.bn_mean[0] + cq), __ldg(e.bn_invstd[0] + cq) * (e.bn_gamma[0] ? __ldg(e.bn_gamma[0] + cq) : 1.0f),
+                       e.bn_beta[0] ? __ldg(e.bn_beta[0] + cq) : 0.0f);
+        if (e.n_sets > 1)
+          z = z + fmaf(xb[q] - __ldg(e.bn_mean[1] + cq), __ldg(e.bn_invstd[1] + cq) * (e.bn_gamma[1] ? __ldg(e.bn_gamma[1] + cq) : 1.0f),
+                       e.bn_beta[1] ? __ldg(e.bn_beta[1] + cq) : 0.0f);
+        if (e.relu_res) z = z + rr[q];
+        d[q] = z >= 0.f ? d[q] : 0.f;
+      }
+      v = make_float4(d[0], d[1], d[2], d[3]);
+    }
     const float vv[4] = {v.x, v.y, v.z, v.w};
     if constexpr ((EF & EF_STATS) != 0) {
       if (n == 0.f) {
@@ -1498,7 +1527,9 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
     if (prm.epi.stat_kind == EPI_STATS) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_STATS>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
   }
   if constexpr (WMODE == W_KRSC_DGRAD) {
-    if (prm.epi.stat_kind == EPI_BNBWD && add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+    if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu && add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_RELU | EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+    else if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_RELU>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+    else if (prm.epi.stat_kind == EPI_BNBWD && add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
     else if (prm.epi.stat_kind == EPI_BNBWD) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
     else if (add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
   }
@@ -1561,7 +1592,12 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
     prm.epi.stat_kind = fuse->kind;
     prm.epi.n_sets = fuse->n_sets;
     prm.epi.stat_out = fuse->stats_out;
-    for (int i = 0; i < 2; ++i) { prm.epi.bn_x[i] = fuse->bn_x[i]; prm.epi.bn_mean[i] = fuse->bn_mean[i]; prm.epi.bn_invstd[i] = fuse->bn_invstd[i]; }
+    for (int i = 0; i < 2; ++i) {
+      prm.epi.bn_x[i] = fuse->bn_x[i]; prm.epi.bn_mean[i] = fuse->bn_mean[i]; prm.epi.bn_invstd[i] = fuse->bn_invstd[i];
+      prm.epi.bn_gamma[i] = fuse->bn_gamma[i]; prm.epi.bn_beta[i] = fuse->bn_beta[i];
+    }
+    prm.epi.relu = fuse->relu;
+    prm.epi.relu_res = fuse->relu_res;
   }
   prm.out = out; prm.n_img = N; prm.OH = OH; prm.OW = OW; prm.n_out = n_out; prm.R = R; prm.cblks = cp / 32;
   prm.dh0 = dh0; prm.dw0 = dh0; prm.sgn = sgn; prm.stride = stride; prm.c_red = actC; prm.par_pad = par_pad;
@@ -1815,27 +1851,48 @@ __global__ void __launch_bounds__(256) stem_cols_kernel(const float* __restrict_
                                                         int H, int W, int R, int pad, int stride, int OH, int OW, int krsc) {
   pdl_sync();
   const int taps = R * R, cols = C * taps;
-  const size_t total = (size_t)N * OH * OW * 8;  // a float4 (four columns) per thread
-  const size_t step = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const int q = (int)(i & 7);
-    size_t t = i >> 3;
-    const int ow = (int)(t % OW);
-    t /= OW;
+  // eight threads per pixel, a float4 (four columns) each. Which four columns is fixed per thread (the grid step is a
+  // multiple of 8): their (channel, row offset, column offset) are decoded once, outside the pixel loop.
+  const int q = (int)(threadIdx.x & 7);
+  int dh[4], dw[4];
+  size_t coff[4];
+  bool live[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = q * 4 + u;
+    live[u] = j < cols;
+    const int tap = live[u] ? (krsc ? j / C : j % taps) : 0, c = live[u] ? (krsc ? j % C : j / taps) : 0;
+    dh[u] = tap / R - pad;
+    dw[u] = tap % R - pad;
+    coff[u] = nchw ? (size_t)c * H * W : (size_t)c;
+  }
+  const size_t pixels = (size_t)N * OH * OW;
+  const size_t step = ((size_t)gridDim.x * blockDim.x) >> 3;
+  const int pix_stride = nchw ? 1 : C;
+  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < pixels; pix += step) {
+    const int ow = (int)(pix % OW);
+    const size_t t = pix / OW;
     const int oh = (int)(t % OH), n = (int)(t / OH);
+    const float* xn = x + (size_t)n * C * H * W;
+    const int ih0 = oh * stride, iw0 = ow * stride;
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int j = q * 4 + u;
+      const int ih = ih0 + dh[u], iw = iw0 + dw[u];
       v[u] = 0.f;
-      if (j < cols) {
-        const int tap = krsc ? j / C : j % taps, c = krsc ? j % C : j / taps;
-        const int ih = oh * stride + tap / R - pad, iw = ow * stride + tap % R - pad;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-          v[u] = __ldg(x + (nchw ? (((size_t)n * C + c) * H + ih) * W + iw : (((size_t)n * H + ih) * W + iw) * C + c));
-      }
+      if (live[u] && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+        v[u] = __ldg(xn + coff[u] + ((size_t)ih * W + iw) * pix_stride);
     }
-    reinterpret_cast<float4*>(col)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(col)[pix * 8 + q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+// Wp[k][32] = the first-layer weights in the column order of stem_cols_kernel (dW's own memory order), zero padded
+__global__ void __launch_bounds__(256) stem_pad_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int K, int cols) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * 32) {
+    const int k = i >> 5, j = i & 31;
+    wp[i] = j < cols ? __ldg(w + (size_t)k * cols + j) : 0.f;
   }
 }
 // on by default (DFB_STEM_TC=0: the gather kernel in every mode). ResNet stem at batch 256: 74 us -> the column pass plus
@@ -1875,6 +1932,29 @@ dfb_status tc_stem_wgrad(const float* x, int x_layout, const float* dy, float* d
 }
 
 size_t tc_conv_workspace_floats(int, int, int, int, int, int, int, int) { return 0; }
+
+// ---- first layer through its column matrix, for callers that keep the matrix between forward and backward --------------
+// (DeepFlows/nn/functional.py:_conv2d): col = receptive fields [pixels x 32]; the forward convolution is then a 1x1
+// convolution of `col` with the padded weights (dfb_conv2d_fprop_stats on the tensor pipe, statistics included), and the
+// weight gradient the 1x1 wgrad of `col` - the 33 us gather kernel of the forward pass and the second column pass of the
+// backward pass disappear.
+dfb_status tc_stem_cols(const float* x, int x_layout, float* col, int N, int C, int H, int W, int R, int pad, int stride, int w_layout) {
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
+  const size_t pixels = (size_t)N * OH * OW;
+  launch_k(stem_cols_kernel, bw_grid(pixels * 8, 256), 256, 0, compute_stream(), x, x_layout == DFB_LAYOUT_NCHW ? 1 : 0, col, N, C, H, W, R,
+           pad, stride, OH, OW, w_layout == DFB_WLAYOUT_KRSC ? 1 : 0);
+  DFB_LAUNCH_CHECK("stem_cols");
+  return DFB_OK;
+}
+dfb_status tc_stem_pad_weights(const float* w, float* wp, int K, int cols) {
+  launch_k(stem_pad_weights_kernel, cdiv((size_t)K * 32, 256), 256, 0, compute_stream(), w, wp, K, cols);
+  DFB_LAUNCH_CHECK("stem_pad_weights");
+  return DFB_OK;
+}
+dfb_status tc_wgrad_cols(const float* col, const float* dy, float* dw, int w_layout, int N, int OH, int OW, int K, int cols, int mode,
+                         bool* handled) {
+  return wgrad_impl(col, dy, dw, w_layout, N, 32, OH, OW, K, 1, 0, 1, mode, cols, handled);
+}
 
 #ifdef DFB_TC_TIMING
 extern "C" __attribute__((visibility("default"))) int dfb_debug_tc_stamps(unsigned long long* out32) {

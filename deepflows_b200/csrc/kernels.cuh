@@ -34,6 +34,12 @@ struct ConvFuse {
   const float* bn_x[2];
   const float* bn_mean[2];
   const float* bn_invstd[2];
+  // relu != 0 (with FUSE_BNBWD): the gradient belongs to relu(bn_0(x_0) [+ bn_1(x_1)] [+ relu_res]); it is masked with
+  // the recomputed pre-activation (>= 0 passes) before it is written and summed
+  int relu;
+  const float* bn_gamma[2];
+  const float* bn_beta[2];
+  const float* relu_res;
 };
 
 // gemm_tc.cu — TMA + tcgen05/TMEM path. Each returns DFB_OK and sets *handled = true when it ran
@@ -54,5 +60,10 @@ dfb_status tc_conv_wgrad(const float* x, const float* dy, float* dw, int w_layou
 dfb_status tc_stem_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H, int W,
                          int K, int R, int pad, int stride, int mode, bool* handled);
 size_t tc_conv_workspace_floats(int N, int C, int H, int W, int K, int R, int pad, int stride);
+// the first layer's column matrix as a separate step (see gemm_tc.cu)
+dfb_status tc_stem_cols(const float* x, int x_layout, float* col, int N, int C, int H, int W, int R, int pad, int stride, int w_layout);
+dfb_status tc_stem_pad_weights(const float* w, float* wp, int K, int cols);
+dfb_status tc_wgrad_cols(const float* col, const float* dy, float* dw, int w_layout, int N, int OH, int OW, int K, int cols, int mode,
+                         bool* handled);
 
 }  // namespace dfb

@@ -380,12 +380,33 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
                                  int C, int H, int W, int K, int R, int pad, int stride, int mode, const py::object& mean_var) {
     check(dfb_conv2d_fprop_stats(dptr(x), x_layout, dptr(w), w_layout, dptr(y), N, C, H, W, K, R, pad, stride, mode, dptr(mean_var)));
   });
+  // BatchNorms as 5-tuples (x, save_mean, save_invstd, gamma, beta), like relu_bwd_bn; n_bn = how many are given
   m.def("conv2d_dgrad_fused", [](const py::object& dy, const py::object& w, int w_layout, const py::object& dx, int N, int C, int H,
                                  int W, int K, int R, int pad, int stride, int mode, int dgrad_mode, const py::object& addend,
-                                 int n_bn, const py::object& x0, const py::object& mean0, const py::object& invstd0,
-                                 const py::object& x1, const py::object& mean1, const py::object& invstd1, const py::object& sums) {
+                                 const py::object& bn0, const py::object& bn1, const py::object& sums, bool relu,
+                                 const py::object& relu_res) {
+    float* b[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};
+    int n_bn = 0;
+    const py::object* bns[2] = {&bn0, &bn1};
+    for (int i = 0; i < 2; ++i) {
+      if (bns[i]->is_none()) break;
+      py::tuple t = bns[i]->cast<py::tuple>();
+      if (t.size() != 5) throw py::value_error("conv2d_dgrad_fused: a BatchNorm is a 5-tuple");
+      for (int j = 0; j < 5; ++j) b[i][j] = dptr(t[j]);
+      ++n_bn;
+    }
     check(dfb_conv2d_dgrad_fused(dptr(dy), dptr(w), w_layout, dptr(dx), N, C, H, W, K, R, pad, stride, mode, dgrad_mode, dptr(addend),
-                                 n_bn, dptr(x0), dptr(mean0), dptr(invstd0), dptr(x1), dptr(mean1), dptr(invstd1), dptr(sums)));
+                                 n_bn, b[0][0], b[0][1], b[0][2], b[1][0], b[1][1], b[1][2], dptr(sums), relu ? 1 : 0, b[0][3], b[0][4],
+                                 b[1][3], b[1][4], dptr(relu_res)));
+  });
+  m.def("stem_cols", [](const py::object& x, int x_layout, const py::object& col, int N, int C, int H, int W, int R, int pad, int stride,
+                        int w_layout) { check(dfb_stem_cols(dptr(x), x_layout, dptr(col), N, C, H, W, R, pad, stride, w_layout)); });
+  m.def("stem_pad_weights", [](const py::object& w, const py::object& wp, int K, int cols) {
+    check(dfb_stem_pad_weights(dptr(w), dptr(wp), K, cols));
+  });
+  m.def("conv2d_wgrad_cols", [](const py::object& col, const py::object& dy, const py::object& dw, int w_layout, int N, int OH, int OW,
+                                int K, int cols, int mode) {
+    check(dfb_conv2d_wgrad_cols(dptr(col), dptr(dy), dptr(dw), w_layout, N, OH, OW, K, cols, mode));
   });
   m.def("colstats_mean_var", [](const py::object& x, size_t rows, int C, const py::object& mean_var) {
     check(dfb_colstats_mean_var(dptr(x), rows, C, dptr(mean_var)));

@@ -250,7 +250,10 @@ DFB_API dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* d
  *                            BatchNorm that follows needs (dfb_bn_fwd_apply), without a statistics pass over y.
  *   dfb_conv2d_dgrad_fused : dx = dgrad(dy, w) [+ addend], and for n_bn (0, 1, 2) BatchNorms whose OUTPUT gradient dx
  *                            is: sums[0][C] = sum(dx), sums[1+i][C] = sum(dx * x_hat_i), x_hat_i = (bn_x_i - mean_i) *
- *                            invstd_i - the two reductions of BatchNorm backward (dfb_bn_bwd_apply does the rest). */
+ *                            invstd_i - the two reductions of BatchNorm backward (dfb_bn_bwd_apply does the rest).
+ *                            relu != 0: dx is the gradient of relu(bn_0(x_0) [+ bn_1(x_1)] [+ relu_res]) - the output of
+ *                            dfb_bn_fwd_apply(.., relu = 1): the ReLU's backward (pre-activation recomputed, >= 0 passes,
+ *                            tensor.py:872-877) is applied before dx is written and summed. */
 DFB_API dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, int w_layout, float* y, int N,
                                           int C, int H, int W, int K, int R, int pad, int stride, int mode,
                                           float* mean_var);
@@ -258,7 +261,21 @@ DFB_API dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w
                                           int W, int K, int R, int pad, int stride, int mode, int dgrad_mode,
                                           const float* addend, int n_bn, const float* bn_x0, const float* bn_mean0,
                                           const float* bn_invstd0, const float* bn_x1, const float* bn_mean1,
-                                          const float* bn_invstd1, float* sums);
+                                          const float* bn_invstd1, float* sums, int relu, const float* gamma0,
+                                          const float* beta0, const float* gamma1, const float* beta1,
+                                          const float* relu_res);
+
+/* First layer (image input, C*R*R <= 32) through its column matrix, kept between forward and backward:
+ *   dfb_stem_cols         : col[pixel][32] = the receptive field of every output pixel (zero padded to 32 columns, in the
+ *                           weight's own memory order) - the reference's im2col (functional.py:249-283) for this layer only;
+ *   dfb_stem_pad_weights  : wp[K][32] = the weights with every row padded to 32;
+ *   forward               = dfb_conv2d_fprop_stats(col as an (N,OH,OW,32) channels-last tensor, wp as (K,1,1,32), R = 1);
+ *   dfb_conv2d_wgrad_cols : dW[K][cols] = sum_pixels dy[pixel][K] * col[pixel][cols]  (the layer's weight gradient). */
+DFB_API dfb_status dfb_stem_cols(const float* x, int x_layout, float* col, int N, int C, int H, int W, int R, int pad,
+                                 int stride, int w_layout);
+DFB_API dfb_status dfb_stem_pad_weights(const float* w, float* wp, int K, int cols);
+DFB_API dfb_status dfb_conv2d_wgrad_cols(const float* col, const float* dy, float* dw, int w_layout, int N, int OH, int OW,
+                                         int K, int cols, int mode);
 
 /* y[r, c] = x[r, c] + v[c]   (conv bias (1,K,1,1) on channels-last, Linear bias (1,out);
  * replaces broadcast_to + compact + ewise_add, backend_tensor.py:533-542) */

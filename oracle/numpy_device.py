@@ -412,16 +412,17 @@ def bn_bwd_apply(x, dy, gamma, save_mean, save_invstd, dbeta, dgamma, dx, rows, 
     _flat(dx)[: rows * C] = (g * invstd * (ga - db / rows - (xa - mean) * invstd * dg / rows)).astype(F32).reshape(-1)
 
 
-def conv2d_dgrad_fused(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, addend, n_bn, x0, mean0, invstd0,
-                       x1, mean1, invstd1, sums):
+def conv2d_dgrad_fused(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, addend, bn0, bn1, sums, relu, relu_res):
     _count("conv2d_dgrad_fused")
     conv2d_dgrad(dy, w, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, None, 0, w_layout)
     n = N * C * H * W
     if addend is not None:
         _flat(dx)[:n] = _flat(dx)[:n] + _flat(addend)[:n]
     rows = N * H * W
-    for i, (bx, bm, bi) in enumerate(((x0, mean0, invstd0), (x1, mean1, invstd1))[:n_bn]):
-        bn_bwd_sums(bx, dx, bm, bi, (sums, 0) if not isinstance(sums, tuple) else sums, _off(sums, (1 + i) * C), rows, C)
+    if relu:
+        relu_bwd_bn(bn0, bn1, relu_res, dx, dx, rows, C)
+    for i, bn in enumerate([b for b in (bn0, bn1) if b is not None]):
+        bn_bwd_sums(bn[0], dx, bn[1], bn[2], (sums, 0) if not isinstance(sums, tuple) else sums, _off(sums, (1 + i) * C), rows, C)
 
 
 def _off(h, k):

@@ -82,10 +82,9 @@ def test_conv_dgrad_fused(cuda_device, geom, mode_name, n_bn):
     hbx, hmean, hinv = [_dev(m, b) for b in bx], [_dev(m, v) for v in mean], [_dev(m, v) for v in invstd]
     dx0, dx1, sums = m.Array(n * h * w * c), m.Array(n * h * w * c), m.Array(3 * c)
     m.conv2d_dgrad(hdy, hw, dx0, n, c, h, w, k, r, p, s, mode, m.DGRAD_EXACT, None, 0, m.WLAYOUT_KRSC)
-    m.conv2d_dgrad_fused(hdy, hw, m.WLAYOUT_KRSC, dx1, n, c, h, w, k, r, p, s, mode, m.DGRAD_EXACT, hadd, n_bn,
-                         hbx[0] if n_bn > 0 else None, hmean[0] if n_bn > 0 else None, hinv[0] if n_bn > 0 else None,
-                         hbx[1] if n_bn > 1 else None, hmean[1] if n_bn > 1 else None, hinv[1] if n_bn > 1 else None,
-                         sums if n_bn else None)
+    bns = [(hbx[i], hmean[i], hinv[i], None, None) for i in range(2)]
+    m.conv2d_dgrad_fused(hdy, hw, m.WLAYOUT_KRSC, dx1, n, c, h, w, k, r, p, s, mode, m.DGRAD_EXACT, hadd,
+                         bns[0] if n_bn > 0 else None, bns[1] if n_bn > 1 else None, sums if n_bn else None, False, None)
     plain = _host(m, dx0, (n * h * w, c))
     got = _host(m, dx1, (n * h * w, c))
     want = plain + addend.reshape(-1, c)
@@ -99,6 +98,52 @@ def test_conv_dgrad_fused(cuda_device, geom, mode_name, n_bn):
             xh = (bx[i].reshape(-1, c).astype(np.float64) - mean[i]) * invstd[i]
             ref = (g64 * xh).sum(0)
             assert np.abs(sm[1 + i] - ref).max() <= 4e-6 * np.abs(g64 * xh).sum(0).max(), i
+
+
+@pytest.mark.parametrize("dual,res,addend", [(False, False, False), (False, True, True), (True, False, False), (True, True, True)])
+@pytest.mark.parametrize("mode_name", ["tf32", "fp32"])
+@pytest.mark.parametrize("geom", [CONV_SHAPES[0], CONV_SHAPES[1], CONV_SHAPES[4], CONV_SHAPES[5], CONV_SHAPES[7]])
+def test_conv_dgrad_fused_relu(cuda_device, geom, mode_name, dual, res, addend):
+    """dgrad whose output is the gradient of relu(bn_0(x_0) [+ bn_1(x_1)] [+ residual]): masked with the recomputed
+    pre-activation, then summed - against dgrad (+ addend), dfb_relu_bwd_bn and numpy sums."""
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = geom
+    mode = m.MODE_TF32 if mode_name == "tf32" else m.MODE_FP32
+    oh, ow = (h + 2 * p - r) // s + 1, (w + 2 * p - r) // s + 1
+    rng = np.random.RandomState(6)
+    rows = n * h * w
+    dy = rng.randn(n, oh, ow, k).astype(F32)
+    wt = (rng.randn(k, r, r, c) / np.sqrt(c * r * r)).astype(F32)
+    add = rng.randn(rows, c).astype(F32)
+    resid = rng.randn(rows, c).astype(F32)
+    bx = [(rng.randn(rows, c) * (1 + i) + 0.3 * i).astype(F32) for i in range(2)]
+    gam = [(rng.rand(c) + 0.5).astype(F32) for _ in range(2)]
+    bet = [(rng.randn(c) * 0.3).astype(F32) for _ in range(2)]
+    mean = [b.mean(0).astype(F32) for b in bx]
+    invstd = [(1.0 / np.sqrt(b.astype(np.float64).var(0) + 1e-5)).astype(F32) for b in bx]
+    hdy, hw, hadd, hres = _dev(m, dy), _dev(m, wt), _dev(m, add), _dev(m, resid)
+    bns = [(_dev(m, bx[i]), _dev(m, mean[i]), _dev(m, invstd[i]), _dev(m, gam[i]), _dev(m, bet[i])) for i in range(2)]
+    n_bn = 2 if dual else 1
+    # separate kernels: dgrad, add, relu backward through the BatchNorm(s)
+    d0 = m.Array(rows * c)
+    m.conv2d_dgrad(hdy, hw, d0, n, c, h, w, k, r, p, s, mode, m.DGRAD_EXACT, None, 0, m.WLAYOUT_KRSC)
+    if addend:
+        m.ewise_add(d0, hadd, d0)
+    want_h = m.Array(rows * c)
+    m.relu_bwd_bn(bns[0], bns[1] if dual else None, hres if res else None, d0, want_h, rows, c)
+    want = _host(m, want_h, (rows, c))
+    # fused
+    dx, sums = m.Array(rows * c), m.Array(3 * c)
+    m.conv2d_dgrad_fused(hdy, hw, m.WLAYOUT_KRSC, dx, n, c, h, w, k, r, p, s, mode, m.DGRAD_EXACT, hadd if addend else None,
+                         bns[0], bns[1] if dual else None, sums, True, hres if res else None)
+    got = _host(m, dx, (rows, c))
+    assert np.array_equal(got, want), "fused ReLU mask differs from dfb_relu_bwd_bn"
+    sm = _host(m, sums, (3, c))
+    g64 = got.astype(np.float64)
+    assert np.abs(sm[0] - g64.sum(0)).max() <= 2e-6 * max(np.abs(g64).sum(0).max(), 1e-30)
+    for i in range(n_bn):
+        xh = (bx[i].astype(np.float64) - mean[i]) * invstd[i]
+        assert np.abs(sm[1 + i] - (g64 * xh).sum(0)).max() <= 4e-6 * max(np.abs(g64 * xh).sum(0).max(), 1e-30), i
 
 
 @pytest.mark.parametrize("relu", [False, True])
