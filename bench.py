@@ -247,8 +247,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the eager-mode and fp32-mode extra measurements")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="repeat the K-step block until this much has been timed")
+    ap.add_argument("--dropout", default=os.environ.get("DEEPFLOWS_DROPOUT", "host"), choices=["host", "device"],
+                    help="where Dropout draws its masks: host = numpy like the reference (default), device = Philox kernel")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    os.environ["DEEPFLOWS_DROPOUT"] = args.dropout   # read by DeepFlows.backend.backend_tensor at import
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -256,7 +259,8 @@ def main():
     cpu_batch, cpu_steps, cpu_warm = cfg["cpu"]
     if args.cpu_batch:
         cpu_batch = args.cpu_batch
-    config = {"workload": cfg["workload"], "name": args.config,
+    config = {"workload": cfg["workload"] + ("" if args.dropout == "host" else " [dropout masks drawn on the device: --dropout device]"),
+              "name": args.config,
               "batch_per_gpu": B, "global_batch": B * world,
               "image": "x".join(str(v) for v in cfg["shape"]), "parallelism": "dp%d" % world,
               "launch": "one CUDA graph per step (captured from the unchanged DeepFlows step)" if args.mode == "graph"
@@ -543,7 +547,8 @@ def profile_dominant_kernel(dev, step_fn, hbm, tc):
     conv_geom = lambda off: (lambda a: tuple(int(v) for v in a[off:off + 8]))  # noqa: E731
     saved = {}
     specs = [("conv2d_fprop", conv_geom(4)), ("conv2d_dgrad", conv_geom(3)), ("conv2d_wgrad", conv_geom(4)),
-             ("conv2d_fprop_stats", conv_geom(5)), ("conv2d_dgrad_fused", lambda a: tuple(int(v) for v in a[4:12]) + (int(a[14] is not None), int(a[15]))),
+             ("conv2d_fprop_stats", conv_geom(5)), ("conv2d_dgrad_fused", lambda a: tuple(int(v) for v in a[4:12]) + (int(a[14] is not None), int(a[15] is not None) + int(a[16] is not None),
+                                                                              int(bool(a[18])), int(a[19] is not None))),
              ("gemm", lambda a: tuple(int(v) for v in a[3:8])),
              ("bn_fwd_train", lambda a: (int(a[10]), int(a[11]))), ("bn_bwd", lambda a: (int(a[8]), int(a[9]))),
              ("bn_fwd_apply", lambda a: (int(a[4]), int(a[5]), int(a[1] is not None), int(a[2] is not None), int(bool(a[6])))),
@@ -646,12 +651,12 @@ def profile_dominant_kernel(dev, step_fn, hbm, tc):
             desc = "gemm M=%d N=%d K=%d ta=%d tb=%d" % geom
         else:
             flops, bytes_min = conv_work(geom[:8])
-            if name == "conv2d_dgrad_fused":   # + the addend and the BatchNorm inputs it reads, all of the output's size
+            if name == "conv2d_dgrad_fused":   # + the addend, the BatchNorm inputs and the residual it reads, all of the output's size
                 n_, c_, h_, w_ = geom[:4]
-                bytes_min += 4.0 * n_ * c_ * h_ * w_ * (geom[8] + geom[9])
+                bytes_min += 4.0 * n_ * c_ * h_ * w_ * (geom[8] + geom[9] + geom[11])
             desc = "%s N=%d C=%d H=%d W=%d K=%d R=%d pad=%d stride=%d" % ((name,) + geom[:8])
             if len(geom) > 8:
-                desc += " addend=%d bn=%d" % geom[8:10]
+                desc += " addend=%d bn=%d relu=%d res=%d" % geom[8:12]
         t_tc_us = flops / (tc[0] * 1e12) * 1e6
         t_hbm_us = bytes_min / (hbm[0] * 1e9) * 1e6
         bound = "tensor" if t_tc_us > t_hbm_us else "hbm"

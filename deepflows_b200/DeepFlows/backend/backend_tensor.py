@@ -25,6 +25,7 @@ __all__ = [
     "broadcast_to", "reshape", "maximum", "max", "log", "exp", "tanh", "flip", "summation", "mean", "pad",
     "expand_dims", "register_numpy_device", "set_precision", "get_precision", "set_dgrad_mode",
     "get_dgrad_mode", "set_fix_mean", "get_fix_mean", "set_fusion", "get_fusion", "PendingTensor", "BnApply",
+    "set_dropout_rng", "get_dropout_rng",
 ]
 
 
@@ -236,6 +237,22 @@ def set_fusion(enabled):
 
 def get_fusion():
     return _fusion
+
+
+# Where Dropout draws its masks: "host" = numpy's generator like the reference (seeded runs see the reference's masks),
+# "device" = a Philox kernel (nn/modules/dropout.py)
+_dropout_rng = os.environ.get("DEEPFLOWS_DROPOUT", "host").lower()
+
+
+def set_dropout_rng(where):
+    global _dropout_rng
+    if where not in ("host", "device"):
+        raise ValueError("dropout rng must be 'host' or 'device'")
+    _dropout_rng = where
+
+
+def get_dropout_rng():
+    return _dropout_rng
 
 
 # ------------------------------------------------------------------------------------------------

@@ -62,6 +62,38 @@ __global__ void __launch_bounds__(kT) onehot_kernel(const float* __restrict__ la
   }
 }
 
+// Dropout mask on the device (opt-in; the reference draws it on the host with numpy, dropout.py:27-29, which costs
+// milliseconds per step for a 256 x 2048 activation - more than the rest of the step). Philox4x32-10 (Salmon et al., SC'11;
+// the counter-based generator cuRAND and numpy's Philox implement), key = (seed, 0xCAFEF00D), counter = (element / 4, step,
+// 0, 0): mask[i] = u32 * 2^-32 < keep_prob ? 1 : 0. oracle/numpy_ops.py::philox_dropout_mask restates it; bit-exact.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], const uint32_t (&k)[2]) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__global__ void __launch_bounds__(kT) dropout_mask_kernel(float* __restrict__ mask, size_t n, float keep_prob, const float* __restrict__ state) {
+  pdl_sync();
+  const uint32_t seed = (uint32_t)__float2uint_rn(state[0]), step = (uint32_t)__float2uint_rn(state[1]);
+  const size_t groups = (n + 3) / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    uint32_t c[4] = {(uint32_t)g, step, (uint32_t)(g >> 32), 0u};
+    uint32_t k[2] = {seed, 0xCAFEF00Du};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k);
+      k[0] += 0x9E3779B9u;
+      k[1] += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t i = g * 4 + j;
+      if (i < n) mask[i] = (float)c[j] * 2.3283064365386963e-10f < keep_prob ? 1.f : 0.f;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace dfb
 
@@ -91,6 +123,15 @@ dfb_status dfb_onehot_smooth(const float* labels, float* y, size_t n, int classe
   if (n == 0) return DFB_OK;
   launch_k(onehot_kernel, bw_grid(n * (size_t)classes, kT), kT, 0, compute_stream(), labels, y, n, classes, on_value, off_value);
   DFB_LAUNCH_CHECK("onehot_smooth");
+  return DFB_OK;
+}
+
+dfb_status dfb_dropout_mask(float* mask, size_t n, float keep_prob, const float* state) {
+  DFB_INIT();
+  DFB_REQUIRE(mask && state, DFB_ERR_INVALID, "dropout_mask: null pointer");
+  if (n == 0) return DFB_OK;
+  launch_k(dropout_mask_kernel, bw_grid((n + 3) / 4, kT), kT, 0, compute_stream(), mask, n, keep_prob, state);
+  DFB_LAUNCH_CHECK("dropout_mask");
   return DFB_OK;
 }
 

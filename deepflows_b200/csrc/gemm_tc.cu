@@ -272,6 +272,31 @@ struct RowEpi {
   static constexpr int NCG = (BN / 4 <= 32) ? 1 : BN / 128;   // float4 column groups per lane
   float a[NCG][4], b[NCG][4], c[NCG][4];                      // EPI_STATS: shift, m1, m2; EPI_BNBWD: sum d, sum d*xh0, sum d*xh1
   float n;
+  // per-channel constants of the lane's own columns (EF_BNBWD / EF_RELU), loaded once per CTA: mean, invstd,
+  // invstd * gamma, beta of up to two BatchNorms
+  float4 k_mu[2][NCG], k_is[2][NCG], k_sc[2][NCG], k_be[2][NCG];
+  template <int EF>
+  __device__ __forceinline__ void load_consts(const EpiArgs& e, int col_of_group0, int n_out) {
+    if constexpr ((EF & EF_BNBWD) != 0) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        if (s2 >= e.n_sets) break;
+#pragma unroll
+        for (int g = 0; g < NCG; ++g) {
+          const int col = col_of_group0 + g * 128;
+          const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
+          const bool ok = col + 4 <= n_out;
+          k_mu[s2][g] = ok ? __ldg(reinterpret_cast<const float4*>(e.bn_mean[s2] + col)) : zero;
+          k_is[s2][g] = ok ? __ldg(reinterpret_cast<const float4*>(e.bn_invstd[s2] + col)) : zero;
+          if constexpr ((EF & EF_RELU) != 0) {
+            const float4 gm = (ok && e.bn_gamma[s2]) ? __ldg(reinterpret_cast<const float4*>(e.bn_gamma[s2] + col)) : one;
+            k_be[s2][g] = (ok && e.bn_beta[s2]) ? __ldg(reinterpret_cast<const float4*>(e.bn_beta[s2] + col)) : zero;
+            k_sc[s2][g] = make_float4(k_is[s2][g].x * gm.x, k_is[s2][g].y * gm.y, k_is[s2][g].z * gm.z, k_is[s2][g].w * gm.w);
+          }
+        }
+      }
+    }
+  }
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int g = 0; g < NCG; ++g)
@@ -284,9 +309,8 @@ struct RowEpi {
   struct Extras { float4 add, x0, x1, res; };
   template <int EF>
   __device__ __forceinline__ static Extras load_extras(const EpiArgs& e, const float* out, const float* row_out, int col, int n_out) {
-    Extras x;
+    Extras x{};
     if constexpr (EF == EF_NONE || EF == EF_STATS) return x;
-    x.add = x.x0 = x.x1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row_out == nullptr || col + 4 > n_out) return x;
     const size_t off = (size_t)(row_out - out) + col;
     if constexpr ((EF & EF_ADDEND) != 0) x.add = __ldg(reinterpret_cast<const float4*>(e.addend + off));
@@ -310,15 +334,15 @@ struct RowEpi {
       // z = fmaf(x - mean, invstd * gamma, beta) [+ the same of the second BatchNorm] [+ residual]: dfb_bn_fwd_apply's
       // operations in its order, so the mask is the one the forward pass applied; the gradient passes where z >= 0
       const float xa[4] = {x.x0.x, x.x0.y, x.x0.z, x.x0.w}, xb[4] = {x.x1.x, x.x1.y, x.x1.z, x.x1.w}, rr[4] = {x.res.x, x.res.y, x.res.z, x.res.w};
+      const float m0[4] = {k_mu[0][g].x, k_mu[0][g].y, k_mu[0][g].z, k_mu[0][g].w}, s0[4] = {k_sc[0][g].x, k_sc[0][g].y, k_sc[0][g].z, k_sc[0][g].w},
+                  b0[4] = {k_be[0][g].x, k_be[0][g].y, k_be[0][g].z, k_be[0][g].w};
+      const float m1[4] = {k_mu[1][g].x, k_mu[1][g].y, k_mu[1][g].z, k_mu[1][g].w}, s1[4] = {k_sc[1][g].x, k_sc[1][g].y, k_sc[1][g].z, k_sc[1][g].w},
+                  b1[4] = {k_be[1][g].x, k_be[1][g].y, k_be[1][g].z, k_be[1][g].w};
       float d[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int cq = col + q;
-        float z = fmaf(xa[q] - __ldg(e.bn_mean[0] + cq), __ldg(e.bn_invstd[0] + cq) * (e.bn_gamma[0] ? __ldg(e.bn_gamma[0] + cq) : 1.0f),
-                       e.bn_beta[0] ? __ldg(e.bn_beta[0] + cq) : 0.0f);
-        if (e.n_sets > 1)
-          z = z + fmaf(xb[q] - __ldg(e.bn_mean[1] + cq), __ldg(e.bn_invstd[1] + cq) * (e.bn_gamma[1] ? __ldg(e.bn_gamma[1] + cq) : 1.0f),
-                       e.bn_beta[1] ? __ldg(e.bn_beta[1] + cq) : 0.0f);
+        float z = fmaf(xa[q] - m0[q], s0[q], b0[q]);
+        if (e.n_sets > 1) z = z + fmaf(xb[q] - m1[q], s1[q], b1[q]);
         if (e.relu_res) z = z + rr[q];
         d[q] = z >= 0.f ? d[q] : 0.f;
       }
@@ -333,12 +357,12 @@ struct RowEpi {
 #pragma unroll
       for (int q = 0; q < 4; ++q) { const float d = vv[q] - a[g][q]; b[g][q] += d; c[g][q] = fmaf(d, d, c[g][q]); }
     } else if constexpr ((EF & EF_BNBWD) != 0) {
-      const float4 mu0 = __ldg(reinterpret_cast<const float4*>(e.bn_mean[0] + col)), is0 = __ldg(reinterpret_cast<const float4*>(e.bn_invstd[0] + col));
+      const float4 mu0 = k_mu[0][g], is0 = k_is[0][g];
       const float xh0[4] = {(x.x0.x - mu0.x) * is0.x, (x.x0.y - mu0.y) * is0.y, (x.x0.z - mu0.z) * is0.z, (x.x0.w - mu0.w) * is0.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) { a[g][q] += vv[q]; b[g][q] = fmaf(vv[q], xh0[q], b[g][q]); }
       if (e.n_sets > 1) {
-        const float4 mu1 = __ldg(reinterpret_cast<const float4*>(e.bn_mean[1] + col)), is1 = __ldg(reinterpret_cast<const float4*>(e.bn_invstd[1] + col));
+        const float4 mu1 = k_mu[1][g], is1 = k_is[1][g];
         const float xh1[4] = {(x.x1.x - mu1.x) * is1.x, (x.x1.y - mu1.y) * is1.y, (x.x1.z - mu1.z) * is1.z, (x.x1.w - mu1.w) * is1.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[g][q] = fmaf(vv[q], xh1[q], c[g][q]);
@@ -486,7 +510,9 @@ __global__ void __launch_bounds__(128) epi_finalize_kernel(const float* __restri
 // KR: reduction rows per stage (MN-major operands only: 32 or 128). BSUB: B tiles per stage (the row-halo conv
 // kernel keeps the three taps of one filter column in a stage, with AROWS = 192 halo rows of A)
 // BKR: rows of one B chunk when they differ from KR (wgrad row-halo: 128-pixel A chunks, 192-row B halo chunks).
-template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K, int BSUB = 1, int BKR = KR>
+// OUT: a dedicated output staging tile behind the ring (the persistent kernel's epilogue overlaps the next tile's loads,
+// so it cannot borrow the pipeline stages)
+template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K, int BSUB = 1, int BKR = KR, bool OUT = false>
 struct SmemLayout {
   // What one SM can pull through TMA is bounded by the bytes it keeps in flight (loads take microseconds to
   // return under load), and a CTA's prologue / epilogue / split-K reduction are pure latency: TWO CTAs per SM
@@ -500,8 +526,9 @@ struct SmemLayout {
   static constexpr uint32_t kBTile = (BN / 32) * kBChunk;
   static constexpr uint32_t kBBytes = BSUB * kBTile;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kBudget = BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
-                                               : (BN >= 256 ? (192u << 10) : (100u << 10));  // (128 x 256 at two CTAs per SM with two stages: measured 7% slower)
+  static constexpr uint32_t kOutBytes = OUT ? ((BLOCK_M * (BN + 4) * 4 + 1023) & ~1023u) : 0;
+  static constexpr uint32_t kBudget = (BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
+                                                : (BN >= 256 ? (192u << 10) : (100u << 10))) - kOutBytes;  // (128 x 256 at two CTAs per SM with two stages: measured 7% slower)
   static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
   static constexpr int kMinStages = (BSUB > 1 || BKR != KR) ? 2 : 3;   // halo variants: two CTAs per SM with two stages each
   static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < kMinStages ? kMinStages : kStagesFit);
@@ -514,7 +541,8 @@ struct SmemLayout {
   // [4 warps][4 values][BN columns]
   static constexpr uint32_t kEpiOffset = kBarOffset + kOverRead + (2 * kStages + 1) * 8 + 16;
   static constexpr uint32_t kEpiBytes = 1024 + 64 * BN;
-  static constexpr uint32_t kTotal = kEpiOffset + 16 + kEpiBytes + 1024;  // +1024 for manual alignment
+  static constexpr uint32_t kOutOffset = (kEpiOffset + 16 + kEpiBytes + 48 + 15) & ~15u;   // (+48: the persistent kernel's three extra barriers)
+  static constexpr uint32_t kTotal = kOutOffset + kOutBytes + 1024;  // +1024 for manual alignment
   // split-K partial tile staged in the (idle) pipeline stages: 128 rows, padded pitch against bank conflicts
   static constexpr uint32_t kRedPitch = BN + 4;
   // (the 128 x 256 kernels never split K: they are only chosen for problems with hundreds of tiles)
@@ -694,6 +722,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
         constexpr int LPR = RowEpi<BN>::LPR, RPI = RowEpi<BN>::RPI, NCG = RowEpi<BN>::NCG;
         constexpr int U = NCG == 1 ? 4 : 2;   // rows in flight per lane
         const int lr = lane / LPR, lc = lane % LPR;
+        P::epi_consts(prm, tile, epi, lc * 4);
 #pragma unroll 1
         for (int rr = 0; rr < 32; rr += RPI * U) {
           float* rp[U];
@@ -739,6 +768,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       constexpr int kVecPerRow = P::kAccTiles * BN / 4;
       constexpr uint32_t kRedPitch = P::kAccTiles * BN + 4;
       const uint32_t red_base = smem_u32(smem);
+      if constexpr (P::kRowMajor) P::epi_consts(prm, tile, epi, (t % kVecPerRow) * 4);   // this lane's columns never change
       for (int idx = t; idx < rows_per * kVecPerRow; idx += 128) {
         const int r = rank * rows_per + idx / kVecPerRow;
         if (P::kDynRedRows && r >= red_rows) break;
@@ -788,6 +818,186 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc<P::kTmemCols>(tmem_base);
     TC_STAMP(13);
+  }
+}
+
+// ---- persistent variant: many small tiles ------------------------------------------------------------------------------
+// A convolution whose output has many more 128-pixel tiles than the GPU has CTA slots (first layer: 2048 tiles, layer 1
+// of the ResNet: 512) and few channels pays the per-CTA prologue (barrier init, TMEM allocation, descriptor fetch, the
+// first L2/HBM round trip) and a serial load -> MMA -> write-out chain once per TILE, in ~1.7 waves. Here a CTA lives
+// for the whole launch and walks tiles blockIdx.x, + gridDim.x, ...: the producer warp keeps the TMA ring full across
+// tile boundaries, the MMA warp alternates between two TMEM accumulators, and the epilogue warps drain accumulator i
+// (TMEM -> dedicated staging tile -> coalesced stores, statistics in registers across ALL tiles of the CTA: one partial
+// per CTA) while the MMAs of tile i + 1 run. Row-major problems without split-K only.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <class P>
+__global__ void __launch_bounds__(kThreads) tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                 const __grid_constant__ CUtensorMap map_b,
+                                                                 const typename P::Params prm, const int n_tiles) {
+  constexpr int BN = P::BN;
+  static_assert(P::kRowMajor && P::kAccTiles == 1 && P::kAccStride == 0, "persistent kernel: row-major, one accumulator tile");
+  using L = SmemLayout<BN, P::AROWS, P::KR, P::kBSub, P::BKR, true>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset + L::kOverRead);
+  constexpr int kStages = L::kStages;
+  uint64_t* empty_bar = full_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_bar + kStages + 1);
+  float** row_tab = reinterpret_cast<float**>(smem + ((L::kEpiOffset + 15) & ~15u));
+  float* wstat = reinterpret_cast<float*>(row_tab + BLOCK_M);
+  uint64_t* tmem_full_bar = reinterpret_cast<uint64_t*>(smem + L::kOutOffset - 48);   // [2] full, [2] empty
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  constexpr int kAccCols = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators (BN is a power of two >= 32)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar + a, 1);
+      mbar_init(tmem_empty_bar + a, 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kAccCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp == 0) {
+    // ===== TMA producer: the ring runs across tile boundaries =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+      const typename P::Tile tile = P::tile_at(prm, ti);
+      const uint32_t tx = P::tx_bytes(prm, tile);
+      typename P::Iter it = P::iter_init(prm, tile, tile.kb_begin);
+      for (int kb = tile.kb_begin; kb < tile.kb_end; ++kb) {
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        const uint32_t a_dst = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t b_dst = a_dst + L::kABytes;
+        if (elect_one()) {
+          mbar_expect_tx(full_bar + stage, tx);
+          P::load_a(prm, tile, it, &map_a, full_bar + stage, a_dst);
+          P::load_b(prm, tile, it, &map_b, full_bar + stage, b_dst);
+        }
+        __syncwarp();
+        P::iter_next(prm, tile, it);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator lt & 1 for the lt-th tile of this CTA =====
+    constexpr uint32_t idesc = instr_desc_tf32<P::A_MAJOR, P::B_MAJOR, P::kMmaN>();
+    int stage = 0;
+    uint32_t phase = 0;
+    int lt = 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++lt) {
+      const typename P::Tile tile = P::tile_at(prm, ti);
+      const int acc = lt & 1;
+      if (lt >= 2) {   // the epilogue must have drained this accumulator's previous tile
+        mbar_wait(tmem_empty_bar + acc, (uint32_t)(((lt >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = tile.kb_begin; kb < tile.kb_end; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t b_base = a_base + L::kABytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < P::KR / UMMA_K; ++j) {
+#pragma unroll
+            for (int t = 0; t < P::kSubTiles; ++t) {
+              const uint32_t a_sub = a_base + P::a_sub_offset(prm, t), b_sub = b_base + P::b_sub_offset(prm, t, L::kBTile);
+              umma_tf32(d_tmem, operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_sub, j),
+                        operand_desc<P::B_MAJOR, L::kBChunk>(b_sub, j), idesc, (kb > tile.kb_begin || t > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar + stage);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(tmem_full_bar + acc);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps: drain accumulator lt & 1 while the next tile's MMAs run =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t stage_u32 = smem_u32(smem + L::kOutOffset);
+    const uint32_t rowtab_u32 = smem_u32(row_tab);
+    constexpr uint32_t kPitch = BN + 4;
+    constexpr int LPR = RowEpi<BN>::LPR, RPI = RowEpi<BN>::RPI, NCG = RowEpi<BN>::NCG;
+    constexpr int U = NCG == 1 ? 4 : 2;
+    const int lr = lane / LPR, lc = lane % LPR;
+    RowEpi<BN> epi;
+    epi.init();
+    typename P::Tile tile = P::tile_at(prm, blockIdx.x < (unsigned)n_tiles ? (int)blockIdx.x : 0);
+    P::epi_consts(prm, tile, epi, lc * 4);
+    int lt = 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++lt) {
+      tile = P::tile_at(prm, ti);
+      const int acc = lt & 1;
+      mbar_wait(tmem_full_bar + acc, (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+      row_tab[row] = P::row_ptr(prm, tile, row);   // (this warp finished reading the previous tile's entries)
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cc), v);
+        const uint32_t dst = stage_u32 + (uint32_t)(row * kPitch + cc) * 4u;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) sts_f4(dst + i * 4, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(tmem_empty_bar + acc);   // the accumulator is free for the tile after next
+      __syncwarp();
+#pragma unroll 1
+      for (int rr = 0; rr < 32; rr += RPI * U) {
+        float* rp[U];
+        float4 val[U][NCG];
+        typename P::Extras ex[U][NCG];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = quarter * 32 + rr + u * RPI + lr;
+          rp[u] = lds_ptr(rowtab_u32 + r * 8);
+#pragma unroll
+          for (int g = 0; g < NCG; ++g) val[u][g] = lds_f4(stage_u32 + (uint32_t)(r * kPitch + (g * 32 + lc) * 4) * 4u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int g = 0; g < NCG; ++g) ex[u][g] = P::load_extras(prm, tile, rp[u], (g * 32 + lc) * 4);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (rp[u]) {
+#pragma unroll
+            for (int g = 0; g < NCG; ++g) P::emit4(prm, tile, epi, rp[u], (g * 32 + lc) * 4, g, val[u][g], ex[u][g]);
+            epi.n += 1.f;
+          }
+        }
+      }
+      __syncwarp();   // the staging rows and row pointers of this warp are free for the next tile
+    }
+    // one statistics partial per CTA, over all its tiles (a CTA without tiles contributes an empty one)
+    P::epi_finish(prm, tile, epi, wstat, nullptr, (warp - 2) * 32 + lane);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kAccCols>(tmem_base);
   }
 }
 
@@ -871,6 +1081,30 @@ static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensor
   return DFB_OK;
 }
 
+template <class P>
+static dfb_status launch_persistent(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
+                                    int n_tiles, unsigned ctas) {
+  using L = SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR, true>;
+  static bool configured = false;
+  if (!configured) {
+    DFB_CUDA(cudaFuncSetAttribute(tc_persistent_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    configured = true;
+  }
+  launch_k(tc_persistent_kernel<P>, dim3(ctas, 1, 1), kThreads, L::kTotal, compute_stream(), ma, mb, prm, n_tiles);
+  DFB_LAUNCH_CHECK(name);
+  g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  return DFB_OK;
+}
+// DFB_CONV_PERSISTENT=0 switches the persistent variant off (every tile its own CTA again)
+static bool persistent_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_CONV_PERSISTENT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // Split-K factor (cluster size along z, a power of two <= 8): enough CTAs to occupy the machine, at least
 // four k-blocks per CTA.
 static int pick_splits(size_t base_ctas, int k_blocks) {
@@ -943,6 +1177,7 @@ struct GemmProblem {
     }
   }
   __device__ static void epi_finish(const Params&, const Tile&, RowEpi<BN_>&, float*, float*, int) {}
+  __device__ static void epi_consts(const Params&, const Tile&, RowEpi<BN_>&, int) {}
   __device__ static Tile tile(const Params& p) {
     return {(int)blockIdx.x * BLOCK_M, (int)blockIdx.y * BN, 0, (p.K + BLOCK_K - 1) / BLOCK_K};
   }
@@ -1069,8 +1304,9 @@ struct ConvProblem {
   __device__ static void finish_cluster(const ConvParams&, const ConvTile&, int, int, int) {}
   using Params = ConvParams;
   using Tile = ConvTile;
-  __device__ static Tile tile(const Params& p) {
-    int t = blockIdx.x;
+  __device__ static Tile tile(const Params& p) { return tile_at(p, (int)blockIdx.x); }
+  static constexpr bool kPersistentOk = BN_ == 32;   // (the staging tile of wider outputs does not fit beside the ring at two CTAs per SM)
+  __device__ static Tile tile_at(const Params& p, int t) {
     int tw = t % p.tiles_w;
     t /= p.tiles_w;
     int th = t % p.tiles_h;
@@ -1165,6 +1401,10 @@ struct ConvProblem {
   __device__ static void emit4(const Params& p, const Tile& t, RowEpi<BN_>& epi, float* row_out, int c, int g, const float4& q, const Extras& x) {
     epi.template emit<EF>(p.epi, row_out, t.col0 + c, g, q, x, p.n_out);
   }
+  // c = the lane's first column inside the tile (column group 0)
+  __device__ static void epi_consts(const Params& p, const Tile& t, RowEpi<BN_>& epi, int c) {
+    epi.template load_consts<EF>(p.epi, t.col0 + c, p.n_out);
+  }
   __device__ static void epi_finish(const Params& p, const Tile& t, RowEpi<BN_>& epi, float* wstat, float* scratch, int tid) {
     if constexpr ((EF & (EF_STATS | EF_BNBWD)) != 0)
       epi.finish(p.epi, wstat, scratch, tid, t.col0, p.n_out, (int)(blockIdx.x * gridDim.z + blockIdx.z), (int)(gridDim.x * gridDim.z),
@@ -1222,6 +1462,7 @@ struct WgradProblem {
   __device__ static Extras load_extras(const WgradParams&, const WgradTile&, const float*, int) { return Extras{}; }
   __device__ static void emit4(const WgradParams&, const WgradTile&, RowEpi<BN_>&, float*, int, int, const float4&, const Extras&) {}
   __device__ static void epi_finish(const WgradParams&, const WgradTile&, RowEpi<BN_>&, float*, float*, int) {}
+  __device__ static void epi_consts(const WgradParams&, const WgradTile&, RowEpi<BN_>&, int) {}
   __device__ static int red_rows(const WgradParams&, const WgradTile&) { return BLOCK_M; }
   __device__ static void finish_cluster(const WgradParams&, const WgradTile&, int, int, int) {}
   using Params = WgradParams;
@@ -1523,11 +1764,38 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
   const bool add = prm.epi.addend != nullptr;
   dfb_status st = DFB_OK;
   bool launched = false;
+  // Many more tiles than CTA slots, one column tile, no split: CTAs that live for the whole launch (tc_persistent_kernel),
+  // as many as balance the tiles over whole waves (512 tiles on 296 slots -> 256 CTAs with two tiles each)
+  if constexpr (BN == 32 && WMODE != W_PACKED) {
+    const size_t slots = (size_t)sm_count() * 2;
+    if (persistent_enabled() && classes == 1 && prm.splits == 1 && grid.y == 1 && (size_t)grid.x > slots) {
+      const int n_tiles = (int)grid.x;
+      const int waves = (int)((grid.x + slots - 1) / slots);
+      const unsigned ctas = (unsigned)((n_tiles + waves - 1) / waves);
+      if (part) {   // one partial per CTA instead of one per tile
+        prm.epi.stat_cnt = part + (size_t)ctas * 3 * n_out;
+      }
+      grid = dim3(ctas, 1, 1);
+      if constexpr (WMODE == W_KRSC_FPROP) {
+        if (prm.epi.stat_kind == EPI_STATS) st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_STATS>>(name, ma, mb, prm, n_tiles, ctas);
+        else st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_NONE>>(name, ma, mb, prm, n_tiles, ctas);
+      } else {
+        if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu && add) st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_RELU | EF_ADDEND>>(name, ma, mb, prm, n_tiles, ctas);
+        else if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu) st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_RELU>>(name, ma, mb, prm, n_tiles, ctas);
+        else if (prm.epi.stat_kind == EPI_BNBWD && add) st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_ADDEND>>(name, ma, mb, prm, n_tiles, ctas);
+        else if (prm.epi.stat_kind == EPI_BNBWD) st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_BNBWD>>(name, ma, mb, prm, n_tiles, ctas);
+        else if (add) st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_ADDEND>>(name, ma, mb, prm, n_tiles, ctas);
+        else st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_NONE>>(name, ma, mb, prm, n_tiles, ctas);
+      }
+      launched = true;
+    }
+  }
   if constexpr (WMODE == W_KRSC_FPROP) {
-    if (prm.epi.stat_kind == EPI_STATS) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_STATS>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+    if (!launched && prm.epi.stat_kind == EPI_STATS) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_STATS>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
   }
   if constexpr (WMODE == W_KRSC_DGRAD) {
-    if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu && add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_RELU | EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
+    if (launched) {
+    } else if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu && add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_RELU | EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
     else if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_RELU>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
     else if (prm.epi.stat_kind == EPI_BNBWD && add) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD | EF_ADDEND>>(name, ma, mb, prm, grid, prm.splits); launched = true; }
     else if (prm.epi.stat_kind == EPI_BNBWD) { st = launch<ConvProblem<BN, WMODE, ROWS, EF_BNBWD>>(name, ma, mb, prm, grid, prm.splits); launched = true; }

@@ -556,6 +556,9 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
                             bool clip, float lo, float hi) {
     check(dfb_augment_batch(dptr(x), dptr(y), dptr(table), N, C, H, W, pad, clip ? 1 : 0, lo, hi));
   });
+  m.def("dropout_mask", [](const py::object& mask, size_t n, float keep_prob, const py::object& state) {
+    check(dfb_dropout_mask(dptr(mask), n, keep_prob, dptr(state)));
+  });
   m.def("onehot_smooth", [](const py::object& labels, const py::object& y, size_t n, int classes, float on_value, float off_value) {
     check(dfb_onehot_smooth(dptr(labels), dptr(y), n, classes, on_value, off_value));
   });

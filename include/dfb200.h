@@ -123,6 +123,11 @@ DFB_API dfb_status dfb_prefetch_wait(void);
 #define DFB_AUGMENT_FIELDS 8
 DFB_API dfb_status dfb_augment_batch(const float* x, float* y, const float* table, int N, int C, int H, int W,
                                      int pad, int clip, float clip_lo, float clip_hi);
+/* Dropout mask on the device (opt-in, DEEPFLOWS_DROPOUT=device): mask[i] = Philox4x32-10(key (seed, 0xCAFEF00D), counter
+ * (i / 4, step, i >> 34, 0))[i % 4] * 2^-32 < keep_prob ? 1 : 0, with seed = state[0], step = state[1] read from device
+ * memory (floats holding integers < 2^24), so a captured graph draws a new mask at every replay when the host bumps
+ * state[1]. The reference draws the mask with numpy on the host (nn/modules/dropout.py:27-29): that remains the default. */
+DFB_API dfb_status dfb_dropout_mask(float* mask, size_t n, float keep_prob, const float* state);
 DFB_API dfb_status dfb_onehot_smooth(const float* labels, float* y, size_t n, int classes, float on_value,
                                      float off_value);
 

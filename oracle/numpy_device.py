@@ -429,6 +429,12 @@ def _off(h, k):
     return (h[0], h[1] + k) if isinstance(h, tuple) else (h, k)
 
 
+def dropout_mask(mask, n, keep_prob, state):
+    _count("dropout_mask")
+    st = _flat(state)
+    _flat(mask)[:n] = ops.philox_dropout_mask(n, keep_prob, int(round(float(st[0]))), int(round(float(st[1]))))
+
+
 def relu_fwd(x, y, n):
     _count("relu_fwd"); _flat(y)[:n] = ops.relu_fwd(_flat(x)[:n])
 

@@ -352,3 +352,25 @@ def smooth_one_hot(labels, num_classes, eps):
     """float32 one-hot rows * (1 - eps) + eps / num_classes, each step rounded to float32 [181-183]."""
     hot = (np.asarray(labels).reshape(-1, 1) == np.arange(num_classes)[None, :]).astype(F32)
     return hot * F32(1 - eps) + F32(eps / num_classes)
+
+
+def philox_dropout_mask(n, keep_prob, seed, step):
+    """Restates dfb_dropout_mask (deepflows_b200/csrc/data_ops.cu): Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel
+    random numbers: as easy as 1, 2, 3", SC'11 - the published algorithm; constants 0xD2511F53 / 0xCD9E8D57 / Weyl
+    0x9E3779B9, 0xBB67AE85), key (seed, 0xCAFEF00D), counter (i // 4, step, (i // 4) >> 32, 0); element i takes word i % 4;
+    mask = float32(word) * 2^-32 < keep_prob. (Opt-in device RNG; the reference itself draws with numpy on the host.)"""
+    groups = (n + 3) // 4
+    g = np.arange(groups, dtype=np.uint64)
+    c = [g & np.uint64(0xFFFFFFFF), np.full(groups, step, np.uint64), g >> np.uint64(32), np.zeros(groups, np.uint64)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64(0xCAFEF00D)
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    words = np.stack(c, axis=1).reshape(-1)[:n].astype(np.uint32)
+    u = words.astype(np.float32) * np.float32(2.3283064365386963e-10)
+    return (u < np.float32(keep_prob)).astype(np.float32)

@@ -133,3 +133,38 @@ def check_adagrad_adadelta(device):
                     ref[i] = ref[i] - upd
         for p, r in zip(params, ref):
             assert rel_err(p.data.numpy(), r) < 1e-5, name
+
+
+def check_device_dropout(device, mask_of):
+    """Opt-in device RNG for Dropout: the Philox mask kernel against its oracle restatement (bit-exact), the published
+    Philox4x32-10 known answer, and the module path (train scaling 1/(1-p), a new mask every step, reproducible by seed)."""
+    from oracle import numpy_ops as ops
+    from DeepFlows import backend_api, nn, tensor
+    from DeepFlows.tensor import Tensor
+    # Random123 known-answer test: counter (0,0,0,0), key (0,0) -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8
+    g = np.zeros(1, np.uint64)
+    c = [g.copy(), g.copy(), g.copy(), g.copy()]
+    k0, k1, m32 = np.uint64(0), np.uint64(0), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c[0], np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & m32, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & m32]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+    assert [int(v[0]) for v in c] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    for n, keep, seed, step in [(1000, 0.5, 12345, 1), (4099, 0.8, 7, 300), (8, 0.25, 16777215, 2)]:
+        assert np.array_equal(mask_of(n, keep, seed, step), ops.philox_dropout_mask(n, keep, seed, step)), (n, keep, seed, step)
+    backend_api.set_dropout_rng("device")
+    try:
+        outs = []
+        for _ in range(2):
+            tensor.Graph.free_graph_all()
+            np.random.seed(3)
+            drop = nn.Dropout(0.25)
+            drop.train()
+            x = Tensor(np.ones((64, 128), F32), device=device)
+            a, b = drop(x).numpy(), drop(x).numpy()
+            assert set(np.unique(a)) <= {0.0, np.float32(1 / 0.75)} and 0.6 < (a > 0).mean() < 0.9
+            assert not np.array_equal(a, b), "the second step must draw a new mask"
+            outs.append((a, b))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), "same numpy seed, same masks"
+    finally:
+        backend_api.set_dropout_rng("host")

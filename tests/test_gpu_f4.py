@@ -22,3 +22,15 @@ def test_activation_modules(cuda_device):
 
 def test_adagrad_adadelta(cuda_device):
     ops_f4.check_adagrad_adadelta(cuda_device)
+
+
+def test_device_dropout(cuda_device):
+    import numpy as np
+    m = cuda_device.mod
+
+    def mask_of(n, keep, seed, step):
+        hm, hs = m.Array(n), m.Array(2)
+        m.from_numpy(np.array([seed, step], np.float32), hs)
+        m.dropout_mask(hm, n, keep, hs)
+        return m.to_numpy(hm, [n], [1], 0)
+    ops_f4.check_device_dropout(cuda_device, mask_of)

@@ -22,6 +22,9 @@ CONV_SHAPES = [  # N, C, H, W, K, R, pad, stride
     (256, 128, 4, 4, 256, 3, 1, 2),    # layer 4 entry
     (3, 8, 7, 9, 12, 3, 1, 1),         # ragged: 189 pixels, 12 output channels
     (10, 16, 20, 20, 272, 3, 1, 1),    # three column tiles, last one partial
+    (256, 32, 16, 16, 32, 3, 1, 1),    # 512 tiles of 32 channels: the persistent kernel (row-halo), two tiles per CTA
+    (150, 32, 32, 32, 32, 1, 0, 1),    # 1200 tiles, 1x1 (the first layer's column-matrix convolution), uneven tiles per CTA
+    (301, 8, 12, 12, 24, 3, 1, 1),     # persistent, ragged: 339 tiles, the last one partial, 8 -> 24 channels
 ]
 
 
