@@ -223,7 +223,7 @@ class _conv2d(FusedOperator):
         mode = precision_mode()
         if xd.is_channels_last():
             layout = LAYOUT_NHWC
-        elif xd.is_compact() and (mode in (0, 3) or c <= 4):
+        elif xd.is_compact() and (mode == 3 or c <= 4):
             layout = LAYOUT_NCHW  # the FFMA / first-layer kernels gather straight from NCHW (network input)
         else:
             xd, layout = xd.channels_last(), LAYOUT_NHWC
@@ -236,14 +236,17 @@ class _conv2d(FusedOperator):
         y = dev.Array(n * oh * ow * k)
         if (c <= 4 and c * r * r <= 32 and k % 4 == 0 and mode == 1 and n * oh * ow >= 16384 and self._want_stats and get_fusion()
                 and w_layout == WLAYOUT_KRSC and dev.has("stem_cols") and tensor.is_grad_enable()):
-            # First layer (image input) at training batch sizes in TF32 mode: the receptive fields are written once as a
+            # First layer (image input) at training batch sizes in TF32 mode (fp32 mode keeps the exact FFMA first-layer kernels): the receptive fields are written once as a
             # [pixels x 32] column matrix; the convolution is its 1x1 convolution with the padded weights on the tensor
             # pipe (statistics for the BatchNorm included), and the matrix is kept for the weight gradient.
             cols = c * r * r
             col, wp, mean_var = dev.Array(n * oh * ow * 32), dev.Array(k * 32), dev.Array(2 * k)
             dev.stem_cols(xd._handle, layout, col, n, c, h, w, r, p, s, w_layout)
             dev.stem_pad_weights(wd._handle, wp, k, cols)
-            dev.conv2d_fprop_stats(col, LAYOUT_NHWC, wp, WLAYOUT_KRSC, y, n, 32, oh, ow, k, 1, 0, 1, mode, mean_var)
+            # (in the fp32-accurate three-term mode 0: 27-75 taps of an HBM-bound layer cost nothing extra, and the network's
+            # input layer keeps its precision in TF32 mode as it did on the FFMA first-layer kernels - with TF32 operands
+            # here the BatchNorm behind it turns a 5e-4 output error into a 1e-1 error of this layer's weight gradient)
+            dev.conv2d_fprop_stats(col, LAYOUT_NHWC, wp, WLAYOUT_KRSC, y, n, 32, oh, ow, k, 1, 0, 1, 0, mean_var)
             self._col = (col, oh, ow, cols)
             out = _nhwc_view(y, n, k, oh, ow, dev)
             out._aux = ("colstats", mean_var)

@@ -1,13 +1,15 @@
 // Dispatchers for the dense contractions: matmul / gemm / conv2d fprop, dgrad, wgrad.
 //
-// mode DFB_MODE_FP32 and DFB_MODE_SIMT run the exact-fp32 FFMA kernels (gemm_simt.cu);
-// DFB_MODE_TF32 / DFB_MODE_BF16 run the TMA + tcgen05 kernels (gemm_tc.cu) when the shape
-// qualifies and otherwise the FFMA kernels (which are more accurate, never less).
+// DFB_MODE_TF32 runs the TMA + tcgen05 kernels (gemm_tc.cu) with one kind::tf32 MMA per k-step; DFB_MODE_FP32 runs the
+// same kernels in their fp32-accurate form (operands split into TF32 high and low parts in shared memory, three MMAs per
+// k-step into the fp32 accumulator; DFB_FP32_TC=0 keeps it on the FFMA kernels). Shapes the tensor-core path does not
+// take, DFB_MODE_BF16 (no separate bf16 operand format exists: it is served like SIMT, never less accurate than asked
+// for) and DFB_MODE_SIMT run the exact-fp32 FFMA kernels (gemm_simt.cu).
 #include "kernels.cuh"
 
 using namespace dfb;
 
-static bool want_tc(int mode) { return mode == DFB_MODE_TF32 || mode == DFB_MODE_BF16; }
+static bool want_tc(int mode) { return mode == DFB_MODE_TF32 || mode == DFB_MODE_FP32; }   // gemm_tc.cu: select_mode
 
 static dfb_status check_mode(const char* name, int mode) {
   DFB_REQUIRE(mode >= DFB_MODE_FP32 && mode <= DFB_MODE_SIMT, DFB_ERR_INVALID, "%s: unknown mode %d", name, mode);

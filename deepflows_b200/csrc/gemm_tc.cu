@@ -512,7 +512,9 @@ __global__ void __launch_bounds__(128) epi_finalize_kernel(const float* __restri
 // BKR: rows of one B chunk when they differ from KR (wgrad row-halo: 128-pixel A chunks, 192-row B halo chunks).
 // OUT: a dedicated output staging tile behind the ring (the persistent kernel's epilogue overlaps the next tile's loads,
 // so it cannot borrow the pipeline stages)
-template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K, int BSUB = 1, int BKR = KR, bool OUT = false>
+// XMUL = 2 (the fp32-accurate "3xTF32" kernels): every stage is followed by a second copy of itself that holds the
+// low-order parts of the operands (same relative layout, so the same descriptors + kStageBytes address them)
+template <int BN, int AROWS = BLOCK_M, int KR = BLOCK_K, int BSUB = 1, int BKR = KR, bool OUT = false, int XMUL = 1>
 struct SmemLayout {
   // What one SM can pull through TMA is bounded by the bytes it keeps in flight (loads take microseconds to
   // return under load), and a CTA's prologue / epilogue / split-K reduction are pure latency: TWO CTAs per SM
@@ -525,21 +527,25 @@ struct SmemLayout {
   static constexpr uint32_t kBChunk = BKR * 128;
   static constexpr uint32_t kBTile = (BN / 32) * kBChunk;
   static constexpr uint32_t kBBytes = BSUB * kBTile;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;            // what TMA fills (and the split warps transform)
+  static constexpr uint32_t kStageStride = XMUL * kStageBytes;          // distance between stages
   static constexpr uint32_t kOutBytes = OUT ? ((BLOCK_M * (BN + 4) * 4 + 1023) & ~1023u) : 0;
-  static constexpr uint32_t kBudget = (BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
-                                                : (BN >= 256 ? (192u << 10) : (100u << 10))) - kOutBytes;  // (128 x 256 at two CTAs per SM with two stages: measured 7% slower)
-  static constexpr int kStagesFit = (int)(kBudget / kStageBytes);
-  static constexpr int kMinStages = (BSUB > 1 || BKR != KR) ? 2 : 3;   // halo variants: two CTAs per SM with two stages each
+  // (XMUL = 2: two CTAs per SM while two double stages fit 100 KB, else one CTA with ~200 KB)
+  static constexpr uint32_t kBudget = XMUL > 1 ? (2 * kStageStride <= (100u << 10) ? (100u << 10) : (200u << 10))
+                                               : (BSUB > 1 ? (BN >= 128 ? (216u << 10) : (108u << 10))
+                                                           : (BN >= 256 ? (192u << 10) : (100u << 10))) - kOutBytes;  // (128 x 256 at two CTAs per SM with two stages: measured 7% slower)
+  static constexpr int kStagesFit = (int)(kBudget / kStageStride);
+  static constexpr int kMinStages = (BSUB > 1 || BKR != KR || XMUL > 1) ? 2 : 3;   // halo variants: two CTAs per SM with two stages each
   static constexpr int kStages = kStagesFit > 12 ? 12 : (kStagesFit < kMinStages ? kMinStages : kStagesFit);
-  static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+  static constexpr uint32_t kBarOffset = kStages * kStageStride;
+  static constexpr int kNumBars = (XMUL > 1 ? 3 : 2) * kStages + 1;     // full, empty, accumulator-complete [, split done]
   // the M = 128 MMA always addresses four 32-row chunks of A: with AROWS < 128 it reads past the A tile (into the
   // B tile / the next stage: rows that are never stored), so the last stage needs that much slack behind it
   // (AROWS == 32: the A descriptor's chunk stride is 0, all four chunks alias the one that is loaded - no over-read)
   static constexpr uint32_t kOverRead = (AROWS == 32 || AROWS >= BLOCK_M) ? 0 : ((BLOCK_M - AROWS) / 32) * kChunk;
   // fused-epilogue scratch behind the barriers (row-major problems): 128 row pointers + per-warp column statistics
   // [4 warps][4 values][BN columns]
-  static constexpr uint32_t kEpiOffset = kBarOffset + kOverRead + (2 * kStages + 1) * 8 + 16;
+  static constexpr uint32_t kEpiOffset = kBarOffset + kOverRead + kNumBars * 8 + 16;
   static constexpr uint32_t kEpiBytes = 1024 + 64 * BN;
   static constexpr uint32_t kOutOffset = (kEpiOffset + 16 + kEpiBytes + 48 + 15) & ~15u;   // (+48: the persistent kernel's three extra barriers)
   static constexpr uint32_t kTotal = kOutOffset + kOutBytes + 1024;  // +1024 for manual alignment
@@ -547,22 +553,49 @@ struct SmemLayout {
   static constexpr uint32_t kRedPitch = BN + 4;
   // (the 128 x 256 kernels never split K: they are only chosen for problems with hundreds of tiles)
   static_assert(AROWS < BLOCK_M || BLOCK_M * kRedPitch * 4 <= kBarOffset, "output tile does not fit the pipeline stages");
-  static_assert(kTotal <= 227u * 1024u, "more shared memory than a CTA can have");
+  static constexpr bool kFits = kTotal <= 227u * 1024u;
+  static_assert(XMUL > 1 || kFits, "more shared memory than a CTA can have");
 };
 
-template <class P>
+// X3 = true: fp32-accurate contraction on the tensor pipe ("3xTF32", the package's default fp32 mode). TMA delivers fp32
+// operands; the four epilogue warps, idle during the main loop, split every stage in shared memory into a TF32-exact high
+// part (written back in place: hi = rna_tf32(v)) and a low part (lo = rna_tf32(v - hi), the second half of the stage), and
+// the MMA warp issues hi*hi + lo*hi + hi*lo into the same fp32 accumulator. What is dropped is lo*lo and the rounding of
+// lo: <= 2^-21 per product relative to |a||b| - the size of fp32's own accumulation error (measured against the fp64
+// contraction in tests/test_gpu_l1.py), and independent of how the hardware rounds fp32 operands to TF32.
+// Replaces the FFMA kernels of gemm_simt.cu as what an unchanged script runs (reference kernel being replaced:
+// ndarray_backend_cuda.cu:443-466).
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class P, bool X3 = false>
 __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                       const __grid_constant__ CUtensorMap map_b,
                                                       const typename P::Params prm) {
   constexpr int BN = P::BN;
-  using L = SmemLayout<BN, P::AROWS, P::KR, P::kBSub, P::BKR>;
+  using L = SmemLayout<BN, P::AROWS, P::KR, P::kBSub, P::BKR, false, X3 ? 2 : 1>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset + L::kOverRead);
   constexpr int kStages = L::kStages;
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* split_bar = tmem_full_bar + 1;   // [kStages] (X3 only): the stage's hi / lo parts are in place
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + (X3 ? kStages : 0));
+  (void)split_bar;
+  // X3: a second accumulator (columns + kTmemCols) takes the two small terms lo*hi + hi*lo. The tensor core's fp32
+  // accumulation is not round-to-nearest (measured: the error against float64 grows linearly with the number of MMAs
+  // accumulated into a tile, ~1.2e-8 per MMA relative to the accumulator), so the large term hi*hi gets one accumulation
+  // per k-step instead of three, and the small terms, whose own rounding is 2^-11 further down, are added once at the end.
+  constexpr int kTmemAlloc = X3 ? 2 * P::kTmemCols : P::kTmemCols;
+  static_assert(kTmemAlloc <= 512, "TMEM columns");
   // fused-epilogue scratch: output row pointers of the tile, per-warp column statistics
   float** row_tab = reinterpret_cast<float**>(smem + ((L::kEpiOffset + 15) & ~15u));
   float* wstat = reinterpret_cast<float*>(row_tab + BLOCK_M);
@@ -594,11 +627,12 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
+      if constexpr (X3) mbar_init(split_bar + s, 4);   // one arrival per split (epilogue) warp
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<P::kTmemCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<kTmemAlloc>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -623,7 +657,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     typename P::Iter it = P::iter_init(prm, tile, kb_begin);
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(empty_bar + stage, phase ^ 1);
-      const uint32_t a_dst = smem_u32(smem + stage * L::kStageBytes);
+      const uint32_t a_dst = smem_u32(smem + stage * L::kStageStride);
       const uint32_t b_dst = a_dst + L::kABytes;
       if (elect_one()) {
         mbar_expect_tx(full_bar + stage, tx);
@@ -643,10 +677,10 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
-      mbar_wait(full_bar + stage, phase);
+      mbar_wait((X3 ? split_bar : full_bar) + stage, phase);   // X3: the split warps waited for the TMA bytes
       tc_fence_after();
       if (kb == kb_begin) TC_STAMP(5);
-      const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
+      const uint32_t a_base = smem_u32(smem + stage * L::kStageStride);
       const uint32_t b_base = a_base + L::kABytes;
       if (elect_one()) {
         // sub-tiles (taps that share a halo tile of this stage) are the INNER loop: with separate accumulators
@@ -658,9 +692,14 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
           for (int t = 0; t < P::kSubTiles; ++t) {
             const uint32_t a_sub = a_base + P::a_sub_offset(prm, t), b_sub = b_base + P::b_sub_offset(prm, t, L::kBTile);
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * P::kAccStride);  // kAccStride == 0: one shared accumulator
-            const uint64_t b_desc = P::kRuntimeLbo ? operand_desc_mn(b_sub, j, P::b_lbo(prm)) : operand_desc<P::B_MAJOR, L::kBChunk>(b_sub, j);
-            umma_tf32(d_tmem, operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_sub, j), b_desc, idesc,
-                      (kb > kb_begin || (P::kAccStride == 0 && t > 0) || j > 0) ? 1u : 0u);
+            const uint32_t first = (kb > kb_begin || (P::kAccStride == 0 && t > 0) || j > 0) ? 1u : 0u;
+#pragma unroll
+            for (int term = 0; term < (X3 ? 3 : 1); ++term) {   // hi*hi, lo*hi, hi*lo (the low parts: + kStageBytes)
+              const uint32_t a_op = a_sub + (term == 1 ? L::kStageBytes : 0u), b_op = b_sub + (term == 2 ? L::kStageBytes : 0u);
+              const uint64_t b_desc = P::kRuntimeLbo ? operand_desc_mn(b_op, j, P::b_lbo(prm)) : operand_desc<P::B_MAJOR, L::kBChunk>(b_op, j);
+              umma_tf32(d_tmem + (term > 0 ? (uint32_t)P::kTmemCols : 0u), operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_op, j), b_desc, idesc,
+                        term == 2 ? 1u : first);
+            }
           }
         }
         umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs have read it
@@ -675,6 +714,33 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    if constexpr (X3) {
+      // ----- split warps: hi in place, lo behind the stage -----
+      const int t = (warp - 2) * 32 + lane;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        const uint32_t base = smem_u32(smem + stage * L::kStageStride) + (uint32_t)t * 16u;
+        constexpr int kVecs = (int)(L::kStageBytes / 16 / 128);   // 16-byte vectors per thread (stages are multiples of 4 KB)
+        static_assert(L::kStageBytes % 2048 == 0, "stage size");
+#pragma unroll 4
+        for (int i = 0; i < kVecs; ++i) {
+          const uint32_t addr = base + (uint32_t)i * 2048u;
+          const float4 v = lds_f4(addr);
+          float4 hi, lo;
+          hi.x = rna_tf32(v.x); hi.y = rna_tf32(v.y); hi.z = rna_tf32(v.z); hi.w = rna_tf32(v.w);
+          lo.x = rna_tf32(v.x - hi.x); lo.y = rna_tf32(v.y - hi.y); lo.z = rna_tf32(v.z - hi.z); lo.w = rna_tf32(v.w - hi.w);
+          sts_f4(addr, hi);
+          sts_f4(addr + L::kStageBytes, lo);
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (elect_one()) mbar_arrive_cta(split_bar + stage);
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
     if (kb_end > kb_begin) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -693,6 +759,12 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       float v[32];
       if (kb_end > kb_begin) {
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc, v);
+        if constexpr (X3) {   // + the accumulator of the small terms
+          float v2[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(P::kTmemCols + cc), v2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += v2[i];
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -816,7 +888,7 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
   if (warp == 2) TC_STAMP(12);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<P::kTmemCols>(tmem_base);
+    tmem_dealloc<kTmemAlloc>(tmem_base);
     TC_STAMP(13);
   }
 }
@@ -832,24 +904,29 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-template <class P>
-__global__ void __launch_bounds__(kThreads) tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                 const __grid_constant__ CUtensorMap map_b,
-                                                                 const typename P::Params prm, const int n_tiles) {
+// X3 (fp32-accurate form, see tc_kernel): four more warps (6-9) split every stage into its TF32 high / low parts - the
+// epilogue warps are busy with the previous tile here - and each of the two accumulators has a second one for the small terms.
+template <class P, bool X3 = false>
+__global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads) tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                                       const __grid_constant__ CUtensorMap map_b,
+                                                                                       const typename P::Params prm, const int n_tiles) {
   constexpr int BN = P::BN;
   static_assert(P::kRowMajor && P::kAccTiles == 1 && P::kAccStride == 0, "persistent kernel: row-major, one accumulator tile");
-  using L = SmemLayout<BN, P::AROWS, P::KR, P::kBSub, P::BKR, true>;
+  using L = SmemLayout<BN, P::AROWS, P::KR, P::kBSub, P::BKR, true, X3 ? 2 : 1>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset + L::kOverRead);
   constexpr int kStages = L::kStages;
   uint64_t* empty_bar = full_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_bar + kStages + 1);
+  uint64_t* split_bar = empty_bar + kStages + 1;   // [kStages], X3 only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + (X3 ? kStages : 0));
+  (void)split_bar;
   float** row_tab = reinterpret_cast<float**>(smem + ((L::kEpiOffset + 15) & ~15u));
   float* wstat = reinterpret_cast<float*>(row_tab + BLOCK_M);
   uint64_t* tmem_full_bar = reinterpret_cast<uint64_t*>(smem + L::kOutOffset - 48);   // [2] full, [2] empty
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  constexpr int kAccCols = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators (BN is a power of two >= 32)
+  constexpr int kAccW = X3 ? 2 * BN : BN;               // columns of one accumulator (X3: + the small-term accumulator)
+  constexpr int kAccCols = 2 * kAccW < 32 ? 32 : 2 * kAccW;   // two accumulators (BN is a power of two >= 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -858,6 +935,7 @@ __global__ void __launch_bounds__(kThreads) tc_persistent_kernel(const __grid_co
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
+      if constexpr (X3) mbar_init(split_bar + s, 4);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar + a, 1);
@@ -882,7 +960,7 @@ __global__ void __launch_bounds__(kThreads) tc_persistent_kernel(const __grid_co
       typename P::Iter it = P::iter_init(prm, tile, tile.kb_begin);
       for (int kb = tile.kb_begin; kb < tile.kb_end; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
-        const uint32_t a_dst = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t a_dst = smem_u32(smem + stage * L::kStageStride);
         const uint32_t b_dst = a_dst + L::kABytes;
         if (elect_one()) {
           mbar_expect_tx(full_bar + stage, tx);
@@ -907,11 +985,11 @@ __global__ void __launch_bounds__(kThreads) tc_persistent_kernel(const __grid_co
         mbar_wait(tmem_empty_bar + acc, (uint32_t)(((lt >> 1) - 1) & 1));
         tc_fence_after();
       }
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccW);
       for (int kb = tile.kb_begin; kb < tile.kb_end; ++kb) {
-        mbar_wait(full_bar + stage, phase);
+        mbar_wait((X3 ? split_bar : full_bar) + stage, phase);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t a_base = smem_u32(smem + stage * L::kStageStride);
         const uint32_t b_base = a_base + L::kABytes;
         if (elect_one()) {
 #pragma unroll
@@ -919,8 +997,13 @@ __global__ void __launch_bounds__(kThreads) tc_persistent_kernel(const __grid_co
 #pragma unroll
             for (int t = 0; t < P::kSubTiles; ++t) {
               const uint32_t a_sub = a_base + P::a_sub_offset(prm, t), b_sub = b_base + P::b_sub_offset(prm, t, L::kBTile);
-              umma_tf32(d_tmem, operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_sub, j),
-                        operand_desc<P::B_MAJOR, L::kBChunk>(b_sub, j), idesc, (kb > tile.kb_begin || t > 0 || j > 0) ? 1u : 0u);
+              const uint32_t first = (kb > tile.kb_begin || t > 0 || j > 0) ? 1u : 0u;
+#pragma unroll
+              for (int term = 0; term < (X3 ? 3 : 1); ++term) {   // hi*hi | lo*hi, hi*lo into the small-term accumulator
+                const uint32_t a_op = a_sub + (term == 1 ? L::kStageBytes : 0u), b_op = b_sub + (term == 2 ? L::kStageBytes : 0u);
+                umma_tf32(d_tmem + (term > 0 ? (uint32_t)BN : 0u), operand_desc<P::A_MAJOR, (P::AROWS == 32 ? 0u : L::kChunk)>(a_op, j),
+                          operand_desc<P::B_MAJOR, L::kBChunk>(b_op, j), idesc, term == 2 ? 1u : first);
+              }
             }
           }
           umma_commit(empty_bar + stage);
@@ -930,6 +1013,36 @@ __global__ void __launch_bounds__(kThreads) tc_persistent_kernel(const __grid_co
       }
       if (elect_one()) umma_commit(tmem_full_bar + acc);
       __syncwarp();
+    }
+  } else if (warp >= 6) {
+    // ===== split warps (X3): hi in place, lo behind the stage =====
+    if constexpr (X3) {
+      const int t = (warp - 6) * 32 + lane;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+        const typename P::Tile tile = P::tile_at(prm, ti);
+        for (int kb = tile.kb_begin; kb < tile.kb_end; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          const uint32_t base = smem_u32(smem + stage * L::kStageStride) + (uint32_t)t * 16u;
+          constexpr int kVecs = (int)(L::kStageBytes / 16 / 128);
+#pragma unroll 4
+          for (int i = 0; i < kVecs; ++i) {
+            const uint32_t addr = base + (uint32_t)i * 2048u;
+            const float4 v = lds_f4(addr);
+            float4 hi, lo;
+            hi.x = rna_tf32(v.x); hi.y = rna_tf32(v.y); hi.z = rna_tf32(v.z); hi.w = rna_tf32(v.w);
+            lo.x = rna_tf32(v.x - hi.x); lo.y = rna_tf32(v.y - hi.y); lo.z = rna_tf32(v.z - hi.z); lo.w = rna_tf32(v.w - hi.w);
+            sts_f4(addr, hi);
+            sts_f4(addr + L::kStageBytes, lo);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) mbar_arrive_cta(split_bar + stage);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else {
     // ===== epilogue warps: drain accumulator lt & 1 while the next tile's MMAs run =====
@@ -955,7 +1068,13 @@ __global__ void __launch_bounds__(kThreads) tc_persistent_kernel(const __grid_co
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
         float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cc), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccW + cc), v);
+        if constexpr (X3) {
+          float v2[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccW + BN + cc), v2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += v2[i];
+        }
         const uint32_t dst = stage_u32 + (uint32_t)(row * kPitch + cc) * 4u;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) sts_f4(dst + i * 4, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
@@ -1043,13 +1162,18 @@ static bool make_map(CUtensorMap* map, const float* base, int rank, const uint64
   return r == CUDA_SUCCESS;
 }
 
+// fp32-accurate mode of the current call (set by the tc_* entry points): launch() then picks tc_kernel<P, true>
+static thread_local bool g_x3 = false;
 template <class P>
-static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
-                         dim3 grid, int splits = 1) {
-  using L = SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR>;
+static constexpr bool x3_fits() { return SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR, false, 2>::kFits; }
+
+template <class P, bool X3>
+static dfb_status launch_variant(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
+                                 dim3 grid, int splits) {
+  using L = SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR, false, X3 ? 2 : 1>;
   static bool configured = false;
   if (!configured) {
-    DFB_CUDA(cudaFuncSetAttribute(tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    DFB_CUDA(cudaFuncSetAttribute(tc_kernel<P, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
     configured = true;
   }
   if (P::kClusterSplit) {
@@ -1068,32 +1192,61 @@ static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensor
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel<P>, ma, mb, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel<P, X3>, ma, mb, prm);
     if (e != cudaSuccess) {
       cudaGetLastError();
       DFB_FAIL(DFB_ERR_RUNTIME, "%s cluster launch (splits %d) failed: %s", name, splits, cudaGetErrorString(e));
     }
   } else {
-    launch_k(tc_kernel<P>, grid, kThreads, L::kTotal, compute_stream(), ma, mb, prm);
+    launch_k(tc_kernel<P, X3>, grid, kThreads, L::kTotal, compute_stream(), ma, mb, prm);
   }
   DFB_LAUNCH_CHECK(name);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return DFB_OK;
 }
-
 template <class P>
-static dfb_status launch_persistent(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
-                                    int n_tiles, unsigned ctas) {
-  using L = SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR, true>;
+static dfb_status launch(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
+                         dim3 grid, int splits = 1) {
+  if (g_x3) {
+    if constexpr (x3_fits<P>()) {
+      return launch_variant<P, true>(name, ma, mb, prm, grid, splits);
+    } else {
+      DFB_FAIL(DFB_ERR_RUNTIME, "%s: this tile variant has no fp32-accurate form (host selection error)", name);
+    }
+  }
+  return launch_variant<P, false>(name, ma, mb, prm, grid, splits);
+}
+
+template <class P, bool X3>
+static dfb_status launch_persistent_variant(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
+                                            int n_tiles, unsigned ctas) {
+  using L = SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR, true, X3 ? 2 : 1>;
   static bool configured = false;
   if (!configured) {
-    DFB_CUDA(cudaFuncSetAttribute(tc_persistent_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
+    DFB_CUDA(cudaFuncSetAttribute(tc_persistent_kernel<P, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal));
     configured = true;
   }
-  launch_k(tc_persistent_kernel<P>, dim3(ctas, 1, 1), kThreads, L::kTotal, compute_stream(), ma, mb, prm, n_tiles);
+  launch_k(tc_persistent_kernel<P, X3>, dim3(ctas, 1, 1), X3 ? kThreads + 128 : kThreads, L::kTotal, compute_stream(), ma, mb, prm, n_tiles);
   DFB_LAUNCH_CHECK(name);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return DFB_OK;
+}
+// fp32-accurate form only where two CTAs still share an SM (the grid is sized for that): the kernels without row halo
+template <class P>
+static constexpr bool x3_persistent_ok() {
+  return P::kSubTiles == 1 && SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR, true, 2>::kTotal <= 113u * 1024u;
+}
+template <class P>
+static dfb_status launch_persistent(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm,
+                                    int n_tiles, unsigned ctas) {
+  if (g_x3) {
+    if constexpr (x3_persistent_ok<P>()) {
+      return launch_persistent_variant<P, true>(name, ma, mb, prm, n_tiles, ctas);
+    } else {
+      DFB_FAIL(DFB_ERR_RUNTIME, "%s: no fp32-accurate persistent form of this variant (host selection error)", name);
+    }
+  }
+  return launch_persistent_variant<P, false>(name, ma, mb, prm, n_tiles, ctas);
 }
 // DFB_CONV_PERSISTENT=0 switches the persistent variant off (every tile its own CTA again)
 static bool persistent_enabled() {
@@ -1229,7 +1382,10 @@ static dfb_status run_gemm(const float* A, const float* B, const GemmParams& prm
   if (!ok) return DFB_OK;  // not representable as a tensor map -> FFMA path
   *handled = true;
   dim3 grid(cdiv(prm.M, BLOCK_M), cdiv(prm.N, BN), 1);
-  const int splits = BN >= 256 ? 1 : pick_splits((size_t)grid.x * grid.y, (prm.K + BLOCK_K - 1) / BLOCK_K);
+  const int k_blocks = (prm.K + BLOCK_K - 1) / BLOCK_K;
+  int splits = BN >= 256 ? 1 : pick_splits((size_t)grid.x * grid.y, k_blocks);
+  if (BN < 256 && g_x3)   // fp32-accurate mode: at most 128 k-blocks per TMEM accumulator (the partial tiles are added in true fp32)
+    while (splits < 8 && k_blocks / splits > 128) splits *= 2;
   grid.z = (unsigned)splits;
   return launch<GemmProblem<A_MAJ, B_MAJ, BN>>("tc_gemm", ma, mb, prm, grid, splits);
 }
@@ -1240,7 +1396,7 @@ static dfb_status run_gemm_bn(const float* A, const float* B, const GemmParams& 
   if (prm.N <= 64) return run_gemm<A_MAJ, B_MAJ, 64>(A, B, prm, lda, ldb, handled);
   // 128 x 256 tiles move a third fewer operand bytes per FLOP through L2 -> SM, which is what bounds the big
   // problems; only when they still fill the machine twice over
-  if (prm.N > 128 && (size_t)cdiv(prm.M, BLOCK_M) * cdiv(prm.N, 256) >= (size_t)sm_count() * 2)
+  if (prm.N > 128 && (size_t)cdiv(prm.M, BLOCK_M) * cdiv(prm.N, 256) >= (size_t)sm_count() * 2 && !(g_x3 && prm.K > 128 * BLOCK_K))
     return run_gemm<A_MAJ, B_MAJ, 256>(A, B, prm, lda, ldb, handled);
   return run_gemm<A_MAJ, B_MAJ, 128>(A, B, prm, lda, ldb, handled);
 }
@@ -1750,6 +1906,8 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
   // stride-2 dgrad classes hold about a quarter of the taps each
   const int kblocks = ROWS ? prm.R * prm.cblks : prm.R * prm.R * prm.cblks / (classes == 4 ? 4 : 1);
   prm.splits = BN >= 256 ? 1 : pick_splits((size_t)grid.x * grid.y * classes, kblocks > 0 ? kblocks : 1);
+  if (BN < 256 && g_x3)
+    while (prm.splits < 8 && kblocks * (ROWS ? 3 : 1) / prm.splits > 128) prm.splits *= 2;
   grid.z = (unsigned)(classes * prm.splits);
   float* part = nullptr;
   if (prm.epi.stat_kind != EPI_NONE) {  // one partial per (pixel tile, class / split rank) + its row count
@@ -1768,7 +1926,7 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
   // as many as balance the tiles over whole waves (512 tiles on 296 slots -> 256 CTAs with two tiles each)
   if constexpr (BN == 32 && WMODE != W_PACKED) {
     const size_t slots = (size_t)sm_count() * 2;
-    if (persistent_enabled() && classes == 1 && prm.splits == 1 && grid.y == 1 && (size_t)grid.x > slots) {
+    if (persistent_enabled() && (!g_x3 || !ROWS) && classes == 1 && prm.splits == 1 && grid.y == 1 && (size_t)grid.x > slots) {
       const int n_tiles = (int)grid.x;
       const int waves = (int)((grid.x + slots - 1) / slots);
       const unsigned ctas = (unsigned)((n_tiles + waves - 1) / waves);
@@ -1873,7 +2031,7 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
   // Row-halo kernel: 3x3, stride 1, at most 128 output channels (beyond that the weights dominate the traffic),
   // and a 128-pixel tile of ow_t x oh_t pixels inside one image with ow_t in {8, 16, 32}.
   bool rows = false;
-  if (conv_rows_enabled() && stride == 1 && par_pad < 0 && R == 3 && n_out <= 128) {
+  if (conv_rows_enabled() && stride == 1 && par_pad < 0 && R == 3 && n_out <= (g_x3 ? 64 : 128)) {   // (fp32-accurate mode: two double stages of the 128-wide halo variant do not fit)
     const int ow_r = std::min(32, pow2_ceil(OW)), oh_r = BLOCK_M / ow_r;
     if (ow_r >= 8 && pow2_ceil(OH) >= oh_r) {
       rows = true;
@@ -1942,6 +2100,22 @@ static dfb_status run_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradP
   if (prm.Kout <= 64) return launch<WgradProblem<BN, 64, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
   return launch<WgradProblem<BN, 128, 32>>("tc_conv_wgrad", ma, mb, prm, grid);
 }
+// which kernel family serves `mode`: TF32 -> one MMA per k-step; FP32 -> the fp32-accurate three-term kernels (X3), unless
+// DFB_FP32_TC=0 keeps the fp32 mode on the FFMA kernels of gemm_simt.cu; BF16 / SIMT -> not here
+static bool select_mode(int mode) {
+  static int fp32_tc = -1;
+  if (fp32_tc < 0) {
+    const char* e = getenv("DFB_FP32_TC");
+    fp32_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (mode == DFB_MODE_TF32) { g_x3 = false; return true; }
+  if (mode == DFB_MODE_FP32 && fp32_tc) { g_x3 = true; return true; }
+  return false;
+}
+// The first layer (through its column matrix) is fp32-accurate in TF32 mode as well: its weight gradient is a sum over
+// every pixel of the batch of terms that the BatchNorm behind it has made cancel (measured with TF32 operands: 4e-2 of its
+// own size at batch 256), and three MMAs instead of one cost an HBM-bound layer nothing.
+static int stem_mode(int mode) { return (mode == DFB_MODE_TF32 && select_mode(DFB_MODE_FP32)) ? DFB_MODE_FP32 : mode; }
 }  // namespace tc
 
 static bool tc_disabled() {
@@ -1957,7 +2131,7 @@ dfb_status tc_gemm(const float* A, const float* B, float* C, int M, int N, int K
                    int ldc, int accumulate, const float* bias, int mode, bool* handled) {
   using namespace tc;
   *handled = false;
-  if (tc_disabled() || mode != DFB_MODE_TF32) return DFB_OK;
+  if (tc_disabled() || !select_mode(mode)) return DFB_OK;
   if (K <= 0 || (lda & 3) || (ldb & 3)) return DFB_OK;
   if ((size_t)M * N < 4096 || K < 16) return DFB_OK;  // launch-latency territory: FFMA kernel is as fast
   const int vec_ok = ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) ? 1 : 0;
@@ -1969,7 +2143,7 @@ dfb_status tc_gemm(const float* A, const float* B, float* C, int M, int N, int K
 }
 
 static bool conv_tc_ok(int N, int C, int H, int W, int K, int R, int pad, int stride, int mode) {
-  if (tc_disabled() || mode != DFB_MODE_TF32) return false;
+  if (tc_disabled() || !tc::select_mode(mode)) return false;
   if ((C & 3) || (K & 3) || R > 11 || stride < 1 || stride > 2) return false;
   if (stride == 2 && ((H & 1) || (W & 1))) return false;
   if (H + 2 * pad < R || W + 2 * pad < R) return false;
@@ -2043,6 +2217,10 @@ static dfb_status wgrad_impl(const float* x, const float* dy, float* dw, int w_l
   int splits = (int)std::max<size_t>(1, ((size_t)sm_count() * 2 + base_ctas - 1) / base_ctas);  // two CTAs per SM
   splits = std::min(splits, std::max(1, prm.pix_blocks / 8));
   splits = std::min(splits, 128);
+  // fp32-accurate mode: at most 512 k-steps accumulate into one TMEM tile (see tc_kernel: the tensor core's accumulation
+  // error grows with their number); the partial tiles are then added in true fp32
+  const int x3_need = g_x3 ? std::min(512, (int)cdiv(prm.pix_blocks, 4096 / prm.kr)) : 1;
+  splits = std::max(splits, x3_need);
   prm.csize = 1; prm.groups = 1;
   prm.krsc = w_layout == DFB_WLAYOUT_KRSC ? 1 : 0;
   prm.dw = dw;
@@ -2055,6 +2233,7 @@ static dfb_status wgrad_impl(const float* x, const float* dy, float* dw, int w_l
     // and a second wave would double the kernel's time
     const size_t slots = cs == 8 ? 256 : (cs == 4 ? 288 : (size_t)sm_count() * 2);
     int groups = (int)std::max<size_t>(1, std::min<size_t>((size_t)(splits / cs), slots / (base_ctas * cs)));
+    groups = std::max(groups, (int)cdiv(x3_need, cs));
     prm.blocks_per_split = (prm.pix_blocks + groups - 1) / groups;  // per group; the kernel cuts it by cluster rank
     groups = (prm.pix_blocks + prm.blocks_per_split - 1) / prm.blocks_per_split;
     prm.csize = cs; prm.groups = groups;
@@ -2176,7 +2355,7 @@ static bool stem_tc_enabled() {
 dfb_status tc_stem_wgrad(const float* x, int x_layout, const float* dy, float* dw, int w_layout, int N, int C, int H, int W, int K, int R,
                          int pad, int stride, int mode, bool* handled) {
   *handled = false;
-  if (!stem_tc_enabled() || tc_disabled() || mode != DFB_MODE_TF32) return DFB_OK;
+  if (!stem_tc_enabled() || tc_disabled() || mode != DFB_MODE_TF32) return DFB_OK;   // (fp32 mode: the exact FFMA gather kernel)
   const int cols = C * R * R;
   if (C > 4 || cols > 32 || (K & 3) || stride < 1 || H + 2 * pad < R || W + 2 * pad < R) return DFB_OK;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
@@ -2194,7 +2373,7 @@ dfb_status tc_stem_wgrad(const float* x, int x_layout, const float* dy, float* d
     DFB_FAIL(DFB_ERR_RUNTIME, "stem_cols launch failed: %s", cudaGetErrorString(e));
   }
   // the column matrix is an (N, OH, OW, 32) channels-last activation; its 1x1 wgrad has cols valid channels
-  st = wgrad_impl(col, dy, dw, w_layout, N, 32, OH, OW, K, 1, 0, 1, mode, cols, handled);
+  st = wgrad_impl(col, dy, dw, w_layout, N, 32, OH, OW, K, 1, 0, 1, tc::stem_mode(mode), cols, handled);
   dfb_free(col);
   return st;
 }
@@ -2221,7 +2400,7 @@ dfb_status tc_stem_pad_weights(const float* w, float* wp, int K, int cols) {
 }
 dfb_status tc_wgrad_cols(const float* col, const float* dy, float* dw, int w_layout, int N, int OH, int OW, int K, int cols, int mode,
                          bool* handled) {
-  return wgrad_impl(col, dy, dw, w_layout, N, 32, OH, OW, K, 1, 0, 1, mode, cols, handled);
+  return wgrad_impl(col, dy, dw, w_layout, N, 32, OH, OW, K, 1, 0, 1, tc::stem_mode(mode), cols, handled);
 }
 
 #ifdef DFB_TC_TIMING

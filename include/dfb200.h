@@ -48,9 +48,11 @@ enum {
 /* GEMM / conv operand precision modes (north star: fp32-accurate, TF32, BF16 operand modes;
  * accumulation is always fp32). */
 enum {
-  DFB_MODE_FP32 = 0,  /* exact fp32 operands and FFMA accumulation (parity within 1e-5 of the reference)      */
+  DFB_MODE_FP32 = 0,  /* fp32-accurate (parity within 1e-5 of the reference): tcgen05 with operands split into TF32 high and
+                         low parts, three MMAs per k-step, fp32 accumulation in TMEM ("3xTF32"); FFMA kernels for shapes
+                         the tensor-core path does not take, or for everything with DFB_FP32_TC=0                     */
   DFB_MODE_TF32 = 1,  /* tcgen05 kind::tf32: fp32 operands read as TF32, fp32 accumulation in TMEM (2e-2)      */
-  DFB_MODE_BF16 = 2,  /* reserved for a bf16-operand tcgen05 path; currently served by the exact FFMA kernels  */
+  DFB_MODE_BF16 = 2,  /* accepted for API completeness: no bf16 operand format exists, served by the exact FFMA kernels    */
   DFB_MODE_SIMT = 3   /* force the generic FFMA kernels (no first-layer / tensor-core specialisations; tests)  */
 };
 

@@ -212,6 +212,67 @@ def test_tf32_conv_runs_on_the_tensor_pipe(cuda_device, shape):
     assert rel_err(got[0], want[0]) > 1e-6
 
 
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_fp32_conv_runs_on_the_tensor_pipe(cuda_device, shape):
+    """fp32 mode (the package default): fprop / dgrad / wgrad launch the fp32-accurate tcgen05 kernels (operands split into
+    TF32 high and low parts, three MMAs per k-step; gemm_tc.cu tc_kernel<P, true>) and agree with the float64 contraction
+    (the exact FFMA kernels, MODE_SIMT, for the largest cases) within north_star's 1e-5."""
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = shape
+    rng = np.random.RandomState(sum(shape) + 5)
+    x = rng.randn(n, c, h, w).astype(F32)
+    wt = (rng.randn(k, c, r, r) / np.sqrt(c * r * r)).astype(F32)
+    oh, ow = ops.out_size(h, r, p, s), ops.out_size(w, r, p, s)
+    gy = rng.randn(n, k, oh, ow).astype(F32)
+    hx, hw, hgy = up(m, nhwc(x)), up(m, wt), up(m, nhwc(gy))
+    hy, hdx, hdw = m.Array(n * oh * ow * k), m.Array(x.size), m.Array(wt.size)
+    t0 = m.tc_launch_count()
+    m.conv2d_fprop(hx, m.LAYOUT_NHWC, hw, hy, n, c, h, w, k, r, p, s, m.MODE_FP32, None, 0)
+    t1 = m.tc_launch_count()
+    m.conv2d_dgrad(hgy, hw, hdx, n, c, h, w, k, r, p, s, m.MODE_FP32, m.DGRAD_EXACT, None, 0)
+    t2 = m.tc_launch_count()
+    m.conv2d_wgrad(hx, m.LAYOUT_NHWC, hgy, hdw, n, c, h, w, k, r, p, s, m.MODE_FP32, None, 0)
+    t3 = m.tc_launch_count()
+    assert t1 == t0 + 1 and t3 == t2 + 1 and t2 == t1 + 1
+    if n * oh * ow * k > 50000:
+        ry, rdx, rdw = m.Array(n * oh * ow * k), m.Array(x.size), m.Array(wt.size)
+        m.conv2d_fprop(hx, m.LAYOUT_NHWC, hw, ry, n, c, h, w, k, r, p, s, m.MODE_SIMT, None, 0)
+        m.conv2d_dgrad(hgy, hw, rdx, n, c, h, w, k, r, p, s, m.MODE_SIMT, m.DGRAD_EXACT, None, 0)
+        m.conv2d_wgrad(hx, m.LAYOUT_NHWC, hgy, rdw, n, c, h, w, k, r, p, s, m.MODE_SIMT, None, 0)
+        want = (down(m, ry, (n, oh, ow, k)), down(m, rdx, (n, h, w, c)), down(m, rdw, wt.shape))
+    else:
+        want = (nhwc(ops.conv2d_fprop(x, wt, p, s)), nhwc(ops.conv2d_dgrad_exact(gy, wt, x.shape, p, s)),
+                ops.conv2d_wgrad(x, gy, wt.shape, p, s))
+    got = (down(m, hy, (n, oh, ow, k)), down(m, hdx, (n, h, w, c)), down(m, hdw, wt.shape))
+    for name, a, b in zip(("fprop", "dgrad", "wgrad"), got, want):
+        e = rel_err(a, b)
+        assert e < 1e-5, (name, e)
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(256, 128, 512, 0, 0), (256, 128, 512, 0, 1), (256, 128, 512, 1, 0), (256, 128, 512, 1, 1),
+                                         (300, 72, 200, 0, 0), (1000, 260, 36, 1, 0), (8192, 64, 4096, 0, 1), (129, 33, 40, 1, 1),
+                                         (19000, 512, 64, 0, 0), (19000, 300, 40, 1, 0)])
+def test_fp32_gemm_runs_on_the_tensor_pipe(cuda_device, M, N, K, ta, tb):
+    """fp32 mode with TMA-compatible operands: ONE tcgen05 launch (the three-term kernel) and the float64 product within
+    1e-5 - and an error three orders of magnitude below the TF32 kernel's on the same operands."""
+    m = cuda_device.mod
+    rng = np.random.RandomState(M * 7 + N + 1)
+    ra, ca = (K, M) if ta else (M, K)
+    rb, cb = (N, K) if tb else (K, N)
+    lda, ldb = (ca + 3) // 4 * 4, (cb + 3) // 4 * 4
+    A, B = rng.randn(ra, lda).astype(F32), rng.randn(rb, ldb).astype(F32)
+    a = (A[:, :ca].T if ta else A[:, :ca]).astype(np.float64)
+    b = (B[:, :cb].T if tb else B[:, :cb]).astype(np.float64)
+    hA, hB, hC, hT = up(m, A), up(m, B), m.Array(M * N), m.Array(M * N)
+    before = m.tc_launch_count()
+    m.gemm(hA, hB, hC, M, N, K, ta, tb, lda, ldb, N, 0, None, m.MODE_FP32)
+    assert m.tc_launch_count() == before + 1
+    m.gemm(hA, hB, hT, M, N, K, ta, tb, lda, ldb, N, 0, None, m.MODE_TF32)
+    err, err_tf32 = rel_err(down(m, hC, (M, N)), a @ b), rel_err(down(m, hT, (M, N)), a @ b)
+    assert err < 1e-5, err
+    assert err * 100 < err_tf32, (err, err_tf32)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K,ta,tb", [(64, 10, 3136, 0, 0), (256, 100, 784, 0, 0), (100, 784, 256, 1, 0), (256, 784, 100, 0, 1),
                                          (33, 65, 129, 1, 1), (128, 128, 128, 0, 0), (512, 256, 1024, 0, 1), (4096, 10, 256, 0, 0),
