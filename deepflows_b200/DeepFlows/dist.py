@@ -191,6 +191,8 @@ class DataParallel:
     def _launch_bucket(self, b):
         flat, slots = self._plan[b]
         dev = flat.device
+        if dev.has("side_join"):
+            dev.side_join()   # the bucket's weight gradients may still be on the side stream (lagged joins of conv backward)
         srcs, dsts, sizes = [], [], []
         for i, off, n in slots:
             p = self.params[i]

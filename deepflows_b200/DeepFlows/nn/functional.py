@@ -14,6 +14,7 @@ implemented as ONE graph node over the device's fused (L1) entry points.
 Activations flow between these ops as logical (N,C,H,W) views over channels-last memory, which is
 also the physical order the reference's conv output has before its final transpose [343-344].
 """
+import os
 from typing import Optional
 
 from .. import tensor
@@ -196,6 +197,17 @@ def cross_entropy(input: Tensor, target: Tensor, reduction: str = "mean", dim: i
 # ------------------------------------------------------------------------------------------------
 # convolution
 # ------------------------------------------------------------------------------------------------
+_SIDE_STREAM = os.environ.get("DEEPFLOWS_SIDE", "1") != "0"   # 0: weight gradients stay on the compute stream (measurements)
+_SIDE_LAG = int(os.environ.get("DEEPFLOWS_SIDE_LAG", "2"))      # 0: join the weight gradient right behind its dgrad (round 1)
+
+
+def _lazy(dev):
+    """Trailing `lazy` argument of conv2d_fprop_stats / conv2d_dgrad_fused on a device that has statistic slots
+    (include/dfb200.h: dfb_conv2d_fprop_stats_lazy): the statistics go ONLY to the BatchNorm kernels - here: to the BnApply
+    record of the BatchNorm behind the convolution, and to `bn_bwd_apply` of the BatchNorm(s) that receive the gradient."""
+    return (True,) if dev.has("STATS_LAZY") else ()
+
+
 class _conv2d(FusedOperator):
     def __init__(self, x: Tensor, kernel: Tensor, padding: int, stride: int, want_stats: bool = False):
         self.padding, self.stride = int(padding), int(stride)
@@ -246,7 +258,7 @@ class _conv2d(FusedOperator):
             # (in the fp32-accurate three-term mode 0: 27-75 taps of an HBM-bound layer cost nothing extra, and the network's
             # input layer keeps its precision in TF32 mode as it did on the FFMA first-layer kernels - with TF32 operands
             # here the BatchNorm behind it turns a 5e-4 output error into a 1e-1 error of this layer's weight gradient)
-            dev.conv2d_fprop_stats(col, LAYOUT_NHWC, wp, WLAYOUT_KRSC, y, n, 32, oh, ow, k, 1, 0, 1, 0, mean_var)
+            dev.conv2d_fprop_stats(col, LAYOUT_NHWC, wp, WLAYOUT_KRSC, y, n, 32, oh, ow, k, 1, 0, 1, 0, mean_var, *_lazy(dev))
             self._col = (col, oh, ow, cols)
             out = _nhwc_view(y, n, k, oh, ow, dev)
             out._aux = ("colstats", mean_var)
@@ -254,7 +266,7 @@ class _conv2d(FusedOperator):
         if self._want_stats and get_fusion() and dev.has("conv2d_fprop_stats") and tensor.is_grad_enable():
             # the BatchNorm that follows gets the per-channel mean / variance of y from this kernel's epilogue
             mean_var = dev.Array(2 * k)
-            dev.conv2d_fprop_stats(xd._handle, layout, wd._handle, w_layout, y, n, c, h, w, k, r, p, s, mode, mean_var)
+            dev.conv2d_fprop_stats(xd._handle, layout, wd._handle, w_layout, y, n, c, h, w, k, r, p, s, mode, mean_var, *_lazy(dev))
             out = _nhwc_view(y, n, k, oh, ow, dev)
             out._aux = ("colstats", mean_var)
             return out
@@ -274,7 +286,12 @@ class _conv2d(FusedOperator):
         dx = dw = None
         # dgrad and wgrad only share their inputs: when both are needed the wgrad goes to the side stream
         # and the two kernels (neither fills 148 SMs on the small layers) run concurrently
-        both = needs[0] and needs[1] and dev.has("side_begin")
+        both = needs[0] and needs[1] and dev.has("side_begin") and _SIDE_STREAM
+        # The weight gradient is read by nobody before the end of backward() (Tensor.backward joins the side stream there;
+        # DeepFlows.dist joins before it packs a bucket), so the compute stream only waits for the weight gradient of
+        # _SIDE_LAG layers ago: wgrad overlaps the next layers' dgrad / BatchNorm chain instead of sitting on it. Not when
+        # the weight already holds a gradient (shared weights, accumulation): the sum would read dw right away.
+        lazy_join = both and _SIDE_LAG > 0 and dev.has("side_join_lag") and self.inputs[1].grad is None
         if needs[1]:
             # the weight gradient is produced in the weight's own layout, so optimizer and all-reduce walk
             # the two buffers side by side
@@ -302,7 +319,7 @@ class _conv2d(FusedOperator):
                 dev.conv2d_dgrad_fused(gy._handle, self._w._handle, self._wl[0] if self._wl else WLAYOUT_KCRS, buf, n, c, h, w, k, r, p,
                                        s, self._mode, dmode, addend._handle if addend is not None else None,
                                        recs[0].bwd_tuple() if len(recs) > 0 else None, recs[1].bwd_tuple() if len(recs) > 1 else None,
-                                       sums, relu_expr is not None, res._handle if res is not None else None)
+                                       sums, relu_expr is not None, res._handle if res is not None else None, *_lazy(dev))
                 dx = _nhwc_view(buf, n, c, h, w, dev)
                 if recs:
                     # (the 4th entry tells the ReLU node between this convolution and the BatchNorm(s) that its mask is applied)
@@ -314,7 +331,10 @@ class _conv2d(FusedOperator):
                                  *self._wl)
                 dx = _nhwc_view(buf, n, c, h, w, dev)
         if both:
-            dev.side_join()
+            if lazy_join:
+                dev.side_join_lag(_SIDE_LAG)
+            else:
+                dev.side_join()
         return dx, dw
 
     def _dgrad_fusion(self, dev, n, c, h, w):
@@ -552,9 +572,11 @@ class _batch_norm_train(FusedOperator):
             sums, row = aux[1], aux[2][id(self._rec)]
             db = BackendTensor.make((1, c, 1, 1), None, dev, sums, 0)
             dg = BackendTensor.make((1, c, 1, 1), None, dev, sums, row * c)
+            if dx is None and dev.has("STATS_LAZY"):
+                dx = dev.Array(rows * c)   # lazily delivered sums become dbeta / dgamma in this kernel: it has to run
             if dx is not None:
                 dev.bn_bwd_apply(xd._handle, gy._handle, gh, self._mean, self._invstd, (sums, 0), (sums, row * c), dx, rows, c)
-            out = [_nhwc_view(dx, n, c, h, w, dev) if dx is not None else None]
+            out = [_nhwc_view(dx, n, c, h, w, dev) if needs[0] else None]
             if self._affine:
                 out += [dg if needs[1] else None, db if needs[2] else None]
             return out

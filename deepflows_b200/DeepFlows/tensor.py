@@ -351,6 +351,9 @@ class Tensor:
                 node._ngrads = 0
                 if not node.is_leaf:
                     node.grad = None
+            dev = self.data.device
+            if dev.has("side_join"):
+                dev.side_join()   # weight gradients still on the side stream (nn/functional.py: _conv2d.backward_all)
         hook = Tensor._post_backward_hook
         if hook is not None:
             hook()

@@ -84,9 +84,27 @@ static inline unsigned bw_grid(size_t work_items, unsigned threads, unsigned cta
 // dependencies. This hides most of the per-kernel launch latency that dominates a step made of ~190 kernels of
 // a few microseconds each. DFB_PDL=0 disables the attribute (pdl_sync() is then a no-op).
 bool pdl_enabled();
+// ---- step timeline (dfb_trace_begin / dfb_trace_end, scripts/step_timeline.py) -------------------------------------------
+// While a trace is armed, thread 0 of CTA (0,0,0) of every kernel appends (%globaltimer, grid / block fingerprint) to a
+// device buffer right after pdl_sync() - the moment its real work starts, also inside a replayed CUDA graph, where no
+// host-side tool of this image sees individual kernels - and the host notes (name, fingerprint, stream) of every launch it
+// makes (during a graph's capture: the same sequence the replay runs). Unarmed, the cost is one predicated load per kernel.
+void trace_host_launch(const void* func, dim3 grid, dim3 block, cudaStream_t stream);
+bool trace_host_armed();
+void trace_register_symbol(void (*setter)(unsigned long long*));
 #ifdef __CUDACC__
+static __device__ unsigned long long* d_trace_buf = nullptr;   // one copy per translation unit, all set by dfb_trace_begin
+namespace {
+struct TraceSymbolInit {
+  TraceSymbolInit() {
+    trace_register_symbol(+[](unsigned long long* p) { cudaMemcpyToSymbol(d_trace_buf, &p, sizeof(p)); });
+  }
+};
+static TraceSymbolInit trace_symbol_init_;
+}  // namespace
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  if (trace_host_armed()) trace_host_launch(reinterpret_cast<const void*>(kernel), grid, block, stream);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -103,6 +121,19 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+    unsigned long long* tb = d_trace_buf;   // [0] = records so far, [1] = capacity, then (time, fingerprint) pairs
+    if (tb) {
+      const unsigned long long i = atomicAdd(tb, 1ull);
+      if (i < tb[1]) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        tb[2 + 2 * i] = now;
+        tb[3 + 2 * i] = (unsigned long long)gridDim.x | ((unsigned long long)gridDim.y << 24) | ((unsigned long long)gridDim.z << 40) |
+                        ((unsigned long long)blockDim.x << 52);
+      }
+    }
+  }
 }
 #endif
 
@@ -139,6 +170,7 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t remote) {
 template <typename... KArgs, typename... Args>
 inline void launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, unsigned cluster_x,
                              Args&&... args) {
+  if (trace_host_armed()) trace_host_launch(reinterpret_cast<const void*>(kernel), grid, block, stream);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -121,8 +121,8 @@ dfb_status dfb_conv2d_wgrad(const float* x, int x_layout, const float* dy, float
 
 // y = conv(x, w) and mean_var[2][K] = per-channel mean / biased variance of y over (N, OH, OW): what the BatchNorm that
 // follows needs (DeepFlows/nn/modules/batchnorm.py:33-42), without a pass of its own over y
-dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H,
-                                  int W, int K, int R, int pad, int stride, int mode, float* mean_var) {
+static dfb_status fprop_stats_impl(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H,
+                                   int W, int K, int R, int pad, int stride, int mode, float* mean_var, int lazy) {
   DFB_INIT();
   DFB_REQUIRE(x && w && y && mean_var, DFB_ERR_INVALID, "conv2d_fprop_stats: null pointer");
   DFB_REQUIRE(x_layout == DFB_LAYOUT_NCHW || x_layout == DFB_LAYOUT_NHWC, DFB_ERR_INVALID, "conv2d_fprop_stats: bad layout");
@@ -130,6 +130,7 @@ dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, 
   if (st != DFB_OK) return st;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - R) / stride + 1;
   DFB_REQUIRE(OH > 0 && OW > 0 && N > 0, DFB_ERR_INVALID, "conv2d_fprop_stats: empty output");
+  stat_slot_drop(mean_var);
   bool handled = false;
   if (mode != DFB_MODE_SIMT) {
     st = direct_conv_fprop(x, x_layout, w, w_layout, y, N, C, H, W, K, R, pad, stride, &handled);
@@ -139,6 +140,7 @@ dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, 
     ConvFuse f{};
     f.kind = FUSE_STATS;
     f.stats_out = mean_var;
+    f.lazy = lazy;
     st = tc_conv_fprop(x, w, w_layout, y, N, C, H, W, K, R, pad, stride, mode, nullptr, 0, &handled, &f);
     if (st != DFB_OK || handled) return st;
   }
@@ -148,15 +150,23 @@ dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, 
   }
   return dfb_colstats_mean_var(y, (size_t)N * OH * OW, K, mean_var);
 }
+dfb_status dfb_conv2d_fprop_stats(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H,
+                                  int W, int K, int R, int pad, int stride, int mode, float* mean_var) {
+  return fprop_stats_impl(x, x_layout, w, w_layout, y, N, C, H, W, K, R, pad, stride, mode, mean_var, 0);
+}
+dfb_status dfb_conv2d_fprop_stats_lazy(const float* x, int x_layout, const float* w, int w_layout, float* y, int N, int C, int H,
+                                       int W, int K, int R, int pad, int stride, int mode, float* mean_var) {
+  return fprop_stats_impl(x, x_layout, w, w_layout, y, N, C, H, W, K, R, pad, stride, mode, mean_var, 1);
+}
 
 // dx = dgrad(dy, w) [+ addend], and for n_bn (0..2) BatchNorms whose OUTPUT gradient dx is: sums[0][C] = sum(dx),
 // sums[1 + i][C] = sum(dx * x_hat_i) with x_hat_i = (bn_x_i - bn_mean_i) * bn_invstd_i - the two reductions of the
 // BatchNorm backward (dbeta, dgamma), so that it only needs its elementwise pass (dfb_bn_bwd_apply)
-dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
-                                  int R, int pad, int stride, int mode, int dgrad_mode, const float* addend, int n_bn,
-                                  const float* bn_x0, const float* bn_mean0, const float* bn_invstd0, const float* bn_x1,
-                                  const float* bn_mean1, const float* bn_invstd1, float* sums, int relu, const float* gamma0,
-                                  const float* beta0, const float* gamma1, const float* beta1, const float* relu_res) {
+static dfb_status dgrad_fused_impl(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
+                                   int R, int pad, int stride, int mode, int dgrad_mode, const float* addend, int n_bn,
+                                   const float* bn_x0, const float* bn_mean0, const float* bn_invstd0, const float* bn_x1,
+                                   const float* bn_mean1, const float* bn_invstd1, float* sums, int relu, const float* gamma0,
+                                   const float* beta0, const float* gamma1, const float* beta1, const float* relu_res, int lazy) {
   DFB_INIT();
   DFB_REQUIRE(dy && w && dx, DFB_ERR_INVALID, "conv2d_dgrad_fused: null pointer");
   DFB_REQUIRE(n_bn >= 0 && n_bn <= 2, DFB_ERR_INVALID, "conv2d_dgrad_fused: n_bn must be 0, 1 or 2");
@@ -167,8 +177,10 @@ dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout,
               "conv2d_dgrad_fused: bad dgrad_mode %d", dgrad_mode);
   dfb_status st = check_mode("conv2d_dgrad_fused", mode);
   if (st != DFB_OK) return st;
+  stat_slot_drop(sums);
   if (want_tc(mode) && dgrad_mode == DFB_DGRAD_EXACT) {
     ConvFuse f{};
+    f.lazy = lazy;
     f.addend = addend;
     f.kind = n_bn ? FUSE_BNBWD : FUSE_NONE;
     f.n_sets = n_bn;
@@ -207,6 +219,23 @@ dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout,
     if (st != DFB_OK) return st;
   }
   return DFB_OK;
+}
+
+dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
+                                  int R, int pad, int stride, int mode, int dgrad_mode, const float* addend, int n_bn,
+                                  const float* bn_x0, const float* bn_mean0, const float* bn_invstd0, const float* bn_x1,
+                                  const float* bn_mean1, const float* bn_invstd1, float* sums, int relu, const float* gamma0,
+                                  const float* beta0, const float* gamma1, const float* beta1, const float* relu_res) {
+  return dgrad_fused_impl(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, addend, n_bn, bn_x0, bn_mean0, bn_invstd0,
+                          bn_x1, bn_mean1, bn_invstd1, sums, relu, gamma0, beta0, gamma1, beta1, relu_res, 0);
+}
+dfb_status dfb_conv2d_dgrad_fused_lazy(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H, int W, int K,
+                                       int R, int pad, int stride, int mode, int dgrad_mode, const float* addend, int n_bn,
+                                       const float* bn_x0, const float* bn_mean0, const float* bn_invstd0, const float* bn_x1,
+                                       const float* bn_mean1, const float* bn_invstd1, float* sums, int relu, const float* gamma0,
+                                       const float* beta0, const float* gamma1, const float* beta1, const float* relu_res) {
+  return dgrad_fused_impl(dy, w, w_layout, dx, N, C, H, W, K, R, pad, stride, mode, dgrad_mode, addend, n_bn, bn_x0, bn_mean0, bn_invstd0,
+                          bn_x1, bn_mean1, bn_invstd1, sums, relu, gamma0, beta0, gamma1, beta1, relu_res, 1);
 }
 
 // ---- first layer (image input) through its column matrix ---------------------------------------------------------------

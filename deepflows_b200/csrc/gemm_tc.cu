@@ -248,6 +248,10 @@ struct EpiArgs {
   const float* bn_beta[2];
   const float* relu_res;
   int relu;
+  // statistic slot (kernels.cuh): when set, every CTA adds its sums to stat_acc[3][kStatSlotChannels] with fp64 atomics
+  // (EPI_STATS: the unshifted sum and sum of squares) instead of writing a partial, and no reduction kernel follows
+  double* stat_acc;
+  int lazy;                  // host only: the caller allows the slot
 };
 // (shift, sum of (v - shift), sum of (v - shift)^2, count) of one column over some rows
 struct Moments {
@@ -425,6 +429,21 @@ struct RowEpi {
         r0 = r1 = r2 = 0.f; rn = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) { r0 += wstat[(w * 4 + 0) * BN + cl]; r1 += wstat[(w * 4 + 1) * BN + cl]; r2 += wstat[(w * 4 + 2) * BN + cl]; }
+      }
+      if (e.stat_acc) {
+        double* acc = e.stat_acc + col;
+        if (stats) {
+          if (rn > 0.f) {   // sums of (v - s), (v - s)^2 over rn rows -> sums of v, v^2
+            const double s = (double)r0, m1 = (double)r1, m2 = (double)r2, n_ = (double)rn;
+            atomicAdd(acc, m1 + n_ * s);
+            atomicAdd(acc + kStatSlotChannels, m2 + 2.0 * s * m1 + n_ * s * s);
+          }
+        } else {
+          atomicAdd(acc, (double)r0);
+          atomicAdd(acc + kStatSlotChannels, (double)r1);
+          if (e.n_sets > 1) atomicAdd(acc + 2 * kStatSlotChannels, (double)r2);
+        }
+        continue;
       }
       float* dst = e.stat_part + (size_t)pidx * 3 * n_out + col;
       dst[0] = r0; dst[n_out] = r1; dst[2 * n_out] = r2;
@@ -841,33 +860,49 @@ __global__ void __launch_bounds__(kThreads) tc_kernel(const __grid_constant__ CU
       constexpr uint32_t kRedPitch = P::kAccTiles * BN + 4;
       const uint32_t red_base = smem_u32(smem);
       if constexpr (P::kRowMajor) P::epi_consts(prm, tile, epi, (t % kVecPerRow) * 4);   // this lane's columns never change
-      for (int idx = t; idx < rows_per * kVecPerRow; idx += 128) {
-        const int r = rank * rows_per + idx / kVecPerRow;
-        if (P::kDynRedRows && r >= red_rows) break;
-        const int c = (idx % kVecPerRow) * 4;
-        const uint32_t addr = red_base + (uint32_t)(r * kRedPitch + c) * 4u;
-        float* row_out = nullptr;
-        typename P::Extras ex{};
-        if constexpr (P::kRowMajor) {
-          row_out = lds_ptr(smem_u32(row_tab) + r * 8);
-          ex = P::load_extras(prm, tile, row_out, c);   // in flight together with the remote loads below
-        }
-        float4 pv[8];
+      // Two items per pass: every load of a pass (remote shared memory, the epilogue's global operands) is issued before
+      // its first global store - a store to a generic pointer orders the next item's loads behind it, and this loop is
+      // nothing but load latency (measured 2.2 - 4 us per kernel with one item per pass).
+      const int total = rows_per * kVecPerRow;
+      for (int idx0 = t; idx0 < total; idx0 += 256) {
+        int rr[2], cc[2];
+        bool ok[2];
+        float* row_out[2] = {nullptr, nullptr};
+        typename P::Extras ex[2] = {};
+        float4 pv[2][8];
 #pragma unroll
-        for (int s2 = 0; s2 < 8; ++s2)
-          if (s2 < nsplit) pv[s2] = ld_dsmem_f4(dsmem_addr(addr, (uint32_t)s2));
-        float4 acc = pv[0];
+        for (int u = 0; u < 2; ++u) {
+          const int idx = idx0 + u * 128;
+          rr[u] = rank * rows_per + idx / kVecPerRow;
+          cc[u] = (idx % kVecPerRow) * 4;
+          ok[u] = idx < total && !(P::kDynRedRows && rr[u] >= red_rows);
+          if (ok[u]) {
+            const uint32_t addr = red_base + (uint32_t)(rr[u] * kRedPitch + cc[u]) * 4u;
+            if constexpr (P::kRowMajor) {
+              row_out[u] = lds_ptr(smem_u32(row_tab) + rr[u] * 8);
+              ex[u] = P::load_extras(prm, tile, row_out[u], cc[u]);   // in flight together with the remote loads below
+            }
 #pragma unroll
-        for (int s2 = 1; s2 < 8; ++s2)  // fixed order: deterministic
-          if (s2 < nsplit) { acc.x += pv[s2].x; acc.y += pv[s2].y; acc.z += pv[s2].z; acc.w += pv[s2].w; }
-        if constexpr (P::kRowMajor) {
-          // (a split launch has at most 128 columns: one float4 column group per lane, every row seen once per lane)
-          if (row_out) {
-            P::emit4(prm, tile, epi, row_out, c, 0, acc, ex);
-            epi.n += 1.f;
+            for (int s2 = 0; s2 < 8; ++s2)
+              if (s2 < nsplit) pv[u][s2] = ld_dsmem_f4(dsmem_addr(addr, (uint32_t)s2));
           }
-        } else {
-          P::store4(prm, tile, r, c, acc);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!ok[u]) continue;
+          float4 acc = pv[u][0];
+#pragma unroll
+          for (int s2 = 1; s2 < 8; ++s2)  // fixed order: deterministic
+            if (s2 < nsplit) { acc.x += pv[u][s2].x; acc.y += pv[u][s2].y; acc.z += pv[u][s2].z; acc.w += pv[u][s2].w; }
+          if constexpr (P::kRowMajor) {
+            // (a split launch has at most 128 columns: one float4 column group per lane, every row seen once per lane)
+            if (row_out[u]) {
+              P::emit4(prm, tile, epi, row_out[u], cc[u], 0, acc, ex[u]);
+              epi.n += 1.f;
+            }
+          } else {
+            P::store4(prm, tile, rr[u], cc[u], acc);
+          }
         }
       }
     }
@@ -1192,6 +1227,7 @@ static dfb_status launch_variant(const char* name, const CUtensorMap& ma, const 
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
+    if (trace_host_armed()) trace_host_launch(reinterpret_cast<const void*>(tc_kernel<P, X3>), grid, dim3(kThreads, 1, 1), cfg.stream);
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel<P, X3>, ma, mb, prm);
     if (e != cudaSuccess) {
       cudaGetLastError();
@@ -1910,7 +1946,10 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
     while (prm.splits < 8 && kblocks * (ROWS ? 3 : 1) / prm.splits > 128) prm.splits *= 2;
   grid.z = (unsigned)(classes * prm.splits);
   float* part = nullptr;
-  if (prm.epi.stat_kind != EPI_NONE) {  // one partial per (pixel tile, class / split rank) + its row count
+  prm.epi.stat_acc = nullptr;
+  if (prm.epi.stat_kind != EPI_NONE && prm.epi.lazy)   // the consumer kernel takes the sums from a statistic slot: no partials, no reduction kernel
+    prm.epi.stat_acc = stat_slot_acquire(prm.epi.stat_out, prm.epi.stat_kind == EPI_BNBWD ? prm.epi.n_sets : 1, n_out);
+  if (prm.epi.stat_kind != EPI_NONE && !prm.epi.stat_acc) {  // one partial per (pixel tile, class / split rank) + its row count
     const size_t partials = (size_t)grid.x * grid.z;
     dfb_status st = dfb_malloc(partials * 3 * n_out + partials, &part);
     if (st != DFB_OK) return st;
@@ -2024,6 +2063,7 @@ static dfb_status conv_like(const char* name, const float* act, const float* w, 
     }
     prm.epi.relu = fuse->relu;
     prm.epi.relu_res = fuse->relu_res;
+    prm.epi.lazy = fuse->lazy;
   }
   prm.out = out; prm.n_img = N; prm.OH = OH; prm.OW = OW; prm.n_out = n_out; prm.R = R; prm.cblks = cp / 32;
   prm.dh0 = dh0; prm.dw0 = dh0; prm.sgn = sgn; prm.stride = stride; prm.c_red = actC; prm.par_pad = par_pad;

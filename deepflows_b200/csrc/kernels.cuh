@@ -40,7 +40,23 @@ struct ConvFuse {
   const float* bn_gamma[2];
   const float* bn_beta[2];
   const float* relu_res;
+  int lazy;   // the statistics may stay in a statistic slot for dfb_bn_fwd_apply / dfb_bn_bwd_apply (see below)
 };
+
+// Statistic slots (runtime.cu): where a convolution's epilogue hands per-channel sums to the BatchNorm kernel that
+// consumes them WITHOUT a reduction kernel in between. A slot is double[3][kStatSlotChannels] + an arrival counter in device
+// memory, all zeros while free. The producer's CTAs add their (fp32) partial sums with fp64 atomics - the sum of a few
+// hundred fp32 values in fp64 is exact or off by one fp64 ulp, so the fp32 results do not depend on the arrival order
+// in practice; the consumer kernel (bn_apply_fused_kernel / bn_bwd_apply_kernel) reads the sums in its prologue, CTA 0
+// publishes them as floats where the eager path would have put them, and the last CTA to have read clears the slot.
+// Keyed by the statistics buffer the two calls share; only calls that announce themselves as lazy (ConvFuse::lazy,
+// dfb_conv2d_fprop_stats_lazy / dfb_conv2d_dgrad_fused_lazy) use them. DFB_STAT_SLOTS=0 switches them off.
+constexpr int kStatSlots = 96, kStatSlotChannels = 512;
+constexpr size_t kStatSlotBytes = (size_t)3 * kStatSlotChannels * sizeof(double) + 64;   // + counter, padded
+double* stat_slot_acquire(const float* key, int consumers, int channels);   // null: none (the caller reduces eagerly)
+double* stat_slot_take(const float* key, int* last);                        // consumer side; null: the buffer holds floats
+void stat_slot_drop(const float* key);                                      // an eager producer is about to fill `key`
+__device__ __forceinline__ unsigned* stat_slot_counter(double* slot) { return reinterpret_cast<unsigned*>(slot + 3 * kStatSlotChannels); }
 
 // gemm_tc.cu — TMA + tcgen05/TMEM path. Each returns DFB_OK and sets *handled = true when it ran
 // the problem, leaves *handled = false when the shape is outside what the tensor-core kernels

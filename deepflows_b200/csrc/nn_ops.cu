@@ -8,7 +8,7 @@
 //
 // Data layout: activations are (rows = N*H*W, C) row-major, i.e. NHWC. A "column group" is 4
 // adjacent channels (one float4) when C % 4 == 0, otherwise one channel.
-#include "common.cuh"
+#include "kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -579,13 +579,38 @@ bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows,
   }
 }
 
+// Statistic slot as the source of a BatchNorm kernel's per-channel sums (kernels.cuh): `row` = which of the slot's rows
+// holds the second sum, `clear` = this launch is the slot's last consumer.
+struct StatSrc {
+  double* acc;
+  int row, clear;
+};
+// Called by every thread of every CTA after the CTA has read what it needs from the slot (and synchronised): the last CTA
+// to arrive clears the slot for its next user.
+__device__ __forceinline__ void stat_slot_release(double* acc, int C) {
+  __shared__ int s_last;
+  unsigned* counter = stat_slot_counter(acc);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      acc[c] = 0.0;
+      acc[kStatSlotChannels + c] = 0.0;
+      acc[2 * kStatSlotChannels + c] = 0.0;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
 // pass 2: dx = gamma * invstd * (dy - dbeta/n - x_hat * dgamma/n)
 template <int V>
 __global__ void __launch_bounds__(kT)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
                     size_t rows, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ gamma, const float* __restrict__ dbeta,
-                    const float* __restrict__ dgamma) {
+                    const float* __restrict__ gamma, float* dbeta, float* dgamma, StatSrc src) {
   pdl_sync();
   extern __shared__ float sm[];  // mean, invstd, k1 = gamma*invstd, mb = dbeta/n, mg = dgamma/n
   float* s_mean = sm;
@@ -595,13 +620,23 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
   float* s_mg = sm + 4 * C;
   float inv_n = 1.0f / (float)rows;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float db, dg;
+    if (src.acc) {   // the sums are still in the statistic slot the dgrad epilogue added them to (kernels.cuh)
+      db = (float)__ldcg(src.acc + c);
+      dg = (float)__ldcg(src.acc + src.row * kStatSlotChannels + c);
+      if (blockIdx.x == 0) { dbeta[c] = db; dgamma[c] = dg; }   // the parameter gradients themselves
+    } else {
+      db = dbeta[c];
+      dg = dgamma[c];
+    }
     s_mean[c] = mean[c];
     s_is[c] = invstd[c];
     s_k1[c] = invstd[c] * (gamma ? gamma[c] : 1.0f);
-    s_mb[c] = dbeta[c] * inv_n;
-    s_mg[c] = dgamma[c] * inv_n;
+    s_mb[c] = db * inv_n;
+    s_mg[c] = dg * inv_n;
   }
   __syncthreads();
+  if (src.acc && src.clear) stat_slot_release(src.acc, C);
   const int G = C / V;
   size_t total = rows * G;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -870,10 +905,23 @@ struct BnSide {
   float* running_mean;
   float* running_var;
   float momentum, eps;
+  double* acc;             // statistic slot with sum / sum of squares (lazy producer), or null: mean_var holds the floats
+  float* mean_var_out;     // where CTA 0 publishes mean / variance taken from the slot
+  float inv_rows;
 };
 __device__ __forceinline__ void bn_side_prologue(const BnSide& s, int C, float* s_mean, float* s_scale, float* s_shift) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mean = s.mean_var[c], var = s.mean_var[C + c];
+    float mean, var;
+    if (s.acc) {
+      const double m = __ldcg(s.acc + c) * (double)s.inv_rows;
+      const double v = __ldcg(s.acc + kStatSlotChannels + c) * (double)s.inv_rows - m * m;   // biased variance (batchnorm.py:38-42)
+      mean = (float)m;
+      var = fmaxf((float)v, 0.0f);
+      if (blockIdx.x == 0) { s.mean_var_out[c] = mean; s.mean_var_out[C + c] = var; }
+    } else {
+      mean = s.mean_var[c];
+      var = s.mean_var[C + c];
+    }
     const float invstd = 1.0f / sqrtf(var + s.eps);
     s_mean[c] = mean;
     s_scale[c] = invstd * (s.gamma ? s.gamma[c] : 1.0f);
@@ -896,6 +944,8 @@ bn_apply_fused_kernel(BnSide a, BnSide b, const float* __restrict__ res, float* 
   bn_side_prologue(a, C, am, as, ah);
   if (DUAL) bn_side_prologue(b, C, bm, bs, bh);
   __syncthreads();
+  if (a.acc) stat_slot_release(a.acc, C);
+  if (DUAL && b.acc) stat_slot_release(b.acc, C);
   const int G = C / V;
   const size_t total = rows * G;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -1107,9 +1157,9 @@ dfb_status dfb_bn_bwd(const float* x, const float* dy, const float* gamma, const
     bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
     size_t sm2 = (size_t)5 * C * sizeof(float);
     if (C % 4 == 0 && al)
-      launch_k(bn_bwd_apply_kernel<4>, ew_grid(rows * (C / 4)), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, db, dg);
+      launch_k(bn_bwd_apply_kernel<4>, ew_grid(rows * (C / 4)), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, db, dg, StatSrc{nullptr, 0, 0});
     else
-      launch_k(bn_bwd_apply_kernel<1>, ew_grid(rows * C), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, db, dg);
+      launch_k(bn_bwd_apply_kernel<1>, ew_grid(rows * C), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, db, dg, StatSrc{nullptr, 0, 0});
     DFB_LAUNCH_CHECK("bn_bwd_apply");
   }
   dfb_free(scratch);
@@ -1120,6 +1170,7 @@ dfb_status dfb_colstats_mean_var(const float* x, size_t rows, int C, float* mean
   DFB_INIT();
   DFB_REQUIRE(x && mean_var, DFB_ERR_INVALID, "colstats_mean_var: null pointer");
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "colstats_mean_var: empty input");
+  stat_slot_drop(mean_var);
   SumsArgs a{};
   a.x = x;
   a.out0 = mean_var;
@@ -1139,8 +1190,13 @@ dfb_status dfb_bn_fwd_apply(const float* x, const float* mean_var, const float* 
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_fwd_apply: empty input");
   const size_t smem = (size_t)(x2 ? 6 : 3) * C * sizeof(float);
   DFB_REQUIRE(smem <= 48 * 1024, DFB_ERR_INVALID, "bn_fwd_apply: too many channels (%d)", C);
-  BnSide a{x, mean_var, gamma, beta, save_mean, save_invstd, running_mean, running_var, momentum, eps};
-  BnSide b{x2, mean_var2, gamma2, beta2, save_mean2, save_invstd2, running_mean2, running_var2, momentum2, eps2};
+  // lazy statistics (dfb_conv2d_fprop_stats_lazy): still in their statistic slots
+  int last_a = 0, last_b = 0;
+  double* acc_a = stat_slot_take(mean_var, &last_a);
+  double* acc_b = x2 ? stat_slot_take(mean_var2, &last_b) : nullptr;
+  const float inv_rows = 1.0f / (float)rows;
+  BnSide a{x, mean_var, gamma, beta, save_mean, save_invstd, running_mean, running_var, momentum, eps, acc_a, const_cast<float*>(mean_var), inv_rows};
+  BnSide b{x2, mean_var2, gamma2, beta2, save_mean2, save_invstd2, running_mean2, running_var2, momentum2, eps2, acc_b, const_cast<float*>(mean_var2), inv_rows};
   const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(residual) |
                                    reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   cudaStream_t s = compute_stream();
@@ -1201,6 +1257,7 @@ dfb_status dfb_bn_bwd_sums(const float* x, const float* dy, const float* save_me
   DFB_INIT();
   DFB_REQUIRE(x && dy && save_mean && save_invstd && dbeta && dgamma, DFB_ERR_INVALID, "bn_bwd_sums: null pointer");
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_bwd_sums: empty input");
+  stat_slot_drop(dbeta);
   SumsArgs a{};
   a.x = x;
   a.dy = dy;
@@ -1211,7 +1268,7 @@ dfb_status dfb_bn_bwd_sums(const float* x, const float* dy, const float* save_me
   return launch_col_sums<SUMS_BNBWD>("bn_bwd_sums", a, rows, C, x, dy);
 }
 dfb_status dfb_bn_bwd_apply(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
-                            const float* dbeta, const float* dgamma, float* dx, size_t rows, int C) {
+                            float* dbeta, float* dgamma, float* dx, size_t rows, int C) {
   DFB_INIT();
   DFB_REQUIRE(x && dy && save_mean && save_invstd && dbeta && dgamma && dx, DFB_ERR_INVALID, "bn_bwd_apply: null pointer");
   DFB_REQUIRE(rows > 0 && C > 0, DFB_ERR_INVALID, "bn_bwd_apply: empty input");
@@ -1219,10 +1276,18 @@ dfb_status dfb_bn_bwd_apply(const float* x, const float* dy, const float* gamma,
   const size_t sm2 = (size_t)5 * C * sizeof(float);
   DFB_REQUIRE(sm2 <= 48 * 1024, DFB_ERR_INVALID, "bn_bwd_apply: too many channels (%d)", C);
   cudaStream_t s = compute_stream();
+  // lazy sums (dfb_conv2d_dgrad_fused_lazy): still in their statistic slot, keyed by the base of the sums buffer = dbeta
+  StatSrc src{nullptr, 0, 0};
+  int last = 0;
+  if (dgamma > dbeta && (size_t)(dgamma - dbeta) % (size_t)C == 0 && (dgamma - dbeta) / C <= 2) {
+    src.acc = stat_slot_take(dbeta, &last);
+    src.row = (int)((dgamma - dbeta) / C);
+    src.clear = last;
+  }
   if (C % 4 == 0 && al)
-    launch_k(bn_bwd_apply_kernel<4>, ew_grid(rows * (C / 4)), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, dbeta, dgamma);
+    launch_k(bn_bwd_apply_kernel<4>, ew_grid(rows * (C / 4)), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, dbeta, dgamma, src);
   else
-    launch_k(bn_bwd_apply_kernel<1>, ew_grid(rows * C), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, dbeta, dgamma);
+    launch_k(bn_bwd_apply_kernel<1>, ew_grid(rows * C), kT, sm2, s, x, dy, dx, rows, C, save_mean, save_invstd, gamma, dbeta, dgamma, src);
   DFB_LAUNCH_CHECK("bn_bwd_apply");
   return DFB_OK;
 }

@@ -194,6 +194,17 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
   });
   m.def("launch_count", []() { return (unsigned long long)dfb_launch_count(); });
   m.def("tc_launch_count", []() { return (unsigned long long)dfb_tc_launch_count(); });
+  // step timeline (dfb_trace_*): trace_end() -> (records as an (n, 2) uint64 array, host launch lines)
+  m.def("trace_begin", [](size_t capacity) { check(dfb_trace_begin(capacity)); });
+  m.def("trace_reset", []() { check(dfb_trace_reset()); });
+  m.def("trace_end", [](size_t capacity) {
+    py::array_t<unsigned long long> rec({(py::ssize_t)capacity, (py::ssize_t)2});
+    size_t n = 0;
+    check(dfb_trace_end(rec.mutable_data(), capacity, &n));
+    py::list lines;
+    for (size_t i = 0; i < dfb_trace_host_count(); ++i) lines.append(py::str(dfb_trace_host_line(i)));
+    return py::make_tuple(rec, n, lines);
+  });
   m.def("set_matmul_mode", [](int mode) { g_matmul_mode = mode; });
   m.def("get_matmul_mode", []() { return g_matmul_mode; });
   m.def("event_create", []() { void* e = nullptr; check(dfb_event_create(&e)); return (size_t)e; });
@@ -204,6 +215,7 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
   m.def("side_begin", []() { check(dfb_side_begin()); });
   m.def("side_end", []() { check(dfb_side_end()); });
   m.def("side_join", []() { check(dfb_side_join()); });
+  m.def("side_join_lag", [](int lag) { check(dfb_side_join_lag(lag)); });
   m.def("graph_begin_capture", []() { check(dfb_graph_begin_capture()); });
   m.def("graph_end_capture", []() { void* g = nullptr; check(dfb_graph_end_capture(&g)); return (size_t)g; });
   m.def("graph_launch", [](size_t g) { check(dfb_graph_launch((void*)g)); });
@@ -376,15 +388,19 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
                      rows, C));
   });
   // ---- fused epilogue / BatchNorm halves (include/dfb200.h: dfb_conv2d_fprop_stats ... dfb_bn_bwd_apply) ----
+  // lazy = true: the statistics go only to bn_fwd_apply / bn_bwd_apply (dfb_conv2d_fprop_stats_lazy, dfb_conv2d_dgrad_fused_lazy)
+  m.attr("STATS_LAZY") = 1;
   m.def("conv2d_fprop_stats", [](const py::object& x, int x_layout, const py::object& w, int w_layout, const py::object& y, int N,
-                                 int C, int H, int W, int K, int R, int pad, int stride, int mode, const py::object& mean_var) {
-    check(dfb_conv2d_fprop_stats(dptr(x), x_layout, dptr(w), w_layout, dptr(y), N, C, H, W, K, R, pad, stride, mode, dptr(mean_var)));
-  });
+                                 int C, int H, int W, int K, int R, int pad, int stride, int mode, const py::object& mean_var, bool lazy) {
+    check((lazy ? dfb_conv2d_fprop_stats_lazy : dfb_conv2d_fprop_stats)(dptr(x), x_layout, dptr(w), w_layout, dptr(y), N, C, H, W, K, R, pad,
+                                                                      stride, mode, dptr(mean_var)));
+  }, py::arg("x"), py::arg("x_layout"), py::arg("w"), py::arg("w_layout"), py::arg("y"), py::arg("N"), py::arg("C"), py::arg("H"), py::arg("W"),
+     py::arg("K"), py::arg("R"), py::arg("pad"), py::arg("stride"), py::arg("mode"), py::arg("mean_var"), py::arg("lazy") = false);
   // BatchNorms as 5-tuples (x, save_mean, save_invstd, gamma, beta), like relu_bwd_bn; n_bn = how many are given
   m.def("conv2d_dgrad_fused", [](const py::object& dy, const py::object& w, int w_layout, const py::object& dx, int N, int C, int H,
                                  int W, int K, int R, int pad, int stride, int mode, int dgrad_mode, const py::object& addend,
                                  const py::object& bn0, const py::object& bn1, const py::object& sums, bool relu,
-                                 const py::object& relu_res) {
+                                 const py::object& relu_res, bool lazy) {
     float* b[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};
     int n_bn = 0;
     const py::object* bns[2] = {&bn0, &bn1};
@@ -395,10 +411,13 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
       for (int j = 0; j < 5; ++j) b[i][j] = dptr(t[j]);
       ++n_bn;
     }
-    check(dfb_conv2d_dgrad_fused(dptr(dy), dptr(w), w_layout, dptr(dx), N, C, H, W, K, R, pad, stride, mode, dgrad_mode, dptr(addend),
-                                 n_bn, b[0][0], b[0][1], b[0][2], b[1][0], b[1][1], b[1][2], dptr(sums), relu ? 1 : 0, b[0][3], b[0][4],
-                                 b[1][3], b[1][4], dptr(relu_res)));
-  });
+    check((lazy ? dfb_conv2d_dgrad_fused_lazy : dfb_conv2d_dgrad_fused)(dptr(dy), dptr(w), w_layout, dptr(dx), N, C, H, W, K, R, pad, stride, mode,
+                                                                        dgrad_mode, dptr(addend), n_bn, b[0][0], b[0][1], b[0][2], b[1][0], b[1][1],
+                                                                        b[1][2], dptr(sums), relu ? 1 : 0, b[0][3], b[0][4], b[1][3], b[1][4],
+                                                                        dptr(relu_res)));
+  }, py::arg("dy"), py::arg("w"), py::arg("w_layout"), py::arg("dx"), py::arg("N"), py::arg("C"), py::arg("H"), py::arg("W"), py::arg("K"),
+     py::arg("R"), py::arg("pad"), py::arg("stride"), py::arg("mode"), py::arg("dgrad_mode"), py::arg("addend"), py::arg("bn0"), py::arg("bn1"),
+     py::arg("sums"), py::arg("relu"), py::arg("relu_res"), py::arg("lazy") = false);
   m.def("stem_cols", [](const py::object& x, int x_layout, const py::object& col, int N, int C, int H, int W, int R, int pad, int stride,
                         int w_layout) { check(dfb_stem_cols(dptr(x), x_layout, dptr(col), N, C, H, W, R, pad, stride, w_layout)); });
   m.def("stem_pad_weights", [](const py::object& w, const py::object& wp, int K, int cols) {

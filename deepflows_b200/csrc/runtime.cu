@@ -4,9 +4,10 @@
 // Replaces what the reference does implicitly through the CUDA runtime on device 0 / stream 0
 // with one cudaMalloc + cudaFree per temporary and blocking cudaMemcpy
 // (reference: DeepFlows/backend/backend_src/ndarray_backend_cuda.cu:48-83, 667-716).
-#include "common.cuh"
+#include "kernels.cuh"
 
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -32,6 +33,7 @@ struct Runtime {
   cudaStream_t compute = nullptr;
   cudaStream_t comm = nullptr;
   unsigned* tickets = nullptr;
+  void* stat_slots = nullptr;   // kStatSlots x kStatSlotBytes (kernels.cuh)
   // side stream: independent work of one op (the wgrad of a conv backward) runs beside the main stream
   // between dfb_side_begin() and dfb_side_end(); dfb_side_join() orders the main stream after it.
   cudaStream_t side = nullptr;
@@ -41,7 +43,13 @@ struct Runtime {
   cudaEvent_t ev_copy_ready = nullptr, ev_copy_done = nullptr;
   bool prefetch_pending = false;
   bool on_side = false;
-  std::vector<void*> side_frees;  // blocks freed while on the side stream: recycled at the join
+  // Side tasks (side_begin .. side_end) are numbered; main-stream work is ordered after task j once it has waited for
+  // ev_side[j % kSideEvents] (side_joined >= j). A block freed while some task is not joined yet may still be read by it:
+  // it is parked with the number of the last task launched and recycled when the main stream has joined that task.
+  static constexpr int kSideEvents = 64;
+  cudaEvent_t ev_side[kSideEvents] = {};
+  unsigned long long side_seq = 0, side_joined = 0;
+  std::vector<std::pair<void*, unsigned long long>> side_frees;
 
   // caching allocator: exact (rounded) size classes; blocks are never returned to the driver
   // unless dfb_empty_cache() is called or cudaMalloc fails.
@@ -112,11 +120,14 @@ dfb_status ensure_init() {
   DFB_CUDA(cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking));
   DFB_CUDA(cudaEventCreateWithFlags(&r.ev_fork, cudaEventDisableTiming));
   DFB_CUDA(cudaEventCreateWithFlags(&r.ev_join, cudaEventDisableTiming));
+  for (int i = 0; i < Runtime::kSideEvents; ++i) DFB_CUDA(cudaEventCreateWithFlags(&r.ev_side[i], cudaEventDisableTiming));
   DFB_CUDA(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
   DFB_CUDA(cudaEventCreateWithFlags(&r.ev_copy_ready, cudaEventDisableTiming));
   DFB_CUDA(cudaEventCreateWithFlags(&r.ev_copy_done, cudaEventDisableTiming));
   DFB_CUDA(cudaMalloc(&r.tickets, kTicketWords * sizeof(unsigned)));
   DFB_CUDA(cudaMemset(r.tickets, 0, kTicketWords * sizeof(unsigned)));
+  DFB_CUDA(cudaMalloc(&r.stat_slots, (size_t)kStatSlots * kStatSlotBytes));
+  DFB_CUDA(cudaMemset(r.stat_slots, 0, (size_t)kStatSlots * kStatSlotBytes));
   DFB_CUDA(cudaDeviceSynchronize());
   r.ready = true;
   return DFB_OK;
@@ -133,6 +144,92 @@ bool pdl_enabled() {
   }
   return v == 1;
 }
+// ---- step timeline (common.cuh) ------------------------------------------------------------------------------------------
+namespace {
+struct TraceState {
+  std::vector<void (*)(unsigned long long*)> setters;   // one per translation unit with kernels
+  unsigned long long* dev = nullptr;
+  size_t capacity = 0;
+  bool armed = false;
+  std::vector<std::string> host;   // "stream grid.x grid.y grid.z block name" per launch since dfb_trace_begin
+};
+TraceState& trace_state() {
+  static TraceState t;
+  return t;
+}
+}  // namespace
+void trace_register_symbol(void (*setter)(unsigned long long*)) { trace_state().setters.push_back(setter); }
+bool trace_host_armed() { return trace_state().armed; }
+void trace_host_launch(const void* func, dim3 grid, dim3 block, cudaStream_t stream) {
+  const char* name = nullptr;
+  if (cudaFuncGetName(&name, func) != cudaSuccess || !name) name = "?";
+  char line[512];
+  snprintf(line, sizeof(line), "%s %u %u %u %u %s", stream == rt().side ? "side" : (stream == rt().compute ? "main" : "other"), grid.x, grid.y,
+           grid.z, block.x, name);
+  trace_state().host.emplace_back(line);
+}
+
+// ---- statistic slots (kernels.cuh) -----------------------------------------------------------------------------------
+// Host-side bookkeeping only; the device memory of a free slot is all zeros (cleared at start-up, then by the last CTA of
+// the slot's last consumer kernel, or - for a slot whose consumer never came - by a memset when it is reclaimed).
+namespace {
+struct StatSlotState {
+  const float* key = nullptr;   // the statistics buffer of the producer call (what the consumer is given)
+  int remaining = 0;            // consumer kernels still to come; 0 = free
+  unsigned long long stamp = 0;
+};
+StatSlotState g_slot[kStatSlots];
+unsigned long long g_slot_clock = 0;
+bool stat_slots_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_STAT_SLOTS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+double* slot_ptr(int i) { return reinterpret_cast<double*>(reinterpret_cast<char*>(rt().stat_slots) + (size_t)i * kStatSlotBytes); }
+}  // namespace
+
+void stat_slot_drop(const float* key) {
+  if (!key) return;
+  for (int i = 0; i < kStatSlots; ++i)
+    if (g_slot[i].remaining > 0 && g_slot[i].key == key) {   // never consumed: its sums are still in the slot
+      cudaMemsetAsync(slot_ptr(i), 0, kStatSlotBytes, compute_stream());
+      g_slot[i] = StatSlotState{};
+    }
+}
+double* stat_slot_acquire(const float* key, int consumers, int channels) {
+  if (!stat_slots_enabled() || !key || consumers < 1 || channels > kStatSlotChannels || rt().on_side) return nullptr;
+  stat_slot_drop(key);
+  int pick = -1, oldest = -1;
+  for (int i = 0; i < kStatSlots; ++i) {
+    if (g_slot[i].remaining == 0) { pick = i; break; }
+    if (oldest < 0 || g_slot[i].stamp < g_slot[oldest].stamp) oldest = i;
+  }
+  if (pick < 0) {   // every slot waits for a consumer that never came: take the oldest back
+    pick = oldest;
+    cudaMemsetAsync(slot_ptr(pick), 0, kStatSlotBytes, compute_stream());
+  }
+  g_slot[pick].key = key;
+  g_slot[pick].remaining = consumers;
+  g_slot[pick].stamp = ++g_slot_clock;
+  return slot_ptr(pick);
+}
+double* stat_slot_take(const float* key, int* last) {
+  *last = 0;
+  if (!key || rt().on_side) return nullptr;
+  for (int i = 0; i < kStatSlots; ++i)
+    if (g_slot[i].remaining > 0 && g_slot[i].key == key) {
+      if (--g_slot[i].remaining == 0) {
+        *last = 1;
+        g_slot[i].key = nullptr;
+      }
+      return slot_ptr(i);
+    }
+  return nullptr;
+}
+
 // work on the side stream may overlap main-stream kernels of the same family: it gets its own counters (32..63)
 unsigned* ticket_counter(int slot) { return rt().tickets + slot + ((rt().on_side && slot < 32) ? 32 : 0); }
 
@@ -275,8 +372,8 @@ dfb_status dfb_free(float* ptr) {
   auto it = r.live.find((void*)ptr);
   DFB_REQUIRE(it != r.live.end(), DFB_ERR_INVALID, "dfb_free: pointer %p not owned by the pool", (void*)ptr);
   size_t bytes = it->second;
-  if (r.on_side) {  // still in use by side-stream work the main stream is not ordered after yet
-    r.side_frees.push_back((void*)ptr);
+  if (r.on_side || r.side_joined < r.side_seq) {  // possibly still in use by side-stream work the main stream is not ordered after yet
+    r.side_frees.emplace_back((void*)ptr, r.on_side ? r.side_seq + 1 : r.side_seq);
     return DFB_OK;
   }
   r.live.erase(it);
@@ -316,6 +413,50 @@ dfb_status dfb_mem_stats(size_t* bytes_in_use, size_t* bytes_reserved, size_t* n
 
 uint64_t dfb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 uint64_t dfb_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
+
+dfb_status dfb_trace_begin(size_t capacity) {
+  DFB_INIT();
+  TraceState& t = trace_state();
+  DFB_REQUIRE(capacity > 0 && capacity <= (1u << 22), DFB_ERR_INVALID, "trace_begin: capacity out of range");
+  DFB_CUDA(cudaDeviceSynchronize());
+  if (t.dev) cudaFree(t.dev);
+  t.dev = nullptr;
+  DFB_CUDA(cudaMalloc(&t.dev, (2 + 2 * capacity) * sizeof(unsigned long long)));
+  DFB_CUDA(cudaMemset(t.dev, 0, (2 + 2 * capacity) * sizeof(unsigned long long)));
+  const unsigned long long cap = capacity;
+  DFB_CUDA(cudaMemcpy(t.dev + 1, &cap, sizeof(cap), cudaMemcpyHostToDevice));
+  t.capacity = capacity;
+  t.host.clear();
+  for (auto set : t.setters) set(t.dev);
+  DFB_CUDA(cudaDeviceSynchronize());
+  t.armed = true;
+  return DFB_OK;
+}
+dfb_status dfb_trace_reset(void) {   // forget what was recorded so far (e.g. the capture pass), stay armed
+  TraceState& t = trace_state();
+  DFB_REQUIRE(t.dev != nullptr, DFB_ERR_RUNTIME, "trace_reset: no trace armed");
+  DFB_CUDA(cudaDeviceSynchronize());
+  DFB_CUDA(cudaMemset(t.dev, 0, sizeof(unsigned long long)));
+  return DFB_OK;
+}
+dfb_status dfb_trace_end(unsigned long long* records, size_t capacity, size_t* count) {
+  TraceState& t = trace_state();
+  DFB_REQUIRE(t.dev != nullptr && count != nullptr, DFB_ERR_RUNTIME, "trace_end: no trace armed");
+  DFB_CUDA(cudaDeviceSynchronize());
+  for (auto set : t.setters) set(nullptr);
+  t.armed = false;
+  unsigned long long n = 0;
+  DFB_CUDA(cudaMemcpy(&n, t.dev, sizeof(n), cudaMemcpyDeviceToHost));
+  if (n > t.capacity) n = t.capacity;
+  if (n > capacity) n = capacity;
+  if (records && n) DFB_CUDA(cudaMemcpy(records, t.dev + 2, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  *count = (size_t)n;
+  cudaFree(t.dev);
+  t.dev = nullptr;
+  return DFB_OK;
+}
+size_t dfb_trace_host_count(void) { return trace_state().host.size(); }
+const char* dfb_trace_host_line(size_t i) { return i < trace_state().host.size() ? trace_state().host[i].c_str() : ""; }
 
 // ---- host <-> device ------------------------------------------------------------------------
 dfb_status dfb_from_host(const float* host_src, float* dst, size_t n) {
@@ -429,25 +570,62 @@ dfb_status dfb_side_begin(void) {
   r.on_side = true;
   return DFB_OK;
 }
+// the main stream waits for side task `upto` (and with it every earlier one); blocks parked for those tasks are recycled
+static dfb_status side_join_upto(unsigned long long upto) {
+  Runtime& r = rt();
+  if (upto > r.side_seq) upto = r.side_seq;
+  if (upto <= r.side_joined) return DFB_OK;
+  DFB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_side[upto % Runtime::kSideEvents], 0));
+  std::vector<void*> frees;
+  {
+    std::lock_guard<std::mutex> lk(r.mu);
+    r.side_joined = upto;
+    size_t keep = 0;
+    for (size_t i = 0; i < r.side_frees.size(); ++i) {
+      if (r.side_frees[i].second <= upto) frees.push_back(r.side_frees[i].first);
+      else r.side_frees[keep++] = r.side_frees[i];
+    }
+    r.side_frees.resize(keep);
+  }
+  if (r.side_joined == r.side_seq) {
+    for (void* p : frees) dfb_free((float*)p);
+  } else {   // later tasks are still out: dfb_free would park the blocks again, recycle them directly
+    std::lock_guard<std::mutex> lk(r.mu);
+    for (void* p : frees) {
+      auto it = r.live.find(p);
+      if (it == r.live.end()) continue;
+      const size_t bytes = it->second;
+      r.live.erase(it);
+      r.bytes_in_use -= bytes;
+      auto ow = r.owner.find(p);
+      if (ow != r.owner.end()) ow->second->free_blocks[bytes].push_back(p);
+      else r.free_blocks[bytes].push_back(p);
+    }
+  }
+  return DFB_OK;
+}
 dfb_status dfb_side_end(void) {
   Runtime& r = rt();
   DFB_REQUIRE(r.on_side, DFB_ERR_RUNTIME, "side_end: not on the side stream");
   r.on_side = false;
-  DFB_CUDA(cudaEventRecord(r.ev_join, r.side));
+  ++r.side_seq;
+  DFB_CUDA(cudaEventRecord(r.ev_side[r.side_seq % Runtime::kSideEvents], r.side));
+  if (r.side_seq - r.side_joined >= Runtime::kSideEvents / 2) return side_join_upto(r.side_seq - Runtime::kSideEvents / 4);   // events are a ring
   return DFB_OK;
 }
 dfb_status dfb_side_join(void) {
   DFB_INIT();
   Runtime& r = rt();
   DFB_REQUIRE(!r.on_side, DFB_ERR_RUNTIME, "side_join: still on the side stream");
-  DFB_CUDA(cudaStreamWaitEvent(r.compute, r.ev_join, 0));
-  std::vector<void*> frees;
-  {
-    std::lock_guard<std::mutex> lk(r.mu);
-    frees.swap(r.side_frees);
-  }
-  for (void* p : frees) dfb_free((float*)p);
-  return DFB_OK;
+  return side_join_upto(r.side_seq);
+}
+dfb_status dfb_side_join_lag(int lag) {
+  DFB_INIT();
+  Runtime& r = rt();
+  DFB_REQUIRE(!r.on_side, DFB_ERR_RUNTIME, "side_join_lag: still on the side stream");
+  DFB_REQUIRE(lag >= 0, DFB_ERR_INVALID, "side_join_lag: negative lag");
+  if (r.side_seq <= (unsigned long long)lag) return DFB_OK;
+  return side_join_upto(r.side_seq - (unsigned long long)lag);
 }
 
 // ---- CUDA graph capture ---------------------------------------------------------------------
@@ -502,6 +680,7 @@ dfb_status dfb_graph_begin_capture(void) {
 dfb_status dfb_graph_end_capture(void** graph_exec) {
   Runtime& r = rt();
   DFB_REQUIRE(r.capturing, DFB_ERR_RUNTIME, "no graph capture active");
+  if (!r.on_side) side_join_upto(r.side_seq);   // every forked branch has to be back on the capturing stream
   cudaGraph_t g = nullptr;
   Runtime::GraphPool* pool;
   {

@@ -92,6 +92,15 @@ DFB_API uint64_t dfb_launch_count(void);
 /* how many of those were tcgen05 (TMA + tensor-core) kernels: lets tests and bench.py prove that a
  * TF32/BF16-mode call really ran on the tensor pipe and did not fall back to the FFMA kernels */
 DFB_API uint64_t dfb_tc_launch_count(void);
+/* Step timeline (diagnostics; scripts/step_timeline.py): between dfb_trace_begin and dfb_trace_end every kernel of the
+ * library records (%globaltimer in ns, grid / block fingerprint: grid.x | grid.y << 24 | grid.z << 40 | block.x << 52) when
+ * its work starts - also inside a replayed CUDA graph - and the host notes "stream grid.x grid.y grid.z block name" of every
+ * launch it makes (dfb_trace_host_count / dfb_trace_host_line). dfb_trace_reset forgets the device records so far. */
+DFB_API dfb_status dfb_trace_begin(size_t capacity);
+DFB_API dfb_status dfb_trace_reset(void);
+DFB_API dfb_status dfb_trace_end(unsigned long long* records, size_t capacity, size_t* count);
+DFB_API size_t dfb_trace_host_count(void);
+DFB_API const char* dfb_trace_host_line(size_t i);
 
 /* Host <-> device. Replaces from_numpy / to_numpy (ndarray_backend_cuda.cu:667-716). The copy
  * is staged through pinned memory owned by the library and is complete on return. */
@@ -136,11 +145,16 @@ DFB_API dfb_status dfb_onehot_smooth(const float* labels, float* y, size_t n, in
 /* Side stream: work enqueued between dfb_side_begin() and dfb_side_end() runs on a second stream that is
  * ordered after everything enqueued on the compute stream so far, concurrently with what the compute
  * stream gets next (used for the wgrad of a convolution's backward, which nothing on the dgrad chain
- * depends on). dfb_side_join() makes the compute stream wait for it; buffers freed while on the side
- * stream are recycled only then. Call the three from one thread, in this order. */
+ * depends on). Several such tasks may be outstanding (they run one after the other on the side stream):
+ * dfb_side_join() makes the compute stream wait for all of them, dfb_side_join_lag(n) for all but the n most
+ * recent ones - a backward pass joins with a lag of a few layers, so that a weight gradient overlaps the next
+ * layers' data-gradient chain instead of sitting on it, and joins everything before anyone reads the weight
+ * gradients. A buffer freed while a task is outstanding is recycled only when the compute stream has joined
+ * that task. Call them from one thread; begin / end pair up. */
 DFB_API dfb_status dfb_side_begin(void);
 DFB_API dfb_status dfb_side_end(void);
 DFB_API dfb_status dfb_side_join(void);
+DFB_API dfb_status dfb_side_join_lag(int lag);
 
 /* CUDA-graph capture of everything enqueued on the compute stream (and, through the comm events, on the
  * communication stream) between begin/end: a whole training step - forward, loss, backward, gradient
@@ -271,6 +285,22 @@ DFB_API dfb_status dfb_conv2d_dgrad_fused(const float* dy, const float* w, int w
                                           const float* bn_invstd1, float* sums, int relu, const float* gamma0,
                                           const float* beta0, const float* gamma1, const float* beta1,
                                           const float* relu_res);
+/* The same two calls for a caller that hands the statistics ONLY to the BatchNorm kernels: mean_var is then consumed by
+ * exactly one dfb_bn_fwd_apply (as its mean_var or mean_var2), `sums` by n_bn calls of dfb_bn_bwd_apply (dbeta = sums,
+ * dgamma = sums + (1 + i) * C). The convolution's CTAs then leave their per-channel sums in a device-side accumulator
+ * (fp64 atomics) that the BatchNorm kernel reads in its prologue - no reduction kernel between the two launches - and
+ * mean_var / sums hold their float values only after that consumer has run (it writes them). Falls back to the eager
+ * behaviour whenever no accumulator is free or the tensor-core path does not take the problem; DFB_STAT_SLOTS=0 always. */
+DFB_API dfb_status dfb_conv2d_fprop_stats_lazy(const float* x, int x_layout, const float* w, int w_layout, float* y, int N,
+                                               int C, int H, int W, int K, int R, int pad, int stride, int mode,
+                                               float* mean_var);
+DFB_API dfb_status dfb_conv2d_dgrad_fused_lazy(const float* dy, const float* w, int w_layout, float* dx, int N, int C, int H,
+                                               int W, int K, int R, int pad, int stride, int mode, int dgrad_mode,
+                                               const float* addend, int n_bn, const float* bn_x0, const float* bn_mean0,
+                                               const float* bn_invstd0, const float* bn_x1, const float* bn_mean1,
+                                               const float* bn_invstd1, float* sums, int relu, const float* gamma0,
+                                               const float* beta0, const float* gamma1, const float* beta1,
+                                               const float* relu_res);
 
 /* First layer (image input, C*R*R <= 32) through its column matrix, kept between forward and backward:
  *   dfb_stem_cols         : col[pixel][32] = the receptive field of every output pixel (zero padded to 32 columns, in the
@@ -334,8 +364,9 @@ DFB_API dfb_status dfb_relu_bwd_bn(const float* x, const float* mean, const floa
 DFB_API dfb_status dfb_bn_bwd_sums(const float* x, const float* dy, const float* save_mean, const float* save_invstd,
                                    float* dbeta, float* dgamma, size_t rows, int C);
 DFB_API dfb_status dfb_bn_bwd_apply(const float* x, const float* dy, const float* gamma, const float* save_mean,
-                                    const float* save_invstd, const float* dbeta, const float* dgamma, float* dx,
-                                    size_t rows, int C);
+                                    const float* save_invstd, float* dbeta, float* dgamma, float* dx,
+                                    size_t rows, int C);   /* (dbeta / dgamma are WRITTEN when they come from
+                                                              dfb_conv2d_dgrad_fused_lazy: see there) */
 
 /* ReLU (F.relu = maximum(x, 0), functional.py:15-16). Backward follows maximum.grad_fn
  * (tensor.py:872-877): dx = (y == x) * dy, i.e. the gradient passes where x >= 0. */

@@ -146,7 +146,7 @@ def _compare(got, want, init, tol, tol_loss, stem_tol=None):
         # elements whose gradient sits at rounding-noise level take +-lr steps of arbitrary sign in any implementation (the
         # gradients themselves are held to their bounds above): a small fraction of the elements, a few of them in the
         # per-channel tensors of 32 .. 256 elements (whose gradients are sums BatchNorm has made cancel)
-        allowed = max(4.0, (0.02 if tol <= 1e-3 else 0.15) * bad.size)
+        allowed = max(4.0, (0.03 if tol <= 1e-3 else 0.15) * bad.size)
         assert bad.sum() <= allowed, "%s: %d of %d elements differ by more than %g" % (k, bad.sum(), bad.size, tol)
     return noise
 

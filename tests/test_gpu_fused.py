@@ -103,6 +103,83 @@ def test_conv_dgrad_fused(cuda_device, geom, mode_name, n_bn):
             assert np.abs(sm[1 + i] - ref).max() <= 4e-6 * np.abs(g64 * xh).sum(0).max(), i
 
 
+@pytest.mark.parametrize("geom", CONV_SHAPES)
+def test_lazy_statistics_forward(cuda_device, geom):
+    """dfb_conv2d_fprop_stats_lazy -> dfb_bn_fwd_apply: the statistics travel through a statistic slot (fp64 atomics in the
+    convolution's epilogue, read in the BatchNorm kernel's prologue, no reduction kernel). Same output, saved statistics
+    and running statistics as the eager pair; mean_var holds its floats afterwards; and the slot is clean for its next
+    user (the pair is run three times, with a never-consumed lazy call in between)."""
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = geom
+    oh, ow = (h + 2 * p - r) // s + 1, (w + 2 * p - r) // s + 1
+    rows = n * oh * ow
+    rng = np.random.RandomState(11)
+    x = (rng.randn(n, h, w, c) + 0.5).astype(F32)
+    wt = (rng.randn(k, r, r, c) / np.sqrt(c * r * r)).astype(F32)
+    wt[0] += 0.3
+    gamma, beta = (rng.rand(k) + 0.5).astype(F32), rng.randn(k).astype(F32)
+    hx, hw, hg, hb = _dev(m, x), _dev(m, wt), _dev(m, gamma), _dev(m, beta)
+
+    def run(lazy):
+        y, mv, out = m.Array(rows * k), m.Array(2 * k), m.Array(rows * k)
+        sm_, si_, rm, rv = m.Array(k), m.Array(k), _dev(m, np.zeros(k, F32)), _dev(m, np.ones(k, F32))
+        launches = m.launch_count()
+        m.conv2d_fprop_stats(hx, m.LAYOUT_NHWC, hw, m.WLAYOUT_KRSC, y, n, c, h, w, k, r, p, s, m.MODE_TF32, mv, lazy)
+        launches = m.launch_count() - launches
+        m.bn_fwd_apply((y, mv, hg, hb, sm_, si_, rm, rv, 0.1, 1e-5), None, None, out, rows, k, True)
+        return [_host(m, a, sh) for a, sh in ((out, (rows, k)), (mv, (2, k)), (sm_, (k,)), (si_, (k,)), (rm, (k,)), (rv, (k,)))], launches
+
+    want, eager_launches = run(False)
+    for rep in range(3):
+        got, lazy_launches = run(True)
+        assert lazy_launches <= eager_launches, "the lazy call must not launch more kernels than the eager one"
+        for name, a, b in zip(("y", "mean_var", "save_mean", "save_invstd", "running_mean", "running_var"), got, want):
+            assert np.abs(a.astype(np.float64) - b).max() <= 2e-5 * max(1.0, np.abs(b).max()), (rep, name)
+        if rep == 0:   # a lazy producer whose consumer never comes must not poison later users of its slot or key
+            y2, mv2 = m.Array(rows * k), m.Array(2 * k)
+            m.conv2d_fprop_stats(hx, m.LAYOUT_NHWC, hw, m.WLAYOUT_KRSC, y2, n, c, h, w, k, r, p, s, m.MODE_TF32, mv2, True)
+            m.conv2d_fprop_stats(hx, m.LAYOUT_NHWC, hw, m.WLAYOUT_KRSC, y2, n, c, h, w, k, r, p, s, m.MODE_TF32, mv2, False)
+            assert np.abs(_host(m, mv2, (2, k)) - want[1]).max() <= 2e-5 * max(1.0, np.abs(want[1]).max())
+
+
+@pytest.mark.parametrize("n_bn", [1, 2])
+@pytest.mark.parametrize("geom", [g for g in CONV_SHAPES if not (g[7] == 2 and (g[2] % 2 or g[3] % 2))])
+def test_lazy_statistics_backward(cuda_device, geom, n_bn):
+    """dfb_conv2d_dgrad_fused_lazy -> n_bn x dfb_bn_bwd_apply: dx of the BatchNorm(s), dbeta and dgamma equal the eager
+    chain's; repeated so that the slot is seen to be clean again."""
+    m = cuda_device.mod
+    n, c, h, w, k, r, p, s = geom
+    oh, ow = (h + 2 * p - r) // s + 1, (w + 2 * p - r) // s + 1
+    rows = n * h * w
+    rng = np.random.RandomState(12)
+    dy = rng.randn(n, oh, ow, k).astype(F32)
+    wt = (rng.randn(k, r, r, c) / np.sqrt(c * r * r)).astype(F32)
+    bx = [(rng.randn(n, h, w, c) * (1 + i) + i).astype(F32) for i in range(2)]
+    mean = [b.reshape(-1, c).mean(0).astype(F32) for b in bx]
+    invstd = [(1.0 / np.sqrt(b.reshape(-1, c).var(0) + 1e-5)).astype(F32) for b in bx]
+    gamma = (rng.rand(c) + 0.5).astype(F32)
+    hdy, hw, hg = _dev(m, dy), _dev(m, wt), _dev(m, gamma)
+    hbx, hmean, hinv = [_dev(m, b) for b in bx], [_dev(m, v) for v in mean], [_dev(m, v) for v in invstd]
+    bns = [(hbx[i], hmean[i], hinv[i], None, None) for i in range(2)]
+
+    def run(lazy):
+        dx, sums = m.Array(rows * c), m.Array(3 * c)
+        m.conv2d_dgrad_fused(hdy, hw, m.WLAYOUT_KRSC, dx, n, c, h, w, k, r, p, s, m.MODE_TF32, m.DGRAD_EXACT, None,
+                             bns[0], bns[1] if n_bn > 1 else None, sums, False, None, lazy)
+        outs = []
+        for i in range(n_bn):
+            dxi = m.Array(rows * c)
+            m.bn_bwd_apply(hbx[i], dx, hg, hmean[i], hinv[i], (sums, 0), (sums, (1 + i) * c), dxi, rows, c)
+            outs.append(_host(m, dxi, (rows, c)))
+        return outs + [_host(m, sums, (3, c))[: 1 + n_bn]]
+
+    want = run(False)
+    for rep in range(2):
+        got = run(True)
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert np.abs(a.astype(np.float64) - b).max() <= 2e-5 * max(1.0, np.abs(b).max()), (rep, i)
+
+
 @pytest.mark.parametrize("dual,res,addend", [(False, False, False), (False, True, True), (True, False, False), (True, True, True)])
 @pytest.mark.parametrize("mode_name", ["tf32", "fp32"])
 @pytest.mark.parametrize("geom", [CONV_SHAPES[0], CONV_SHAPES[1], CONV_SHAPES[4], CONV_SHAPES[5], CONV_SHAPES[7]])
