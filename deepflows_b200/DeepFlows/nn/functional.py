@@ -420,11 +420,41 @@ class _pool2d(FusedOperator):
         dev = xd.device
         gy = grad.channels_last()
         dx = dev.Array(n * h * w * c)
+        fused = self._bn_relu_below(dev, n, c, h, w) if self.is_max else None
+        if fused is not None:
+            # conv -> BatchNorm -> ReLU -> MaxPool (the first stage of the ResNet, every VGG stage): pool backward, the ReLU's
+            # mask and the BatchNorm's two reductions in ONE pass over the BatchNorm's input instead of three
+            rec, relu_expr = fused
+            sums = dev.Array(3 * c)
+            dev.maxpool_relu_bn_bwd(rec.bwd_tuple(), self._y._handle, gy._handle, dx, sums, n, h, w, c, self.k)
+            out = _nhwc_view(dx, n, c, h, w, dev)
+            out._aux = ("bn_sums", sums, {id(rec): 1}, id(relu_expr))   # (the ReLU node passes it through, the BatchNorm applies)
+            return (out,)
         if self.is_max:  # every tied maximum receives the gradient (reference semantics)
             dev.maxpool2d_bwd(xd._handle, self._y._handle, gy._handle, dx, n, h, w, c, self.k)
         else:
             dev.avgpool2d_bwd(gy._handle, dx, n, h, w, c, self.k)
         return (_nhwc_view(dx, n, c, h, w, dev),)
+
+    def _bn_relu_below(self, dev, n, c, h, w):
+        """(BnApply record, fused ReLU expression) when this pool's input is relu(bn(x)) written by ONE dfb_bn_fwd_apply
+        launch, this gradient is everything the ReLU will receive, and the BatchNorm feeds nothing but the ReLU."""
+        if not (get_fusion() and dev.has("maxpool_relu_bn_bwd") and dev.has("bn_bwd_apply")):
+            return None
+        x = self.inputs[0]
+        if not (isinstance(x, _relu) and x._expr is not None and len(x.parents) == 1):
+            return None
+        if len(x.children) != 1:
+            return None
+        below = x.parents[0]
+        if not (isinstance(below, _batch_norm_train) and len(below.children) == 1 and below._ngrads == 0):
+            return None
+        rec, expr = getattr(below, "_rec", None), x._expr
+        if rec is None or not rec.applied or rec.x.shape != (n, c, h, w):
+            return None
+        if [id(r_) for r_ in expr.sides] != [id(rec)] or expr.residual is not None:
+            return None
+        return rec, expr
 
     def release(self):
         self._x = self._y = None

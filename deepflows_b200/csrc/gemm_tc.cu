@@ -1867,14 +1867,21 @@ __global__ void __launch_bounds__(256) weight_transform_kernel(const float* __re
     out[i] = (k < K && c < C) ? __ldg(w + ((size_t)k * C + c) * taps + tap) : 0.f;
   }
 }
-// dW[k][c][tap] (KCRS) or dW[k][tap][c] (KRSC) = sum_z partial[z][k][tap][c]
+// dW[k][c][tap] (KCRS) or dW[k][tap][c] (KRSC) = sum_z partial[z][k][tap][c]. LPO lanes share one output: lane l adds the
+// splits l, l + LPO, ... and a shuffle tree (fixed order) adds the lanes - with one thread per output the first layer's
+// 864 outputs x 128 splits were a 34 us chain of dependent loads at the very end of the backward pass.
+template <int LPO>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
                                                           int K, int C, int Cp, int taps, int krsc) {
   pdl_sync();
-  size_t total = (size_t)K * C * taps;
-  size_t slab = (size_t)K * taps * Cp;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+  const size_t total = (size_t)K * C * taps;
+  const size_t slab = (size_t)K * taps * Cp;
+  const size_t stride = (size_t)gridDim.x * blockDim.x / LPO;
+  const int l = threadIdx.x % LPO;
+  // (every lane of a group runs the same trip count: the shuffles below are warp-convergent)
+  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / LPO; i0 < (total + stride - 1) / stride * stride; i0 += stride) {
+    const bool ok = i0 < total;
+    const size_t i = ok ? i0 : 0;
     int tap, c, k;
     if (krsc) {
       c = (int)(i % C);
@@ -1889,8 +1896,18 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
     const float* src = partial + ((size_t)k * taps + tap) * Cp + c;
     float acc = 0.f;
-    for (int z = 0; z < splits; ++z) acc += src[(size_t)z * slab];
-    dw[i] = acc;
+    if (ok) {
+      int z = l;
+      for (; z + 3 * LPO < splits; z += 4 * LPO) {
+        const float q0 = __ldcg(src + (size_t)z * slab), q1 = __ldcg(src + (size_t)(z + LPO) * slab),
+                    q2 = __ldcg(src + (size_t)(z + 2 * LPO) * slab), q3 = __ldcg(src + (size_t)(z + 3 * LPO) * slab);
+        acc += q0; acc += q1; acc += q2; acc += q3;
+      }
+      for (; z < splits; z += LPO) acc += __ldcg(src + (size_t)z * slab);
+    }
+#pragma unroll
+    for (int off = LPO / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (ok && l == 0) dw[i] = acc;
   }
 }
 
@@ -2308,8 +2325,11 @@ static dfb_status wgrad_impl(const float* x, const float* dy, float* dw, int w_l
   else if (bn == 64) st = run_wgrad<64>(ma, mb, prm, splits);
   else st = run_wgrad<32>(ma, mb, prm, splits);
   if (st == DFB_OK && !prm.tickets) {
-    launch_k(wgrad_reduce_kernel, bw_grid((size_t)K * c_valid * taps, 256), 256, 0, compute_stream(), partial, dw, splits, K, c_valid, prm.Cp, taps,
-                                                                                          w_layout == DFB_WLAYOUT_KRSC ? 1 : 0);
+    const size_t outs = (size_t)K * c_valid * taps;
+    const int krsc = w_layout == DFB_WLAYOUT_KRSC ? 1 : 0;
+    if (splits > 16) launch_k(wgrad_reduce_kernel<32>, bw_grid(outs * 32, 256), 256, 0, compute_stream(), partial, dw, splits, K, c_valid, prm.Cp, taps, krsc);
+    else if (splits > 4) launch_k(wgrad_reduce_kernel<4>, bw_grid(outs * 4, 256), 256, 0, compute_stream(), partial, dw, splits, K, c_valid, prm.Cp, taps, krsc);
+    else launch_k(wgrad_reduce_kernel<1>, bw_grid(outs, 256), 256, 0, compute_stream(), partial, dw, splits, K, c_valid, prm.Cp, taps, krsc);
     cudaError_t e = cudaGetLastError();
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) {

@@ -102,7 +102,10 @@ __device__ __forceinline__ bool last_cta_arrives(unsigned* ticket) {
 // Thread t owns column group (t % G) on row lane (t / G); a warp reads whole 128-byte lines. Each CTA writes
 // its partial sums, the last CTA to finish adds the partials (fixed order => deterministic) and hands the
 // totals to `Fin`.
-enum { SUMS_STATS = 0, SUMS_BNBWD = 1, SUMS_COLSUM = 2 };
+//   POOLBN: BNBWD of a gradient that is computed on the way: dy = max-pool backward (tie-faithful) of the pooled gradient,
+//           masked by the ReLU between the BatchNorm and the pool - the backward of conv -> BatchNorm -> ReLU -> MaxPool
+//           up to the BatchNorm's reductions in ONE pass over the BatchNorm's input (dy is also written out)
+enum { SUMS_STATS = 0, SUMS_BNBWD = 1, SUMS_COLSUM = 2, SUMS_POOLBN = 3 };
 struct SumsArgs {
   const float* x;
   const float* dy;       // BNBWD
@@ -117,6 +120,12 @@ struct SumsArgs {
   float* running_var;    // STATS
   float eps, momentum;
   int raw_var;           // STATS: out1 = biased variance instead of 1/sqrt(var + eps); running statistics untouched
+  // POOLBN: dy = gradient of the POOLED tensor; rows are the pixels (n, h, w) of the BatchNorm's input x
+  const float* gamma;    // affine parameters of the BatchNorm (null: 1 / 0)
+  const float* beta;
+  const float* pool_y;   // the pool's output [N, OH, OW, C]
+  float* dy_out;         // [rows, C]: the gradient that reaches the BatchNorm's output
+  int H, W, OH, OW, pool_k;
 };
 
 // Pairwise (tree) sum over the row lanes of a CTA through shared memory; the result lands in lane 0. A tree
@@ -150,6 +159,25 @@ __device__ __forceinline__ void lane_tree_sum(float* sm, float (&s0)[V], float (
   }
 }
 
+// POOLBN helpers. Row r = pixel (n, h, w) of the pool's input; its window is row (n, h / k, w / k) of the pooled tensors
+// (pixels beyond OH * k / OW * k belong to no window: no gradient).
+__device__ __forceinline__ size_t pooled_row(const SumsArgs& a, size_t r, bool* inside) {
+  const int w = (int)(r % (size_t)a.W);
+  const size_t t = r / (size_t)a.W;
+  const int h = (int)(t % (size_t)a.H);
+  const size_t n = t / (size_t)a.H;
+  const int oh = h / a.pool_k, ow = w / a.pool_k;
+  *inside = oh < a.OH && ow < a.OW;
+  return *inside ? (n * a.OH + oh) * a.OW + ow : 0;
+}
+// z = the BatchNorm's output (pre-activation), act = relu(z) = what the pool saw; every maximum of the window (ties
+// included, SURVEY Q2: maxpool2d_bwd) takes the pooled gradient, and the ReLU passes it where z >= 0 (tensor.py:872-877)
+__device__ __forceinline__ float pool_relu_grad(float x, float mean, float scale, float shift, float pooled, float g, bool inside) {
+  const float z = fmaf(x - mean, scale, shift);
+  const float act = fmaxf(z, 0.f);
+  return (inside && act == pooled && z >= 0.f) ? g : 0.f;
+}
+
 template <int V, int KIND>
 __global__ void __launch_bounds__(kT, 2)
 col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
@@ -163,26 +191,37 @@ col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
   for (int gp = 0; gp < p.gpass; ++gp) {
     const int g = gp * kT + gsel;
     const bool active = g < G && lane < p.lanes;
-    float s0[V], s1[V], c0[V], c1[V];
+    constexpr bool kBwd = KIND == SUMS_BNBWD || KIND == SUMS_POOLBN;
+    float s0[V], s1[V], c0[V], c1[V], c2[V], c3[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) { s0[v] = 0.f; s1[v] = 0.f; c0[v] = 0.f; c1[v] = 0.f; }
+    for (int v = 0; v < V; ++v) { s0[v] = 0.f; s1[v] = 0.f; c0[v] = 0.f; c1[v] = 0.f; c2[v] = 0.f; c3[v] = 0.f; }
     if (active) {
       if (KIND == SUMS_STATS) Vec<V>::get(a.x + (size_t)g * V, c0);  // shift = row 0
-      if (KIND == SUMS_BNBWD) {
+      if (kBwd) {
 #pragma unroll
         for (int v = 0; v < V; ++v) { c0[v] = a.mean[g * V + v]; c1[v] = a.invstd[g * V + v]; }
+      }
+      if (KIND == SUMS_POOLBN) {   // the pre-activation exactly as bn_apply_fused_kernel computed it: fmaf(x - mean, invstd * gamma, beta)
+#pragma unroll
+        for (int v = 0; v < V; ++v) { c2[v] = c1[v] * (a.gamma ? a.gamma[g * V + v] : 1.0f); c3[v] = a.beta ? a.beta[g * V + v] : 0.0f; }
       }
       const size_t step = p.lanes;
       size_t r = r0 + lane;
       // kU independent rows in flight per thread: ~64-128 bytes per thread, enough outstanding loads across the
       // grid to cover HBM latency at full bandwidth
-      constexpr int kU = KIND == SUMS_BNBWD ? 4 : 8;
+      constexpr int kU = kBwd ? 4 : 8;
       for (; r + (kU - 1) * step < r1; r += kU * step) {
-        float xv[kU][V], dv[KIND == SUMS_BNBWD ? kU : 1][V];
+        float xv[kU][V], dv[kBwd ? kU : 1][V], yv[KIND == SUMS_POOLBN ? kU : 1][V];
+        bool in_pool[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           Vec<V>::get_stream(a.x + (r + u * step) * C + (size_t)g * V, xv[u]);
           if (KIND == SUMS_BNBWD) Vec<V>::get_stream(a.dy + (r + u * step) * C + (size_t)g * V, dv[u]);
+          if (KIND == SUMS_POOLBN) {
+            const size_t pr = pooled_row(a, r + u * step, &in_pool[u]);
+            Vec<V>::get(a.dy + pr * C + (size_t)g * V, dv[u]);       // (re-read by the k*k pixels of the window: cached)
+            Vec<V>::get(a.pool_y + pr * C + (size_t)g * V, yv[u]);
+          }
         }
         // compiler fence on the loaded values: keeps the arithmetic below behind ALL the loads above, so the
         // loads are issued back to back instead of being paired with their consumers
@@ -191,14 +230,22 @@ col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
 #pragma unroll
           for (int v = 0; v < V; ++v) {
             asm volatile("" : "+f"(xv[u][v]));
-            if (KIND == SUMS_BNBWD) asm volatile("" : "+f"(dv[u][v]));
+            if (kBwd) asm volatile("" : "+f"(dv[u][v]));
           }
+        if (KIND == SUMS_POOLBN) {
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) dv[u][v] = pool_relu_grad(xv[u][v], c0[v], c2[v], c3[v], yv[u][v], dv[u][v], in_pool[u]);
+            Vec<V>::put(a.dy_out + (r + u * step) * C + (size_t)g * V, dv[u]);
+          }
+        }
 #pragma unroll
         for (int u = 0; u < kU; ++u)
 #pragma unroll
           for (int v = 0; v < V; ++v) {
             if (KIND == SUMS_STATS) { float d = xv[u][v] - c0[v]; s0[v] += d; s1[v] = fmaf(d, d, s1[v]); }
-            if (KIND == SUMS_BNBWD) { s0[v] += dv[u][v]; s1[v] = fmaf(dv[u][v], (xv[u][v] - c0[v]) * c1[v], s1[v]); }
+            if (kBwd) { s0[v] += dv[u][v]; s1[v] = fmaf(dv[u][v], (xv[u][v] - c0[v]) * c1[v], s1[v]); }
             if (KIND == SUMS_COLSUM) s0[v] += xv[u][v];
           }
       }
@@ -206,10 +253,20 @@ col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
         float xv[V], dv[V];
         Vec<V>::get(a.x + r * C + (size_t)g * V, xv);
         if (KIND == SUMS_BNBWD) Vec<V>::get(a.dy + r * C + (size_t)g * V, dv);
+        if (KIND == SUMS_POOLBN) {
+          bool inside;
+          const size_t pr = pooled_row(a, r, &inside);
+          float yv[V];
+          Vec<V>::get(a.dy + pr * C + (size_t)g * V, dv);
+          Vec<V>::get(a.pool_y + pr * C + (size_t)g * V, yv);
+#pragma unroll
+          for (int v = 0; v < V; ++v) dv[v] = pool_relu_grad(xv[v], c0[v], c2[v], c3[v], yv[v], dv[v], inside);
+          Vec<V>::put(a.dy_out + r * C + (size_t)g * V, dv);
+        }
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           if (KIND == SUMS_STATS) { float d = xv[v] - c0[v]; s0[v] += d; s1[v] = fmaf(d, d, s1[v]); }
-          if (KIND == SUMS_BNBWD) { s0[v] += dv[v]; s1[v] = fmaf(dv[v], (xv[v] - c0[v]) * c1[v], s1[v]); }
+          if (kBwd) { s0[v] += dv[v]; s1[v] = fmaf(dv[v], (xv[v] - c0[v]) * c1[v], s1[v]); }
           if (KIND == SUMS_COLSUM) s0[v] += xv[v];
         }
       }
@@ -271,7 +328,7 @@ col_sums_kernel(SumsArgs a, size_t rows, int C, ColPlan p) {
           if (a.running_var) a.running_var[c] = a.running_var[c] * (1.0f - a.momentum) + var * a.momentum;
         } else {
           if (a.out0) a.out0[c] = s0[v];
-          if (KIND == SUMS_BNBWD && a.out1) a.out1[c] = s1[v];
+          if ((KIND == SUMS_BNBWD || KIND == SUMS_POOLBN) && a.out1) a.out1[c] = s1[v];
         }
       }
     }
@@ -1266,6 +1323,27 @@ dfb_status dfb_bn_bwd_sums(const float* x, const float* dy, const float* save_me
   a.out0 = dbeta;
   a.out1 = dgamma;
   return launch_col_sums<SUMS_BNBWD>("bn_bwd_sums", a, rows, C, x, dy);
+}
+dfb_status dfb_maxpool_relu_bn_bwd(const float* x, const float* save_mean, const float* save_invstd, const float* gamma,
+                                   const float* beta, const float* pool_y, const float* pool_dy, float* dy, float* sums, int N, int H,
+                                   int W, int C, int k) {
+  DFB_INIT();
+  DFB_REQUIRE(x && save_mean && save_invstd && pool_y && pool_dy && dy && sums, DFB_ERR_INVALID, "maxpool_relu_bn_bwd: null pointer");
+  DFB_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && k >= 1 && H >= k && W >= k, DFB_ERR_INVALID, "maxpool_relu_bn_bwd: bad geometry");
+  stat_slot_drop(sums);
+  SumsArgs a{};
+  a.x = x;
+  a.dy = pool_dy;
+  a.mean = save_mean;
+  a.invstd = save_invstd;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.pool_y = pool_y;
+  a.dy_out = dy;
+  a.out0 = sums;
+  a.out1 = sums + C;
+  a.H = H; a.W = W; a.OH = (H - k) / k + 1; a.OW = (W - k) / k + 1; a.pool_k = k;
+  return launch_col_sums<SUMS_POOLBN>("maxpool_relu_bn_bwd", a, (size_t)N * H * W, C, x, dy);
 }
 dfb_status dfb_bn_bwd_apply(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
                             float* dbeta, float* dgamma, float* dx, size_t rows, int C) {

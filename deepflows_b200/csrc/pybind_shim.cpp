@@ -466,6 +466,13 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
                           const py::object& dbeta, const py::object& dgamma, size_t rows, int C) {
     check(dfb_bn_bwd_sums(dptr(x), dptr(dy), dptr(save_mean), dptr(save_invstd), dptr(dbeta), dptr(dgamma), rows, C));
   });
+  // bn = (x, save_mean, save_invstd, gamma, beta)
+  m.def("maxpool_relu_bn_bwd", [](const py::tuple& bn, const py::object& pool_y, const py::object& pool_dy, const py::object& dy,
+                                  const py::object& sums, int N, int H, int W, int C, int k) {
+    if (bn.size() != 5) throw py::value_error("maxpool_relu_bn_bwd: a BatchNorm is a 5-tuple");
+    check(dfb_maxpool_relu_bn_bwd(dptr(bn[0]), dptr(bn[1]), dptr(bn[2]), dptr(bn[3]), dptr(bn[4]), dptr(pool_y), dptr(pool_dy), dptr(dy),
+                                  dptr(sums), N, H, W, C, k));
+  });
   m.def("bn_bwd_apply", [](const py::object& x, const py::object& dy, const py::object& gamma, const py::object& save_mean,
                            const py::object& save_invstd, const py::object& dbeta, const py::object& dgamma, const py::object& dx,
                            size_t rows, int C) {

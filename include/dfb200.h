@@ -363,6 +363,15 @@ DFB_API dfb_status dfb_relu_bwd_bn(const float* x, const float* mean, const floa
                                    float* dx, size_t rows, int C);
 DFB_API dfb_status dfb_bn_bwd_sums(const float* x, const float* dy, const float* save_mean, const float* save_invstd,
                                    float* dbeta, float* dgamma, size_t rows, int C);
+/* Backward of conv -> BatchNorm -> ReLU -> MaxPool(k, stride k) from the pool's gradient down to the BatchNorm's two
+ * reductions, in ONE pass over the BatchNorm's input x [N,H,W,C] (replaces dfb_maxpool2d_bwd + dfb_relu_bwd_bn +
+ * dfb_bn_bwd_sums: three passes over the largest activation of the net): dy[n,h,w,c] = pool_dy of the window if
+ * relu(bn(x)) equals the window's maximum pool_y (ties included, like dfb_maxpool2d_bwd) and bn(x) >= 0, else 0;
+ * sums[0][C] = sum(dy), sums[1][C] = sum(dy * x_hat). dfb_bn_bwd_apply(x, dy, .., sums, sums + C, ..) finishes. */
+DFB_API dfb_status dfb_maxpool_relu_bn_bwd(const float* x, const float* save_mean, const float* save_invstd,
+                                           const float* gamma, const float* beta, const float* pool_y,
+                                           const float* pool_dy, float* dy, float* sums, int N, int H, int W, int C,
+                                           int k);
 DFB_API dfb_status dfb_bn_bwd_apply(const float* x, const float* dy, const float* gamma, const float* save_mean,
                                     const float* save_invstd, float* dbeta, float* dgamma, float* dx,
                                     size_t rows, int C);   /* (dbeta / dgamma are WRITTEN when they come from

@@ -142,6 +142,42 @@ def test_lazy_statistics_forward(cuda_device, geom):
             assert np.abs(_host(m, mv2, (2, k)) - want[1]).max() <= 2e-5 * max(1.0, np.abs(want[1]).max())
 
 
+@pytest.mark.parametrize("n,h,w,c,k", [(8, 16, 16, 32, 2), (3, 9, 11, 12, 2), (2, 12, 12, 64, 3), (5, 7, 7, 5, 2), (64, 32, 32, 32, 2)])
+def test_maxpool_relu_bn_backward_fused(cuda_device, n, h, w, c, k):
+    """dfb_maxpool_relu_bn_bwd = dfb_maxpool2d_bwd -> dfb_relu_bwd_bn -> dfb_bn_bwd_sums in one pass: the gradient bit for
+    bit (ties and the ReLU's z >= 0 rule included: the input is quantised so that windows hold equal maxima and exact
+    zeros), the sums to summation-order rounding."""
+    m = cuda_device.mod
+    rows, oh, ow = n * h * w, (h - k) // k + 1, (w - k) // k + 1
+    rng = np.random.RandomState(21)
+    x = (np.round(rng.randn(n, h, w, c) * 2) / 2).astype(F32)        # few distinct values: ties
+    gamma, beta = np.ones(c, F32), np.zeros(c, F32)
+    gamma[::3] = 0.5
+    mean, invstd = np.zeros(c, F32), np.ones(c, F32)                 # z = x * gamma exactly: zeros stay zeros
+    mean[1::4] = 0.5
+    gp = rng.randn(n, oh, ow, c).astype(F32)
+    hx, hg, hb, hm, hi, hgp = _dev(m, x), _dev(m, gamma), _dev(m, beta), _dev(m, mean), _dev(m, invstd), _dev(m, gp)
+    # forward the way the step runs it: relu(bn(x)) by bn_fwd_apply from given statistics, then the pool
+    var = np.zeros(c, F32)   # invstd = 1 / sqrt(var + eps) ~ 1 is not exactly 1: take the kernel's own saved values below
+    act, mv, sm_, si_, py_ = m.Array(rows * c), _dev(m, np.concatenate([mean, var])), m.Array(c), m.Array(c), m.Array(n * oh * ow * c)
+    m.bn_fwd_apply((hx, mv, hg, hb, sm_, si_, None, None, 0.1, 1e-5), None, None, act, rows, c, True)
+    m.maxpool2d_fwd(act, py_, None, n, h, w, c, k)
+    # reference chain
+    d1, d2, sums_ref = m.Array(rows * c), m.Array(rows * c), m.Array(3 * c)
+    m.maxpool2d_bwd(act, py_, hgp, d1, n, h, w, c, k)
+    m.relu_bwd_bn((hx, sm_, si_, hg, hb), None, None, d1, d2, rows, c)
+    m.bn_bwd_sums(hx, d2, sm_, si_, (sums_ref, 0), (sums_ref, c), rows, c)
+    # fused
+    d3, sums = m.Array(rows * c), m.Array(3 * c)
+    m.maxpool_relu_bn_bwd((hx, sm_, si_, hg, hb), py_, hgp, d3, sums, n, h, w, c, k)
+    want, got = _host(m, d2, (rows, c)), _host(m, d3, (rows, c))
+    assert np.array_equal(got, want)
+    assert np.count_nonzero(want) > 0
+    sr, sg = _host(m, sums_ref, (3, c))[:2], _host(m, sums, (3, c))[:2]
+    scale = np.abs(want).sum(0).max()
+    assert np.abs(sr - sg).max() <= 4e-6 * max(scale, 1.0)
+
+
 @pytest.mark.parametrize("n_bn", [1, 2])
 @pytest.mark.parametrize("geom", [g for g in CONV_SHAPES if not (g[7] == 2 and (g[2] % 2 or g[3] % 2))])
 def test_lazy_statistics_backward(cuda_device, geom, n_bn):
