@@ -28,6 +28,7 @@ unsigned* ticket_counter(int slot);
 // CUDA-graph capture support (runtime.cu)
 bool graph_capturing();
 dfb_status graph_staging(size_t bytes, int kind, void** host, void** dev);
+dfb_status graph_early_h2d(void* dev, const void* host, size_t bytes);
 dfb_status graph_hyper_slot(void* graph_exec, int index, int kind, void** host);
 
 #define DFB_FAIL(code, ...)         \

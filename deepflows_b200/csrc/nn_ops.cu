@@ -162,13 +162,12 @@ __device__ __forceinline__ void lane_tree_sum(float* sm, float (&s0)[V], float (
 // POOLBN helpers. Row r = pixel (n, h, w) of the pool's input; its window is row (n, h / k, w / k) of the pooled tensors
 // (pixels beyond OH * k / OW * k belong to no window: no gradient).
 __device__ __forceinline__ size_t pooled_row(const SumsArgs& a, size_t r, bool* inside) {
-  const int w = (int)(r % (size_t)a.W);
-  const size_t t = r / (size_t)a.W;
-  const int h = (int)(t % (size_t)a.H);
-  const size_t n = t / (size_t)a.H;
-  const int oh = h / a.pool_k, ow = w / a.pool_k;
-  *inside = oh < a.OH && ow < a.OW;
-  return *inside ? (n * a.OH + oh) * a.OW + ow : 0;
+  const unsigned r32 = (unsigned)r;   // (rows < 2^31, checked on the host: 32-bit divisions, a tenth of the 64-bit ones' cost)
+  const unsigned t = r32 / (unsigned)a.W, w = r32 - t * (unsigned)a.W;
+  const unsigned n = t / (unsigned)a.H, h = t - n * (unsigned)a.H;
+  const unsigned oh = h / (unsigned)a.pool_k, ow = w / (unsigned)a.pool_k;
+  *inside = oh < (unsigned)a.OH && ow < (unsigned)a.OW;
+  return *inside ? ((size_t)n * a.OH + oh) * a.OW + ow : 0;
 }
 // z = the BatchNorm's output (pre-activation), act = relu(z) = what the pool saw; every maximum of the window (ties
 // included, SURVEY Q2: maxpool2d_bwd) takes the pooled gradient, and the ReLU passes it where z >= 0 (tensor.py:872-877)
@@ -1330,6 +1329,7 @@ dfb_status dfb_maxpool_relu_bn_bwd(const float* x, const float* save_mean, const
   DFB_INIT();
   DFB_REQUIRE(x && save_mean && save_invstd && pool_y && pool_dy && dy && sums, DFB_ERR_INVALID, "maxpool_relu_bn_bwd: null pointer");
   DFB_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && k >= 1 && H >= k && W >= k, DFB_ERR_INVALID, "maxpool_relu_bn_bwd: bad geometry");
+  DFB_REQUIRE((size_t)N * H * W < (1ull << 31), DFB_ERR_INVALID, "maxpool_relu_bn_bwd: more than 2^31 pixels");
   stat_slot_drop(sums);
   SumsArgs a{};
   a.x = x;

@@ -179,7 +179,12 @@ static dfb_status upload_table(const std::vector<TensorRef>& tab, const void* hy
   }
   memcpy(host, hyper, hyper_bytes);
   memcpy((char*)host + kHyperBytes, tab.data(), tab.size() * sizeof(TensorRef));
-  DFB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, compute_stream()));
+  if (graph_capturing()) {
+    dfb_status st = graph_early_h2d(dev, host, bytes);   // a branch off the graph's root, not a node in front of the kernel
+    if (st != DFB_OK) return st;
+  } else {
+    DFB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, compute_stream()));
+  }
   if (!graph_capturing()) {
     TableStage& st = g_stage;
     int s = (st.next + TableStage::kSlots - 1) % TableStage::kSlots;
