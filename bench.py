@@ -444,7 +444,21 @@ def main():
         agree = bool(np.all(sums == sums[0]))
         dp_check = {"param_checksum": checksum, "ranks_agree": agree}
         if not agree:
-            raise SystemExit("bench: data-parallel replicas diverged: per-rank parameter checksums %s" % sums.tolist())
+            # which parameters: every rank's per-parameter checksums side by side (same two-word transport)
+            named = list(model.named_parameters())
+            per = np.array([float(p.data.numpy().astype(np.float64).sum()) for _, p in named])
+            tab = np.zeros((world, per.size), np.float64)
+            tab[rank] = per
+            hi2 = tab.astype(F32)
+            lo2 = (tab - hi2.astype(np.float64)).astype(F32)
+            b2 = backend_api.Btensor(np.concatenate([hi2.reshape(-1), lo2.reshape(-1)]), device=dev)
+            dev.comm_allreduce_async(b2._handle, 2 * tab.size)
+            dev.comm_wait()
+            g2 = b2.numpy().astype(np.float64)
+            full = (g2[:tab.size] + g2[tab.size:]).reshape(world, per.size)
+            differ = [(named[i][0], full[:, i].tolist()) for i in range(per.size) if not np.all(full[:, i] == full[0, i])]
+            raise SystemExit("bench: data-parallel replicas diverged: per-rank parameter checksums %s; %d of %d parameters differ, first: %s"
+                             % (sums.tolist(), len(differ), per.size, differ[:6]))
 
     # ---- extras (N = 1): the same step launched eagerly, and in fp32 mode ---------------------------------------------
     extra = {}

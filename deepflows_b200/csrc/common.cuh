@@ -28,7 +28,9 @@ unsigned* ticket_counter(int slot);
 // CUDA-graph capture support (runtime.cu)
 bool graph_capturing();
 dfb_status graph_staging(size_t bytes, int kind, void** host, void** dev);
-dfb_status graph_early_h2d(void* dev, const void* host, size_t bytes);
+dfb_status graph_early_h2d(void* dev, const void* host, size_t bytes, void* ack_host = nullptr, size_t ack_offset = 0);
+void* graph_last_hyper_ack();                      // the echo word of the optimizer block graph_staging handed out last
+constexpr size_t kGraphHyperSeqOffset = 252;       // last word of the 256-byte hyper-parameter block: its sequence number
 dfb_status graph_hyper_slot(void* graph_exec, int index, int kind, void** host);
 
 #define DFB_FAIL(code, ...)         \

@@ -180,7 +180,14 @@ static dfb_status upload_table(const std::vector<TensorRef>& tab, const void* hy
   memcpy(host, hyper, hyper_bytes);
   memcpy((char*)host + kHyperBytes, tab.data(), tab.size() * sizeof(TensorRef));
   if (graph_capturing()) {
-    dfb_status st = graph_early_h2d(dev, host, bytes);   // a branch off the graph's root, not a node in front of the kernel
+    static_assert(kGraphHyperSeqOffset + 4 <= kHyperBytes && sizeof(AdamHyper) <= kGraphHyperSeqOffset && sizeof(SgdHyper) <= kGraphHyperSeqOffset,
+                  "the sequence word sits behind the hyper-parameters");
+    void* ack = (kind == 0 || kind == 1) ? graph_last_hyper_ack() : nullptr;
+    if (ack) {
+      const unsigned seq = 1u;
+      memcpy((char*)host + kGraphHyperSeqOffset, &seq, sizeof(seq));
+    }
+    dfb_status st = graph_early_h2d(dev, host, bytes, ack, kGraphHyperSeqOffset);   // a branch off the graph's root, not a node in front of the kernel
     if (st != DFB_OK) return st;
   } else {
     DFB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, compute_stream()));

@@ -70,6 +70,12 @@ struct Runtime {
     std::vector<void*> dev_allocs;
     std::vector<void*> hyper_host;    // one per captured optimizer step, in capture order
     std::vector<int> hyper_kind;      // 0 = Adam, 1 = SGD
+    // A replay reads its hyper-parameter block from pinned memory when it STARTS, which can be long after the host
+    // launched it: the host must not write the next replay's values before. Every block carries a sequence number in its
+    // last word; the replay echoes it into `hyper_ack` (a 4-byte device -> host copy behind the upload) and
+    // graph_hyper_slot waits for the echo of the previous values before it hands the block out again.
+    std::vector<volatile unsigned*> hyper_ack;
+    std::vector<unsigned> hyper_seq;
     int n_nodes = 0, n_kernel_nodes = 0;
   };
   std::unordered_map<void*, GraphPool*> owner;          // block -> pool, for graph-owned blocks
@@ -642,18 +648,17 @@ bool graph_capturing() { return rt().capturing; }
 // A host -> device copy of a captured step that depends only on the graph's root: it runs while the step's first kernels
 // do, and the stream that needs the data (the optimizer's table, a bucket's pointer list) only joins it. As a node on the
 // compute stream itself the copy sat between the last backward kernel and the optimizer (~25 us of DMA latency per step).
-dfb_status graph_early_h2d(void* dev, const void* host, size_t bytes) {
+dfb_status graph_early_h2d(void* dev, const void* host, size_t bytes, void* ack_host, size_t ack_offset) {
   Runtime& r = rt();
   DFB_REQUIRE(r.capturing, DFB_ERR_RUNTIME, "graph_early_h2d outside a capture");
   DFB_CUDA(cudaStreamWaitEvent(r.aux, r.ev_root, 0));
   DFB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, r.aux));
+  if (ack_host)   // echo of the block's sequence number: "these values have been read" (GraphPool::hyper_ack)
+    DFB_CUDA(cudaMemcpyAsync(ack_host, (const char*)dev + ack_offset, sizeof(unsigned), cudaMemcpyDeviceToHost, r.aux));
   DFB_CUDA(cudaEventRecord(r.ev_aux, r.aux));
   DFB_CUDA(cudaStreamWaitEvent(compute_stream(), r.ev_aux, 0));
   return DFB_OK;
 }
-// Persistent pinned + device staging owned by the graph being captured (optimizer pointer table and
-// hyper-parameters: the captured memcpy node re-reads the pinned copy at every replay, which is how
-// lr / bias corrections change between replays without re-capturing).
 dfb_status graph_staging(size_t bytes, int kind, void** host, void** dev) {
   Runtime& r = rt();
   DFB_REQUIRE(r.active_pool != nullptr, DFB_ERR_RUNTIME, "graph_staging outside a capture");
@@ -663,10 +668,20 @@ dfb_status graph_staging(size_t bytes, int kind, void** host, void** dev) {
   r.active_pool->host_allocs.push_back(*host);
   r.active_pool->dev_allocs.push_back(*dev);
   if (kind == 0 || kind == 1) {  // optimizer steps are addressable afterwards (dfb_graph_set_adam / _sgd)
+    void* ack = nullptr;
+    if (cudaHostAlloc(&ack, 64, cudaHostAllocDefault) != cudaSuccess) DFB_FAIL(DFB_ERR_NOMEM, "graph_staging: pinned allocation failed");
+    *reinterpret_cast<volatile unsigned*>(ack) = 0u;
+    r.active_pool->host_allocs.push_back(ack);
     r.active_pool->hyper_host.push_back(*host);
     r.active_pool->hyper_kind.push_back(kind);
+    r.active_pool->hyper_ack.push_back(reinterpret_cast<volatile unsigned*>(ack));
+    r.active_pool->hyper_seq.push_back(1u);   // the values written during the capture are sequence 1
   }
   return DFB_OK;
+}
+void* graph_last_hyper_ack() {
+  Runtime& r = rt();
+  return (r.active_pool && !r.active_pool->hyper_ack.empty()) ? (void*)r.active_pool->hyper_ack.back() : nullptr;
 }
 dfb_status graph_hyper_slot(void* graph_exec, int index, int kind, void** host) {
   Runtime& r = rt();
@@ -677,6 +692,16 @@ dfb_status graph_hyper_slot(void* graph_exec, int index, int kind, void** host) 
               "graph has %zu captured optimizer steps, index %d requested", it->second->hyper_host.size(), index);
   DFB_REQUIRE(it->second->hyper_kind[index] == kind, DFB_ERR_INVALID, "captured optimizer step %d is of another kind", index);
   *host = it->second->hyper_host[index];
+  // the replay that reads the current values must have read them (it echoes their sequence number when it starts);
+  // a graph that was never launched with them (or an idle stream) has nothing in flight
+  volatile unsigned* ack = it->second->hyper_ack[index];
+  const unsigned want = it->second->hyper_seq[index];
+  for (unsigned long long spins = 0; *ack != want; ++spins) {
+    if ((spins & 0xfff) == 0xfff && cudaStreamQuery(r.compute) == cudaSuccess) break;
+  }
+  const unsigned next = want + 1u;
+  it->second->hyper_seq[index] = next;
+  memcpy((char*)*host + kGraphHyperSeqOffset, &next, sizeof(next));
   return DFB_OK;
 }
 }  // namespace dfb

@@ -77,7 +77,9 @@ mean_grads = [np.mean([shard_grads[r][i] for r in range(world)], axis=0) for i i
 for p, g in zip(single.parameters(), mean_grads):
     p.grad = backend_api.Btensor(g.astype(F32), device=dev)
 opt1 = df.optim.SGD(single.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+saved_ctx, dist._ctx = dist._ctx, None                        # the reference step is a single-process one: no 1/world
 opt1.step()
+dist._ctx = saved_ctx
 want_params = [p.data.numpy().copy() for p in single.parameters()]
 Tensor._post_backward_hook, Tensor._grad_ready_hook = dist_ctx_hooks
 
@@ -139,6 +141,8 @@ assert cap.captured
 graph3 = [p.data.numpy().copy() for p in model.parameters()]
 for i, (a, b) in enumerate(zip(graph3, eager3)):
     assert np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1e-6), "captured data-parallel step differs from eager, parameter %d" % i
+sums = allgather(np.array([float(np.sum([a.astype(np.float64).sum() for a in graph3]))], F32))
+assert all(sums[r, 0] == sums[0, 0] for r in range(world)), "replicas diverged after the captured steps: %s" % sums[:, 0]
 cap.destroy()
 dist.shutdown()
 print("rank %d of %d: data-parallel NCCL parity ok" % (rank, world), flush=True)
