@@ -106,6 +106,9 @@ def _recv_exact(conn, n):
     return buf
 
 
+_BUCKETS_ON_SIDE = os.environ.get("DEEPFLOWS_BUCKETS_ON_SIDE", "1") != "0"   # 0: the compute stream joins the side stream before a bucket is packed
+
+
 class DataParallel:
     """Bucketed gradient all-reduce for a fixed parameter list, overlapped with backward.
 
@@ -191,8 +194,25 @@ class DataParallel:
     def _launch_bucket(self, b):
         flat, slots = self._plan[b]
         dev = flat.device
-        if dev.has("side_join"):
-            dev.side_join()   # the bucket's weight gradients may still be on the side stream (lagged joins of conv backward)
+        # The bucket's weight gradients may still be on the side stream (lagged joins of conv backward). Packing and reducing
+        # the bucket as one more side task orders it behind them WITHOUT making the compute stream wait: the side stream forks
+        # from everything the compute stream has enqueued so far (the BatchNorm gradients), the all-reduce is ordered after
+        # the pack through the event it records on the current (= side) stream, the optimizer waits for the communication
+        # stream, and backward() joins the side stream when it ends.
+        on_side = dev.has("side_join_lag") and dev.has("side_begin") and _BUCKETS_ON_SIDE
+        if on_side:
+            dev.side_begin()
+        elif dev.has("side_join"):
+            dev.side_join()
+        try:
+            self._pack_and_reduce(b, flat, slots, dev)
+        finally:
+            if on_side:
+                dev.side_end()
+        self._launched.add(b)
+        self._pending = True
+
+    def _pack_and_reduce(self, b, flat, slots, dev):
         srcs, dsts, sizes = [], [], []
         for i, off, n in slots:
             p = self.params[i]
@@ -218,8 +238,6 @@ class DataParallel:
             p = self.params[i]
             if p.grad is not None:
                 p.grad = BackendTensor.make(p.data.shape, p.data.strides, p.device, flat._handle, off)
-        self._launched.add(b)
-        self._pending = True
 
     # ---- after backward -----------------------------------------------------------------------------------
     def reduce_gradients(self):

@@ -14,7 +14,7 @@ timeout 700 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --sectio
     --clock-control none -s $skip -c $count -f -o /tmp/${tag}_step \
     python bench.py --config $cfg --steps 2 --warmup 3 --no-cpu-baseline --no-extra --mode eager > $out/${tag}_ncu_step_bench.log 2>&1
 ncu -i /tmp/${tag}_step.ncu-rep --page raw --csv > $out/${tag}_${cfg}_step_raw.csv 2>/dev/null
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:Wgrad -s 40 -c 10 -f -o /tmp/${tag}_wgrad \
+timeout 400 ncu --set full --import-source on --clock-control none -k regex:tc_ -s 60 -c 24 -f -o /tmp/${tag}_wgrad \
     python bench.py --config $cfg --steps 2 --warmup 3 --no-cpu-baseline --no-extra --mode eager > $out/${tag}_ncu_wgrad_bench.log 2>&1
 ncu -i /tmp/${tag}_wgrad.ncu-rep --page raw --csv > $out/${tag}_${cfg}_wgrad_full_raw.csv 2>/dev/null
 for i in 0 3; do python scripts/ncu_top_stalls.py /tmp/${tag}_wgrad.ncu-rep $i 30 > $out/${tag}_${cfg}_wgrad_stalls_$i.txt 2>&1; done

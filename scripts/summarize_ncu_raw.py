@@ -54,13 +54,15 @@ for r in data:
         kernel=short(r[col["Kernel Name"]]), grid=int(f(r, "launch__grid_size")), block=int(f(r, "launch__block_size")),
         us=to_us(r, "gpu__time_duration.sum"),
         dram_mb=to_mb(r, "dram__bytes_read.sum") + to_mb(r, "dram__bytes_write.sum"),
-        dram_pct=f(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+        dram_pct=0.0,
         l2_pct=f(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
         l1_pct=f(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
         tensor_pct=f(r, "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
                      f(r, "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed")),
         regs=int(f(r, "launch__registers_per_thread")), smem_kb=f(r, "launch__shared_mem_per_block_dynamic"),
         warps_pct=f(r, "sm__warps_active.avg.pct_of_peak_sustained_active"), stall=top))
+    o = out[-1]   # DRAM bytes over the duration against the measured copy bandwidth (MEASURED_PEAKS.json: 6454 GB/s)
+    o["dram_pct"] = 100.0 * (o["dram_mb"] * 1e6 / max(o["us"] * 1e-6, 1e-12)) / 6454e9
 
 if by_kernel:
     agg = OrderedDict()

@@ -97,6 +97,52 @@ def test_graph_replay_is_bit_identical_to_eager(cuda_device, opt_name, precision
         backend_api.set_dgrad_mode("exact")
 
 
+def test_replays_launched_ahead_keep_their_own_hyper_parameters(cuda_device):
+    """Replays queued back to back (the host never waits for the device, as in bench.py's timed loop): every replay must
+    see ITS step's Adam bias corrections and learning rate. The hyper-parameter block lives in pinned memory and is read
+    when the replay starts - the runtime makes the host wait for the previous replay's echo before it writes the next
+    values (runtime.cu: GraphPool::hyper_ack); without that, step t ran with the values of step t + k."""
+    from DeepFlows import backend_api, tensor
+    from DeepFlows.tensor import Tensor
+    from DeepFlows.cuda_graph import CapturedStep
+    dev = cuda_device
+    backend_api.set_precision("tf32")
+    try:
+        df = parity.df_namespace()
+        xb, tb = _batches(1, batch=64)[0]
+        steps = 40
+
+        def run(graph):
+            model, opt, crit = _setup(df, "adam")
+            base_lr = opt.lr
+            x = Tensor(backend_api.Btensor(xb, device=dev))
+            t = Tensor(backend_api.Btensor(tb, device=dev))
+
+            def step_fn():
+                loss = crit(model(x), t)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                tensor.Graph.free_graph()
+                return loss
+
+            step = CapturedStep(step_fn, device=dev, warmup=1) if graph else step_fn
+            for i in range(steps):
+                opt.lr = base_lr * (0.5 if i % 7 == 3 else 1.0)   # changes between replays as well
+                step()                                             # no read-back, no synchronisation in between
+            dev.synchronize()
+            params = [p.data.numpy().copy() for _, p in workloads.all_parameters(model)]
+            if graph:
+                step.destroy()
+            return params
+
+        eager, replayed = run(False), run(True)
+        for a, b in zip(eager, replayed):   # (a wrong bias correction moves a parameter by ~1e-2 of the step; same kernels otherwise)
+            assert np.abs(a - b).max() <= 1e-5 * max(np.abs(a).max(), 1e-3)
+    finally:
+        backend_api.set_precision("fp32")
+
+
 def test_capture_rejects_host_copies(cuda_device):
     from DeepFlows import backend_api
     from DeepFlows.tensor import Tensor
