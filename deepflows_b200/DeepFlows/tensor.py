@@ -357,6 +357,8 @@ class Tensor:
         hook = Tensor._post_backward_hook
         if hook is not None:
             hook()
+            if dev.has("side_join"):
+                dev.side_join()   # buckets flushed by the hook were packed as side tasks (DeepFlows.dist)
         if not retain_graph:
             Graph.free_graph()
 

@@ -712,6 +712,11 @@ dfb_status dfb_graph_begin_capture(void) {
   DFB_INIT();
   Runtime& r = rt();
   DFB_REQUIRE(!r.capturing, DFB_ERR_RUNTIME, "graph capture already active");
+  DFB_REQUIRE(!r.on_side, DFB_ERR_RUNTIME, "graph capture cannot begin on the side stream");
+  {   // side tasks of eager work must not leak into the capture (a join inside it would wait for an uncaptured event)
+    dfb_status st = side_join_upto(r.side_seq);
+    if (st != DFB_OK) return st;
+  }
   DFB_CUDA(cudaStreamSynchronize(r.compute));
   DFB_CUDA(cudaStreamSynchronize(r.comm));
   DFB_CUDA(cudaStreamBeginCapture(r.compute, cudaStreamCaptureModeRelaxed));
