@@ -442,7 +442,12 @@ def main():
         got = buf.numpy()
         sums = got[:world].astype(np.float64) + got[world:].astype(np.float64)
         agree = bool(np.all(sums == sums[0]))
-        dp_check = {"param_checksum": checksum, "ranks_agree": agree}
+        tr = dist.context().transport
+        if hasattr(tr, "check"):
+            tr.check()   # a peer that stopped answering makes the kernels fall through: never report such a run
+        dp_check = {"param_checksum": checksum, "ranks_agree": agree,
+                    "transport": "peer-memory all-reduce kernel over NVLink (csrc/peer.cu), awaited inside multi_adam_kernel"
+                    if getattr(tr, "peer", False) else "ncclAllReduce on the communication stream"}
         if not agree:
             # which parameters: every rank's per-parameter checksums side by side (same two-word transport)
             named = list(model.named_parameters())

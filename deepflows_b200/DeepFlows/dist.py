@@ -47,6 +47,68 @@ class NcclTransport:
         self.device.comm_destroy()
 
 
+class PeerTransport(NcclTransport):
+    """Gradient buckets in NVLink peer memory (csrc/peer.cu): every bucket is a window of one arena that all ranks of
+    the box map through CUDA IPC, `allreduce_sum` is one kernel on the stream that packed the bucket (no communication
+    stream, no event hops), and its completion is awaited inside the fused Adam / SGD kernel (`optimizer_waits`).
+    NCCL still carries the set-up (IPC handles, the self-test's verdict) and the initial broadcast, and stays the
+    transport if `peer_init` fails on any rank (e.g. GPUs that cannot map each other) - all ranks decide together."""
+
+    optimizer_waits = True
+
+    def __init__(self, device, rank, world, master_addr, master_port):
+        super().__init__(device, rank, world, master_addr, master_port)
+        self.peer = False
+        self._windows = {}      # arena offset -> (slot, padded size)
+        self._nccl_busy = False
+
+    def make_buckets(self, sizes, device):
+        """One flat BackendTensor per bucket inside the peer arena (None: no peer memory, allocate them normally)."""
+        if self.world < 2 or not device.has("peer_init") or len(sizes) > 63:
+            return None
+        offsets, total = [], 0
+        for n in sizes:
+            offsets.append(total)
+            total += (n + 3) & ~3
+        try:
+            arena = device.peer_init(total)
+        except RuntimeError as e:
+            if self.rank == 0:
+                import sys
+                print("DeepFlows.dist: %s; gradient buckets stay on NCCL" % (e,), file=sys.stderr)
+            return None
+        self.peer = True
+        flats = []
+        for slot, (off, n) in enumerate(zip(offsets, sizes)):
+            self._windows[off] = (slot, (n + 3) & ~3)
+            flats.append(BackendTensor.make((n,), (1,), device, arena, off))
+        self._arena = arena
+        return flats
+
+    def allreduce_sum(self, flat):
+        w = self._windows.get(flat._offset) if self.peer and flat._handle is self._arena else None
+        if w is None:
+            self._nccl_busy = True
+            return super().allreduce_sum(flat)
+        self.device.peer_allreduce_async(flat._offset, w[1], w[0])
+
+    def broadcast(self, flat, root=0):
+        self._nccl_busy = True
+        super().broadcast(flat, root)
+
+    def wait(self):
+        if self.peer:
+            self.device.peer_wait()
+        if self._nccl_busy:
+            self._nccl_busy = False
+            super().wait()
+
+    def check(self):
+        """Raises if a peer stopped answering (the kernels time out and fall through instead of hanging the GPU)."""
+        if self.peer and self.device.peer_status():
+            raise RuntimeError("data parallel: a peer did not answer within the time-out; gradients are not reduced")
+
+
 def _prefer_bundled_nccl():
     """libdfb200 dlopens NCCL (DFB_NCCL_LIB, else libnccl.so.2 from the loader path). When the Python
     environment ships its own NCCL wheel (nvidia-nccl-cu12, the build PyTorch is tested against on this
@@ -120,8 +182,13 @@ class DataParallel:
     ends (parameters without gradient) is flushed then. Inside a captured CUDA graph the same calls become
     parallel branches of the step graph."""
 
-    def __init__(self, params, transport, bucket_mb=4.0):
+    def __init__(self, params, transport, bucket_mb=4.0, tail_mb=None):
         self.params = [p for p in params]
+        # The bucket that completes LAST (the first-registered layers) is the only one whose reduction nothing overlaps:
+        # it is kept small, so what stands between the end of backward and the optimizer is a latency, not a transfer.
+        if tail_mb is None:
+            tail_mb = float(os.environ.get("DEEPFLOWS_DP_TAIL_MB", "0.25"))
+        self.tail_elems = int(min(tail_mb, bucket_mb) * (1 << 20) / 4)
         self.transport = transport
         self.world = transport.world
         self.rank = transport.rank
@@ -141,8 +208,20 @@ class DataParallel:
     def _build_plan(self):
         dev = self.params[0].device
         plan, cur, cur_n = [], [], 0
+        # the first-registered parameters (as many as fit tail_elems) form the last bucket
+        tail, acc = 0, 0
+        for i in range(len(self.params)):
+            acc += self.params[i].data.size
+            if acc > self.tail_elems:
+                break
+            tail = i + 1
+        if tail == len(self.params):
+            tail = 0
         for i in reversed(range(len(self.params))):
             n = self.params[i].data.size
+            if tail and i == tail - 1 and cur:
+                plan.append((cur, cur_n))
+                cur, cur_n = [], 0
             if cur and cur_n + n > self.bucket_elems:
                 plan.append((cur, cur_n))
                 cur, cur_n = [], 0
@@ -150,7 +229,12 @@ class DataParallel:
             cur_n += n
         if cur:
             plan.append((cur, cur_n))
-        self._plan = [(BackendTensor.make((n,), device=dev), slots) for slots, n in plan]
+        flats = None
+        if hasattr(self.transport, "make_buckets"):
+            flats = self.transport.make_buckets([n for _, n in plan], dev)
+        if flats is None:
+            flats = [BackendTensor.make((n,), device=dev) for _, n in plan]
+        self._plan = [(flat, slots) for flat, (slots, _) in zip(flats, plan)]
         self._bucket_of = {}
         for b, (_, slots) in enumerate(self._plan):
             for i, _, _ in slots:
@@ -237,7 +321,7 @@ class DataParallel:
         for i, off, n in slots:
             p = self.params[i]
             if p.grad is not None:
-                p.grad = BackendTensor.make(p.data.shape, p.data.strides, p.device, flat._handle, off)
+                p.grad = BackendTensor.make(p.data.shape, p.data.strides, p.device, flat._handle, flat._offset + off)
 
     # ---- after backward -----------------------------------------------------------------------------------
     def reduce_gradients(self):
@@ -250,17 +334,20 @@ class DataParallel:
             if b in self._launched:
                 for i, off, n in slots:  # a late contribution would have replaced the bucket view
                     g = self.params[i].grad
-                    if g is not None and (g._handle is not flat._handle or g._offset != off):
+                    if g is not None and (g._handle is not flat._handle or g._offset != flat._offset + off):
                         raise RuntimeError("data parallel: parameter %d received a gradient after its bucket was reduced" % i)
             else:
                 self._launch_bucket(b)
         self._reset_step()
 
-    def pre_step(self):
+    def pre_step(self, fused=False):
         """Called by Optimizer.step(): order the compute stream after the reductions and return the
-        gradient scale (1/world) to fold into the fused optimizer kernel."""
+        gradient scale (1/world) to fold into the fused optimizer kernel. `fused`: the caller is about to launch
+        multi_adam_step / multi_sgd_step, which wait for peer-memory buckets inside their kernel."""
         if self._pending:
-            self.transport.wait()
+            if not (fused and getattr(self.transport, "optimizer_waits", False) and getattr(self.transport, "peer", False)
+                    and not getattr(self.transport, "_nccl_busy", False)):
+                self.transport.wait()
             self._pending = False
         return 1.0 / self.world
 
@@ -273,8 +360,10 @@ def init(params, transport=None, bucket_mb=4.0, broadcast=True):
         rank = int(os.environ.get("RANK", "0"))
         world = int(os.environ.get("WORLD_SIZE", "1"))
         dev = params[0].device
-        transport = NcclTransport(dev, rank, world, os.environ.get("MASTER_ADDR", "127.0.0.1"),
-                                  os.environ.get("MASTER_PORT", "29500"))
+        # DEEPFLOWS_DP_TRANSPORT=nccl keeps the buckets on ncclAllReduce (the round-1 path; before / after numbers)
+        cls = NcclTransport if os.environ.get("DEEPFLOWS_DP_TRANSPORT", "peer") == "nccl" else PeerTransport
+        transport = cls(dev, rank, world, os.environ.get("MASTER_ADDR", "127.0.0.1"),
+                        os.environ.get("MASTER_PORT", "29500"))
     _ctx = DataParallel(params, transport, bucket_mb)
     Tensor._post_backward_hook = _ctx.reduce_gradients
     Tensor._grad_ready_hook = _ctx.grad_arrived
@@ -298,8 +387,8 @@ def context():
     return _ctx
 
 
-def pre_step():
-    return _ctx.pre_step() if _ctx is not None else 1.0
+def pre_step(fused=False):
+    return _ctx.pre_step(fused) if _ctx is not None else 1.0
 
 
 def get_rank():

@@ -18,7 +18,7 @@ class Adam(Optimizer):
         self.t = 1
 
     def step(self):
-        grad_scale = self._grad_scale()
+        grad_scale = self._grad_scale(fused=True)
         active = self._active()
         if active:
             dev = active[0][1].device

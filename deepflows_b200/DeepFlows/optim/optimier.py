@@ -43,9 +43,9 @@ class Optimizer:
         return state if state.strides == p.data.strides and state.is_dense() else state.with_layout_of(p.data)
 
     @staticmethod
-    def _grad_scale():
+    def _grad_scale(fused=False):
         from .. import dist
-        return dist.pre_step()
+        return dist.pre_step(fused)
 
     @staticmethod
     def _grad_scale_value():

@@ -16,7 +16,7 @@ class SGD(Optimizer):
         self.v = [backend_api.zeros(p.shape, device=p.device) for p in self.params]
 
     def step(self):
-        grad_scale = self._grad_scale()
+        grad_scale = self._grad_scale(fused=True)
         active = self._active()
         if not active:
             return

@@ -31,7 +31,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
 ]
-CU_SOURCES = ["runtime.cu", "ewise.cu", "gemm_simt.cu", "gemm_tc.cu", "conv_direct.cu", "gemm.cu", "nn_ops.cu", "data_ops.cu", "optim.cu", "comm.cu"]
+CU_SOURCES = ["runtime.cu", "ewise.cu", "gemm_simt.cu", "gemm_tc.cu", "conv_direct.cu", "gemm.cu", "nn_ops.cu", "data_ops.cu", "optim.cu", "comm.cu", "peer.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.cuh"), os.path.join(ROOT, "include", "dfb200.h")]
 
 

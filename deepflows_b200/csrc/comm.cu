@@ -8,6 +8,7 @@
 // NCCL is loaded with dlopen so that libdfb200.so itself has no link-time dependency on it
 // (single-GPU users never touch it).
 #include "common.cuh"
+#include "peer.cuh"
 
 #include <dlfcn.h>
 
@@ -17,8 +18,8 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat32 = 7 };
-enum { ncclSum = 0 };
+enum { ncclInt8 = 0, ncclInt32 = 2, ncclFloat32 = 7 };
+enum { ncclSum = 0, ncclMin = 3 };
 
 struct Nccl {
   void* lib = nullptr;
@@ -28,6 +29,7 @@ struct Nccl {
   int (*CommAbort)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   int (*GetVersion)(int*) = nullptr;
 };
@@ -52,6 +54,7 @@ dfb_status load_nccl() {
   SYM(CommAbort, "ncclCommAbort");
   SYM(AllReduce, "ncclAllReduce");
   SYM(Broadcast, "ncclBroadcast");
+  SYM(AllGather, "ncclAllGather");
   SYM(GetErrorString, "ncclGetErrorString");
   SYM(GetVersion, "ncclGetVersion");
 #undef SYM
@@ -67,6 +70,33 @@ dfb_status load_nccl() {
   } while (0)
 
 }  // namespace
+
+// Small blocking exchanges of HOST values for the peer-memory set-up (peer.cu): IPC handles and verdicts travel through
+// the communicator that already exists instead of a second rendezvous.
+dfb_status comm_allgather_bytes(const void* mine, size_t bytes, void* all) {
+  DFB_REQUIRE(g_comm != nullptr, DFB_ERR_RUNTIME, "comm_allgather: communicator not initialised");
+  unsigned char* dev = nullptr;
+  DFB_CUDA(cudaMalloc((void**)&dev, bytes * (size_t)(g_world + 1)));
+  cudaStream_t s = comm_stream();
+  DFB_CUDA(cudaMemcpyAsync(dev, mine, bytes, cudaMemcpyHostToDevice, s));
+  DFB_NCCL(g_nccl.AllGather(dev, dev + bytes, bytes, ncclInt8, g_comm, s));
+  DFB_CUDA(cudaMemcpyAsync(all, dev + bytes, bytes * (size_t)g_world, cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(cudaStreamSynchronize(s));
+  DFB_CUDA(cudaFree(dev));
+  return DFB_OK;
+}
+dfb_status comm_allreduce_min_int(int* value) {
+  DFB_REQUIRE(g_comm != nullptr, DFB_ERR_RUNTIME, "comm_allreduce: communicator not initialised");
+  int* dev = nullptr;
+  DFB_CUDA(cudaMalloc((void**)&dev, sizeof(int)));
+  cudaStream_t s = comm_stream();
+  DFB_CUDA(cudaMemcpyAsync(dev, value, sizeof(int), cudaMemcpyHostToDevice, s));
+  DFB_NCCL(g_nccl.AllReduce(dev, dev, 1, ncclInt32, ncclMin, g_comm, s));
+  DFB_CUDA(cudaMemcpyAsync(value, dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(cudaStreamSynchronize(s));
+  DFB_CUDA(cudaFree(dev));
+  return DFB_OK;
+}
 }  // namespace dfb
 
 using namespace dfb;
@@ -101,6 +131,7 @@ dfb_status dfb_comm_init(const unsigned char* id128, int rank, int world_size) {
 
 dfb_status dfb_comm_destroy(void) {
   if (!g_comm) return DFB_OK;
+  dfb_peer_destroy();   // the peers' arenas are unmapped while the communicator can still synchronise the ranks
   // All collectives this rank enqueued have completed once the streams are idle. The communicator object
   // itself is then dropped, not destroyed: ncclCommDestroy / ncclCommAbort block for as long as a captured
   // CUDA graph still references the communicator (NCCL 2.27.3: both were observed to hang here with the

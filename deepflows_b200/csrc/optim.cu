@@ -7,6 +7,7 @@
 // grid-stride kernel walks fixed-size chunks of all tensors. The arithmetic follows the
 // reference's operation order in fp32 (no FMA contraction) so a step is reproducible against it.
 #include "common.cuh"
+#include "peer.cuh"
 
 #include <vector>
 
@@ -55,9 +56,12 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(256)
 multi_adam_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks,
-                  const AdamHyper* __restrict__ hp) {
+                  const AdamHyper* __restrict__ hp, const PeerDev* __restrict__ peer, unsigned long long peer_slots) {
   pdl_sync();
   const AdamHyper h = *hp;
+  // data parallel over peer memory (peer.cu): the gradients are bucket views, and the buckets named by `peer_slots` are
+  // complete once every rank's slice has landed - awaited here, behind the launch and the hyper-parameter load
+  peer_wait_slots(peer, peer_slots);
   for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int ti = find_tensor(tensors, count, chunk);
     TensorRef t = tensors[ti];
@@ -99,9 +103,10 @@ __device__ __forceinline__ void sgd_one(float& p, float g, float* vel, const Sgd
 
 __global__ void __launch_bounds__(256)
 multi_sgd_kernel(const TensorRef* __restrict__ tensors, int count, unsigned long long total_chunks,
-                 const SgdHyper* __restrict__ hp) {
+                 const SgdHyper* __restrict__ hp, const PeerDev* __restrict__ peer, unsigned long long peer_slots) {
   pdl_sync();
   const SgdHyper h = *hp;
+  peer_wait_slots(peer, peer_slots);
   for (unsigned long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int ti = find_tensor(tensors, count, chunk);
     TensorRef t = tensors[ti];
@@ -282,7 +287,8 @@ dfb_status dfb_multi_adam_step(float* const* params, const float* const* grads, 
   st = upload_table(tab, &h, sizeof(h), 0, &dev, &dev_h);
   if (st != DFB_OK) return st;
   unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
-  launch_k(multi_adam_kernel, grid, 256, 0, compute_stream(), dev, (int)tab.size(), chunks, (const AdamHyper*)dev_h);
+  launch_k(multi_adam_kernel, grid, 256, 0, compute_stream(), dev, (int)tab.size(), chunks, (const AdamHyper*)dev_h, peer_dev(),
+           peer_pending_take());
   DFB_LAUNCH_CHECK("multi_adam_step");
   return DFB_OK;
 }
@@ -303,7 +309,8 @@ dfb_status dfb_multi_sgd_step(float* const* params, const float* const* grads, f
   st = upload_table(tab, &h, sizeof(h), 1, &dev, &dev_h);
   if (st != DFB_OK) return st;
   unsigned grid = (unsigned)std::min<unsigned long long>(chunks, (unsigned long long)sm_count() * 8);
-  launch_k(multi_sgd_kernel, grid, 256, 0, compute_stream(), dev, (int)tab.size(), chunks, (const SgdHyper*)dev_h);
+  launch_k(multi_sgd_kernel, grid, 256, 0, compute_stream(), dev, (int)tab.size(), chunks, (const SgdHyper*)dev_h, peer_dev(),
+           peer_pending_take());
   DFB_LAUNCH_CHECK("multi_sgd_step");
   return DFB_OK;
 }

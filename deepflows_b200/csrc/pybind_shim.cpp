@@ -12,6 +12,7 @@
 #include <pybind11/stl.h>
 
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -42,11 +43,13 @@ void check(dfb_status st) {
 struct Array {
   float* ptr = nullptr;
   size_t size = 0;
+  bool owned = true;   // false: a window on memory the library owns (the peer-memory gradient arena)
   explicit Array(size_t n) : size(n) { check(dfb_malloc(n, &ptr)); }
+  Array(float* p, size_t n) : ptr(p), size(n), owned(false) {}
   Array(const Array&) = delete;
   Array& operator=(const Array&) = delete;
   ~Array() {
-    if (ptr) dfb_free(ptr);
+    if (ptr && owned) dfb_free(ptr);
   }
 };
 
@@ -606,4 +609,19 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
   m.def("comm_allreduce_async", [](const py::object& buf, size_t n) { check(dfb_comm_allreduce_async(dptr(buf), n)); });
   m.def("comm_broadcast_async", [](const py::object& buf, size_t n, int root) { check(dfb_comm_broadcast_async(dptr(buf), n, root)); });
   m.def("comm_wait", []() { check(dfb_comm_wait()); });
+  // peer-memory gradient exchange (csrc/peer.cu); peer_init -> an Array over the library-owned arena
+  m.def("peer_init", [](size_t n) {
+    float* a = nullptr;
+    dfb_status st;
+    {
+      py::gil_scoped_release nogil;
+      st = dfb_peer_init(n, &a);
+    }
+    check(st);
+    return std::unique_ptr<Array>(new Array(a, (n + 3) & ~size_t(3)));
+  });
+  m.def("peer_allreduce_async", [](size_t offset, size_t n, int slot) { check(dfb_peer_allreduce_async(offset, n, slot)); });
+  m.def("peer_wait", []() { check(dfb_peer_wait()); });
+  m.def("peer_status", []() { unsigned e = 0; dfb_peer_status(&e); return e; });
+  m.def("peer_destroy", []() { check(dfb_peer_destroy()); });
 }

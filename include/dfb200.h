@@ -445,6 +445,27 @@ DFB_API dfb_status dfb_comm_broadcast_async(float* buf, size_t n, int root);
 /* make the compute stream wait for all communication enqueued so far */
 DFB_API dfb_status dfb_comm_wait(void);
 
+/* ---------------------------------------------------------------------------------------------
+ * Gradient exchange through NVLink / NVSwitch peer memory (new, csrc/peer.cu): the all-reduce of a bucket
+ * as one kernel on the stream that packed it, its completion awaited inside the fused optimizer kernel.
+ * ncclAllReduce (above) stays as the fallback; dfb_peer_init decides for all ranks together.
+ * ------------------------------------------------------------------------------------------- */
+/* Collective over the communicator of dfb_comm_init (2..8 ranks of one box). Allocates this rank's arena of
+ * `arena_floats` floats (zero-filled; the gradient buckets live in it), maps every other rank's arena through CUDA
+ * IPC and runs a self-test. Fails on EVERY rank (DFB_ERR_RUNTIME, nothing left allocated) if any rank could not map
+ * a peer or the self-test did not reproduce the expected sums. `*arena` is owned by the library. */
+DFB_API dfb_status dfb_peer_init(size_t arena_floats, float** arena);
+/* In-place sum over all ranks of arena[offset, offset + n) (multiples of 4 floats), enqueued on the current compute
+ * (or side) stream behind whatever filled the range. `slot` in [0, 63) identifies the bucket: every rank must issue
+ * the same sequence of (offset, n, slot). Returns without waiting for the other ranks' slices: dfb_multi_adam_step /
+ * dfb_multi_sgd_step wait for all outstanding slots inside their kernel, dfb_peer_wait for everything else. */
+DFB_API dfb_status dfb_peer_allreduce_async(size_t offset, size_t n, int slot);
+/* the compute stream waits (in a one-CTA kernel) until every outstanding slot is complete on this rank */
+DFB_API dfb_status dfb_peer_wait(void);
+/* sticky error word: non-zero after a peer did not answer within 20 s (the kernels then fall through) */
+DFB_API dfb_status dfb_peer_status(unsigned* error_word);
+DFB_API dfb_status dfb_peer_destroy(void);
+
 #ifdef __cplusplus
 }
 #endif

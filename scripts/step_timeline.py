@@ -41,10 +41,16 @@ def main():
     cfg["batch"] = B
     dev = backend_api.cuda()
     m = dev.mod
+    # under torchrun (WORLD_SIZE > 1): the data-parallel step; every rank runs it, rank 0 prints its own timeline
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     backend_api.set_precision(args.precision)
     backend_api.set_dgrad_mode("exact")
     df, model, opt, crit = bench.build_training("cuda", cfg, args.precision)
-    x_host, t_host = bench.synthetic_batch(B, 100, cfg["shape"], cfg["smooth"])
+    if world > 1:
+        from DeepFlows import dist
+        dist.init(model.parameters())
+    x_host, t_host = bench.synthetic_batch(B, 100 + rank, cfg["shape"], cfg["smooth"])
     x_dev = Tensor(backend_api.Btensor(x_host, device=dev))
     t_dev = Tensor(backend_api.Btensor(t_host, device=dev))
 
@@ -71,6 +77,11 @@ def main():
         step()
     dev.synchronize()
     rec, n, _ = m.trace_end(1 << 14)
+    if world > 1:
+        from DeepFlows import dist
+        dist.shutdown()
+        if rank != 0:
+            os._exit(0)
     rec = np.asarray(rec)[:n]
     per = n // args.replays
     rec = rec[(args.replays - 1) * per:]            # the last replay
@@ -78,7 +89,7 @@ def main():
     host = []
     for line in host_lines:
         st, gx, gy, gz, bx, name = line.split(" ", 5)
-        host.append((st, (int(gx), int(gy), int(gz), int(bx)), short(name)))
+        host.append((st if st != "other" else "comm", (int(gx), int(gy), int(gz), int(bx)), short(name)))
     host = host[-per:] if len(host) >= per else host
     by_fp = collections.defaultdict(collections.deque)
     for h in host:
@@ -96,13 +107,13 @@ def main():
     print("# start = when the kernel's work begins (after griddepcontrol.wait), us since the step's first kernel;")
     print("# cost = start of the next MAIN-stream kernel minus this start (main-stream kernels only)")
     print("%9s %8s %5s %-22s %s" % ("start us", "cost us", "strm", "grid x block", "kernel"))
-    main_idx = [i for i, r in enumerate(rows) if r[1] != "side"]
+    main_idx = [i for i, r in enumerate(rows) if r[1] not in ("side", "comm")]
     nxt = {a: b for a, b in zip(main_idx, main_idx[1:])}
     cost_by_kernel = collections.OrderedDict()
     for i, (t, st, key, name) in enumerate(rows):
         cost = rows[nxt[i]][0] - t if i in nxt else float("nan")
         print("%9.2f %8.2f %5s %-22s %s" % (t, cost, st, "%dx%dx%d x %d" % key, name[:110]))
-        if st != "side" and i in nxt:
+        if st not in ("side", "comm") and i in nxt:
             a = cost_by_kernel.setdefault(name, [0, 0.0])
             a[0] += 1
             a[1] += cost

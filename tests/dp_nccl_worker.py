@@ -61,6 +61,7 @@ def allgather(vec):
 # ---- replicas start from different weights; dist.init broadcasts rank 0's -----------------------------------------------
 model = build(100 + rank)
 ctx = dist.init(model.parameters(), bucket_mb=0.05)          # small buckets: several of them, launched during backward
+want_peer = os.environ.get("DEEPFLOWS_DP_TRANSPORT", "peer") != "nccl"
 w0 = [p.data.numpy().copy() for p in model.parameters()]
 head = np.concatenate([w.ravel()[:8] for w in w0])
 heads = allgather(head)
@@ -144,6 +145,12 @@ for i, (a, b) in enumerate(zip(graph3, eager3)):
 sums = allgather(np.array([float(np.sum([a.astype(np.float64).sum() for a in graph3]))], F32))
 assert all(sums[r, 0] == sums[0, 0] for r in range(world)), "replicas diverged after the captured steps: %s" % sums[:, 0]
 cap.destroy()
+if want_peer:
+    # the buckets really went through the peer-memory kernels (no silent NCCL fallback on a box whose GPUs see each other)
+    assert getattr(ctx.transport, "peer", False), "peer-memory transport was requested but the buckets stayed on NCCL"
+    ctx.transport.check()
+else:
+    assert not getattr(ctx.transport, "peer", False)
 dist.shutdown()
 print("rank %d of %d: data-parallel NCCL parity ok" % (rank, world), flush=True)
 os._exit(0)
