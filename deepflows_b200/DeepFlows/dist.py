@@ -47,6 +47,12 @@ class NcclTransport:
         self.device.comm_destroy()
 
 
+# Which buckets the peer kernels reduce (the rest: NCCL). Measured (C4, profiles/r04*): the one-shot kernel on the exposed
+# bucket beats NCCL at 2 and 8 GPUs; the two-shot pull on the overlapped buckets costs the convolutions beside it more
+# than NCCL's kernels do (2 GPUs +9 us per step, 8 GPUs +170 us) - so "tail" is the default, "all" / "mid" the experiments.
+_PEER_PARTS = os.environ.get("DEEPFLOWS_DP_PEER_PARTS", "tail")
+
+
 class PeerTransport(NcclTransport):
     """Gradient buckets in NVLink peer memory (csrc/peer.cu): every bucket is a window of one arena that all ranks of
     the box map through CUDA IPC, `allreduce_sum` is one kernel on the stream that packed the bucket (no communication
@@ -80,17 +86,25 @@ class PeerTransport(NcclTransport):
         self.peer = True
         flats = []
         for slot, (off, n) in enumerate(zip(offsets, sizes)):
-            self._windows[off] = (slot, (n + 3) & ~3)
+            # the last bucket (the first-registered layers) completes when backward ends: nothing overlaps its reduction
+            self._windows[off] = (slot, (n + 3) & ~3, slot == len(sizes) - 1 and len(sizes) > 1)
             flats.append(BackendTensor.make((n,), (1,), device, arena, off))
         self._arena = arena
         return flats
 
     def allreduce_sum(self, flat):
         w = self._windows.get(flat._offset) if self.peer and flat._handle is self._arena else None
+        if w is not None and _PEER_PARTS != "all" and (_PEER_PARTS == "tail") != bool(w[2]):
+            w = None   # experiment switch: only the exposed bucket ("tail") or only the overlapped ones ("mid") on the peer kernels
         if w is None:
             self._nccl_busy = True
             return super().allreduce_sum(flat)
-        self.device.peer_allreduce_async(flat._offset, w[1], w[0])
+        self.device.peer_allreduce_async(flat._offset, w[1], w[0], w[2])
+
+    def exposed(self, flat):
+        """True for the bucket the one-shot kernel reduces on the compute stream itself (DataParallel._launch_bucket)."""
+        w = self._windows.get(flat._offset) if self.peer and flat._handle is self._arena else None
+        return bool(w is not None and w[2] and w[1] <= 65536 and _PEER_PARTS != "mid")
 
     def broadcast(self, flat, root=0):
         self._nccl_busy = True
@@ -284,6 +298,10 @@ class DataParallel:
         # the pack through the event it records on the current (= side) stream, the optimizer waits for the communication
         # stream, and backward() joins the side stream when it ends.
         on_side = dev.has("side_join_lag") and dev.has("side_begin") and _BUCKETS_ON_SIDE
+        if on_side and getattr(self.transport, "exposed", lambda f: False)(flat):
+            # the last bucket, reduced by the one-shot peer kernel: nothing is left to overlap, so the compute stream joins the
+            # side stream now (backward() would a moment later) and pack, reduction and optimizer follow each other on it
+            on_side = False
         if on_side:
             dev.side_begin()
         elif dev.has("side_join"):

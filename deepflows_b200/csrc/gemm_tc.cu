@@ -1155,6 +1155,242 @@ __global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads) tc_persistent_
   }
 }
 
+// ---- persistent variant for the BIG layers: 128 x 256 tiles, two 256-column accumulators ---------------------------------
+// The 128 x 256 kernels above run one tile per CTA at one CTA per SM (208 KB of ring): nothing overlaps a tile's epilogue,
+// and the fused epilogues of the training step are not small - a dgrad tile that applies the ReLU mask and takes the
+// BatchNorm-backward sums re-reads 128 KB of the BatchNorm's input and costs ~26 us next to a ~30 us main loop
+// (VGG / ResNet-34 at 224 x 224, batch 128: conv 256 -> 256 at 56 x 56 fprop 804 us, the same contraction as fused dgrad
+// 1186 us). Here a CTA lives for the whole launch, the MMA warp alternates between the two halves of TMEM (512 columns =
+// 2 x 256), and the epilogue warps drain tile i while the MMAs of tile i + 1 run.
+// There is no room for a 133 KB staging tile beside a four-stage ring, and none is needed: every epilogue warp passes its
+// 32 rows through its own 32-column staging chunk (4.6 KB), eight chunks per tile, and writes 128-byte row segments -
+// whole cache lines. Per-channel statistics leave per warp and chunk: lanes that share columns are merged by shuffles and
+// added to the statistic slot with fp64 atomics (kernels.cuh), so the launch needs the slot (the host falls back to
+// the one-tile-per-CTA kernel without it).
+// Tile order: column tile fastest, so the CTAs running at any moment share their activation tiles in L2.
+template <class P>
+struct WideLayout {
+  using LS = SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR>;
+  static constexpr int kStages = 4;
+  static constexpr uint32_t kStageBytes = LS::kStageBytes;
+  static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+  static constexpr uint32_t kRowTabOffset = kBarOffset + 128;                    // 2 * kStages + 4 barriers, the TMEM slot
+  static constexpr uint32_t kChunkPitch = 36;                                    // floats: 32 columns + 4 (bank spread)
+  static constexpr uint32_t kChunkOffset = kRowTabOffset + BLOCK_M * 8;
+  static constexpr uint32_t kChunkBytes = 32 * kChunkPitch * 4;                  // per epilogue warp
+  static constexpr uint32_t kTotal = kChunkOffset + 4 * kChunkBytes + 1024;      // + manual alignment
+  static_assert(kTotal <= 227u * 1024u, "shared memory");
+  static_assert(2 * kStages + 4 <= 15, "barrier block");
+};
+// lanes of a warp that hold the same columns (different rows of one warp instruction) are merged, and the lanes of row
+// slot 0 add the warp's sums to the statistic slot (RowEpi<32>: 8 lanes per row, 4 row slots)
+template <int EF>
+__device__ __forceinline__ void wide_flush_stats(RowEpi<32>& epi, const EpiArgs& e, int lane, int col, int n_out) {
+  if constexpr ((EF & (EF_STATS | EF_BNBWD)) == 0) return;
+  constexpr bool stats = (EF & EF_STATS) != 0;
+#pragma unroll
+  for (int off = RowEpi<32>::LPR; off < 32; off <<= 1) {
+    const float on = __shfl_xor_sync(0xffffffffu, epi.n, off);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float oa = __shfl_xor_sync(0xffffffffu, epi.a[0][q], off), ob = __shfl_xor_sync(0xffffffffu, epi.b[0][q], off),
+                  oc = __shfl_xor_sync(0xffffffffu, epi.c[0][q], off);
+      if (stats) {
+        Moments m{epi.a[0][q], epi.b[0][q], epi.c[0][q], epi.n};
+        Moments o{oa, ob, oc, on};
+        if (lane & off) { o.merge(m); m = o; } else { m.merge(o); }
+        epi.a[0][q] = m.s; epi.b[0][q] = m.m1; epi.c[0][q] = m.m2;
+      } else {
+        epi.a[0][q] += oa; epi.b[0][q] += ob; epi.c[0][q] += oc;
+      }
+    }
+    epi.n += on;
+  }
+  if (lane < RowEpi<32>::LPR && col + 4 <= n_out) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double* acc = e.stat_acc + col + q;
+      if (stats) {
+        if (epi.n > 0.f) {   // sums of (v - s), (v - s)^2 over n rows -> sums of v, v^2
+          const double s_ = (double)epi.a[0][q], m1 = (double)epi.b[0][q], m2 = (double)epi.c[0][q], n_ = (double)epi.n;
+          atomicAdd(acc, m1 + n_ * s_);
+          atomicAdd(acc + kStatSlotChannels, m2 + 2.0 * s_ * m1 + n_ * s_ * s_);
+        }
+      } else {
+        atomicAdd(acc, (double)epi.a[0][q]);
+        atomicAdd(acc + kStatSlotChannels, (double)epi.b[0][q]);
+        if (e.n_sets > 1) atomicAdd(acc + 2 * kStatSlotChannels, (double)epi.c[0][q]);
+      }
+    }
+  }
+}
+
+template <class P, int EF>
+__global__ void __launch_bounds__(kThreads) tc_wide_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                           const __grid_constant__ CUtensorMap map_b,
+                                                           const typename P::Params prm, const int n_tiles, const int col_tiles) {
+  constexpr int BN = P::BN;
+  static_assert(BN == 256 && P::kRowMajor && P::kSubTiles == 1 && P::kAccTiles == 1, "wide kernel: 128 x 256 row-major tiles");
+  using W = WideLayout<P>;
+  using LS = typename W::LS;
+  constexpr int kStages = W::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + W::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float** row_tab = reinterpret_cast<float**>(smem + W::kRowTabOffset);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar + a, 1);
+      mbar_init(tmem_empty_bar + a, 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  // tile ti -> (pixel tile ti / col_tiles, column tile ti % col_tiles)
+  auto tile_of = [&](int ti) {
+    typename P::Tile t = P::tile_at(prm, ti / col_tiles);
+    t.col0 = (ti % col_tiles) * BN;
+    return t;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer: the ring runs across tile boundaries =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+      const typename P::Tile tile = tile_of(ti);
+      const uint32_t tx = P::tx_bytes(prm, tile);
+      typename P::Iter it = P::iter_init(prm, tile, tile.kb_begin);
+      for (int kb = tile.kb_begin; kb < tile.kb_end; ++kb) {
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        const uint32_t a_dst = smem_u32(smem + stage * W::kStageBytes);
+        const uint32_t b_dst = a_dst + LS::kABytes;
+        if (elect_one()) {
+          mbar_expect_tx(full_bar + stage, tx);
+          P::load_a(prm, tile, it, &map_a, full_bar + stage, a_dst);
+          P::load_b(prm, tile, it, &map_b, full_bar + stage, b_dst);
+        }
+        __syncwarp();
+        P::iter_next(prm, tile, it);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator lt & 1 (TMEM columns 0..255 / 256..511) for the lt-th tile of this CTA =====
+    constexpr uint32_t idesc = instr_desc_tf32<P::A_MAJOR, P::B_MAJOR, BN>();
+    int stage = 0;
+    uint32_t phase = 0;
+    int lt = 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++lt) {
+      const typename P::Tile tile = tile_of(ti);
+      const int acc = lt & 1;
+      if (lt >= 2) {   // the epilogue must have drained this accumulator's previous tile
+        mbar_wait(tmem_empty_bar + acc, (uint32_t)(((lt >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = tile.kb_begin; kb < tile.kb_end; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * W::kStageBytes);
+        const uint32_t b_base = a_base + LS::kABytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < P::KR / UMMA_K; ++j)
+            umma_tf32(d_tmem, operand_desc<P::A_MAJOR, LS::kChunk>(a_base, j), operand_desc<P::B_MAJOR, LS::kBChunk>(b_base, j), idesc,
+                      (kb > tile.kb_begin || j > 0) ? 1u : 0u);
+          umma_commit(empty_bar + stage);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(tmem_full_bar + acc);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter (warp & 3); each warp stages and writes its own 32 rows, chunk by chunk =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t chunk_u32 = smem_u32(smem + W::kChunkOffset + quarter * W::kChunkBytes);
+    const uint32_t rowtab_u32 = smem_u32(row_tab);
+    constexpr int LPR = RowEpi<32>::LPR, RPI = RowEpi<32>::RPI, U = 4;
+    const int lr = lane / LPR, lc = lane % LPR;
+    int lt = 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++lt) {
+      const typename P::Tile tile = tile_of(ti);
+      const int acc = lt & 1;
+      row_tab[row] = P::row_ptr(prm, tile, row);   // (this warp's entries only; its previous tile is written out)
+      mbar_wait(tmem_full_bar + acc, (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cc), v);
+        if (cc + 32 == BN) {   // the last read of this accumulator: free it for the tile after next
+          tc_fence_before();
+          __syncwarp();
+          if (elect_one()) mbar_arrive(tmem_empty_bar + acc);
+        }
+        __syncwarp();          // the previous chunk's rows have been read by every lane
+        const uint32_t dst = chunk_u32 + (uint32_t)(lane * W::kChunkPitch) * 4u;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) sts_f4(dst + i * 4, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        __syncwarp();
+        const int col = tile.col0 + cc + lc * 4;     // this lane's four columns of the chunk
+        RowEpi<32> epi;
+        epi.init();
+        epi.template load_consts<EF>(prm.epi, col, prm.n_out);
+#pragma unroll 1
+        for (int rr = 0; rr < 32; rr += RPI * U) {
+          float* rp[U];
+          float4 val[U];
+          typename RowEpi<32>::Extras ex[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = rr + u * RPI + lr;
+            rp[u] = lds_ptr(rowtab_u32 + (quarter * 32 + r) * 8);
+            val[u] = lds_f4(chunk_u32 + (uint32_t)(r * W::kChunkPitch + lc * 4) * 4u);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) ex[u] = RowEpi<32>::template load_extras<EF>(prm.epi, prm.out, rp[u], col, prm.n_out);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (rp[u]) {
+              epi.template emit<EF>(prm.epi, rp[u], col, 0, val[u], ex[u], prm.n_out);
+              epi.n += 1.f;
+            }
+          }
+        }
+        wide_flush_stats<EF>(epi, prm.epi, lane, col, prm.n_out);
+      }
+      __syncwarp();   // row pointers are free for the next tile
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1292,6 +1528,34 @@ static bool persistent_enabled() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
+}
+
+// DFB_CONV_WIDE=0 switches the persistent 128 x 256 kernel off (one tile per CTA again)
+static bool wide_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_CONV_WIDE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <class P, int EF>
+static dfb_status launch_wide(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const typename P::Params& prm, int n_tiles,
+                              int col_tiles) {
+  using W = WideLayout<P>;
+  static bool configured = false;
+  if (!configured) {
+    DFB_CUDA(cudaFuncSetAttribute(tc_wide_kernel<P, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::kTotal));
+    configured = true;
+  }
+  // whole waves: every CTA walks the same number of tiles (+-1)
+  const int sms = sm_count();
+  const int waves = (n_tiles + sms - 1) / sms;
+  const unsigned ctas = (unsigned)((n_tiles + waves - 1) / waves);
+  launch_k(tc_wide_kernel<P, EF>, dim3(ctas, 1, 1), kThreads, W::kTotal, compute_stream(), ma, mb, prm, n_tiles, col_tiles);
+  DFB_LAUNCH_CHECK(name);
+  g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  return DFB_OK;
 }
 
 // Split-K factor (cluster size along z, a power of two <= 8): enough CTAs to occupy the machine, at least
@@ -2001,6 +2265,30 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
         else if (add) st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_ADDEND>>(name, ma, mb, prm, n_tiles, ctas);
         else st = launch_persistent<ConvProblem<BN, WMODE, ROWS, EF_NONE>>(name, ma, mb, prm, n_tiles, ctas);
       }
+      launched = true;
+    }
+  }
+  // Big layers (128 x 256 tiles, hundreds of them): CTAs that live for the whole launch and overlap a tile's epilogue
+  // with the next tile's MMAs (tc_wide_kernel). Statistics go to the statistic slot, so the call needs one.
+  if constexpr (BN == 256 && !ROWS) {
+    const int n_tiles = (int)(grid.x * grid.y), col_tiles = (int)grid.y;
+    const bool slot_ok = prm.epi.stat_kind == EPI_NONE || prm.epi.stat_acc != nullptr;
+    if (wide_enabled() && !g_x3 && classes == 1 && prm.splits == 1 && slot_ok && (size_t)n_tiles >= (size_t)sm_count() * 2) {
+#define DFB_WIDE(EFV) st = launch_wide<ConvProblem<BN, WMODE, ROWS, (EFV)>, (EFV)>(name, ma, mb, prm, n_tiles, col_tiles)
+      if constexpr (WMODE == W_KRSC_FPROP) {
+        if (prm.epi.stat_kind == EPI_STATS) DFB_WIDE(EF_STATS);
+        else DFB_WIDE(EF_NONE);
+      } else if constexpr (WMODE == W_KRSC_DGRAD) {
+        if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu && add) DFB_WIDE(EF_BNBWD | EF_RELU | EF_ADDEND);
+        else if (prm.epi.stat_kind == EPI_BNBWD && prm.epi.relu) DFB_WIDE(EF_BNBWD | EF_RELU);
+        else if (prm.epi.stat_kind == EPI_BNBWD && add) DFB_WIDE(EF_BNBWD | EF_ADDEND);
+        else if (prm.epi.stat_kind == EPI_BNBWD) DFB_WIDE(EF_BNBWD);
+        else if (add) DFB_WIDE(EF_ADDEND);
+        else DFB_WIDE(EF_NONE);
+      } else {
+        DFB_WIDE(EF_NONE);
+      }
+#undef DFB_WIDE
       launched = true;
     }
   }

@@ -6,8 +6,14 @@ namespace dfb {
 
 constexpr int kPeerMaxWorld = 8;      // one NVLink / NVSwitch domain
 constexpr int kPeerSlots = 64;        // buckets in flight (the last one belongs to the self-test)
-constexpr int kPeerMaxCtas = 32;      // CTAs of one reduction launch: one per kPeerBytesPerCta of the rank's slice
+constexpr int kPeerMaxCtas = 16;      // CTAs of one two-shot reduction launch: one per kPeerBytesPerCta of the rank's slice
 constexpr size_t kPeerBytesPerCta = 128u << 10;
+// one-shot "push" form for the bucket nothing overlaps (the last one of a step): every rank stores its copy into a
+// receive area on every peer and sums all copies itself
+constexpr int kPushMaxCtas = 32;
+constexpr size_t kPushCapFloats = 64u << 10;      // 256 KB per copy
+constexpr size_t kPushFlagBytes = (size_t)kPeerMaxWorld * kPushMaxCtas * sizeof(unsigned);
+constexpr size_t kPushRecvBytes = 2 * (size_t)kPeerMaxWorld * 2 * kPushCapFloats * sizeof(float);   // [parity][source rank][copy as {value, launch number} pairs]
 constexpr int kPeerThreads = 256;
 constexpr int kPeerFlagWords = 16;    // per slot: [0, 8) phase-0 arrivals per source rank, [8] phase-1 arrivals
 constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000 * 1000 * 1000;
@@ -17,6 +23,9 @@ struct PeerDev {
   float* arena[kPeerMaxWorld];      // every rank's gradient arena
   unsigned* epoch;                  // local: [slot] launches so far, then [kPeerSlots + slot] phase-1 arrivals expected so far
   unsigned* error;                  // mapped pinned host word, sticky
+  unsigned* push_flags[kPeerMaxWorld];   // every rank's [source rank][cta] arrival words of the push form
+  float* push_recv[kPeerMaxWorld];       // every rank's receive area
+  unsigned* push_epoch;                  // local: [cta] launches so far
   int world, rank;
 };
 

@@ -620,7 +620,9 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
     check(st);
     return std::unique_ptr<Array>(new Array(a, (n + 3) & ~size_t(3)));
   });
-  m.def("peer_allreduce_async", [](size_t offset, size_t n, int slot) { check(dfb_peer_allreduce_async(offset, n, slot)); });
+  m.def("peer_allreduce_async", [](size_t offset, size_t n, int slot, bool exposed) {
+    check(dfb_peer_allreduce_async(offset, n, slot, exposed ? 1 : 0));
+  });
   m.def("peer_wait", []() { check(dfb_peer_wait()); });
   m.def("peer_status", []() { unsigned e = 0; dfb_peer_status(&e); return e; });
   m.def("peer_destroy", []() { check(dfb_peer_destroy()); });

@@ -458,8 +458,10 @@ DFB_API dfb_status dfb_peer_init(size_t arena_floats, float** arena);
 /* In-place sum over all ranks of arena[offset, offset + n) (multiples of 4 floats), enqueued on the current compute
  * (or side) stream behind whatever filled the range. `slot` in [0, 63) identifies the bucket: every rank must issue
  * the same sequence of (offset, n, slot). Returns without waiting for the other ranks' slices: dfb_multi_adam_step /
- * dfb_multi_sgd_step wait for all outstanding slots inside their kernel, dfb_peer_wait for everything else. */
-DFB_API dfb_status dfb_peer_allreduce_async(size_t offset, size_t n, int slot);
+ * dfb_multi_sgd_step wait for all outstanding slots inside their kernel, dfb_peer_wait for everything else.
+ * `exposed` != 0 (the bucket nothing overlaps: the last one of a step, at most 256 KB, one per step) selects the
+ * one-shot form: one kernel that stores this rank's copy to every peer, waits for theirs and sums all copies. */
+DFB_API dfb_status dfb_peer_allreduce_async(size_t offset, size_t n, int slot, int exposed);
 /* the compute stream waits (in a one-CTA kernel) until every outstanding slot is complete on this rank */
 DFB_API dfb_status dfb_peer_wait(void);
 /* sticky error word: non-zero after a peer did not answer within 20 s (the kernels then fall through) */

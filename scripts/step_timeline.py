@@ -80,7 +80,10 @@ def main():
     if world > 1:
         from DeepFlows import dist
         dist.shutdown()
-        if rank != 0:
+        prefix = os.environ.get("DFB_TIMELINE_PREFIX")   # every rank writes <prefix>_rank<r>.txt (else only rank 0 prints)
+        if prefix:
+            sys.stdout = open("%s_rank%d.txt" % (prefix, rank), "w")
+        elif rank != 0:
             os._exit(0)
     rec = np.asarray(rec)[:n]
     per = n // args.replays
@@ -104,6 +107,7 @@ def main():
         rows.append(((t - t0) / 1000.0, h[0], key, h[2]))
     print("# %s, batch %d, %s: one replay of the captured step, %d kernels (host noted %d launches in the capture pass)"
           % (args.config, B, args.precision, len(rows), len(host)))
+    print("# rank %d of %d; %%globaltimer of the step's first kernel: %d ns" % (rank, world, t0))
     print("# start = when the kernel's work begins (after griddepcontrol.wait), us since the step's first kernel;")
     print("# cost = start of the next MAIN-stream kernel minus this start (main-stream kernels only)")
     print("%9s %8s %5s %-22s %s" % ("start us", "cost us", "strm", "grid x block", "kernel"))
@@ -125,3 +129,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+    sys.stdout.flush()
+    os._exit(0)

@@ -25,6 +25,7 @@ CONV_SHAPES = [  # N, C, H, W, K, R, pad, stride
     (256, 32, 16, 16, 32, 3, 1, 1),    # 512 tiles of 32 channels: the persistent kernel (row-halo), two tiles per CTA
     (150, 32, 32, 32, 32, 1, 0, 1),    # 1200 tiles, 1x1 (the first layer's column-matrix convolution), uneven tiles per CTA
     (301, 8, 12, 12, 24, 3, 1, 1),     # persistent, ragged: 339 tiles, the last one partial, 8 -> 24 channels
+    (40, 160, 32, 32, 272, 3, 1, 1),   # 320 pixel tiles x 128 x 256: the wide persistent kernel (tc_wide_kernel), partial column tiles
 ]
 
 

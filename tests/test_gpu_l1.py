@@ -87,6 +87,7 @@ SHAPES = [  # N, C, H, W, K, R, pad, stride   (scaled-down versions of the C2-C5
     (2, 64, 14, 14, 64, 3, 1, 1),    # 224-net tail shape, H not a power of two
     (3, 20, 11, 13, 36, 3, 1, 1),    # ragged everything
     (2, 64, 56, 56, 64, 3, 1, 1),    # VGG-like tile
+    (40, 160, 32, 32, 272, 3, 1, 1), # 128 x 256 tiles, more than two per SM: the wide persistent kernel, partial column tiles
 ]
 
 
