@@ -1162,30 +1162,38 @@ __global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads) tc_persistent_
 // (VGG / ResNet-34 at 224 x 224, batch 128: conv 256 -> 256 at 56 x 56 fprop 804 us, the same contraction as fused dgrad
 // 1186 us). Here a CTA lives for the whole launch, the MMA warp alternates between the two halves of TMEM (512 columns =
 // 2 x 256), and the epilogue warps drain tile i while the MMAs of tile i + 1 run.
-// There is no room for a 133 KB staging tile beside a four-stage ring, and none is needed: every epilogue warp passes its
+// There is no room for a 133 KB staging tile beside the ring, and none is needed: every epilogue warp passes its
 // 32 rows through its own 32-column staging chunk (4.6 KB), eight chunks per tile, and writes 128-byte row segments -
-// whole cache lines. Per-channel statistics leave per warp and chunk: lanes that share columns are merged by shuffles and
-// added to the statistic slot with fp64 atomics (kernels.cuh), so the launch needs the slot (the host falls back to
-// the one-tile-per-CTA kernel without it).
+// whole cache lines. Per-channel statistics: lanes that share columns are merged by shuffles, every warp keeps running
+// sums of all channels over all its tiles in shared memory, and the CTA adds them to the statistic slot (fp64 atomics,
+// kernels.cuh) once, at the end - so the launch needs the slot (the host falls back to the one-tile-per-CTA kernel
+// without it) and at most 512 output channels. Three ring stages (144 KB) leave room for that.
 // Tile order: column tile fastest, so the CTAs running at any moment share their activation tiles in L2.
 template <class P>
 struct WideLayout {
   using LS = SmemLayout<P::BN, P::AROWS, P::KR, P::kBSub, P::BKR>;
-  static constexpr int kStages = 4;
+  static constexpr int kStages = 3;
   static constexpr uint32_t kStageBytes = LS::kStageBytes;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kRowTabOffset = kBarOffset + 128;                    // 2 * kStages + 4 barriers, the TMEM slot
   static constexpr uint32_t kChunkPitch = 36;                                    // floats: 32 columns + 4 (bank spread)
   static constexpr uint32_t kChunkOffset = kRowTabOffset + BLOCK_M * 8;
   static constexpr uint32_t kChunkBytes = 32 * kChunkPitch * 4;                  // per epilogue warp
-  static constexpr uint32_t kTotal = kChunkOffset + 4 * kChunkBytes + 1024;      // + manual alignment
+  // per-warp running statistics of every output channel over ALL tiles of the CTA: [4 warps][kMaxChannels][4 floats]
+  static constexpr int kMaxChannels = 512;
+  static constexpr uint32_t kAccOffset = kChunkOffset + 4 * kChunkBytes;
+  static constexpr uint32_t kAccBytes = 4 * kMaxChannels * 16;
+  static constexpr uint32_t kTotal = kAccOffset + kAccBytes + 1024;              // + manual alignment
   static_assert(kTotal <= 227u * 1024u, "shared memory");
   static_assert(2 * kStages + 4 <= 15, "barrier block");
 };
-// lanes of a warp that hold the same columns (different rows of one warp instruction) are merged, and the lanes of row
-// slot 0 add the warp's sums to the statistic slot (RowEpi<32>: 8 lanes per row, 4 row slots)
+// Lanes of a warp that hold the same columns (different rows of one warp instruction) are merged, and the lanes of row
+// slot 0 fold the chunk's sums into the WARP's running statistics of those columns in shared memory (RowEpi<32>: 8 lanes
+// per row, 4 row slots). Global atomics per warp and chunk were the first version: 2048 fp64 atomics per tile on a few
+// hundred addresses serialise in L2 - the 256-channel fprop took 1033 us against 804 us for the one-tile-per-CTA kernel.
+// `acc4`: this warp's [channels][4] block: EF_STATS (shift, m1, m2, n), EF_BNBWD (sum d, sum d*xh0, sum d*xh1, -).
 template <int EF>
-__device__ __forceinline__ void wide_flush_stats(RowEpi<32>& epi, const EpiArgs& e, int lane, int col, int n_out) {
+__device__ __forceinline__ void wide_fold_stats(RowEpi<32>& epi, float4* acc4, int lane, int col, int n_out) {
   if constexpr ((EF & (EF_STATS | EF_BNBWD)) == 0) return;
   constexpr bool stats = (EF & EF_STATS) != 0;
 #pragma unroll
@@ -1209,18 +1217,48 @@ __device__ __forceinline__ void wide_flush_stats(RowEpi<32>& epi, const EpiArgs&
   if (lane < RowEpi<32>::LPR && col + 4 <= n_out) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      double* acc = e.stat_acc + col + q;
+      float4 t = acc4[col + q];
       if (stats) {
-        if (epi.n > 0.f) {   // sums of (v - s), (v - s)^2 over n rows -> sums of v, v^2
-          const double s_ = (double)epi.a[0][q], m1 = (double)epi.b[0][q], m2 = (double)epi.c[0][q], n_ = (double)epi.n;
-          atomicAdd(acc, m1 + n_ * s_);
-          atomicAdd(acc + kStatSlotChannels, m2 + 2.0 * s_ * m1 + n_ * s_ * s_);
-        }
+        Moments m{t.x, t.y, t.z, t.w};
+        m.merge(Moments{epi.a[0][q], epi.b[0][q], epi.c[0][q], epi.n});
+        t = make_float4(m.s, m.m1, m.m2, m.n);
       } else {
-        atomicAdd(acc, (double)epi.a[0][q]);
-        atomicAdd(acc + kStatSlotChannels, (double)epi.b[0][q]);
-        if (e.n_sets > 1) atomicAdd(acc + 2 * kStatSlotChannels, (double)epi.c[0][q]);
+        t.x += epi.a[0][q]; t.y += epi.b[0][q]; t.z += epi.c[0][q];
       }
+      acc4[col + q] = t;
+    }
+  }
+}
+// end of the launch, the 128 epilogue threads (t): the four warps' statistics of a column are merged in warp order and
+// added to the statistic slot - one fp64 atomic per sum, column and CTA
+template <int EF>
+__device__ __forceinline__ void wide_flush_stats(const EpiArgs& e, const float4* acc4_all, int max_channels, int t, int n_out) {
+  if constexpr ((EF & (EF_STATS | EF_BNBWD)) == 0) return;
+  constexpr bool stats = (EF & EF_STATS) != 0;
+  for (int col = t; col < n_out; col += 128) {
+    double* acc = e.stat_acc + col;
+    if (stats) {
+      Moments m{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float4 v = acc4_all[w * max_channels + col];
+        m.merge(Moments{v.x, v.y, v.z, v.w});
+      }
+      if (m.n > 0.f) {   // sums of (v - s), (v - s)^2 over n rows -> sums of v, v^2
+        const double s_ = (double)m.s, m1 = (double)m.m1, m2 = (double)m.m2, n_ = (double)m.n;
+        atomicAdd(acc, m1 + n_ * s_);
+        atomicAdd(acc + kStatSlotChannels, m2 + 2.0 * s_ * m1 + n_ * s_ * s_);
+      }
+    } else {
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float4 v = acc4_all[w * max_channels + col];
+        r0 += v.x; r1 += v.y; r2 += v.z;
+      }
+      atomicAdd(acc, (double)r0);
+      atomicAdd(acc + kStatSlotChannels, (double)r1);
+      if (e.n_sets > 1) atomicAdd(acc + 2 * kStatSlotChannels, (double)r2);
     }
   }
 }
@@ -1333,6 +1371,12 @@ __global__ void __launch_bounds__(kThreads) tc_wide_kernel(const __grid_constant
     const uint32_t rowtab_u32 = smem_u32(row_tab);
     constexpr int LPR = RowEpi<32>::LPR, RPI = RowEpi<32>::RPI, U = 4;
     const int lr = lane / LPR, lc = lane % LPR;
+    float4* acc4_all = reinterpret_cast<float4*>(smem + W::kAccOffset);
+    float4* acc4 = acc4_all + quarter * W::kMaxChannels;        // this warp's running statistics
+    if constexpr ((EF & (EF_STATS | EF_BNBWD)) != 0) {
+      for (int i = lane; i < prm.n_out; i += 32) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+    }
     int lt = 0;
     for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++lt) {
       const typename P::Tile tile = tile_of(ti);
@@ -1379,9 +1423,13 @@ __global__ void __launch_bounds__(kThreads) tc_wide_kernel(const __grid_constant
             }
           }
         }
-        wide_flush_stats<EF>(epi, prm.epi, lane, col, prm.n_out);
+        wide_fold_stats<EF>(epi, acc4, lane, col, prm.n_out);
       }
       __syncwarp();   // row pointers are free for the next tile
+    }
+    if constexpr ((EF & (EF_STATS | EF_BNBWD)) != 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+      wide_flush_stats<EF>(prm.epi, acc4_all, W::kMaxChannels, (warp - 2) * 32 + lane, prm.n_out);
     }
   }
   __syncthreads();
@@ -2273,7 +2321,7 @@ static dfb_status run_conv(const char* name, const CUtensorMap& ma, const float*
   if constexpr (BN == 256 && !ROWS) {
     const int n_tiles = (int)(grid.x * grid.y), col_tiles = (int)grid.y;
     const bool slot_ok = prm.epi.stat_kind == EPI_NONE || prm.epi.stat_acc != nullptr;
-    if (wide_enabled() && !g_x3 && classes == 1 && prm.splits == 1 && slot_ok && (size_t)n_tiles >= (size_t)sm_count() * 2) {
+    if (wide_enabled() && !g_x3 && classes == 1 && prm.splits == 1 && slot_ok && n_out <= 512 && (size_t)n_tiles >= (size_t)sm_count() * 2) {
 #define DFB_WIDE(EFV) st = launch_wide<ConvProblem<BN, WMODE, ROWS, (EFV)>, (EFV)>(name, ma, mb, prm, n_tiles, col_tiles)
       if constexpr (WMODE == W_KRSC_FPROP) {
         if (prm.epi.stat_kind == EPI_STATS) DFB_WIDE(EF_STATS);
