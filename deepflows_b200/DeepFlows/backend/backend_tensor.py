@@ -672,8 +672,20 @@ class BackendTensor:
 
     def sum(self, axis=None, keepdims=False):
         view, out = self.reduce_view_out(axis, keepdims=keepdims)
+        if self._sum_view_div(view, out, 1.0):
+            return out
         self._device.reduce_sum(view.compact()._handle, out._handle, view._shape[-1])
         return out
+
+    def _sum_view_div(self, view, out, divisor):
+        """Short reductions (<= 32 elements: pooling windows, the two means of a global average pool) straight from the
+        strided view, the division of `mean` folded in: one launch instead of compact + reduce_sum + scalar_div, the same
+        additions in the same order (dfb_reduce_sum_view_div). False: not available, the caller composes it."""
+        dev = self._device
+        if not (dev.has("reduce_sum_view_div") and 1 <= view._shape[-1] <= 32 and view.ndim <= 8 and out.size > 0):
+            return False
+        dev.reduce_sum_view_div(view._handle, out._handle, view._shape, view._strides, view._offset, float(divisor))
+        return True
 
     def max(self, axis=None, keepdims=False):
         view, out = self.reduce_view_out(axis, keepdims=keepdims)
@@ -682,10 +694,14 @@ class BackendTensor:
 
     def mean(self, axis=None, keepdims=False):
         # reference quirk Q3 (lines 659-662): divides by the TOTAL element count, also for one axis
+        divisor = prod(self._shape)
         if _fix_mean and axis is not None:
-            ax = axis[0] if isinstance(axis, (tuple, list)) else axis
-            return self.sum(axis, keepdims=keepdims) / self._shape[ax]
-        return self.sum(axis, keepdims=keepdims) / prod(self._shape)
+            divisor = self._shape[axis[0] if isinstance(axis, (tuple, list)) else axis]
+        if divisor != 0 and self._device.has("reduce_sum_view_div"):
+            view, out = self.reduce_view_out(axis, keepdims=keepdims)
+            if self._sum_view_div(view, out, divisor):
+                return out
+        return self.sum(axis, keepdims=keepdims) / divisor
 
     def flip(self, axes):
         assert len(axes) <= len(self._shape)

@@ -370,10 +370,13 @@ class DataParallel:
         return 1.0 / self.world
 
 
-def init(params, transport=None, bucket_mb=4.0, broadcast=True):
-    """Enable data parallelism for `params` (usually `model.parameters()`)."""
+def init(params, transport=None, bucket_mb=None, broadcast=True):
+    """Enable data parallelism for `params` (usually `model.parameters()`). `bucket_mb`: size of the gradient buckets that
+    are reduced while backward runs (default 4, or DEEPFLOWS_DP_BUCKET_MB)."""
     global _ctx
     params = list(params)
+    if bucket_mb is None:
+        bucket_mb = float(os.environ.get("DEEPFLOWS_DP_BUCKET_MB", "4"))
     if transport is None:
         rank = int(os.environ.get("RANK", "0"))
         world = int(os.environ.get("WORLD_SIZE", "1"))

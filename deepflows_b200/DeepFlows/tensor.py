@@ -603,6 +603,13 @@ class mean(UnaryOperator):
             grad = backend_api.expand_dims(grad, axis=self.axis)
         # ones(x.shape) * grad * (out.size / x.size)  [763-766]
         scale = self.data.size / x.data.size
+        dev = grad.device
+        if dev.has("compact_scale") and grad.ndim <= 8:
+            # the same products, written once: scalar_mul + compact of the broadcast view in one pass (dfb_compact_scale)
+            view = grad.broadcast_to(x.shape)
+            out = backend_api.empty(x.shape, device=dev)
+            dev.compact_scale(view._handle, out._handle, view._shape, view._strides, view._offset, float(scale))
+            return out
         return (grad * scale).broadcast_to(x.shape).compact()
 
 

@@ -235,6 +235,30 @@ __global__ void __launch_bounds__(kThreads) strided_kernel(const float* __restri
   }
 }
 
+// out[gid] = a[view(gid)] * scale: a broadcast / permuted view made compact and scaled on the way (the backward of
+// `mean`: ones * grad * (out.size / x.size), tensor.py:763-766 - one pass instead of scalar_mul + compact)
+__global__ void __launch_bounds__(kThreads) strided_scale_kernel(const float* __restrict__ a, float* __restrict__ out, float scale,
+                                                                 size_t n, StridedView v, int64_t offset) {
+  pdl_sync();
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < n; gid += stride) out[gid] = a[offset + view_index(gid, v)] * scale;
+}
+// out[gid] = (sum over j < len of a[view(gid) + j * rstride], ascending j, like reduce_thread_kernel) / divisor: the
+// reduction of the LAST axis of a strided view without making it compact first, the division of `mean` folded in
+// (sum: divisor 1). One thread per output; len <= 32.
+__global__ void __launch_bounds__(kThreads) reduce_view_div_kernel(const float* __restrict__ a, float* __restrict__ out, size_t rows,
+                                                                   uint32_t len, int64_t rstride, float divisor, StridedView v,
+                                                                   int64_t offset) {
+  pdl_sync();
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    const float* p = a + offset + view_index(r, v);
+    float acc = p[0];
+    for (uint32_t i = 1; i < len; ++i) acc = acc + p[(int64_t)i * rstride];
+    out[r] = acc / divisor;
+  }
+}
+
 // Batched 2-D transpose through shared memory for the permute case, i.e. a collapsed view of
 // the form (outer..., R, C) where the *input* is contiguous along R (stride 1) and the output is
 // contiguous along C. in index = offset + outer_off + r*1 + c*sC ; out index = o*R*C + r*C + c.
@@ -382,6 +406,39 @@ dfb_status dfb_compact(const float* a, float* out, size_t out_size, int ndim, co
   }
   launch_k(strided_kernel<0>, bw_grid(out_size, kThreads), kThreads, 0, s, a, out, 0.f, out_size, v, (int64_t)offset);
   DFB_LAUNCH_CHECK("Compact");
+  return DFB_OK;
+}
+
+dfb_status dfb_compact_scale(const float* a, float* out, size_t out_size, int ndim, const int32_t* shape, const int32_t* strides,
+                             size_t offset, float scale) {
+  DFB_INIT();
+  DFB_REQUIRE(a != nullptr && out != nullptr, DFB_ERR_INVALID, "CompactScale: null array");
+  DFB_REQUIRE(out_size != 0, DFB_ERR_INVALID, "CompactScale: out array size cannot be zero");
+  dfb_status st = check_view("CompactScale", ndim, shape);
+  if (st != DFB_OK) return st;
+  StridedView v = collapse(ndim, shape, strides);
+  launch_k(strided_scale_kernel, bw_grid(out_size, kThreads), kThreads, 0, compute_stream(), a, out, scale, out_size, v, (int64_t)offset);
+  DFB_LAUNCH_CHECK("CompactScale");
+  return DFB_OK;
+}
+
+dfb_status dfb_reduce_sum_view_div(const float* a, float* out, size_t out_size, int ndim, const int32_t* shape, const int32_t* strides,
+                                   size_t offset, float divisor) {
+  DFB_INIT();
+  DFB_REQUIRE(a != nullptr && out != nullptr, DFB_ERR_INVALID, "ReduceSumView: null array");
+  DFB_REQUIRE(out_size != 0 && ndim >= 1, DFB_ERR_INVALID, "ReduceSumView: empty output");
+  dfb_status st = check_view("ReduceSumView", ndim, shape);
+  if (st != DFB_OK) return st;
+  const int32_t len = shape[ndim - 1];
+  DFB_REQUIRE(len >= 1 && len <= 32, DFB_ERR_INVALID, "ReduceSumView: the reduced axis has %d elements (1..32 supported; longer rows: compact + reduce_sum)", len);
+  DFB_REQUIRE(divisor != 0.f, DFB_ERR_DOMAIN, "ReduceSumView: division by zero");
+  size_t rows = 1;
+  for (int d = 0; d + 1 < ndim; ++d) rows *= (size_t)shape[d];
+  DFB_REQUIRE(rows == out_size, DFB_ERR_INVALID, "ReduceSumView: out.size != product of the outer shape");
+  StridedView v = collapse(ndim - 1, shape, strides);   // (ndim == 1: one output, collapse() returns the unit view)
+  launch_k(reduce_view_div_kernel, bw_grid(out_size, kThreads), kThreads, 0, compute_stream(), a, out, out_size, (uint32_t)len,
+           (int64_t)strides[ndim - 1], divisor, v, (int64_t)offset);
+  DFB_LAUNCH_CHECK("ReduceSumView");
   return DFB_OK;
 }
 

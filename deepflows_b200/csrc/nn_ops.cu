@@ -1206,6 +1206,132 @@ static unsigned ew_grid(size_t items) { return bw_grid(items, kT, 8); }
 
 }  // namespace dfb
 
+namespace dfb {
+// -------------------------------------------------------------------------------------------------
+// Linear layers with few outputs (the classifier at the end of every network: N <= 16) in ONE launch each way.
+// Through the general path x @ W + b is an FFMA GEMM with split-K, its reduction and a row-vector add (three launches,
+// 10 us inside the captured ResNet step for 0.66 MFLOP), and the backward a column-sum kernel, two GEMMs and another
+// split-K reduction (16 us): all launch floor. F.linear, functional.py:8-12; W is (in, out) like the reference's.
+// -------------------------------------------------------------------------------------------------
+constexpr int kLinN = 16;
+// y[m, :] = x[m, :] . W + b: one warp per row, lanes over k (coalesced x), N running sums per lane, shuffle tree
+__global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ y, int M, int K, int N) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31, m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  float acc[kLinN];
+#pragma unroll
+  for (int n = 0; n < kLinN; ++n) acc[n] = 0.f;
+  for (int k0 = lane; k0 < K; k0 += 128) {   // four k per pass: independent loads in flight together
+    float xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = k0 + u * 32 < K ? x[(size_t)m * K + k0 + u * 32] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * 32;
+      if (k < K) {
+        const float* wr = w + (size_t)k * N;
+#pragma unroll
+        for (int n = 0; n < kLinN; ++n)
+          if (n < N) acc[n] = fmaf(xv[u], wr[n], acc[n]);
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < kLinN; ++n)
+    if (n < N) acc[n] = warp_sum(acc[n]);
+  if (lane == 0) {
+#pragma unroll
+    for (int n = 0; n < kLinN; ++n)
+      if (n < N) y[(size_t)m * N + n] = acc[n] + (bias ? bias[n] : 0.f);
+  }
+}
+// One launch, three kinds of CTA (blockIdx ranges):
+//   dx[m, k] = sum_n dy[m, n] W[k, n]                     one thread per element
+//   dW[k, n] = sum_m x[m, k] dy[m, n]                     a CTA per 32 columns k: warps over rows (coalesced x), lanes own a k,
+//                                                         the eight warps' sums merged through shared memory in warp order
+//   db[n]    = sum_m dy[m, n]                             the last CTA
+__global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ dy, float* __restrict__ dx, float* __restrict__ dw,
+                                                               float* __restrict__ db, int M, int K, int N, int dx_blocks, int dw_blocks) {
+  pdl_sync();
+  __shared__ float red[8][32][kLinN + 1];
+  const int b = blockIdx.x;
+  if (b < dx_blocks) {
+    const size_t i = (size_t)b * 256 + threadIdx.x;
+    if (i < (size_t)M * K) {
+      const int m = (int)(i / K), k = (int)(i - (size_t)m * K);
+      const float* g = dy + (size_t)m * N;
+      const float* wr = w + (size_t)k * N;
+      float acc = 0.f;
+#pragma unroll
+      for (int n = 0; n < kLinN; ++n)
+        if (n < N) acc = fmaf(g[n], wr[n], acc);
+      dx[i] = acc;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (b < dx_blocks + dw_blocks) {
+    const int k = (b - dx_blocks) * 32 + lane;
+    float acc[kLinN];
+#pragma unroll
+    for (int n = 0; n < kLinN; ++n) acc[n] = 0.f;
+    // eight rows per pass: their loads are independent and in flight together (the loop is nothing but load latency)
+    for (int m0 = warp; m0 < M; m0 += 64) {
+      float xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = m0 + u * 8;
+        xv[u] = (k < K && m < M) ? x[(size_t)m * K + k] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = m0 + u * 8;
+        if (m < M) {
+          const float* g = dy + (size_t)m * N;
+#pragma unroll
+          for (int n = 0; n < kLinN; ++n)
+            if (n < N) acc[n] = fmaf(xv[u], g[n], acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < kLinN; ++n) red[warp][lane][n] = acc[n];
+    __syncthreads();
+    // thread t: (k = t / 8 .. , n): 32 x N sums of eight partials each
+    for (int o = threadIdx.x; o < 32 * N; o += 256) {
+      const int kl = o / N, n = o - kl * N;
+      float s2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s2 += red[q][kl][n];
+      const int kk = (b - dx_blocks) * 32 + kl;
+      if (kk < K) dw[(size_t)kk * N + n] = s2;
+    }
+    return;
+  }
+  // db: thread (row lane r = t / 16, n = t % 16)
+  {
+    const int n = threadIdx.x & 15, r = threadIdx.x >> 4;   // 16 row lanes
+    float acc = 0.f;
+    if (n < N) {
+#pragma unroll 8
+      for (int m = r; m < M; m += 16) acc += dy[(size_t)m * N + n];
+    }
+    red[0][r][n] = acc;   // (r < 16, n < 16 fit the [32][17] slab)
+    __syncthreads();
+    if (threadIdx.x < N) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s2 += red[0][q][threadIdx.x];
+      db[threadIdx.x] = s2;
+    }
+  }
+}
+
+}  // namespace dfb
+
 using namespace dfb;
 
 extern "C" {
@@ -1598,6 +1724,28 @@ dfb_status dfb_avgpool2d_bwd(const float* dy, float* dx, int N, int H, int W, in
   bool vec = C % 4 == 0 && all_aligned(dy, dx);
   POOL_DISPATCH(avgpool_bwd_kernel, (size_t)N * H * W * C, dy, dx, N, H, W, C, k, OH, OW);
   DFB_LAUNCH_CHECK("avgpool2d_bwd");
+  return DFB_OK;
+}
+
+dfb_status dfb_linear_small_fwd(const float* x, const float* w, const float* bias, float* y, int M, int K, int N) {
+  DFB_INIT();
+  DFB_REQUIRE(x && w && y, DFB_ERR_INVALID, "linear_small_fwd: null pointer");
+  DFB_REQUIRE(M > 0 && K > 0 && N > 0 && N <= kLinN, DFB_ERR_INVALID, "linear_small_fwd: M = %d, K = %d, N = %d (1 <= N <= %d)", M, K, N, kLinN);
+  launch_k(linear_small_fwd_kernel, (unsigned)((M + 7) / 8), 256, 0, compute_stream(), x, w, bias, y, M, K, N);
+  DFB_LAUNCH_CHECK("linear_small_fwd");
+  return DFB_OK;
+}
+dfb_status dfb_linear_small_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int M, int K, int N) {
+  DFB_INIT();
+  DFB_REQUIRE(dy != nullptr, DFB_ERR_INVALID, "linear_small_bwd: null gradient");
+  DFB_REQUIRE(M > 0 && K > 0 && N > 0 && N <= kLinN, DFB_ERR_INVALID, "linear_small_bwd: M = %d, K = %d, N = %d (1 <= N <= %d)", M, K, N, kLinN);
+  DFB_REQUIRE((!dx || w) && (!dw || x), DFB_ERR_INVALID, "linear_small_bwd: dx needs w, dw needs x");
+  DFB_REQUIRE((size_t)M * K < ((size_t)1 << 38), DFB_ERR_INVALID, "linear_small_bwd: input too large");
+  const int dx_blocks = dx ? (int)(((size_t)M * K + 255) / 256) : 0, dw_blocks = dw ? (K + 31) / 32 : 0, db_blocks = db ? 1 : 0;
+  if (dx_blocks + dw_blocks + db_blocks == 0) return DFB_OK;
+  launch_k(linear_small_bwd_kernel, (unsigned)(dx_blocks + dw_blocks + db_blocks), 256, 0, compute_stream(), x, w, dy, dx, dw, db, M, K, N,
+           dx_blocks, dw_blocks);
+  DFB_LAUNCH_CHECK("linear_small_bwd");
   return DFB_OK;
 }
 

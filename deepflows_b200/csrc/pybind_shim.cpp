@@ -272,6 +272,20 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
     View v = parse_view(shape, strides);
     check(dfb_compact(A.ptr, O.ptr, O.size, v.ndim, v.shape, v.strides, offset));
   });
+  m.def("compact_scale", [](const py::object& a, const py::object& out, const py::sequence& shape, const py::sequence& strides, size_t offset,
+                            float scale) {
+    Array& A = arr(a, "CompactScale: a");
+    Array& O = arr(out, "CompactScale: out");
+    View v = parse_view(shape, strides);
+    check(dfb_compact_scale(A.ptr, O.ptr, O.size, v.ndim, v.shape, v.strides, offset, scale));
+  });
+  m.def("reduce_sum_view_div", [](const py::object& a, const py::object& out, const py::sequence& shape, const py::sequence& strides,
+                                  size_t offset, float divisor) {
+    Array& A = arr(a, "ReduceSumView: a");
+    Array& O = arr(out, "ReduceSumView: out");
+    View v = parse_view(shape, strides);
+    check(dfb_reduce_sum_view_div(A.ptr, O.ptr, O.size, v.ndim, v.shape, v.strides, offset, divisor));
+  });
   m.def("ewise_setitem", [](const py::object& a, const py::object& out, const py::sequence& shape, const py::sequence& strides, size_t offset) {
     Array& A = arr(a, "EwiseSetitem: a");
     Array& O = arr(out, "EwiseSetitem: out");
@@ -501,6 +515,13 @@ PYBIND11_MODULE(CUDA_BACKEND, m) {
   });
   m.def("avgpool2d_bwd", [](const py::object& dy, const py::object& dx, int N, int H, int W, int C, int k) {
     check(dfb_avgpool2d_bwd(dptr(dy), dptr(dx), N, H, W, C, k));
+  });
+  m.def("linear_small_fwd", [](const py::object& x, const py::object& w, const py::object& bias, const py::object& y, int M, int K, int N) {
+    check(dfb_linear_small_fwd(dptr(x), dptr(w), dptr(bias), dptr(y), M, K, N));
+  });
+  m.def("linear_small_bwd", [](const py::object& x, const py::object& w, const py::object& dy, const py::object& dx, const py::object& dw,
+                               const py::object& db, int M, int K, int N) {
+    check(dfb_linear_small_bwd(dptr(x), dptr(w), dptr(dy), dptr(dx), dptr(dw), dptr(db), M, K, N));
   });
   m.def("softmax_ce_fwd", [](const py::object& logits, const py::object& target, const py::object& loss, size_t rows, int cols,
                              float scale) {

@@ -218,6 +218,16 @@ DFB_API dfb_status dfb_matmul(const float* a, const float* b, float* out, uint32
                               uint32_t P, int mode);
 /* reductions over trailing contiguous `reduce_size`: cu:469-509 */
 DFB_API dfb_status dfb_reduce_sum(const float* a, float* out, size_t out_size, size_t reduce_size);
+/* Fused forms of what backend_tensor.py composes for `sum` / `mean` over one axis (bt.py:624-662) and for the backward
+ * of `mean` (tensor.py:763-766); same values bit for bit, fewer passes.
+ * reduce_sum_view_div: the view (shape / strides / offset as in dfb_compact, at most DFB_MAX_DIMS dims) has the reduced
+ *   axis LAST (1..32 elements); out[i] = (a[view(i, 0)] + a[view(i, 1)] + ... in ascending order) / divisor
+ *   = compact + reduce_sum + scalar_div without the compact copy. divisor == 0 -> DFB_ERR_DOMAIN like scalar_div.
+ * compact_scale: out[i] = a[view(i)] * scale = scalar_mul + compact of a (broadcast) view in one pass. */
+DFB_API dfb_status dfb_reduce_sum_view_div(const float* a, float* out, size_t out_size, int ndim, const int32_t* shape,
+                                           const int32_t* strides, size_t offset, float divisor);
+DFB_API dfb_status dfb_compact_scale(const float* a, float* out, size_t out_size, int ndim, const int32_t* shape,
+                                     const int32_t* strides, size_t offset, float scale);
 DFB_API dfb_status dfb_reduce_max(const float* a, float* out, size_t out_size, size_t reduce_size);
 
 /* ---------------------------------------------------------------------------------------------
@@ -396,6 +406,13 @@ DFB_API dfb_status dfb_maxpool2d_bwd_idx(const int32_t* idx, const float* dy, fl
 /* average pooling, same geometry (the reference's avg_pool2d raises) */
 DFB_API dfb_status dfb_avgpool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int k);
 DFB_API dfb_status dfb_avgpool2d_bwd(const float* dy, float* dx, int N, int H, int W, int C, int k);
+
+/* Linear layers with at most 16 outputs (the classifier) in one launch each way (F.linear, functional.py:8-12; W is
+ * (in, out) = K x N row-major like the reference's Linear.weight, x is M x K, bias N floats or NULL):
+ *   fwd: y = x . W + bias          bwd: dx = dy . W^T, dw = x^T . dy, db = column sums of dy (each may be NULL) */
+DFB_API dfb_status dfb_linear_small_fwd(const float* x, const float* w, const float* bias, float* y, int M, int K, int N);
+DFB_API dfb_status dfb_linear_small_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
+                                        int M, int K, int N);
 
 /* Fused softmax cross-entropy with dense targets (F.cross_entropy, functional.py:104-115):
  *   loss = scale * sum_i sum_j -(x_ij - max_i - log sum_j exp(x_ij - max_i)) * t_ij

@@ -131,6 +131,62 @@ def test_compact_and_setitem_bit_exact(cuda_device, case):
     assert np.array_equal(host(m, z).reshape(shape), want)
 
 
+REDUCE_VIEWS = [  # (shape, view with the reduced axis last)
+    ((256, 2, 2, 256), lambda x: x.transpose(0, 3, 2, 1)),      # global average pool, first mean: NHWC buffer viewed (N, C, W, H)
+    ((256, 256, 2), lambda x: x),                                # second mean: already compact
+    ((6, 5, 7, 3), lambda x: x.transpose(1, 3, 0, 2)[1:4]),      # permuted and sliced, 7-element rows
+    ((4, 32), lambda x: x[:, ::-1]),                             # negative stride along the reduced axis
+    ((5, 1, 9), lambda x: np.broadcast_to(x, (5, 4, 9))),        # zero stride in the outer view
+    ((33,), lambda x: x[1:33]),                                  # one output, 32 elements, offset
+]
+
+
+@pytest.mark.parametrize("case", range(len(REDUCE_VIEWS)))
+@pytest.mark.parametrize("divisor", [1.0, 3.0, 1024.0])
+def test_reduce_sum_view_div_equals_the_composed_ops(cuda_device, case, divisor):
+    """dfb_reduce_sum_view_div == compact -> reduce_sum -> scalar_div (what backend_tensor.py composes for sum / mean over
+    one axis) bit for bit, and == numpy's sequential float32 sum."""
+    m = cuda_device.mod
+    shape, view_of = REDUCE_VIEWS[case]
+    rng = np.random.RandomState(100 + case)
+    x = rng.randn(*shape).astype(F32)
+    v = view_of(x)
+    strides = [s // 4 for s in v.strides]
+    offset = (v.__array_interface__["data"][0] - x.__array_interface__["data"][0]) // 4
+    rows, r = int(np.prod(v.shape[:-1], dtype=np.int64)), v.shape[-1]
+    hx = dev_array(m, x)
+    got = m.Array(rows)
+    m.reduce_sum_view_div(hx, got, v.shape, strides, offset, divisor)
+    c, s1, s2 = m.Array(v.size), m.Array(rows), m.Array(rows)
+    m.compact(hx, c, v.shape, strides, offset)
+    m.reduce_sum(c, s1, r)
+    m.scalar_div(s1, divisor, s2)
+    assert np.array_equal(host(m, got), host(m, s2))
+    acc = v.reshape(rows, r)[:, 0].copy()
+    for j in range(1, r):
+        acc = acc + v.reshape(rows, r)[:, j]
+    assert np.array_equal(host(m, got), (acc / F32(divisor)).astype(F32))
+    with pytest.raises(ValueError):
+        m.reduce_sum_view_div(hx, got, v.shape, strides, offset, 0.0)
+
+
+@pytest.mark.parametrize("case", range(len(VIEWS)))
+def test_compact_scale_equals_scalar_mul_then_compact(cuda_device, case):
+    m = cuda_device.mod
+    shape, view_of = VIEWS[case]
+    rng = np.random.RandomState(200 + case)
+    x = rng.randn(*shape).astype(F32)
+    v = view_of(x)
+    strides = [s // 4 for s in v.strides]
+    offset = (v.__array_interface__["data"][0] - x.__array_interface__["data"][0]) // 4
+    hx, out, scaled, ref = dev_array(m, x), m.Array(v.size), m.Array(x.size), m.Array(v.size)
+    m.compact_scale(hx, out, v.shape, strides, offset, 0.37)
+    m.scalar_mul(hx, 0.37, scaled)
+    m.compact(scaled, ref, v.shape, strides, offset)
+    assert np.array_equal(host(m, out), host(m, ref))
+    assert np.array_equal(host(m, out).reshape(v.shape), v * F32(0.37))
+
+
 def test_broadcast_and_negative_strides(cuda_device):
     m = cuda_device.mod
     x = np.random.RandomState(0).randn(1, 5, 1, 7).astype(F32)

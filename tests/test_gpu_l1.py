@@ -423,6 +423,33 @@ def test_softmax_ce(cuda_device):
     assert rel_err(down(m, hloss, (1,)), ops.softmax_ce_fwd(lg, tg, 1 / 4096)) < 1e-5
 
 
+@pytest.mark.parametrize("M,K,N,bias", [(256, 256, 10, True), (64, 20, 10, True), (7, 33, 1, False), (300, 2048, 16, True), (1, 5, 3, False)])
+def test_linear_small(cuda_device, M, K, N, bias):
+    """dfb_linear_small_fwd / _bwd (the classifier in one launch each way) against the float64 contraction at the fp32-mode
+    tolerance of north_star (1e-5 relative), including the partial-output forms of the backward."""
+    m = cuda_device.mod
+    rng = np.random.RandomState(M + K + N)
+    x, w, b, gy = rng.randn(M, K).astype(F32), (rng.randn(K, N) / np.sqrt(K)).astype(F32), rng.randn(N).astype(F32), rng.randn(M, N).astype(F32)
+    hx, hw, hb, hg = up(m, x), up(m, w), up(m, b) if bias else None, up(m, gy)
+    hy = m.Array(M * N)
+    m.linear_small_fwd(hx, hw, hb, hy, M, K, N)
+    want = x.astype(np.float64) @ w.astype(np.float64) + (b if bias else 0.0)
+    assert rel_err(down(m, hy, (M, N)), want) < 1e-5
+    hdx, hdw, hdb = m.Array(M * K), m.Array(K * N), m.Array(N)
+    m.linear_small_bwd(hx, hw, hg, hdx, hdw, hdb, M, K, N)
+    g64 = gy.astype(np.float64)
+    assert rel_err(down(m, hdx, (M, K)), g64 @ w.astype(np.float64).T) < 1e-5
+    assert rel_err(down(m, hdw, (K, N)), x.astype(np.float64).T @ g64) < 1e-5
+    assert rel_err(down(m, hdb, (N,)), g64.sum(0)) < 1e-5
+    # only the weight gradient (frozen input, no bias), only the input gradient
+    hdw2, hdx2 = m.Array(K * N), m.Array(M * K)
+    m.linear_small_bwd(hx, None, hg, None, hdw2, None, M, K, N)
+    m.linear_small_bwd(None, hw, hg, hdx2, None, None, M, K, N)
+    assert np.array_equal(down(m, hdw2, (K, N)), down(m, hdw, (K, N))) and np.array_equal(down(m, hdx2, (M, K)), down(m, hdx, (M, K)))
+    with pytest.raises(ValueError):
+        m.linear_small_fwd(hx, hw, hb, hy, M, K, 17)
+
+
 def test_rowvec_and_colsum(cuda_device):
     m = cuda_device.mod
     rng = np.random.RandomState(0)
