@@ -8,8 +8,10 @@ fused optimizer kernel's `grad_scale`. Scripts stay unchanged apart from one `di
 call (which reads RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT from the launcher's environment); `backward()`
 and `step()` consult this module's context.
 
-The transport is pluggable so the bucketing logic can be tested on CPU: `NcclTransport` (libdfb200
-dfb_comm_*) for GPUs; tests/test_dist_gloo.py supplies a torch.distributed (gloo) transport for the numpy device.
+The transport is pluggable so the bucketing logic can be tested on CPU: `PeerTransport` (the default on GPUs: NCCL
+for the buckets that overlap backward, the library's own one-shot kernel over NVLink peer memory - csrc/peer.cu - for
+the last, exposed one; falls back to plain `NcclTransport` when the GPUs cannot map each other);
+tests/test_dist_gloo.py supplies a torch.distributed (gloo) transport for the numpy device.
 
 Gradient accumulation over several `backward()` calls before one `step()` is not supported: after a backward the
 gradients alias their (already summed) buckets, and a second backward raises instead of reducing them twice.

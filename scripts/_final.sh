@@ -8,7 +8,7 @@ timeout 200 ncu --set full --import-source on --clock-control none -k regex:pool
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra --mode eager > $out/${tag}_ncu_pool2.log 2>&1
 ncu -i /tmp/${tag}_pool2.ncu-rep --page raw --csv > $out/${tag}_pool2_full_raw.csv 2>/dev/null
 echo "== ncu --set full: wide persistent conv kernel (VGG-16 eager step)"
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:tc_wide -s 30 -c 6 -f -o /tmp/${tag}_wide \
+timeout 400 ncu --set full --import-source on --clock-control none -k "regex:tc_wide|WgradProblem" -s 20 -c 10 -f -o /tmp/${tag}_wide \
     python bench.py --config c5-vgg16 --steps 1 --warmup 1 --no-cpu-baseline --no-extra --mode eager > $out/${tag}_ncu_wide.log 2>&1
 ncu -i /tmp/${tag}_wide.ncu-rep --page raw --csv > $out/${tag}_wide_full_raw.csv 2>/dev/null
 python scripts/ncu_top_stalls.py /tmp/${tag}_wide.ncu-rep 0 30 > $out/${tag}_wide_stalls.txt 2>&1
