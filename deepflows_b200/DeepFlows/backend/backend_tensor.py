@@ -537,6 +537,15 @@ class BackendTensor:
                 out = self._like()
                 ewise_func(self._handle, other._handle, out._handle)
                 return out
+            if (other._shape == self._shape and len(self._shape) == 4 and (self.is_channels_last() or other.is_channels_last())
+                    and not isinstance(self, PendingTensor) and not isinstance(other, PendingTensor)):
+                # one operand lives channels-last (an activation or its gradient), the other compact (e.g. the gradient a
+                # `mean` sent back): bring the other one over - one copy, and the result stays in the layout every
+                # convolution / BatchNorm kernel wants - instead of two copies to compact and a third one back
+                a, b = self.channels_last(), other.channels_last()
+                out = a._like()
+                ewise_func(a._handle, b._handle, out._handle)
+                return out
             if self._shape != other._shape:
                 other = other.broadcast_to(self._shape)
             out = BackendTensor.make(self._shape, device=dev)

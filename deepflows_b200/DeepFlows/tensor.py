@@ -607,6 +607,15 @@ class mean(UnaryOperator):
         if dev.has("compact_scale") and grad.ndim <= 8:
             # the same products, written once: scalar_mul + compact of the broadcast view in one pass (dfb_compact_scale)
             view = grad.broadcast_to(x.shape)
+            xd = x.data
+            if view.ndim == 4 and xd.is_channels_last() and not xd.is_compact():
+                # the input is an activation in channels-last memory order: its gradient is written in that order too (what
+                # the BatchNorm / convolution backward kernels it goes to read), not compact and then copied over
+                n, c, h, w = view._shape
+                nhwc = view.permute((0, 2, 3, 1))
+                out = BackendTensor.make((n, c, h, w), (h * w * c, 1, w * c, c), dev, dev.Array(n * c * h * w))
+                dev.compact_scale(nhwc._handle, out._handle, nhwc._shape, nhwc._strides, nhwc._offset, float(scale))
+                return out
             out = backend_api.empty(x.shape, device=dev)
             dev.compact_scale(view._handle, out._handle, view._shape, view._strides, view._offset, float(scale))
             return out
