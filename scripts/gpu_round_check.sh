@@ -20,8 +20,8 @@ timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_
 tail -c 400 $out/${tag}_bench_reference_arm.json
 echo "== ncu launch list of one eager step (numbers under ncu are never bench values)"
 # bench --mode eager runs ~10 identical eager steps of ~160 launches each (warm-up, timed, end-to-end) after ~80 start-up
-# launches: a window of 232 launches (2 x 116) starting at 900 is two whole steady-state steps (check "n=" in the summary: every
+# launches: a window of 222 launches (2 x 111) starting at 900 is two whole steady-state steps (check "n=" in the summary: every
 # per-step count doubled)
-timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 232 --csv --log-file $out/${tag}_launches.csv \
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 222 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --mode eager > $out/${tag}_launches_bench.log 2>&1
 python scripts/summarize_launches.py $out/${tag}_launches.csv 1.0 | tee $out/${tag}_launch_summary.txt | head -30
