@@ -1247,19 +1247,22 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
       if (n < N) y[(size_t)m * N + n] = acc[n] + (bias ? bias[n] : 0.f);
   }
 }
-// One launch, three kinds of CTA (blockIdx ranges):
+// One launch, three kinds of CTA (blockIdx ranges), 1024 threads each:
 //   dx[m, k] = sum_n dy[m, n] W[k, n]                     one thread per element
-//   dW[k, n] = sum_m x[m, k] dy[m, n]                     a CTA per 32 columns k: warps over rows (coalesced x), lanes own a k,
-//                                                         the eight warps' sums merged through shared memory in warp order
+//   dW[k, n] = sum_m x[m, k] dy[m, n]                     a CTA per 32 columns k: 32 warps over rows (coalesced x: 256 rows per
+//                                                         pass, eight independent loads per lane), lanes own a k; the warps'
+//                                                         sums merged through shared memory in warp order, eight warps a round
 //   db[n]    = sum_m dy[m, n]                             the last CTA
-__global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                               const float* __restrict__ dy, float* __restrict__ dx, float* __restrict__ dw,
-                                                               float* __restrict__ db, int M, int K, int N, int dx_blocks, int dw_blocks) {
+// (with 8 warps per CTA the weight-gradient CTAs walked the rows in four dependent passes: 13.5 us in the step)
+constexpr int kLinT = 1024;
+__global__ void __launch_bounds__(kLinT) linear_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ dy, float* __restrict__ dx, float* __restrict__ dw,
+                                                                 float* __restrict__ db, int M, int K, int N, int dx_blocks, int dw_blocks) {
   pdl_sync();
   __shared__ float red[8][32][kLinN + 1];
   const int b = blockIdx.x;
   if (b < dx_blocks) {
-    const size_t i = (size_t)b * 256 + threadIdx.x;
+    const size_t i = (size_t)b * kLinT + threadIdx.x;
     if (i < (size_t)M * K) {
       const int m = (int)(i / K), k = (int)(i - (size_t)m * K);
       const float* g = dy + (size_t)m * N;
@@ -1272,23 +1275,23 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
     }
     return;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // 32 warps
   if (b < dx_blocks + dw_blocks) {
     const int k = (b - dx_blocks) * 32 + lane;
     float acc[kLinN];
 #pragma unroll
     for (int n = 0; n < kLinN; ++n) acc[n] = 0.f;
-    // eight rows per pass: their loads are independent and in flight together (the loop is nothing but load latency)
-    for (int m0 = warp; m0 < M; m0 += 64) {
+    // eight rows per warp and pass: their loads are independent and in flight together (the loop is nothing but load latency)
+    for (int m0 = warp; m0 < M; m0 += 256) {
       float xv[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int m = m0 + u * 8;
+        const int m = m0 + u * 32;
         xv[u] = (k < K && m < M) ? x[(size_t)m * K + k] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int m = m0 + u * 8;
+        const int m = m0 + u * 32;
         if (m < M) {
           const float* g = dy + (size_t)m * N;
 #pragma unroll
@@ -1297,34 +1300,42 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
         }
       }
     }
+    // merge the 32 warps, eight at a time (warp order: deterministic); thread o < 32 * N owns output (k = o / N, n = o % N)
+    const int o = threadIdx.x, kl = o / N, n_o = o - kl * N;
+    float total = 0.f;
+    for (int round = 0; round < 4; ++round) {
+      __syncthreads();   // the previous round's sums have been read
+      if ((warp >> 3) == round) {
 #pragma unroll
-    for (int n = 0; n < kLinN; ++n) red[warp][lane][n] = acc[n];
-    __syncthreads();
-    // thread t: (k = t / 8 .. , n): 32 x N sums of eight partials each
-    for (int o = threadIdx.x; o < 32 * N; o += 256) {
-      const int kl = o / N, n = o - kl * N;
-      float s2 = 0.f;
+        for (int n = 0; n < kLinN; ++n) red[warp & 7][lane][n] = acc[n];
+      }
+      __syncthreads();
+      if (o < 32 * N) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s2 += red[q][kl][n];
+        for (int q = 0; q < 8; ++q) total += red[q][kl][n_o];
+      }
+    }
+    if (o < 32 * N) {
       const int kk = (b - dx_blocks) * 32 + kl;
-      if (kk < K) dw[(size_t)kk * N + n] = s2;
+      if (kk < K) dw[(size_t)kk * N + n_o] = total;
     }
     return;
   }
-  // db: thread (row lane r = t / 16, n = t % 16)
+  // db: thread (row lane r = t / 16 of 64, n = t % 16)
   {
-    const int n = threadIdx.x & 15, r = threadIdx.x >> 4;   // 16 row lanes
+    float* red2 = &red[0][0][0];   // 64 x 16 floats fit the slab (8 x 32 x 17)
+    const int n = threadIdx.x & 15, r = threadIdx.x >> 4;
     float acc = 0.f;
     if (n < N) {
-#pragma unroll 8
-      for (int m = r; m < M; m += 16) acc += dy[(size_t)m * N + n];
+#pragma unroll 4
+      for (int m = r; m < M; m += 64) acc += dy[(size_t)m * N + n];
     }
-    red[0][r][n] = acc;   // (r < 16, n < 16 fit the [32][17] slab)
+    red2[r * 16 + n] = acc;
     __syncthreads();
     if (threadIdx.x < N) {
       float s2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) s2 += red[0][q][threadIdx.x];
+#pragma unroll 8
+      for (int q = 0; q < 64; ++q) s2 += red2[q * 16 + threadIdx.x];
       db[threadIdx.x] = s2;
     }
   }
@@ -1741,10 +1752,10 @@ dfb_status dfb_linear_small_bwd(const float* x, const float* w, const float* dy,
   DFB_REQUIRE(M > 0 && K > 0 && N > 0 && N <= kLinN, DFB_ERR_INVALID, "linear_small_bwd: M = %d, K = %d, N = %d (1 <= N <= %d)", M, K, N, kLinN);
   DFB_REQUIRE((!dx || w) && (!dw || x), DFB_ERR_INVALID, "linear_small_bwd: dx needs w, dw needs x");
   DFB_REQUIRE((size_t)M * K < ((size_t)1 << 38), DFB_ERR_INVALID, "linear_small_bwd: input too large");
-  const int dx_blocks = dx ? (int)(((size_t)M * K + 255) / 256) : 0, dw_blocks = dw ? (K + 31) / 32 : 0, db_blocks = db ? 1 : 0;
+  const int dx_blocks = dx ? (int)(((size_t)M * K + kLinT - 1) / kLinT) : 0, dw_blocks = dw ? (K + 31) / 32 : 0, db_blocks = db ? 1 : 0;
   if (dx_blocks + dw_blocks + db_blocks == 0) return DFB_OK;
-  launch_k(linear_small_bwd_kernel, (unsigned)(dx_blocks + dw_blocks + db_blocks), 256, 0, compute_stream(), x, w, dy, dx, dw, db, M, K, N,
-           dx_blocks, dw_blocks);
+  launch_k(linear_small_bwd_kernel, (unsigned)(dx_blocks + dw_blocks + db_blocks), kLinT, 0, compute_stream(), x, w, dy, dx, dw, db, M, K,
+           N, dx_blocks, dw_blocks);
   DFB_LAUNCH_CHECK("linear_small_bwd");
   return DFB_OK;
 }

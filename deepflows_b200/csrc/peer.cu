@@ -431,7 +431,19 @@ dfb_status dfb_peer_init(size_t arena_floats, float** arena) {
     g_peer.error = (unsigned*)err_dev;
     if (ok && (e = cudaMemcpy(g_peer_dev, &g_peer, sizeof(g_peer), cudaMemcpyHostToDevice)) != cudaSuccess) fail("cudaMemcpy", e);
   }
-  // ---- self-test: two launches of the last slot (the second proves the epoch arithmetic), pattern checked on the device ----
+  // Every rank must have mapped every peer before any kernel touches a peer: agree on that first (one rank that could not
+  // open a handle would otherwise leave the others' self-test waiting for it, and the collectives below out of step).
+  {
+    int mapped = ok;
+    st = comm_allreduce_min_int(&mapped);
+    if (st != DFB_OK) { peer_release(); return st; }
+    if (!mapped) {
+      peer_release();
+      DFB_FAIL(DFB_ERR_RUNTIME, "peer_init: peer-memory exchange unavailable (%s)", ok ? "another rank could not map its peers" : why.c_str());
+    }
+  }
+  // ---- self-test: two launches of each form (the second proves the epoch / parity arithmetic), pattern checked on the device.
+  // Every rank runs every round's collective whatever its own outcome, so the ranks stay in step ----
   unsigned bad_host = 0;
   if (ok) {
     g_ready = true;
@@ -440,19 +452,21 @@ dfb_status dfb_peer_init(size_t arena_floats, float** arena) {
     if ((e = cudaMalloc((void**)&bad, sizeof(unsigned))) != cudaSuccess) fail("cudaMalloc", e);
     if (ok) cudaMemset(bad, 0, sizeof(unsigned));
     cudaStream_t s = compute_stream();
-    for (int round = 0; round < 4 && ok; ++round) {   // two launches of each form (the second proves the epoch / parity arithmetic)
-      peer_test_fill_kernel<<<64, 256, 0, s>>>(g_peer.arena[rank], test_floats, rank);
-      if (round < 2) peer_launch(0, test_floats, kPeerSlots - 1);
-      else peer_launch_push(0, test_floats);
-      launch_k(peer_wait_kernel, dim3(1), dim3(256), 0, s, (const PeerDev*)g_peer_dev, peer_pending_take());
-      peer_test_check_kernel<<<64, 256, 0, s>>>(g_peer.arena[rank], test_floats, world, bad);
-      if ((e = cudaStreamSynchronize(s)) != cudaSuccess) fail("self-test", e);
+    for (int round = 0; round < 4; ++round) {
+      if (ok) {
+        peer_test_fill_kernel<<<64, 256, 0, s>>>(g_peer.arena[rank], test_floats, rank);
+        if (round < 2) peer_launch(0, test_floats, kPeerSlots - 1);
+        else peer_launch_push(0, test_floats);
+        launch_k(peer_wait_kernel, dim3(1), dim3(256), 0, s, (const PeerDev*)g_peer_dev, peer_pending_take());
+        peer_test_check_kernel<<<64, 256, 0, s>>>(g_peer.arena[rank], test_floats, world, bad);
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) fail("self-test", e);
+      }
       // nobody may refill its bucket while a peer still reads it: the next round's fill is ordered behind every rank's
       // check by the all-gather below / the verdict all-reduce (last round)
       if (round < 3) {
         unsigned char z[kRec] = {0};
         st = comm_allgather_bytes(z, kRec, all.data());
-        if (st != DFB_OK) { ok = 0; why = "all-gather between the self-test rounds failed"; }
+        if (st != DFB_OK && ok) { ok = 0; why = "all-gather between the self-test rounds failed"; }
       }
     }
     if (ok) cudaMemcpy(&bad_host, bad, sizeof(unsigned), cudaMemcpyDeviceToHost);
