@@ -55,6 +55,9 @@ class NcclTransport:
 _PEER_PARTS = os.environ.get("DEEPFLOWS_DP_PEER_PARTS", "tail")
 
 
+_ONE_SHOT_FLOATS = 65536   # capacity of one copy in the one-shot kernel's receive area (csrc/peer.cuh: kPushCapFloats)
+
+
 class PeerTransport(NcclTransport):
     """Gradient buckets in NVLink peer memory (csrc/peer.cu): every bucket is a window of one arena that all ranks of
     the box map through CUDA IPC, `allreduce_sum` is one kernel on the stream that packed the bucket (no communication
@@ -96,17 +99,18 @@ class PeerTransport(NcclTransport):
 
     def allreduce_sum(self, flat):
         w = self._windows.get(flat._offset) if self.peer and flat._handle is self._arena else None
-        if w is not None and _PEER_PARTS != "all" and (_PEER_PARTS == "tail") != bool(w[2]):
-            w = None   # experiment switch: only the exposed bucket ("tail") or only the overlapped ones ("mid") on the peer kernels
+        one_shot = w is not None and w[2] and w[1] <= _ONE_SHOT_FLOATS    # the last bucket, small enough for the receive area
+        if w is not None and ((_PEER_PARTS == "tail" and not one_shot) or (_PEER_PARTS == "mid" and w[2])):
+            w = None   # "tail" (default): only the exposed bucket on the peer kernels; "mid": only the overlapped ones
         if w is None:
             self._nccl_busy = True
             return super().allreduce_sum(flat)
-        self.device.peer_allreduce_async(flat._offset, w[1], w[0], w[2])
+        self.device.peer_allreduce_async(flat._offset, w[1], w[0], one_shot)
 
     def exposed(self, flat):
         """True for the bucket the one-shot kernel reduces on the compute stream itself (DataParallel._launch_bucket)."""
         w = self._windows.get(flat._offset) if self.peer and flat._handle is self._arena else None
-        return bool(w is not None and w[2] and w[1] <= 65536 and _PEER_PARTS != "mid")
+        return bool(w is not None and w[2] and w[1] <= _ONE_SHOT_FLOATS and _PEER_PARTS != "mid")
 
     def broadcast(self, flat, root=0):
         self._nccl_busy = True
