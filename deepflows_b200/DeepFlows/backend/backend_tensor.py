@@ -75,8 +75,16 @@ class BackendDevice:
         return (Device, (self.name,))
 
     def has(self, attr):
-        """True when the device module implements the (fused, L1) entry point `attr`."""
-        return self.mod is not None and hasattr(self.mod, attr)
+        """True when the device module implements the (fused, L1) entry point `attr` (remembered: the host layer asks a
+        couple of hundred times per training step, and a module's entry points do not change)."""
+        d = self.__dict__
+        cache = d.get("_has_cache")
+        if cache is None:
+            cache = d["_has_cache"] = {}
+        v = cache.get(attr)
+        if v is None:
+            v = cache[attr] = self.mod is not None and hasattr(self.mod, attr)
+        return v
 
     def randn(self, *shape, dtype="float32"):
         return BackendTensor(np.random.randn(*shape).astype(dtype), device=self)
